@@ -1,0 +1,269 @@
+"""ctypes wrapper around oracle/md_oracle.c (the CPU restatement of the reference hot path).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline leg -- never by the product package lammps_b200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+SRC = HERE / "md_oracle.c"
+LIB = HERE / "libmd_oracle.so"
+
+
+def build(force: bool = False) -> Path:
+    if force or not LIB.exists() or LIB.stat().st_mtime < SRC.stat().st_mtime:
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o",
+                               str(LIB), str(SRC), "-lm"])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(LIB))
+        L.orc_create.restype = C.c_void_p
+        for name in ("orc_nlocal", "orc_nghost", "orc_ncalls", "orc_ndanger", "orc_ago",
+                     "orc_decide", "orc_step", "orc_run"):
+            getattr(L, name).restype = C.c_int
+        L.orc_nneigh.restype = C.c_int64
+        L.orc_eng_vdwl.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """One periodic orthogonal box on one process, driven like the reference's Verlet."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.orc_create())
+        self.ntypes = 1
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.orc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- configuration (mirrors the C-ABI of the product, include/b200_md.h)
+    def set_box(self, lo, hi, periodic=(1, 1, 1)):
+        lo, hi, per = _d(lo), _d(hi), _i(periodic)
+        self.L.orc_set_box(self.h, _p(lo), _p(hi), _p(per))
+
+    def set_atoms(self, x, v, type, tag, mass, mask=None, image=None):
+        x, v, type, tag, mass = _d(x), _d(v), _i(type), _i(tag), _d(mass)
+        n = x.shape[0]
+        self.ntypes = mass.shape[0] - 1
+        mk = _i(mask) if mask is not None else None
+        im = _i(image) if image is not None else None
+        self.L.orc_set_atoms(self.h, C.c_int(n), C.c_int(self.ntypes), _p(mass), _p(x), _p(v),
+                             _p(type), _p(tag), _p(mk) if mk is not None else None,
+                             _p(im) if im is not None else None)
+
+    def set_neighbor(self, skin, every=1, delay=0, check=True):
+        self.L.orc_set_neighbor(self.h, C.c_double(skin), C.c_int(every), C.c_int(delay),
+                                C.c_int(1 if check else 0))
+
+    def fix_nve(self, dt, ftm2v=1.0, groupbit=1):
+        self.L.orc_fix_nve(self.h, C.c_double(dt), C.c_double(ftm2v), C.c_int(groupbit))
+
+    def pair_lj_cut(self, p):
+        """p: dict of (ntypes+1)^2 tables cutsq, lj1..lj4, offset (see lammps_b200.pair_lj)."""
+        t = {k: _d(p[k]) for k in ("cutsq", "lj1", "lj2", "lj3", "lj4", "offset")}
+        sp = _d(p.get("special_lj", [1.0, 1.0, 1.0, 1.0]))
+        self.L.orc_pair_lj_cut(self.h, C.c_int(p["ntypes"]), _p(t["cutsq"]), _p(t["lj1"]),
+                               _p(t["lj2"]), _p(t["lj3"]), _p(t["lj4"]), _p(t["offset"]), _p(sp))
+
+    def pair_eam(self, t):
+        """t: dict from lammps_b200.eam.EAMTables.as_dict()."""
+        a = {k: _i(t[k]) for k in ("type2frho", "type2rhor", "type2z2r")}
+        b = {k: _d(t[k]) for k in ("scale", "frho_spline", "rhor_spline", "z2r_spline")}
+        self.L.orc_pair_eam(self.h, C.c_int(t["ntypes"]), C.c_int(t["nr"]), C.c_int(t["nrho"]),
+                            C.c_double(t["rdr"]), C.c_double(t["rdrho"]), C.c_double(t["rhomax"]),
+                            C.c_double(t["cutforcesq"]), _p(a["type2frho"]), _p(a["type2rhor"]),
+                            _p(a["type2z2r"]), _p(b["scale"]), C.c_int(t["nfrho"]),
+                            _p(b["frho_spline"]), C.c_int(t["nrhor"]), _p(b["rhor_spline"]),
+                            C.c_int(t["nz2r"]), _p(b["z2r_spline"]))
+
+    # ---- driver
+    def setup(self, eflag=1, vflag=1):
+        self.L.orc_setup(self.h, C.c_int(eflag), C.c_int(vflag))
+
+    def step(self, eflag=0, vflag=0) -> int:
+        return self.L.orc_step(self.h, C.c_int(eflag), C.c_int(vflag))
+
+    def run(self, nsteps, step0=0, thermo_every=0):
+        out = np.zeros((nsteps + 1, 10))
+        n = self.L.orc_run(self.h, C.c_int(nsteps), C.c_int(step0), C.c_int(thermo_every),
+                           _p(out), C.c_int(out.shape[0]))
+        return out[:n]
+
+    def pair_compute(self, eflag=1, vflag=1):
+        self.L.orc_force_clear(self.h)
+        self.L.orc_pair_compute(self.h, C.c_int(eflag), C.c_int(vflag))
+
+    def reverse_comm(self):
+        self.L.orc_reverse_comm(self.h)
+
+    # ---- results
+    @property
+    def nlocal(self):
+        return self.L.orc_nlocal(self.h)
+
+    @property
+    def nghost(self):
+        return self.L.orc_nghost(self.h)
+
+    @property
+    def nneigh(self):
+        return self.L.orc_nneigh(self.h)
+
+    @property
+    def ncalls(self):
+        return self.L.orc_ncalls(self.h)
+
+    @property
+    def ndanger(self):
+        return self.L.orc_ndanger(self.h)
+
+    @property
+    def eng_vdwl(self):
+        return self.L.orc_eng_vdwl(self.h)
+
+    @property
+    def virial(self):
+        v = np.zeros(6)
+        self.L.orc_get_virial(self.h, _p(v))
+        return v
+
+    def ke_sum(self):
+        out = C.c_double()
+        self.L.orc_ke_sum(self.h, C.byref(out))
+        return out.value
+
+    def _vec(self, which, ghosts=False):
+        n = self.nlocal + (self.nghost if ghosts else 0)
+        out = np.zeros((n, 3))
+        self.L.orc_get_vec(self.h, C.c_int(which), C.c_int(n), _p(out))
+        return out
+
+    def _ivec(self, which, ghosts=False):
+        n = self.nlocal + (self.nghost if ghosts else 0)
+        out = np.zeros(n, np.int32)
+        self.L.orc_get_ivec(self.h, C.c_int(which), C.c_int(n), _p(out))
+        return out
+
+    def x(self, ghosts=False):
+        return self._vec(0, ghosts)
+
+    def v(self):
+        return self._vec(1)
+
+    def f(self, ghosts=False):
+        return self._vec(2, ghosts)
+
+    def type(self, ghosts=False):
+        return self._ivec(0, ghosts)
+
+    def tag(self, ghosts=False):
+        return self._ivec(1, ghosts)
+
+    def image(self):
+        return self._ivec(3)
+
+    def numneigh(self):
+        return self._ivec(4)
+
+    def bins(self):
+        out = np.zeros(10, np.int32)
+        self.L.orc_get_bins(self.h, _p(out))
+        keys = ("nbinx", "nbiny", "nbinz", "mbinx", "mbiny", "mbinz", "mbinxlo", "mbinylo",
+                "mbinzlo", "nstencil")
+        return dict(zip(keys, out.tolist()))
+
+    def stencil(self):
+        out = np.zeros(self.bins()["nstencil"], np.int32)
+        self.L.orc_get_stencil(self.h, _p(out))
+        return out
+
+    def rho_fp(self, ghosts=False):
+        n = self.nlocal + (self.nghost if ghosts else 0)
+        rho, fp = np.zeros(n), np.zeros(n)
+        self.L.orc_get_rho_fp(self.h, C.c_int(n), _p(rho), _p(fp))
+        return rho, fp
+
+    def pairs(self):
+        n = self.nneigh
+        pi, pj = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.L.orc_get_pairs(self.h, _p(pi), _p(pj))
+        return pi, pj
+
+
+def velocity_loop_geom(x, seed, mass_per_atom):
+    """velocity.cpp:327-352 (`loop geom`, uniform distribution) -- raw velocities before
+    momentum zeroing and temperature scaling."""
+    x = _d(x)
+    m = _d(mass_per_atom)
+    v = np.zeros_like(x)
+    lib().orc_velocity_loop_geom(C.c_int(x.shape[0]), C.c_int(seed), _p(x), _p(m), _p(v))
+    return v
+
+
+def canonical_pairs_box(pi, pj, tag, x, boxlo, boxhi, nlocal=None):
+    """Order-independent identity of a neighbour list: for every stored pair (i, j) the key
+    (tag_a, tag_b, sx, sy, sz) with tag_a <= tag_b and (sx,sy,sz) = the lattice vector (in
+    box lengths) separating the stored image of b from the owned image of a.  Sorted
+    lexicographically -> a multiset that two implementations must reproduce exactly,
+    whatever their atom order and whichever of the two mirror (owned, ghost) images each
+    happened to store.  `tag`, `x` cover owned+ghost atoms (owned first, `nlocal` of them).
+    """
+    pi = np.asarray(pi, np.int64)
+    pj = np.asarray(pj, np.int64)
+    tag = np.asarray(tag, np.int64)
+    boxlo = np.asarray(boxlo, float)
+    prd = np.asarray(boxhi, float) - boxlo
+    if nlocal is None:
+        nlocal = int(pi.max()) + 1 if pi.size else 0
+    owner = np.full(int(tag.max()) + 1, -1, np.int64)
+    owner[tag[:nlocal]] = np.arange(nlocal)
+    # image shift of every atom relative to its owned copy (0 for owned atoms)
+    shift = np.rint((x - x[owner[tag]]) / prd).astype(np.int64)
+    s = shift[pj] - shift[pi]
+    ta, tb = tag[pi], tag[pj]
+    swap = (ta > tb)
+    a = np.where(swap, tb, ta)
+    b = np.where(swap, ta, tb)
+    s = np.where(swap[:, None], -s, s)
+    # self-image pairs (ta == tb): canonical sign = first non-zero component positive
+    same = (ta == tb)
+    if same.any():
+        sgn = np.sign(s[:, 0] * 9 + s[:, 1] * 3 + s[:, 2])
+        flip = same & (sgn < 0)
+        s = np.where(flip[:, None], -s, s)
+    key = np.stack([a, b, s[:, 0], s[:, 1], s[:, 2]], axis=1)
+    order = np.lexsort(key.T[::-1])
+    return key[order]
