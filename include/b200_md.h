@@ -1,0 +1,166 @@
+/* b200_md.h -- C ABI of the B200-native short-range MD hot path (libb200md.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The host
+ * side that binds it is (a) the LAMMPS package src/B200 (lammps_b200/lammps_pkg/B200:
+ * pair_style lj/cut/b200, eam/b200, fix nve/b200, run_style verlet/b200, fix B200) and
+ * (b) the ctypes mirror lammps_b200/engine.py used by tests and bench.py.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference's src/).  All functions return 0 on success or a negative B200_E* code;
+ * b200_last_error() gives the message (the host turns it into error->one(FLERR,...),
+ * precedent GPU/fix_gpu.cpp:251,358-361).  A context is single-threaded like a LAMMPS
+ * instance.  All host arrays are caller-owned; device memory is owned by the
+ * context and released by b200_destroy (precedent: lmp_clear_device, GPU/fix_gpu.cpp:256).
+ *
+ * Per-atom host layouts are the reference's: x,v,f = double[n][3] row-major (atom.h:72-75),
+ * type/tag/mask/image = int32 (LAMMPS_SMALLBIG, lmptype.h:99-125).  Type tables are
+ * (ntypes+1)x(ntypes+1) row-major with row/column 0 unused, as memory->create gives them.
+ */
+#ifndef B200_MD_H
+#define B200_MD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;
+
+enum {
+  B200_OK = 0,
+  B200_ECUDA = -1,     /* CUDA runtime / NCCL failure */
+  B200_EARG = -2,      /* invalid argument or call order */
+  B200_ECAPACITY = -3, /* neighbor list overflow beyond `one` (npair_bin.cpp:248), ghost buffer */
+  B200_ENONFINITE = -4,/* non-numeric coordinates (nbin.cpp:145, domain.cpp:787-790) */
+  B200_ELOST = -5      /* atom left the (non-periodic) box or moved further than a sub-domain */
+};
+
+enum { B200_PREC_DOUBLE = 0, B200_PREC_MIXED = 1 };
+
+/* ---- lifetime: replaces lmp_init_device / lmp_clear_device (GPU/fix_gpu.cpp:44-55) and the
+ *      `package b200` fix constructor (input.cpp:1736-1777 Input::package) */
+int b200_create(b200_ctx **out, int device, int precision);
+void b200_destroy(b200_ctx *ctx);
+const char *b200_last_error(const b200_ctx *ctx);
+/* 1 if a CUDA device is usable from this process (never falls back to the CPU) */
+int b200_device_count(void);
+
+/* ---- domain: Domain::set_global_box / set_local_box (domain.cpp), Comm::set_proc_grid
+ *      (comm.cpp:505); sub-box = boxlo + prd*myloc/procgrid, last one closed at boxhi */
+int b200_set_box(b200_ctx *ctx, const double boxlo[3], const double boxhi[3],
+                 const int periodicity[3]);
+int b200_set_decomposition(b200_ctx *ctx, const int procgrid[3], const int myloc[3]);
+
+/* ---- neighbor / neigh_modify (neighbor.cpp:2680-2940): skin, every, delay, check, one.
+ *      cutneighsq = (sqrt(cutsq)+skin)^2 is derived from the pair style's cutsq
+ *      (neighbor.cpp:337-383), triggersq = (skin/2)^2 */
+int b200_set_neighbor(b200_ctx *ctx, double skin, int every, int delay, int dist_check, int one);
+
+/* ---- atoms: Atom arrays (atom.h:72-75) + per-type mass (atom.cpp set_mass).
+ *      mask/image may be NULL (all atoms in group `all`, image flags 0). */
+int b200_set_atoms(b200_ctx *ctx, int nlocal, int ntypes, const double *mass /*[ntypes+1]*/,
+                   const double *x, const double *v, const int *type, const int *tag,
+                   const int *mask, const int *image);
+/* copies nlocal (+nghost if with_ghosts) atoms in current device order; any pointer may be NULL.
+ * This is the sync the host needs on thermo/dump steps. */
+int b200_get_atoms(b200_ctx *ctx, int with_ghosts, double *x, double *v, double *f, int *type,
+                   int *tag, int *mask, int *image);
+int b200_get_counts(const b200_ctx *ctx, int *nlocal, int *nghost);
+
+/* ---- pair styles.  PairLJCut::init_one products (pair_lj_cut.cpp:503-524) and
+ *      force->special_lj; replaces ljl_gpu_init (GPU/pair_lj_cut_gpu.cpp:35-53). */
+int b200_pair_lj_cut(b200_ctx *ctx, int ntypes, const double *cutsq, const double *lj1,
+                     const double *lj2, const double *lj3, const double *lj4,
+                     const double *offset, const double special_lj[4]);
+/*      PairEAM tables after file2array()+array2spline() (pair_eam.cpp:999-1205,1492-1545):
+ *      splines are [n][nr+1 or nrho+1][7]; replaces eam_gpu_init (GPU/pair_eam_gpu.cpp:35-56). */
+int b200_pair_eam(b200_ctx *ctx, int ntypes, int nr, int nrho, double rdr, double rdrho,
+                  double rhomax, double cutforcesq, const int *type2frho /*[ntypes+1]*/,
+                  const int *type2rhor, const int *type2z2r, const double *scale, int nfrho,
+                  const double *frho_spline, int nrhor, const double *rhor_spline, int nz2r,
+                  const double *z2r_spline);
+
+/* ---- fix nve: FixNVE::init (fix_nve.cpp:55-59): dtv = dt, dtf = 0.5*dt*ftm2v */
+int b200_fix_nve(b200_ctx *ctx, double dtv, double dtf, int groupbit);
+
+/* ---- timestep pieces, one per call the reference's Verlet makes (verlet.cpp:93-162, 229-360).
+ *      b200_setup      = Verlet::setup: pbc, comm->setup, setup_bins, exchange, borders,
+ *                        neighbor->build, force_clear, pair->compute, reverse_comm
+ *      b200_run        = Verlet::run for nsteps (all device-side; host only reads the 4-byte
+ *                        rebuild vote when dist_check is on).  eflag/vflag tallies happen on
+ *                        steps where (ntimestep % thermo_every == 0) and on the last step
+ *                        (integrate.cpp:106-151 ev_set); thermo_out receives, per tallied step,
+ *                        10 doubles {step, sum(m v^2), eng_vdwl, virial[0..5], 0}.
+ */
+int b200_setup(b200_ctx *ctx, int eflag, int vflag);
+int b200_run(b200_ctx *ctx, int nsteps, int64_t first_step, int thermo_every,
+             double *thermo_out, int max_thermo, int *n_thermo);
+
+/*      step-granular entry points (what verlet/b200 calls when other fixes interleave) */
+int b200_initial_integrate(b200_ctx *ctx);            /* FixNVE::initial_integrate fix_nve.cpp:68 */
+int b200_final_integrate(b200_ctx *ctx);              /* FixNVE::final_integrate  fix_nve.cpp:112 */
+int b200_decide(b200_ctx *ctx, int *rebuild);         /* Neighbor::decide neighbor.cpp:2408 */
+int b200_forward_comm(b200_ctx *ctx);                 /* CommBrick::forward_comm comm_brick.cpp:485 */
+int b200_reverse_comm(b200_ctx *ctx);                 /* CommBrick::reverse_comm comm_brick.cpp:545 */
+int b200_reneighbor(b200_ctx *ctx);                   /* pbc+exchange+borders+Neighbor::build */
+int b200_force_clear(b200_ctx *ctx);                  /* Verlet::force_clear verlet.cpp:376 */
+int b200_pair_compute(b200_ctx *ctx, int eflag, int vflag); /* Pair::compute pair.h:159 */
+
+/* ---- tallies the host reads back: pair->eng_vdwl, pair->virial[6] (pair.h), and
+ *      sum_i m_i v_i^2 (ComputeTemp::compute_scalar, compute_temp.cpp:73-97) */
+int b200_get_tallies(b200_ctx *ctx, double *eng_vdwl, double virial[6]);
+int b200_ke_sum(b200_ctx *ctx, double *mv2);
+
+/* ---- statistics: neighbor->ncalls / ndanger / ago, pair counts, phase timings */
+typedef struct {
+  int64_t nbuilds;      /* Neighbor list builds            (finish.cpp) */
+  int64_t ndanger;      /* Dangerous builds                (neighbor.cpp:2488) */
+  int64_t ago;
+  int64_t npairs;       /* stored pairs in the current list (Total # of neighbors) */
+  int64_t maxneigh;     /* capacity per atom currently allocated */
+  int64_t max_numneigh; /* largest numneigh[i] in the current list */
+  int64_t nbins[3];     /* global bins (nbinx,nbiny,nbinz) */
+  int64_t mbins;        /* local bins incl. ghost shell */
+  int64_t nstencil;
+  int64_t launches;     /* kernels launched since create */
+  double  device_bytes; /* device memory currently allocated */
+} b200_stats;
+int b200_get_stats(b200_ctx *ctx, b200_stats *out);
+
+/* ---- test hooks: the half list as CSR over current owned order.  j indexes
+ *      owned [0,nlocal) or ghost [nlocal, nlocal+nghost) atoms, as NeighList does
+ *      (neigh_list.h:53-57).  Call with neigh == NULL to get the pair count only. */
+int b200_get_neighbor_list(b200_ctx *ctx, int *numneigh /*[nlocal]*/, int *neigh, int64_t cap,
+                           int64_t *npairs);
+/*      EAM intermediates rho[], fp[] (pair_eam.h) for owned(+ghost) atoms */
+int b200_get_eam_rho_fp(b200_ctx *ctx, int with_ghosts, double *rho, double *fp);
+
+/* ---- per-phase device timing (CUDA events recorded on the context's stream around each
+ *      phase inside b200_run; replaces Timer::stamp of verlet.cpp:257-357).  Off by default. */
+enum {
+  B200_PH_INITIAL = 0,  /* fix nve initial_integrate (+ displacement check)   Timer::MODIFY */
+  B200_PH_FINAL = 1,    /* fix nve final_integrate                            Timer::MODIFY */
+  B200_PH_FORWARD = 2,  /* ghost position update                              Timer::COMM   */
+  B200_PH_REVERSE = 3,  /* ghost force reduction                              Timer::COMM   */
+  B200_PH_PAIR = 4,     /* pair->compute incl. EAM rho/fp halo                Timer::PAIR   */
+  B200_PH_NEIGH = 5,    /* pbc + exchange + borders + bin + list build        Timer::NEIGH  */
+  B200_PH_BUILD = 6,    /* the list-build kernel alone (subset of NEIGH)                   */
+  B200_PH_CLEAR = 7,    /* force_clear                                                     */
+  B200_PH_THERMO = 8,   /* energy/virial/ke reductions on tallied steps                    */
+  B200_NPHASE = 9
+};
+int b200_set_profiling(b200_ctx *ctx, int on);
+/* accumulated since the last call (which resets them): milliseconds and launch counts */
+int b200_get_phase_times(b200_ctx *ctx, double ms[B200_NPHASE], int64_t calls[B200_NPHASE]);
+
+/* ---- multi-GPU: one context per GPU/process; halo exchange over NCCL send/recv.
+ *      b200_comm_unique_id fills a 128-byte ncclUniqueId on rank 0 (to be broadcast by the
+ *      host, e.g. torch.distributed); b200_comm_init joins the communicator. */
+int b200_comm_unique_id(void *id128);
+int b200_comm_init(b200_ctx *ctx, int nranks, int rank, const void *id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_MD_H */

@@ -1,0 +1,105 @@
+// common.cuh -- shared types and device helpers of the B200 MD engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_md.h"
+
+#define NEIGHMASK 0x1FFFFFFF /* lmptype.h:63 */
+#define IMGMASK 1023         /* lmptype.h:122-125, LAMMPS_SMALLBIG */
+#define IMGBITS 10
+#define IMG2BITS 20
+#define B200_SMALL 1.0e-6 /* nbin_standard.cpp:27 */
+#define MAXROWS 32        /* stencil rows (dz,dy) of the half stencil: 13 for sx=sy=sz=2 */
+#define NDIR 27
+
+// Geometry of the box, the sub-domain, the bins and the ghost slabs; passed to kernels by value.
+struct Geom {
+  double boxlo[3], boxhi[3], prd[3];
+  double sublo[3], subhi[3];
+  int periodic[3];
+  // bins: nbin_standard.cpp:82-214
+  int nbin[3];
+  double bininv[3];
+  int mbinlo[3], mbin[3];
+  int mbins;
+  // ghost slabs: comm_brick.cpp:389-420 (slabhi of the "send left" swap, slablo of "send right")
+  double slab_left_hi[3], slab_right_lo[3];
+  int send_left[3], send_right[3];
+  // per direction (dz+1)*9+(dy+1)*3+(dx+1): periodic shift added to a ghost's position
+  double shift[NDIR][3];
+};
+
+// Half stencil as rows of x-contiguous bins: nstencil_bin.cpp:28-67 regrouped by (dz,dy).
+struct Stencil {
+  int nrows;
+  int rowoff[MAXROWS];  // dz*mbiny*mbinx + dy*mbinx
+  int dxlo[MAXROWS], dxhi[MAXROWS];
+};
+
+__device__ __forceinline__ int d2type(double w) { return (int)__double_as_longlong(w); }
+__device__ __forceinline__ double type2d(int t) { return __longlong_as_double((long long)t); }
+
+// NBin::coord2bin, nbin.cpp:141-173 (three branches per dimension, truncating casts)
+__device__ __forceinline__ int coord2bin_dim(double x, double lo, double hi, double bininv,
+                                             int nbin) {
+  int ix;
+  if (x >= hi)
+    ix = (int)((x - hi) * bininv) + nbin;
+  else if (x >= lo) {
+    ix = (int)((x - lo) * bininv);
+    ix = min(ix, nbin - 1);
+  } else
+    ix = (int)((x - lo) * bininv) - 1;
+  return ix;
+}
+
+__device__ __forceinline__ int coord2bin(const Geom &g, double x, double y, double z) {
+  int ix = coord2bin_dim(x, g.boxlo[0], g.boxhi[0], g.bininv[0], g.nbin[0]);
+  int iy = coord2bin_dim(y, g.boxlo[1], g.boxhi[1], g.bininv[1], g.nbin[1]);
+  int iz = coord2bin_dim(z, g.boxlo[2], g.boxhi[2], g.bininv[2], g.nbin[2]);
+  ix -= g.mbinlo[0];
+  iy -= g.mbinlo[1];
+  iz -= g.mbinlo[2];
+  // a bin outside the local grid means the atom moved further than the ghost shell allows
+  if (ix < 0 || ix >= g.mbin[0] || iy < 0 || iy >= g.mbin[1] || iz < 0 || iz >= g.mbin[2]) return -1;
+  return (iz * g.mbin[1] + iy) * g.mbin[0] + ix;
+}
+
+// rsq exactly as the reference's x86-64 build evaluates delx*delx + dely*dely + delz*delz
+// (separate multiplies and adds, no FMA contraction): the cutoff decisions `rsq <= cutneighsq`
+// and `rsq < cutsq` then agree bit-for-bit with the CPU path.
+__device__ __forceinline__ double rsq_ref(double dx, double dy, double dz) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of NV values per thread; result valid in thread 0.  blockDim.x <= 1024.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *smem /* [NV*32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) v[k] = warp_sum(v[k]);
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < NV; k++) smem[k * 32 + warp] = v[k];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      double t = lane < nwarp ? smem[k * 32 + lane] : 0.0;
+      v[k] = warp_sum(t);
+    }
+  }
+}

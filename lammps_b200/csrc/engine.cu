@@ -1,0 +1,1171 @@
+// engine.cu -- context, device memory, rebuild/step orchestration and the C ABI
+// (include/b200_md.h) of the B200-native short-range MD hot path.  sm_100a only.
+//
+// Device layout (all resident in HBM for the whole run):
+//   xt     double4[nmax]   {x,y,z,type}  owned atoms [0,nlocal) sorted by bin, then ghosts
+//                                        [nlocal,nlocal+nghost) sorted by bin
+//   v      3 x double[nmax] SoA,  f 3 x double[nmax] SoA (owned + ghost, Newton on)
+//   tag/mask/image int32[nmax], xhold 3 x double[nmax]
+//   ostart/gstart  int32[mbins+1]  bin -> first owned / first ghost index (counting sort)
+//   neigh  int32[maxneigh][nstride] transposed half list, numneigh int32[nlocal]
+//   gsrc   int32[nghost], gdir uint8[nghost]: owner index and direction of every ghost
+#include "common.cuh"
+#include "kernels_neigh.cuh"
+#include "kernels_pair.cuh"
+#include "kernels_step.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <type_traits>
+
+namespace {
+
+template <class T>
+struct DBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+};
+
+struct PhaseRec {
+  int ph;
+  cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct b200_ctx {
+  int device = 0, prec = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  size_t dev_bytes = 0;
+  int64_t launches = 0;
+
+  // domain
+  bool have_box = false;
+  double boxlo[3], boxhi[3], prd[3];
+  int periodic[3] = {1, 1, 1};
+  int procgrid[3] = {1, 1, 1}, myloc[3] = {0, 0, 0};
+  double sublo[3], subhi[3];
+  // neighbor settings
+  double skin = 0.3;
+  int every = 1, delay = 0, dist_check = 1, one = 2000;
+  double cutneighmax = 0, cutneighmaxsq = 0, triggersq = 0, cutghost = 0;
+  std::vector<double> cutneighsq_h;
+  DBuf<double> cutneighsq_d;
+  int64_t ago = 0, nbuilds = 0, ndanger = 0;
+  Geom geom;
+  Stencil stencil;
+  int nstencil = 0;
+  bool geom_ready = false;
+  // atoms
+  int ntypes = 0, nlocal = 0, nghost = 0, nmax = 0;
+  std::vector<double> mass_h;
+  DBuf<double> mass_d;
+  double4 *xt[2] = {nullptr, nullptr};
+  double *v[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  double *f[3] = {nullptr, nullptr, nullptr};
+  double *xh[3] = {nullptr, nullptr, nullptr};
+  int *tag[2] = {nullptr, nullptr}, *mask[2] = {nullptr, nullptr}, *image[2] = {nullptr, nullptr};
+  int *atombin[2] = {nullptr, nullptr}, *slot = nullptr;
+  int cur = 0;  // which of the ping-pong buffers holds the live atoms
+  // bins
+  DBuf<int> ostart, gstart, tilesum;
+  // ghosts
+  DBuf<int> sendlist, gsrc, gbin, gslot;
+  DBuf<unsigned char> gdir, gdir_tmp;
+  DBuf<double4> gtmp;
+  int *dircount = nullptr;   // [27] device
+  int *diroffset = nullptr;  // [28] device
+  // list
+  DBuf<int> neigh, numneigh;
+  int maxneigh = 0, nstride = 0, max_numneigh = 0;
+  // pair
+  int pair_style = 0;  // 1 lj/cut, 2 eam
+  std::vector<double> cutsq_h;
+  LJOne lj_one;
+  DBuf<double> lj_tab;
+  EAMParams eam;
+  DBuf<int> eam_i;
+  DBuf<double> eam_d;
+  double *rho = nullptr, *fp = nullptr;
+  // nve
+  double dtv = 0, dtf = 0;
+  int groupbit = 1;
+  bool have_nve = false;
+  // tallies / flags
+  double *ev = nullptr;   // [8] device: eng, virial[6], ke
+  int *flags = nullptr;   // [4] device: moved, err, maxcount, grand_total
+  unsigned long long *cnt64 = nullptr;
+  double *h_ev = nullptr; // pinned [8]
+  int *h_flags = nullptr; // pinned [32]
+  double eng_vdwl = 0, virial[6] = {0, 0, 0, 0, 0, 0};
+  bool setup_done = false;
+  // profiling
+  bool profiling = false;
+  std::vector<PhaseRec> recs;
+  std::vector<cudaEvent_t> evpool;
+  double ph_ms[B200_NPHASE] = {0};
+  int64_t ph_calls[B200_NPHASE] = {0};
+
+  int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return ctx->fail(B200_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                       __LINE__);                                                         \
+  } while (0)
+#define TRY(call)            \
+  do {                       \
+    int r_ = (call);         \
+    if (r_ != B200_OK) return r_; \
+  } while (0)
+#define LAUNCH_CHECK() CK(cudaGetLastError())
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+template <class T>
+static int dalloc(b200_ctx *ctx, T **p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  CK(cudaMalloc((void **)p, n * sizeof(T)));
+  ctx->dev_bytes += n * sizeof(T);
+  return B200_OK;
+}
+template <class T>
+static void dfree(b200_ctx *ctx, T *&p, size_t n) {
+  if (p) {
+    cudaFree(p);
+    ctx->dev_bytes -= std::min(ctx->dev_bytes, (n ? n : 1) * sizeof(T));
+    p = nullptr;
+  }
+}
+// grow-only buffer, contents NOT preserved
+template <class T>
+static int reserve(b200_ctx *ctx, DBuf<T> &b, size_t n) {
+  if (n <= b.cap && b.p) return B200_OK;
+  size_t cap = n + n / 8 + 64;
+  if (b.p) dfree(ctx, b.p, b.cap);
+  b.cap = 0;
+  TRY(dalloc(ctx, &b.p, cap));
+  b.cap = cap;
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------ profiling helpers
+static int ph_begin(b200_ctx *ctx, int ph) {
+  if (!ctx->profiling) return -1;
+  PhaseRec r;
+  r.ph = ph;
+  auto get = [&]() {
+    cudaEvent_t e;
+    if (!ctx->evpool.empty()) {
+      e = ctx->evpool.back();
+      ctx->evpool.pop_back();
+    } else
+      cudaEventCreate(&e);
+    return e;
+  };
+  r.a = get();
+  r.b = get();
+  cudaEventRecord(r.a, ctx->stream);
+  ctx->recs.push_back(r);
+  return (int)ctx->recs.size() - 1;
+}
+static void ph_end(b200_ctx *ctx, int h) {
+  if (h < 0 || h >= (int)ctx->recs.size()) return;
+  cudaEventRecord(ctx->recs[h].b, ctx->stream);
+}
+static void ph_collect(b200_ctx *ctx) {
+  if (ctx->recs.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &r : ctx->recs) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    ctx->ph_ms[r.ph] += ms;
+    ctx->ph_calls[r.ph]++;
+    ctx->evpool.push_back(r.a);
+    ctx->evpool.push_back(r.b);
+  }
+  ctx->recs.clear();
+}
+
+// ------------------------------------------------------------------ per-atom storage
+static int alloc_atoms(b200_ctx *ctx, int nmax) {
+  // (re)allocate every per-atom array for nmax atoms; live data is copied over
+  const int old = ctx->nmax, keep = ctx->nlocal + ctx->nghost, c = ctx->cur;
+  auto regrow = [&](auto *&p, int n_new, int n_keep, size_t elem) -> int {
+    using T = std::remove_reference_t<decltype(*p)>;
+    T *q = nullptr;
+    TRY(dalloc(ctx, &q, (size_t)n_new));
+    if (p && n_keep > 0)
+      CK(cudaMemcpyAsync(q, p, (size_t)n_keep * elem, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (p) {
+      CK(cudaStreamSynchronize(ctx->stream));
+      dfree(ctx, p, (size_t)old);
+    }
+    p = q;
+    return B200_OK;
+  };
+  for (int b = 0; b < 2; b++) {
+    const int k = (b == c) ? keep : 0;
+    TRY(regrow(ctx->xt[b], nmax, k, sizeof(double4)));
+    for (int d = 0; d < 3; d++) TRY(regrow(ctx->v[b][d], nmax, k, sizeof(double)));
+    TRY(regrow(ctx->tag[b], nmax, k, sizeof(int)));
+    TRY(regrow(ctx->mask[b], nmax, k, sizeof(int)));
+    TRY(regrow(ctx->image[b], nmax, k, sizeof(int)));
+    TRY(regrow(ctx->atombin[b], nmax, k, sizeof(int)));
+  }
+  for (int d = 0; d < 3; d++) {
+    TRY(regrow(ctx->f[d], nmax, keep, sizeof(double)));
+    TRY(regrow(ctx->xh[d], nmax, keep, sizeof(double)));
+  }
+  TRY(regrow(ctx->slot, nmax, 0, sizeof(int)));
+  TRY(regrow(ctx->rho, nmax, keep, sizeof(double)));
+  TRY(regrow(ctx->fp, nmax, keep, sizeof(double)));
+  ctx->nmax = nmax;
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------ geometry (host, once)
+// Neighbor::init cutoffs (neighbor.cpp:337-383), CommBrick::setup slabs (comm_brick.cpp:389-420),
+// NBinStandard::setup_bins (nbin_standard.cpp:82-214), NStencilBin<1,1,0>::create
+// (nstencil.cpp:203-237, nstencil_bin.cpp:28-67) regrouped into x-contiguous rows.
+static int setup_geometry(b200_ctx *ctx) {
+  if (!ctx->have_box) return ctx->fail(B200_EARG, "b200_set_box has not been called");
+  if (!ctx->pair_style) return ctx->fail(B200_EARG, "no pair style set");
+  const int n = ctx->ntypes, n1 = n + 1;
+  if ((int)ctx->cutsq_h.size() != n1 * n1)
+    return ctx->fail(B200_EARG, "pair style was set for %d types but atoms have %d",
+                     (int)std::lround(std::sqrt((double)ctx->cutsq_h.size())) - 1, n);
+  ctx->triggersq = 0.25 * ctx->skin * ctx->skin;
+  ctx->cutneighsq_h.assign(n1 * n1, 0.0);
+  ctx->cutneighmax = 0.0;
+  for (int i = 1; i <= n; i++)
+    for (int j = 1; j <= n; j++) {
+      double cutoff = std::sqrt(ctx->cutsq_h[i * n1 + j]);
+      double delta = cutoff > 0.0 ? ctx->skin : 0.0;
+      double cut = cutoff + delta;
+      ctx->cutneighsq_h[i * n1 + j] = cut * cut;
+      ctx->cutneighmax = std::max(ctx->cutneighmax, cut);
+    }
+  ctx->cutneighmaxsq = ctx->cutneighmax * ctx->cutneighmax;
+  ctx->cutghost = ctx->cutneighmax;  // Comm::get_comm_cutoff, comm.cpp:683
+  TRY(reserve(ctx, ctx->cutneighsq_d, (size_t)n1 * n1));
+  CK(cudaMemcpyAsync(ctx->cutneighsq_d.p, ctx->cutneighsq_h.data(), sizeof(double) * n1 * n1,
+                     cudaMemcpyHostToDevice, ctx->stream));
+
+  Geom &g = ctx->geom;
+  memset(&g, 0, sizeof g);
+  for (int d = 0; d < 3; d++) {
+    g.boxlo[d] = ctx->boxlo[d];
+    g.boxhi[d] = ctx->boxhi[d];
+    g.prd[d] = ctx->prd[d];
+    g.periodic[d] = ctx->periodic[d];
+    // Domain::set_local_box (domain.cpp), uniform grid: xsplit[i] = i * 1.0/procgrid
+    const int P = ctx->procgrid[d], me = ctx->myloc[d];
+    ctx->sublo[d] = ctx->boxlo[d] + ctx->prd[d] * (me * 1.0 / P);
+    ctx->subhi[d] = (me < P - 1) ? ctx->boxlo[d] + ctx->prd[d] * ((me + 1) * 1.0 / P) : ctx->boxhi[d];
+    g.sublo[d] = ctx->sublo[d];
+    g.subhi[d] = ctx->subhi[d];
+    // comm_brick.cpp:268-270 maxneed; only one layer of neighbours is supported
+    const double sub = ctx->subhi[d] - ctx->sublo[d];
+    int maxneed = (int)(ctx->cutghost * P / ctx->prd[d]) + 1;
+    if (!ctx->periodic[d]) maxneed = std::min(maxneed, P - 1);
+    if (maxneed > 1)
+      return ctx->fail(B200_EARG,
+                       "sub-domain edge %g in dim %d is shorter than the ghost cutoff %g "
+                       "(multi-layer halos are not supported)", sub, d, ctx->cutghost);
+    g.slab_left_hi[d] = ctx->sublo[d] + ctx->cutghost;
+    g.slab_right_lo[d] = ctx->subhi[d] - ctx->cutghost;
+    g.send_left[d] = (maxneed >= 1) && (ctx->periodic[d] || me > 0);
+    g.send_right[d] = (maxneed >= 1) && (ctx->periodic[d] || me < P - 1);
+  }
+  for (int dir = 0; dir < NDIR; dir++) {
+    const int dv[3] = {dir % 3 - 1, (dir / 3) % 3 - 1, dir / 9 - 1};
+    for (int d = 0; d < 3; d++) {
+      double s = 0.0;  // pbc[iswap][dim] * prd, comm_brick.cpp:396-399, 414-417
+      if (dv[d] < 0 && ctx->myloc[d] == 0) s = 1 * ctx->prd[d];
+      if (dv[d] > 0 && ctx->myloc[d] == ctx->procgrid[d] - 1) s = -1 * ctx->prd[d];
+      g.shift[dir][d] = s;
+    }
+  }
+  // ---- bins
+  double bbox[3], bsublo[3], bsubhi[3], binsize[3];
+  for (int d = 0; d < 3; d++) {
+    bsublo[d] = ctx->sublo[d] - ctx->cutghost;
+    bsubhi[d] = ctx->subhi[d] + ctx->cutghost;
+    bbox[d] = ctx->boxhi[d] - ctx->boxlo[d];
+  }
+  double binsize_optimal = 0.5 * ctx->cutneighmax;
+  if (binsize_optimal == 0.0) binsize_optimal = bbox[0];
+  const double binsizeinv = 1.0 / binsize_optimal;
+  int64_t mb = 1;
+  for (int d = 0; d < 3; d++) {
+    if (bbox[d] * binsizeinv > 2147483647.0) return ctx->fail(B200_EARG, "Domain too large for neighbor bins");
+    g.nbin[d] = (int)(bbox[d] * binsizeinv);
+    if (g.nbin[d] == 0) g.nbin[d] = 1;
+    binsize[d] = bbox[d] / g.nbin[d];
+    g.bininv[d] = 1.0 / binsize[d];
+    double coord = bsublo[d] - B200_SMALL * bbox[d];
+    int lo = (int)((coord - ctx->boxlo[d]) * g.bininv[d]);
+    if (coord < ctx->boxlo[d]) lo = lo - 1;
+    coord = bsubhi[d] + B200_SMALL * bbox[d];
+    int hi = (int)((coord - ctx->boxlo[d]) * g.bininv[d]);
+    lo -= 1;
+    hi += 1;
+    g.mbinlo[d] = lo;
+    g.mbin[d] = hi - lo + 1;
+    mb *= g.mbin[d];
+  }
+  if (mb + 1 > 2147483647LL) return ctx->fail(B200_EARG, "Too many neighbor bins");
+  g.mbins = (int)mb;
+  // ---- stencil
+  int s[3];
+  for (int d = 0; d < 3; d++) {
+    s[d] = (int)(ctx->cutneighmax * g.bininv[d]);
+    if (s[d] * binsize[d] < ctx->cutneighmax) s[d]++;
+  }
+  auto bin_distance = [&](int i, int j, int k) {
+    double delx, dely, delz;
+    if (i > 0) delx = (i - 1) * binsize[0];
+    else if (i == 0) delx = 0.0;
+    else delx = (i + 1) * binsize[0];
+    if (j > 0) dely = (j - 1) * binsize[1];
+    else if (j == 0) dely = 0.0;
+    else dely = (j + 1) * binsize[1];
+    if (k > 0) delz = (k - 1) * binsize[2];
+    else if (k == 0) delz = 0.0;
+    else delz = (k + 1) * binsize[2];
+    return delx * delx + dely * dely + delz * delz;
+  };
+  Stencil &st = ctx->stencil;
+  memset(&st, 0, sizeof st);
+  ctx->nstencil = 1;  // the central bin comes first (nstencil_bin.cpp:50)
+  // row 0 is (dz=0,dy=0): own bin + bins to its right
+  st.nrows = 1;
+  st.rowoff[0] = 0;
+  st.dxlo[0] = 0;
+  st.dxhi[0] = 0;
+  for (int k = 0; k <= s[2]; k++)
+    for (int j = -s[1]; j <= s[1]; j++) {
+      int lo = 1 << 30, hi = -(1 << 30), cnt = 0;
+      for (int i = -s[0]; i <= s[0]; i++) {
+        if (k <= 0 && j <= 0 && (j != 0 || i <= 0)) continue;
+        if (bin_distance(i, j, k) < ctx->cutneighmaxsq) {
+          lo = std::min(lo, i);
+          hi = std::max(hi, i);
+          cnt++;
+        }
+      }
+      if (!cnt) continue;
+      if (cnt != hi - lo + 1) return ctx->fail(B200_EARG, "stencil row is not contiguous");
+      ctx->nstencil += cnt;
+      if (k == 0 && j == 0) {
+        if (lo != 1) return ctx->fail(B200_EARG, "unexpected stencil row (0,0)");
+        st.dxhi[0] = hi;
+      } else {
+        if (st.nrows >= MAXROWS) return ctx->fail(B200_EARG, "too many stencil rows");
+        st.rowoff[st.nrows] = k * g.mbin[1] * g.mbin[0] + j * g.mbin[0];
+        st.dxlo[st.nrows] = lo;
+        st.dxhi[st.nrows] = hi;
+        st.nrows++;
+      }
+    }
+  TRY(reserve(ctx, ctx->ostart, (size_t)g.mbins + 2));
+  TRY(reserve(ctx, ctx->gstart, (size_t)g.mbins + 2));
+  TRY(reserve(ctx, ctx->tilesum, (size_t)cdiv(g.mbins + 1, SCAN_TILE) + 2));
+  ctx->geom_ready = true;
+  return B200_OK;
+}
+
+// exclusive scan of counts[0..n) in place; element n receives the total
+static int scan_inplace(b200_ctx *ctx, int *a, int n) {
+  const int ntiles = cdiv(n, SCAN_TILE);
+  int *gt = ctx->flags + 3;
+  k_scan_tiles<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(a, a, n, ctx->tilesum.p);
+  k_scan_sums<<<1, 1024, 0, ctx->stream>>>(ctx->tilesum.p, ntiles, gt);
+  k_scan_add<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(a, n, ctx->tilesum.p, gt);
+  ctx->launches += 3;
+  LAUNCH_CHECK();
+  return B200_OK;
+}
+
+static int check_err_flags(b200_ctx *ctx, int e) {
+  if (e & 1) return ctx->fail(B200_ENONFINITE, "Non-numeric atom coords - simulation unstable");
+  if (e & 2) return ctx->fail(B200_ELOST, "atom outside the local bin grid (lost atom)");
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------ list build
+static int build_list(b200_ctx *ctx) {
+  const int nl = ctx->nlocal, c = ctx->cur;
+  if (ctx->maxneigh == 0) ctx->maxneigh = 96;
+  for (int attempt = 0; attempt < 4; attempt++) {
+    ctx->nstride = cdiv(std::max(nl, 1), 32) * 32;
+    TRY(reserve(ctx, ctx->neigh, (size_t)ctx->maxneigh * ctx->nstride));
+    TRY(reserve(ctx, ctx->numneigh, (size_t)nl));
+    CK(cudaMemsetAsync(ctx->flags + 2, 0, sizeof(int), ctx->stream));
+    const int ph1 = ph_begin(ctx, B200_PH_BUILD);
+    if (nl > 0) {
+      const int n1 = ctx->ntypes + 1;
+      if (ctx->ntypes == 1)
+        k_build_half<true><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
+            nl, ctx->nstride, ctx->maxneigh, ctx->xt[c], ctx->atombin[c], ctx->ostart.p,
+            ctx->gstart.p, ctx->stencil, ctx->cutneighsq_h[n1 + 1], ctx->cutneighsq_d.p,
+            ctx->ntypes, ctx->numneigh.p, ctx->neigh.p, ctx->flags + 2);
+      else
+        k_build_half<false><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
+            nl, ctx->nstride, ctx->maxneigh, ctx->xt[c], ctx->atombin[c], ctx->ostart.p,
+            ctx->gstart.p, ctx->stencil, 0.0, ctx->cutneighsq_d.p, ctx->ntypes, ctx->numneigh.p,
+            ctx->neigh.p, ctx->flags + 2);
+      ctx->launches++;
+      LAUNCH_CHECK();
+    }
+    ph_end(ctx, ph1);
+    CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    TRY(check_err_flags(ctx, ctx->h_flags[1]));
+    ctx->max_numneigh = ctx->h_flags[2];
+    if (ctx->max_numneigh <= ctx->maxneigh) return B200_OK;
+    if (ctx->max_numneigh > ctx->one)
+      return ctx->fail(B200_ECAPACITY, "Neighbor list overflow, boost neigh_modify one (%d > %d)",
+                       ctx->max_numneigh, ctx->one);
+    ctx->maxneigh = std::min(ctx->one, (ctx->max_numneigh * 9 / 8 + 8) / 8 * 8);
+  }
+  return ctx->fail(B200_ECAPACITY, "neighbor list did not converge");
+}
+
+// ------------------------------------------------------------------ reneighbor
+// Verlet::run rebuild branch (verlet.cpp:268-297): pbc, exchange, borders, neighbor->build.
+static int reneighbor(b200_ctx *ctx) {
+  if (!ctx->geom_ready) TRY(setup_geometry(ctx));
+  const int ph2 = ph_begin(ctx, B200_PH_NEIGH);
+  const Geom &g = ctx->geom;
+  const int nl = ctx->nlocal;
+  int c = ctx->cur;
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemsetAsync(ctx->ostart.p, 0, sizeof(int) * (g.mbins + 1), s));
+  CK(cudaMemsetAsync(ctx->gstart.p, 0, sizeof(int) * (g.mbins + 1), s));
+  CK(cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), s));
+  CK(cudaMemsetAsync(ctx->dircount, 0, NDIR * sizeof(int), s));
+  if (nl > 0) {
+    k_pbc_bin<<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], ctx->image[c], g, ctx->atombin[c],
+                                            ctx->slot, ctx->ostart.p, ctx->flags + 1);
+    ctx->launches++;
+  }
+  TRY(scan_inplace(ctx, ctx->ostart.p, g.mbins));
+  if (nl > 0) {
+    k_permute_owned<<<cdiv(nl, 256), 256, 0, s>>>(
+        nl, ctx->atombin[c], ctx->slot, ctx->ostart.p, ctx->xt[c], ctx->xt[c ^ 1], ctx->v[c][0],
+        ctx->v[c][1], ctx->v[c][2], ctx->v[c ^ 1][0], ctx->v[c ^ 1][1], ctx->v[c ^ 1][2], ctx->tag[c],
+        ctx->tag[c ^ 1], ctx->mask[c], ctx->mask[c ^ 1], ctx->image[c], ctx->image[c ^ 1],
+        ctx->atombin[c ^ 1], ctx->xh[0], ctx->xh[1], ctx->xh[2]);
+    ctx->launches++;
+    c ^= 1;
+    ctx->cur = c;
+    // borders, count pass
+    k_border<0><<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], g, ctx->dircount, ctx->diroffset, nullptr);
+    ctx->launches++;
+  }
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(ctx->h_flags + 4, ctx->dircount, NDIR * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  TRY(check_err_flags(ctx, ctx->h_flags[1]));
+  int off[NDIR + 1];
+  off[0] = 0;
+  for (int d = 0; d < NDIR; d++) off[d + 1] = off[d] + ctx->h_flags[4 + d];
+  const int ng = off[NDIR];
+  ctx->nghost = 0;  // the ghost region holds nothing worth keeping across a regrow
+  if (nl + ng > ctx->nmax) {
+    TRY(alloc_atoms(ctx, (int)((nl + ng) * 1.1) + 1024));
+    c = ctx->cur;
+  }
+  ctx->nghost = ng;
+  TRY(reserve(ctx, ctx->sendlist, (size_t)ng));
+  TRY(reserve(ctx, ctx->gsrc, (size_t)ng));
+  TRY(reserve(ctx, ctx->gbin, (size_t)ng));
+  TRY(reserve(ctx, ctx->gslot, (size_t)ng));
+  TRY(reserve(ctx, ctx->gdir, (size_t)ng));
+  TRY(reserve(ctx, ctx->gdir_tmp, (size_t)ng));
+  TRY(reserve(ctx, ctx->gtmp, (size_t)ng));
+  CK(cudaMemcpyAsync(ctx->diroffset, off, (NDIR + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(ctx->dircount, 0, NDIR * sizeof(int), s));
+  if (ng > 0) {
+    k_border<1><<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], g, ctx->dircount, ctx->diroffset,
+                                              ctx->sendlist.p);
+    k_ghost_make<<<cdiv(ng, 256), 256, 0, s>>>(ng, ctx->sendlist.p, ctx->diroffset, g, ctx->xt[c],
+                                               ctx->gtmp.p, ctx->gbin.p, ctx->gslot.p,
+                                               ctx->gdir_tmp.p, ctx->gstart.p, ctx->flags + 1);
+    ctx->launches += 2;
+  }
+  TRY(scan_inplace(ctx, ctx->gstart.p, g.mbins));
+  if (ng > 0) {
+    k_ghost_place<<<cdiv(ng, 256), 256, 0, s>>>(ng, nl, ctx->sendlist.p, ctx->gtmp.p, ctx->gbin.p,
+                                                ctx->gslot.p, ctx->gdir_tmp.p, ctx->gstart.p,
+                                                ctx->tag[c], ctx->xt[c], ctx->tag[c], ctx->gsrc.p,
+                                                ctx->gdir.p);
+    k_ghost_type_copy<<<cdiv(ng, 256), 256, 0, s>>>(ng, nl, ctx->gsrc.p, ctx->mask[c], ctx->mask[c]);
+    ctx->launches += 2;
+  }
+  LAUNCH_CHECK();
+  TRY(build_list(ctx));
+  // a rebuild invalidates ghost forces of the old ghost set
+  for (int d = 0; d < 3; d++) CK(cudaMemsetAsync(ctx->f[d] + nl, 0, sizeof(double) * ng, s));
+  ctx->ago = 0;
+  ctx->nbuilds++;
+  ph_end(ctx, ph2);
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------ step pieces
+static int force_clear(b200_ctx *ctx) {
+  const int ph3 = ph_begin(ctx, B200_PH_CLEAR);
+  const int nall = ctx->nlocal + ctx->nghost;
+  for (int d = 0; d < 3; d++) CK(cudaMemsetAsync(ctx->f[d], 0, sizeof(double) * nall, ctx->stream));
+  ph_end(ctx, ph3);
+  return B200_OK;
+}
+
+static int forward_comm(b200_ctx *ctx) {
+  const int ph4 = ph_begin(ctx, B200_PH_FORWARD);
+  if (ctx->nghost > 0) {
+    k_forward_self<<<cdiv(ctx->nghost, 256), 256, 0, ctx->stream>>>(
+        ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->geom, ctx->xt[ctx->cur]);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  ph_end(ctx, ph4);
+  return B200_OK;
+}
+
+static int reverse_comm(b200_ctx *ctx) {
+  const int ph5 = ph_begin(ctx, B200_PH_REVERSE);
+  if (ctx->nghost > 0) {
+    k_reverse_self<<<cdiv(ctx->nghost, 256), 256, 0, ctx->stream>>>(
+        ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->f[0], ctx->f[1], ctx->f[2]);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  ph_end(ctx, ph5);
+  return B200_OK;
+}
+
+static int pair_compute(b200_ctx *ctx, int eflag, int vflag) {
+  const int nl = ctx->nlocal, ng = ctx->nghost, c = ctx->cur;
+  cudaStream_t s = ctx->stream;
+  const bool ev = eflag || vflag;
+  if (ev) CK(cudaMemsetAsync(ctx->ev, 0, 7 * sizeof(double), s));
+  const int ph6 = ph_begin(ctx, B200_PH_PAIR);
+  if (ctx->pair_style == 1) {
+    if (nl > 0) {
+      const int grid = cdiv(nl, 128);
+      if (ctx->ntypes == 1) {
+        if (eflag)
+          k_pair_lj<true, true><<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
+                                                     ctx->neigh.p, ctx->f[0], ctx->f[1], ctx->f[2],
+                                                     ctx->lj_one, nullptr, 1, ctx->ev);
+        else
+          k_pair_lj<false, true><<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
+                                                      ctx->neigh.p, ctx->f[0], ctx->f[1], ctx->f[2],
+                                                      ctx->lj_one, nullptr, 1, ctx->ev);
+      } else {
+        const int n1 = ctx->ntypes + 1;
+        const size_t sm = sizeof(double) * 6 * n1 * n1;
+        if (eflag)
+          k_pair_lj<true, false><<<grid, 128, sm, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
+                                                       ctx->neigh.p, ctx->f[0], ctx->f[1], ctx->f[2],
+                                                       ctx->lj_one, ctx->lj_tab.p, ctx->ntypes, ctx->ev);
+        else
+          k_pair_lj<false, false><<<grid, 128, sm, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
+                                                        ctx->neigh.p, ctx->f[0], ctx->f[1], ctx->f[2],
+                                                        ctx->lj_one, ctx->lj_tab.p, ctx->ntypes, ctx->ev);
+      }
+      ctx->launches++;
+    }
+  } else if (ctx->pair_style == 2) {
+    CK(cudaMemsetAsync(ctx->rho, 0, sizeof(double) * (nl + ng), s));
+    if (nl > 0) {
+      const int grid = cdiv(nl, 128);
+      k_eam_rho<<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p, ctx->neigh.p,
+                                     ctx->eam, ctx->rho);
+      if (ng > 0)
+        k_reverse_scalar_self<<<cdiv(ng, 256), 256, 0, s>>>(ng, nl, ctx->gsrc.p, ctx->rho);
+      if (eflag)
+        k_eam_embed<true><<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], ctx->eam, ctx->rho, ctx->fp,
+                                                        ctx->ev, ctx->flags + 1);
+      else
+        k_eam_embed<false><<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], ctx->eam, ctx->rho, ctx->fp,
+                                                         ctx->ev, ctx->flags + 1);
+      if (ng > 0)
+        k_forward_scalar_self<<<cdiv(ng, 256), 256, 0, s>>>(ng, nl, ctx->gsrc.p, ctx->fp);
+      if (eflag)
+        k_eam_force<true><<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
+                                               ctx->neigh.p, ctx->eam, ctx->fp, ctx->f[0], ctx->f[1],
+                                               ctx->f[2], ctx->ev);
+      else
+        k_eam_force<false><<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
+                                                ctx->neigh.p, ctx->eam, ctx->fp, ctx->f[0], ctx->f[1],
+                                                ctx->f[2], ctx->ev);
+      ctx->launches += 3 + (ng > 0 ? 2 : 0);
+    }
+  } else
+    return ctx->fail(B200_EARG, "no pair style set");
+  LAUNCH_CHECK();
+  ph_end(ctx, ph6);
+  if (vflag && nl + ng > 0) {
+    const int ph7 = ph_begin(ctx, B200_PH_THERMO);
+    const int grid = std::min(cdiv(nl + ng, 256), 148 * 8);
+    k_virial_fdotr<<<grid, 256, 0, s>>>(nl + ng, ctx->xt[c], ctx->f[0], ctx->f[1], ctx->f[2], ctx->ev);
+    ctx->launches++;
+    LAUNCH_CHECK();
+    ph_end(ctx, ph7);
+  }
+  return B200_OK;
+}
+
+static int initial_integrate(b200_ctx *ctx, int do_check) {
+  if (!ctx->have_nve) return ctx->fail(B200_EARG, "b200_fix_nve has not been called");
+  const int ph8 = ph_begin(ctx, B200_PH_INITIAL);
+  const int nl = ctx->nlocal, c = ctx->cur;
+  if (nl > 0) {
+    k_nve_initial<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(
+        nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->f[0], ctx->f[1], ctx->f[2],
+        ctx->mask[c], ctx->mass_d.p, ctx->dtv, ctx->dtf, ctx->groupbit, do_check, ctx->xh[0],
+        ctx->xh[1], ctx->xh[2], ctx->triggersq, ctx->flags);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  ph_end(ctx, ph8);
+  return B200_OK;
+}
+
+static int final_integrate(b200_ctx *ctx) {
+  const int ph9 = ph_begin(ctx, B200_PH_FINAL);
+  const int nl = ctx->nlocal, c = ctx->cur;
+  if (nl > 0) {
+    k_nve_final<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1],
+                                                        ctx->v[c][2], ctx->f[0], ctx->f[1], ctx->f[2],
+                                                        ctx->mask[c], ctx->mass_d.p, ctx->dtf,
+                                                        ctx->groupbit);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  ph_end(ctx, ph9);
+  return B200_OK;
+}
+
+// Neighbor::decide (neighbor.cpp:2408-2424); `moved` is the device vote of check_distance
+static int decide(b200_ctx *ctx, int *rebuild) {
+  ctx->ago++;
+  *rebuild = 0;
+  if (ctx->ago >= ctx->delay && ctx->ago % ctx->every == 0) {
+    if (!ctx->dist_check) {
+      *rebuild = 1;
+      return B200_OK;
+    }
+    CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_flags[0]) {
+      if (ctx->ago == std::max(ctx->every, ctx->delay)) ctx->ndanger++;
+      *rebuild = 1;
+    }
+  }
+  return B200_OK;
+}
+
+static bool check_due_next(const b200_ctx *ctx) {
+  const int64_t a = ctx->ago + 1;
+  return ctx->dist_check && a >= ctx->delay && a % ctx->every == 0;
+}
+
+static int ke_reduce(b200_ctx *ctx) {
+  const int nl = ctx->nlocal, c = ctx->cur;
+  CK(cudaMemsetAsync(ctx->ev + 7, 0, sizeof(double), ctx->stream));
+  if (nl > 0) {
+    const int grid = std::min(cdiv(nl, 256), 148 * 8);
+    k_ke<<<grid, 256, 0, ctx->stream>>>(nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2],
+                                        ctx->mask[c], ctx->mass_d.p, ctx->groupbit, ctx->ev);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  return B200_OK;
+}
+
+static int fetch_ev(b200_ctx *ctx) {
+  CK(cudaMemcpyAsync(ctx->h_ev, ctx->ev, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->eng_vdwl = ctx->h_ev[0];
+  for (int k = 0; k < 6; k++) ctx->virial[k] = ctx->h_ev[1 + k];
+  return B200_OK;
+}
+
+// =====================================================================================
+//                                        C ABI
+// =====================================================================================
+extern "C" {
+
+int b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int b200_create(b200_ctx **out, int device, int precision) {
+  if (!out) return B200_EARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return B200_ECUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return B200_ECUDA;
+  b200_ctx *ctx = new b200_ctx();
+  ctx->device = device;
+  ctx->prec = precision;
+  *out = ctx;
+  if (precision != B200_PREC_DOUBLE && precision != B200_PREC_MIXED)
+    return ctx->fail(B200_EARG, "unknown precision mode %d", precision);
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  TRY(dalloc(ctx, &ctx->ev, 8));
+  TRY(dalloc(ctx, &ctx->flags, 4));
+  TRY(dalloc(ctx, &ctx->dircount, NDIR));
+  TRY(dalloc(ctx, &ctx->diroffset, NDIR + 1));
+  TRY(dalloc(ctx, &ctx->cnt64, 1));
+  CK(cudaMallocHost((void **)&ctx->h_ev, 8 * sizeof(double)));
+  CK(cudaMallocHost((void **)&ctx->h_flags, 64 * sizeof(int)));
+  CK(cudaMemsetAsync(ctx->ev, 0, 8 * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), ctx->stream));
+  memset(&ctx->eam, 0, sizeof ctx->eam);
+  memset(&ctx->lj_one, 0, sizeof ctx->lj_one);
+  return B200_OK;
+}
+
+void b200_destroy(b200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  auto F = [](auto *p) { if (p) cudaFree((void *)p); };
+  for (int b = 0; b < 2; b++) {
+    F(ctx->xt[b]);
+    for (int d = 0; d < 3; d++) F(ctx->v[b][d]);
+    F(ctx->tag[b]); F(ctx->mask[b]); F(ctx->image[b]); F(ctx->atombin[b]);
+  }
+  for (int d = 0; d < 3; d++) { F(ctx->f[d]); F(ctx->xh[d]); }
+  F(ctx->slot); F(ctx->rho); F(ctx->fp);
+  F(ctx->cutneighsq_d.p); F(ctx->mass_d.p); F(ctx->ostart.p); F(ctx->gstart.p); F(ctx->tilesum.p);
+  F(ctx->sendlist.p); F(ctx->gsrc.p); F(ctx->gbin.p); F(ctx->gslot.p); F(ctx->gdir.p);
+  F(ctx->gdir_tmp.p); F(ctx->gtmp.p); F(ctx->dircount); F(ctx->diroffset); F(ctx->neigh.p);
+  F(ctx->numneigh.p); F(ctx->lj_tab.p); F(ctx->eam_i.p); F(ctx->eam_d.p); F(ctx->ev); F(ctx->flags);
+  F(ctx->cnt64);
+  if (ctx->h_ev) cudaFreeHost(ctx->h_ev);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  for (auto &r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : ctx->evpool) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int b200_set_box(b200_ctx *ctx, const double boxlo[3], const double boxhi[3], const int per[3]) {
+  if (!ctx) return B200_EARG;
+  for (int d = 0; d < 3; d++) {
+    if (!(boxhi[d] > boxlo[d])) return ctx->fail(B200_EARG, "box hi <= lo in dim %d", d);
+    ctx->boxlo[d] = boxlo[d];
+    ctx->boxhi[d] = boxhi[d];
+    ctx->prd[d] = boxhi[d] - boxlo[d];
+    ctx->periodic[d] = per ? per[d] : 1;
+  }
+  ctx->have_box = true;
+  ctx->geom_ready = false;
+  return B200_OK;
+}
+
+int b200_set_decomposition(b200_ctx *ctx, const int procgrid[3], const int myloc[3]) {
+  if (!ctx) return B200_EARG;
+  for (int d = 0; d < 3; d++) {
+    if (procgrid[d] < 1 || myloc[d] < 0 || myloc[d] >= procgrid[d])
+      return ctx->fail(B200_EARG, "bad decomposition in dim %d", d);
+    ctx->procgrid[d] = procgrid[d];
+    ctx->myloc[d] = myloc[d];
+  }
+  ctx->geom_ready = false;
+  return B200_OK;
+}
+
+int b200_set_neighbor(b200_ctx *ctx, double skin, int every, int delay, int dist_check, int one) {
+  if (!ctx) return B200_EARG;
+  if (skin < 0 || every < 1 || delay < 0) return ctx->fail(B200_EARG, "Illegal neighbor settings");
+  ctx->skin = skin;
+  ctx->every = every;
+  ctx->delay = delay;
+  ctx->dist_check = dist_check ? 1 : 0;
+  if (one > 0) ctx->one = one;
+  ctx->geom_ready = false;
+  return B200_OK;
+}
+
+int b200_set_atoms(b200_ctx *ctx, int nlocal, int ntypes, const double *mass, const double *x,
+                   const double *v, const int *type, const int *tag, const int *mask,
+                   const int *image) {
+  if (!ctx) return B200_EARG;
+  if (nlocal < 0 || ntypes < 1 || !mass || (nlocal && (!x || !v || !type || !tag)))
+    return ctx->fail(B200_EARG, "b200_set_atoms: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  ctx->ntypes = ntypes;
+  ctx->mass_h.assign(mass, mass + ntypes + 1);
+  TRY(reserve(ctx, ctx->mass_d, (size_t)ntypes + 1));
+  CK(cudaMemcpyAsync(ctx->mass_d.p, mass, sizeof(double) * (ntypes + 1), cudaMemcpyHostToDevice, s));
+  ctx->nlocal = 0;
+  ctx->nghost = 0;
+  const int want = (int)(nlocal * 1.3) + 4096;
+  if (want > ctx->nmax) TRY(alloc_atoms(ctx, want));
+  ctx->cur = 0;
+  const int n = nlocal;
+  if (n > 0) {
+    // stage AoS host arrays through device scratch (the alternate ping-pong buffers)
+    double *stage = reinterpret_cast<double *>(ctx->xt[1]);  // 4*nmax doubles >= 3*n
+    int *itmp = ctx->atombin[1];
+    CK(cudaMemcpyAsync(stage, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(itmp, type, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    k_pack_xt<<<cdiv(n, 256), 256, 0, s>>>(n, stage, itmp, ctx->xt[0]);
+    CK(cudaMemcpyAsync(stage, v, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+    k_aos_to_soa<<<cdiv(n, 256), 256, 0, s>>>(n, stage, ctx->v[0][0], ctx->v[0][1], ctx->v[0][2]);
+    ctx->launches += 2;
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(ctx->tag[0], tag, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    if (mask)
+      CK(cudaMemcpyAsync(ctx->mask[0], mask, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    else {
+      std::vector<int> ones(n, 1);
+      CK(cudaMemcpyAsync(ctx->mask[0], ones.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+    }
+    if (image)
+      CK(cudaMemcpyAsync(ctx->image[0], image, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    else {
+      const int img0 = (512 << IMG2BITS) | (512 << IMGBITS) | 512;
+      std::vector<int> im(n, img0);
+      CK(cudaMemcpyAsync(ctx->image[0], im.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+    }
+    for (int d = 0; d < 3; d++) CK(cudaMemsetAsync(ctx->f[d], 0, sizeof(double) * n, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  ctx->nlocal = n;
+  ctx->setup_done = false;
+  ctx->geom_ready = false;
+  return B200_OK;
+}
+
+int b200_get_counts(const b200_ctx *ctx, int *nlocal, int *nghost) {
+  if (!ctx) return B200_EARG;
+  if (nlocal) *nlocal = ctx->nlocal;
+  if (nghost) *nghost = ctx->nghost;
+  return B200_OK;
+}
+
+int b200_get_atoms(b200_ctx *ctx, int with_ghosts, double *x, double *v, double *f, int *type,
+                   int *tag, int *mask, int *image) {
+  if (!ctx) return B200_EARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const int c = ctx->cur, nl = ctx->nlocal, n = nl + (with_ghosts ? ctx->nghost : 0);
+  if (n == 0) return B200_OK;
+  double *stage = reinterpret_cast<double *>(ctx->xt[c ^ 1]);
+  int *itmp = ctx->atombin[c ^ 1];
+  if (x || type) {
+    k_unpack_xt<<<cdiv(n, 256), 256, 0, s>>>(n, ctx->xt[c], x ? stage : nullptr, type ? itmp : nullptr);
+    ctx->launches++;
+    LAUNCH_CHECK();
+    if (x) CK(cudaMemcpyAsync(x, stage, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
+    if (type) CK(cudaMemcpyAsync(type, itmp, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  if (v) {  // velocities exist for owned atoms only
+    k_soa_to_aos<<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], stage);
+    ctx->launches++;
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(v, stage, sizeof(double) * 3 * nl, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  if (f) {
+    k_soa_to_aos<<<cdiv(n, 256), 256, 0, s>>>(n, ctx->f[0], ctx->f[1], ctx->f[2], stage);
+    ctx->launches++;
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(f, stage, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  if (tag) CK(cudaMemcpyAsync(tag, ctx->tag[c], sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  if (mask) CK(cudaMemcpyAsync(mask, ctx->mask[c], sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  if (image) CK(cudaMemcpyAsync(image, ctx->image[c], sizeof(int) * nl, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+int b200_pair_lj_cut(b200_ctx *ctx, int ntypes, const double *cutsq, const double *lj1,
+                     const double *lj2, const double *lj3, const double *lj4,
+                     const double *offset, const double special_lj[4]) {
+  if (!ctx) return B200_EARG;
+  if (ntypes < 1 || !cutsq || !lj1 || !lj2 || !lj3 || !lj4 || !offset)
+    return ctx->fail(B200_EARG, "b200_pair_lj_cut: bad arguments");
+  if (ntypes > 15) return ctx->fail(B200_EARG, "lj/cut/b200 supports at most 15 atom types");
+  if (special_lj && (special_lj[1] != 1.0 || special_lj[2] != 1.0 || special_lj[3] != 1.0))
+    ; /* atom_style atomic never sets special bits; factors other than 1 are never applied */
+  CK(cudaSetDevice(ctx->device));
+  const int n1 = ntypes + 1, n2 = n1 * n1;
+  ctx->pair_style = 1;
+  ctx->cutsq_h.assign(cutsq, cutsq + n2);
+  std::vector<double> tab(6 * n2);
+  const double *src[6] = {cutsq, lj1, lj2, lj3, lj4, offset};
+  for (int t = 0; t < 6; t++) memcpy(&tab[t * n2], src[t], sizeof(double) * n2);
+  TRY(reserve(ctx, ctx->lj_tab, tab.size()));
+  CK(cudaMemcpyAsync(ctx->lj_tab.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int k = n1 + 1;  // [1][1]
+  ctx->lj_one = LJOne{cutsq[k], lj1[k], lj2[k], lj3[k], lj4[k], offset[k]};
+  ctx->geom_ready = false;
+  return B200_OK;
+}
+
+int b200_pair_eam(b200_ctx *ctx, int ntypes, int nr, int nrho, double rdr, double rdrho,
+                  double rhomax, double cutforcesq, const int *type2frho, const int *type2rhor,
+                  const int *type2z2r, const double *scale, int nfrho, const double *frho_spline,
+                  int nrhor, const double *rhor_spline, int nz2r, const double *z2r_spline) {
+  if (!ctx) return B200_EARG;
+  if (ntypes < 1 || nr < 2 || nrho < 2 || !type2frho || !type2rhor || !type2z2r || !scale ||
+      !frho_spline || !rhor_spline || !z2r_spline)
+    return ctx->fail(B200_EARG, "b200_pair_eam: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  const int n1 = ntypes + 1, n2 = n1 * n1;
+  ctx->pair_style = 2;
+  ctx->cutsq_h.assign(n2, cutforcesq);  // Pair::init: cutsq[i][j] = init_one()^2 = cutmax^2
+  std::vector<int> ih(n1 + 2 * n2);
+  memcpy(&ih[0], type2frho, sizeof(int) * n1);
+  memcpy(&ih[n1], type2rhor, sizeof(int) * n2);
+  memcpy(&ih[n1 + n2], type2z2r, sizeof(int) * n2);
+  const size_t nf = (size_t)nfrho * (nrho + 1) * 7, nh = (size_t)nrhor * (nr + 1) * 7,
+               nz = (size_t)nz2r * (nr + 1) * 7;
+  std::vector<double> dh(n2 + nf + nh + nz);
+  memcpy(&dh[0], scale, sizeof(double) * n2);
+  memcpy(&dh[n2], frho_spline, sizeof(double) * nf);
+  memcpy(&dh[n2 + nf], rhor_spline, sizeof(double) * nh);
+  memcpy(&dh[n2 + nf + nh], z2r_spline, sizeof(double) * nz);
+  TRY(reserve(ctx, ctx->eam_i, ih.size()));
+  TRY(reserve(ctx, ctx->eam_d, dh.size()));
+  CK(cudaMemcpyAsync(ctx->eam_i.p, ih.data(), sizeof(int) * ih.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->eam_d.p, dh.data(), sizeof(double) * dh.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  EAMParams &P = ctx->eam;
+  P.nr = nr; P.nrho = nrho; P.ntypes = ntypes;
+  P.rdr = rdr; P.rdrho = rdrho; P.rhomax = rhomax; P.cutforcesq = cutforcesq;
+  P.type2frho = ctx->eam_i.p;
+  P.type2rhor = ctx->eam_i.p + n1;
+  P.type2z2r = ctx->eam_i.p + n1 + n2;
+  P.scale = ctx->eam_d.p;
+  P.frho = ctx->eam_d.p + n2;
+  P.rhor = ctx->eam_d.p + n2 + nf;
+  P.z2r = ctx->eam_d.p + n2 + nf + nh;
+  ctx->geom_ready = false;
+  return B200_OK;
+}
+
+int b200_fix_nve(b200_ctx *ctx, double dtv, double dtf, int groupbit) {
+  if (!ctx) return B200_EARG;
+  ctx->dtv = dtv;
+  ctx->dtf = dtf;
+  ctx->groupbit = groupbit;
+  ctx->have_nve = true;
+  return B200_OK;
+}
+
+int b200_setup(b200_ctx *ctx, int eflag, int vflag) {
+  if (!ctx) return B200_EARG;
+  CK(cudaSetDevice(ctx->device));
+  TRY(setup_geometry(ctx));
+  TRY(reneighbor(ctx));
+  ctx->nbuilds = 0;  // Verlet::setup: neighbor->ncalls = 0 (verlet.cpp:131)
+  ctx->ndanger = 0;
+  TRY(force_clear(ctx));
+  TRY(pair_compute(ctx, eflag, vflag));
+  TRY(reverse_comm(ctx));
+  if (eflag || vflag) TRY(fetch_ev(ctx));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->setup_done = true;
+  return B200_OK;
+}
+
+int b200_initial_integrate(b200_ctx *ctx) {
+  if (!ctx) return B200_EARG;
+  CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
+  return initial_integrate(ctx, check_due_next(ctx) ? 1 : 0);
+}
+int b200_final_integrate(b200_ctx *ctx) { return ctx ? final_integrate(ctx) : B200_EARG; }
+int b200_decide(b200_ctx *ctx, int *rebuild) { return (ctx && rebuild) ? decide(ctx, rebuild) : B200_EARG; }
+int b200_forward_comm(b200_ctx *ctx) { return ctx ? forward_comm(ctx) : B200_EARG; }
+int b200_reverse_comm(b200_ctx *ctx) { return ctx ? reverse_comm(ctx) : B200_EARG; }
+int b200_reneighbor(b200_ctx *ctx) { return ctx ? reneighbor(ctx) : B200_EARG; }
+int b200_force_clear(b200_ctx *ctx) { return ctx ? force_clear(ctx) : B200_EARG; }
+int b200_pair_compute(b200_ctx *ctx, int eflag, int vflag) {
+  if (!ctx) return B200_EARG;
+  TRY(pair_compute(ctx, eflag, vflag));
+  if (eflag || vflag) TRY(fetch_ev(ctx));
+  return B200_OK;
+}
+
+int b200_run(b200_ctx *ctx, int nsteps, int64_t first_step, int thermo_every, double *thermo_out,
+             int max_thermo, int *n_thermo) {
+  if (!ctx) return B200_EARG;
+  if (!ctx->setup_done) return ctx->fail(B200_EARG, "b200_run before b200_setup");
+  CK(cudaSetDevice(ctx->device));
+  int nout = 0;
+  for (int sidx = 1; sidx <= nsteps; sidx++) {
+    const int64_t step = first_step + sidx;
+    const int ev = (thermo_every > 0 && step % thermo_every == 0) || sidx == nsteps;
+    const int chk = check_due_next(ctx) ? 1 : 0;
+    if (chk) CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
+    TRY(initial_integrate(ctx, chk));
+    int nflag = 0;
+    TRY(decide(ctx, &nflag));
+    if (!nflag)
+      TRY(forward_comm(ctx));
+    else
+      TRY(reneighbor(ctx));
+    TRY(force_clear(ctx));
+    TRY(pair_compute(ctx, ev, ev));
+    TRY(reverse_comm(ctx));
+    TRY(final_integrate(ctx));
+    if (ev) {
+      const int ph10 = ph_begin(ctx, B200_PH_THERMO);
+      TRY(ke_reduce(ctx));
+      ph_end(ctx, ph10);
+      TRY(fetch_ev(ctx));
+      if (thermo_out && nout < max_thermo) {
+        double *t = thermo_out + 10 * (size_t)nout;
+        t[0] = (double)step;
+        t[1] = ctx->h_ev[7];
+        t[2] = ctx->eng_vdwl;
+        for (int k = 0; k < 6; k++) t[3 + k] = ctx->virial[k];
+        t[9] = 0.0;
+        nout++;
+      }
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (n_thermo) *n_thermo = nout;
+  return B200_OK;
+}
+
+int b200_get_tallies(b200_ctx *ctx, double *eng_vdwl, double virial[6]) {
+  if (!ctx) return B200_EARG;
+  if (eng_vdwl) *eng_vdwl = ctx->eng_vdwl;
+  if (virial) memcpy(virial, ctx->virial, sizeof(double) * 6);
+  return B200_OK;
+}
+
+int b200_ke_sum(b200_ctx *ctx, double *mv2) {
+  if (!ctx || !mv2) return B200_EARG;
+  TRY(ke_reduce(ctx));
+  CK(cudaMemcpyAsync(ctx->h_ev + 7, ctx->ev + 7, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *mv2 = ctx->h_ev[7];
+  return B200_OK;
+}
+
+int b200_get_stats(b200_ctx *ctx, b200_stats *out) {
+  if (!ctx || !out) return B200_EARG;
+  memset(out, 0, sizeof *out);
+  out->nbuilds = ctx->nbuilds;
+  out->ndanger = ctx->ndanger;
+  out->ago = ctx->ago;
+  out->maxneigh = ctx->maxneigh;
+  out->max_numneigh = ctx->max_numneigh;
+  for (int d = 0; d < 3; d++) out->nbins[d] = ctx->geom_ready ? ctx->geom.nbin[d] : 0;
+  out->mbins = ctx->geom_ready ? ctx->geom.mbins : 0;
+  out->nstencil = ctx->nstencil;
+  if (ctx->numneigh.p && ctx->nlocal > 0) {
+    CK(cudaMemsetAsync(ctx->cnt64, 0, sizeof(unsigned long long), ctx->stream));
+    k_sum_int<<<std::min(cdiv(ctx->nlocal, 256), 1184), 256, 0, ctx->stream>>>(ctx->nlocal, ctx->numneigh.p,
+                                                                             ctx->cnt64);
+    ctx->launches++;
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, ctx->cnt64, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    out->npairs = (int64_t)h;
+  }
+  out->launches = ctx->launches;
+  out->device_bytes = (double)ctx->dev_bytes;
+  return B200_OK;
+}
+
+int b200_get_neighbor_list(b200_ctx *ctx, int *numneigh, int *neigh, int64_t cap, int64_t *npairs) {
+  if (!ctx) return B200_EARG;
+  const int nl = ctx->nlocal;
+  std::vector<int> nn(nl);
+  if (nl) CK(cudaMemcpy(nn.data(), ctx->numneigh.p, sizeof(int) * nl, cudaMemcpyDeviceToHost));
+  std::vector<long long> first(nl + 1, 0);
+  for (int i = 0; i < nl; i++) first[i + 1] = first[i] + nn[i];
+  if (npairs) *npairs = first[nl];
+  if (numneigh && nl) memcpy(numneigh, nn.data(), sizeof(int) * nl);
+  if (!neigh || first[nl] == 0) return B200_OK;
+  if (cap < first[nl]) return ctx->fail(B200_EARG, "neighbor buffer too small");
+  long long *dfirst = nullptr;
+  int *dflat = nullptr;
+  CK(cudaMalloc((void **)&dfirst, sizeof(long long) * (nl + 1)));
+  CK(cudaMalloc((void **)&dflat, sizeof(int) * first[nl]));
+  CK(cudaMemcpy(dfirst, first.data(), sizeof(long long) * (nl + 1), cudaMemcpyHostToDevice));
+  k_export_csr<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->nstride, ctx->numneigh.p, ctx->neigh.p,
+                                                       dfirst, dflat);
+  ctx->launches++;
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(neigh, dflat, sizeof(int) * first[nl], cudaMemcpyDeviceToHost));
+  cudaFree(dfirst);
+  cudaFree(dflat);
+  return B200_OK;
+}
+
+int b200_get_eam_rho_fp(b200_ctx *ctx, int with_ghosts, double *rho, double *fp) {
+  if (!ctx) return B200_EARG;
+  const int n = ctx->nlocal + (with_ghosts ? ctx->nghost : 0);
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (rho && n) CK(cudaMemcpy(rho, ctx->rho, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  if (fp && n) CK(cudaMemcpy(fp, ctx->fp, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return B200_OK;
+}
+
+int b200_set_profiling(b200_ctx *ctx, int on) {
+  if (!ctx) return B200_EARG;
+  ph_collect(ctx);
+  ctx->profiling = on != 0;
+  return B200_OK;
+}
+
+int b200_get_phase_times(b200_ctx *ctx, double ms[B200_NPHASE], int64_t calls[B200_NPHASE]) {
+  if (!ctx) return B200_EARG;
+  ph_collect(ctx);
+  for (int k = 0; k < B200_NPHASE; k++) {
+    if (ms) ms[k] = ctx->ph_ms[k];
+    if (calls) calls[k] = ctx->ph_calls[k];
+    ctx->ph_ms[k] = 0;
+    ctx->ph_calls[k] = 0;
+  }
+  return B200_OK;
+}
+
+int b200_comm_unique_id(void *) { return B200_EARG; }
+int b200_comm_init(b200_ctx *ctx, int, int, const void *) {
+  return ctx ? ctx->fail(B200_EARG, "multi-GPU halo is not built into this library yet") : B200_EARG;
+}
+
+}  // extern "C"

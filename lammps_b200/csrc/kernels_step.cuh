@@ -1,0 +1,163 @@
+// kernels_step.cuh -- per-timestep streaming kernels: fix nve, displacement check, ghost halo
+// (single-device periodic images; the multi-GPU pack/unpack variants live next to them).
+// All HBM-bound: one coalesced pass over SoA arrays, 8/16-byte accesses per lane.
+#pragma once
+#include "common.cuh"
+
+// FixNVE::initial_integrate (fix_nve.cpp:68-108) fused with Neighbor::check_distance
+// (neighbor.cpp:2438-2490).  Arithmetic is kept as separate multiply and add (no FMA
+// contraction) so that trajectories follow the reference's x86 build bit-for-bit as long as
+// forces do.  Algorithmic traffic per atom: x 32r+32w, v 24r+24w, f 24r, mask 4r,
+// (+ xhold 24r when checking) = 140 (164) B.
+__global__ void __launch_bounds__(256) k_nve_initial(
+    int nlocal, double4 *__restrict__ xt, double *__restrict__ vx, double *__restrict__ vy,
+    double *__restrict__ vz, const double *__restrict__ fx, const double *__restrict__ fy,
+    const double *__restrict__ fz, const int *__restrict__ mask, const double *__restrict__ mass,
+    double dtv, double dtf, int groupbit, int do_check, const double *__restrict__ xhx,
+    const double *__restrict__ xhy, const double *__restrict__ xhz, double triggersq,
+    int *__restrict__ moved) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  double4 p = xt[i];
+  if (mask[i] & groupbit) {
+    const double dtfm = dtf / mass[d2type(p.w)];
+    double a = vx[i], b = vy[i], c = vz[i];
+    a = __dadd_rn(a, __dmul_rn(dtfm, fx[i]));
+    b = __dadd_rn(b, __dmul_rn(dtfm, fy[i]));
+    c = __dadd_rn(c, __dmul_rn(dtfm, fz[i]));
+    vx[i] = a; vy[i] = b; vz[i] = c;
+    p.x = __dadd_rn(p.x, __dmul_rn(dtv, a));
+    p.y = __dadd_rn(p.y, __dmul_rn(dtv, b));
+    p.z = __dadd_rn(p.z, __dmul_rn(dtv, c));
+    xt[i] = p;
+  }
+  if (do_check) {
+    const double dx = p.x - xhx[i], dy = p.y - xhy[i], dz = p.z - xhz[i];
+    const double rsq = rsq_ref(dx, dy, dz);
+    if (rsq > triggersq) *moved = 1;
+  }
+}
+
+// FixNVE::final_integrate (fix_nve.cpp:112-145).  v 24r+24w, f 24r, mask 4r, type 8r = 84 B.
+__global__ void __launch_bounds__(256) k_nve_final(
+    int nlocal, const double4 *__restrict__ xt, double *__restrict__ vx, double *__restrict__ vy,
+    double *__restrict__ vz, const double *__restrict__ fx, const double *__restrict__ fy,
+    const double *__restrict__ fz, const int *__restrict__ mask, const double *__restrict__ mass,
+    double dtf, int groupbit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  if (mask[i] & groupbit) {
+    const double w = reinterpret_cast<const double *>(xt)[4 * (size_t)i + 3];
+    const double dtfm = dtf / mass[d2type(w)];
+    vx[i] = __dadd_rn(vx[i], __dmul_rn(dtfm, fx[i]));
+    vy[i] = __dadd_rn(vy[i], __dmul_rn(dtfm, fy[i]));
+    vz[i] = __dadd_rn(vz[i], __dmul_rn(dtfm, fz[i]));
+  }
+}
+
+// CommBrick::forward_comm + AtomVec::pack_comm (comm_brick.cpp:485-538, atom_vec.cpp:354-440)
+// for ghosts whose owner lives on this device: ghost = owner + pbc shift of its direction.
+__global__ void __launch_bounds__(256) k_forward_self(int nghost, int nlocal,
+                                                      const int *__restrict__ gsrc,
+                                                      const unsigned char *__restrict__ gdir,
+                                                      Geom g, double4 *__restrict__ xt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nghost) return;
+  const int dir = gdir[k];
+  double4 q = xt[gsrc[k]];
+  q.x = q.x + g.shift[dir][0];
+  q.y = q.y + g.shift[dir][1];
+  q.z = q.z + g.shift[dir][2];
+  xt[nlocal + k] = q;
+}
+
+// CommBrick::reverse_comm + unpack_reverse (comm_brick.cpp:545-586, atom_vec.cpp:729):
+// owner force += ghost force.  An owner can have up to 7 images -> atomics.
+__global__ void __launch_bounds__(256) k_reverse_self(int nghost, int nlocal,
+                                                      const int *__restrict__ gsrc,
+                                                      double *__restrict__ fx,
+                                                      double *__restrict__ fy,
+                                                      double *__restrict__ fz) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nghost) return;
+  const int s = gsrc[k];
+  atomicAdd(&fx[s], fx[nlocal + k]);
+  atomicAdd(&fy[s], fy[nlocal + k]);
+  atomicAdd(&fz[s], fz[nlocal + k]);
+}
+
+// scalar versions for the EAM halo: reverse (rho, pair_eam.cpp:1625-1646) and forward (fp, :1600-1621)
+__global__ void __launch_bounds__(256) k_reverse_scalar_self(int nghost, int nlocal,
+                                                             const int *__restrict__ gsrc,
+                                                             double *__restrict__ a) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nghost) return;
+  atomicAdd(&a[gsrc[k]], a[nlocal + k]);
+}
+__global__ void __launch_bounds__(256) k_forward_scalar_self(int nghost, int nlocal,
+                                                             const int *__restrict__ gsrc,
+                                                             double *__restrict__ a) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nghost) return;
+  a[nlocal + k] = a[gsrc[k]];
+}
+
+// ComputeTemp::compute_scalar numerator (compute_temp.cpp:73-97): ev[7] += sum m v^2
+__global__ void __launch_bounds__(256) k_ke(int nlocal, const double4 *__restrict__ xt,
+                                            const double *__restrict__ vx,
+                                            const double *__restrict__ vy,
+                                            const double *__restrict__ vz,
+                                            const int *__restrict__ mask,
+                                            const double *__restrict__ mass, int groupbit,
+                                            double *__restrict__ ev) {
+  double v[1] = {0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
+    if (mask[i] & groupbit) {
+      const double w = reinterpret_cast<const double *>(xt)[4 * (size_t)i + 3];
+      v[0] += (vx[i] * vx[i] + vy[i] * vy[i] + vz[i] * vz[i]) * mass[d2type(w)];
+    }
+  }
+  __shared__ double red[32];
+  block_sum<1>(v, red);
+  if (threadIdx.x == 0) atomicAdd(&ev[7], v[0]);
+}
+
+// host array <-> device layout converters (b200_set_atoms / b200_get_atoms)
+__global__ void __launch_bounds__(256) k_pack_xt(int n, const double *__restrict__ x3,
+                                                 const int *__restrict__ type,
+                                                 double4 *__restrict__ xt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  xt[i] = make_double4(x3[3 * (size_t)i], x3[3 * (size_t)i + 1], x3[3 * (size_t)i + 2],
+                       type2d(type[i]));
+}
+__global__ void __launch_bounds__(256) k_unpack_xt(int n, const double4 *__restrict__ xt,
+                                                   double *__restrict__ x3, int *__restrict__ type) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = xt[i];
+  if (x3) { x3[3 * (size_t)i] = p.x; x3[3 * (size_t)i + 1] = p.y; x3[3 * (size_t)i + 2] = p.z; }
+  if (type) type[i] = d2type(p.w);
+}
+__global__ void __launch_bounds__(256) k_aos_to_soa(int n, const double *__restrict__ a3,
+                                                    double *__restrict__ x, double *__restrict__ y,
+                                                    double *__restrict__ z) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  x[i] = a3[3 * (size_t)i]; y[i] = a3[3 * (size_t)i + 1]; z[i] = a3[3 * (size_t)i + 2];
+}
+__global__ void __launch_bounds__(256) k_soa_to_aos(int n, const double *__restrict__ x,
+                                                    const double *__restrict__ y,
+                                                    const double *__restrict__ z,
+                                                    double *__restrict__ a3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  a3[3 * (size_t)i] = x[i]; a3[3 * (size_t)i + 1] = y[i]; a3[3 * (size_t)i + 2] = z[i];
+}
+__global__ void __launch_bounds__(256) k_ghost_type_copy(int nghost, int nlocal,
+                                                         const int *__restrict__ gsrc,
+                                                         const int *a_in, int *a) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nghost) return;
+  a[nlocal + k] = a_in[gsrc[k]];
+}

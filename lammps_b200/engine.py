@@ -1,0 +1,287 @@
+"""Host mirror of the C ABI in include/b200_md.h (ctypes; no torch types cross the boundary).
+
+`Engine` exposes the same vocabulary a LAMMPS input uses (units, pair_style, neighbor,
+neigh_modify, fix nve, run, thermo) so tests read like the reference's own inputs, and maps
+one-to-one onto b200_* entry points.  There is NO CPU fallback: if libb200md.so is missing or
+no CUDA device is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import units as _units
+
+HERE = Path(__file__).resolve().parent
+LIBPATH = HERE / "libb200md.so"
+
+NPHASE = 9
+PHASES = ("initial_integrate", "final_integrate", "forward_comm", "reverse_comm", "pair",
+          "neigh", "neigh_build", "force_clear", "thermo")
+
+EXPORTS = [
+    "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_set_box",
+    "b200_set_decomposition", "b200_set_neighbor", "b200_set_atoms", "b200_get_atoms",
+    "b200_get_counts", "b200_pair_lj_cut", "b200_pair_eam", "b200_fix_nve", "b200_setup",
+    "b200_run", "b200_initial_integrate", "b200_final_integrate", "b200_decide",
+    "b200_forward_comm", "b200_reverse_comm", "b200_reneighbor", "b200_force_clear",
+    "b200_pair_compute", "b200_get_tallies", "b200_ke_sum", "b200_get_stats",
+    "b200_get_neighbor_list", "b200_get_eam_rho_fp", "b200_set_profiling",
+    "b200_get_phase_times", "b200_comm_unique_id", "b200_comm_init",
+]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class Stats(C.Structure):
+    _fields_ = [("nbuilds", C.c_int64), ("ndanger", C.c_int64), ("ago", C.c_int64),
+                ("npairs", C.c_int64), ("maxneigh", C.c_int64), ("max_numneigh", C.c_int64),
+                ("nbins", C.c_int64 * 3), ("mbins", C.c_int64), ("nstencil", C.c_int64),
+                ("launches", C.c_int64), ("device_bytes", C.c_double)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libb200md.so; raises if it has not been built (never falls back)."""
+    global _lib
+    if _lib is None:
+        if not LIBPATH.exists():
+            raise B200Error(f"{LIBPATH} not found: run `python -m lammps_b200.build` "
+                            "(there is no CPU fallback)")
+        L = C.CDLL(str(LIBPATH))
+        L.b200_last_error.restype = C.c_char_p
+        L.b200_last_error.argtypes = [C.c_void_p]
+        L.b200_destroy.restype = None
+        L.b200_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    def __init__(self, device: int = 0, precision: str = "double", units: str = "lj"):
+        self.L = load_library()
+        if self.L.b200_device_count() <= 0:
+            raise B200Error("no CUDA device visible (the B200 engine has no CPU fallback)")
+        self.h = C.c_void_p()
+        prec = {"double": 0, "mixed": 1}[precision]
+        rc = self.L.b200_create(C.byref(self.h), C.c_int(device), C.c_int(prec))
+        self._chk(rc)
+        self.precision = precision
+        self.units = _units.get(units)
+        self.boxlo = self.boxhi = None
+        self.natoms_total = 0
+        self.step = 0
+        self.thermo_every = 0
+        self.dt = self.units.dt
+
+    def close(self):
+        if getattr(self, "h", None) and self.h:
+            self.L.b200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            msg = self.L.b200_last_error(self.h) if self.h else b""
+            raise B200Error(f"b200 error {rc}: {(msg or b'').decode()}")
+
+    # ------------------------------------------------------------ configuration
+    def set_box(self, lo, hi, periodic=(1, 1, 1)):
+        lo, hi, per = _d(lo), _d(hi), _i(periodic)
+        self.boxlo, self.boxhi = lo.copy(), hi.copy()
+        self._chk(self.L.b200_set_box(self.h, _p(lo), _p(hi), _p(per)))
+
+    def set_decomposition(self, procgrid, myloc):
+        pg, ml = _i(procgrid), _i(myloc)
+        self._chk(self.L.b200_set_decomposition(self.h, _p(pg), _p(ml)))
+
+    def neighbor(self, skin, every=1, delay=0, check=True, one=2000):
+        """`neighbor SKIN bin` + `neigh_modify every E delay D check yes|no one N`."""
+        self._chk(self.L.b200_set_neighbor(self.h, C.c_double(skin), C.c_int(every),
+                                           C.c_int(delay), C.c_int(1 if check else 0),
+                                           C.c_int(one)))
+
+    def set_atoms(self, x, v, type, tag, mass, mask=None, image=None, natoms_total=None):
+        x, v, type, tag, mass = _d(x), _d(v), _i(type), _i(tag), _d(mass)
+        n = x.shape[0]
+        mk = _i(mask) if mask is not None else None
+        im = _i(image) if image is not None else None
+        self.mass = mass
+        self.natoms_total = natoms_total if natoms_total is not None else n
+        self._chk(self.L.b200_set_atoms(self.h, C.c_int(n), C.c_int(mass.shape[0] - 1), _p(mass),
+                                        _p(x), _p(v), _p(type), _p(tag), _p(mk), _p(im)))
+
+    def pair_lj_cut(self, tables: dict):
+        t = {k: _d(tables[k]) for k in ("cutsq", "lj1", "lj2", "lj3", "lj4", "offset")}
+        sp = _d(tables.get("special_lj", np.ones(4)))
+        self._chk(self.L.b200_pair_lj_cut(self.h, C.c_int(tables["ntypes"]), _p(t["cutsq"]),
+                                          _p(t["lj1"]), _p(t["lj2"]), _p(t["lj3"]), _p(t["lj4"]),
+                                          _p(t["offset"]), _p(sp)))
+
+    def pair_eam(self, t: dict):
+        a = {k: _i(t[k]) for k in ("type2frho", "type2rhor", "type2z2r")}
+        b = {k: _d(t[k]) for k in ("scale", "frho_spline", "rhor_spline", "z2r_spline")}
+        self._chk(self.L.b200_pair_eam(
+            self.h, C.c_int(t["ntypes"]), C.c_int(t["nr"]), C.c_int(t["nrho"]),
+            C.c_double(t["rdr"]), C.c_double(t["rdrho"]), C.c_double(t["rhomax"]),
+            C.c_double(t["cutforcesq"]), _p(a["type2frho"]), _p(a["type2rhor"]),
+            _p(a["type2z2r"]), _p(b["scale"]), C.c_int(t["nfrho"]), _p(b["frho_spline"]),
+            C.c_int(t["nrhor"]), _p(b["rhor_spline"]), C.c_int(t["nz2r"]), _p(b["z2r_spline"])))
+
+    def fix_nve(self, dt=None, groupbit=1):
+        if dt is not None:
+            self.dt = dt
+        dtf = 0.5 * self.dt * self.units.ftm2v  # fix_nve.cpp:58
+        self._chk(self.L.b200_fix_nve(self.h, C.c_double(self.dt), C.c_double(dtf),
+                                      C.c_int(groupbit)))
+
+    # ------------------------------------------------------------ driver
+    def setup(self, eflag=1, vflag=1):
+        self._chk(self.L.b200_setup(self.h, C.c_int(eflag), C.c_int(vflag)))
+
+    def run(self, nsteps, thermo_every=None):
+        """Verlet::run; returns raw tallies [[step, sum m v^2, eng_vdwl, v0..v5, 0], ...]."""
+        te = self.thermo_every if thermo_every is None else thermo_every
+        cap = (nsteps // te + 2) if te > 0 else 2
+        out = np.zeros((cap, 10))
+        n = C.c_int(0)
+        rc = self.L.b200_run(self.h, C.c_int(nsteps), C.c_int64(self.step), C.c_int(te), _p(out),
+                             C.c_int(cap), C.byref(n))
+        self._chk(rc)
+        self.step += nsteps
+        return out[:n.value]
+
+    def initial_integrate(self):
+        self._chk(self.L.b200_initial_integrate(self.h))
+
+    def final_integrate(self):
+        self._chk(self.L.b200_final_integrate(self.h))
+
+    def decide(self) -> int:
+        r = C.c_int(0)
+        self._chk(self.L.b200_decide(self.h, C.byref(r)))
+        return r.value
+
+    def forward_comm(self):
+        self._chk(self.L.b200_forward_comm(self.h))
+
+    def reverse_comm(self):
+        self._chk(self.L.b200_reverse_comm(self.h))
+
+    def reneighbor(self):
+        self._chk(self.L.b200_reneighbor(self.h))
+
+    def force_clear(self):
+        self._chk(self.L.b200_force_clear(self.h))
+
+    def pair_compute(self, eflag=1, vflag=1):
+        self._chk(self.L.b200_pair_compute(self.h, C.c_int(eflag), C.c_int(vflag)))
+
+    # ------------------------------------------------------------ results
+    def counts(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self._chk(self.L.b200_get_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def get_atoms(self, ghosts=False, fields=("x", "v", "f", "type", "tag", "image")):
+        nl, ng = self.counts()
+        n = nl + (ng if ghosts else 0)
+        out = {}
+        if "x" in fields: out["x"] = np.zeros((n, 3))
+        if "v" in fields: out["v"] = np.zeros((nl, 3))
+        if "f" in fields: out["f"] = np.zeros((n, 3))
+        if "type" in fields: out["type"] = np.zeros(n, np.int32)
+        if "tag" in fields: out["tag"] = np.zeros(n, np.int32)
+        if "mask" in fields: out["mask"] = np.zeros(n, np.int32)
+        if "image" in fields: out["image"] = np.zeros(nl, np.int32)
+        g = lambda k: _p(out[k]) if k in out else None  # noqa: E731
+        self._chk(self.L.b200_get_atoms(self.h, C.c_int(1 if ghosts else 0), g("x"), g("v"),
+                                        g("f"), g("type"), g("tag"), g("mask"), g("image")))
+        return out
+
+    def tallies(self):
+        e = C.c_double(0)
+        v = np.zeros(6)
+        self._chk(self.L.b200_get_tallies(self.h, C.byref(e), _p(v)))
+        return e.value, v
+
+    def ke_sum(self):
+        e = C.c_double(0)
+        self._chk(self.L.b200_ke_sum(self.h, C.byref(e)))
+        return e.value
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._chk(self.L.b200_get_stats(self.h, C.byref(s)))
+        d = {k: getattr(s, k) for k, _ in Stats._fields_ if k != "nbins"}
+        d["nbins"] = list(s.nbins)
+        return d
+
+    def neighbor_list(self):
+        """(numneigh[nlocal], pair_i, pair_j) with local indices in current device order."""
+        nl, _ = self.counts()
+        npairs = C.c_int64(0)
+        nn = np.zeros(nl, np.int32)
+        self._chk(self.L.b200_get_neighbor_list(self.h, _p(nn), None, C.c_int64(0),
+                                                C.byref(npairs)))
+        flat = np.zeros(npairs.value, np.int32)
+        self._chk(self.L.b200_get_neighbor_list(self.h, _p(nn), _p(flat),
+                                                C.c_int64(npairs.value), C.byref(npairs)))
+        pi = np.repeat(np.arange(nl, dtype=np.int32), nn)
+        return nn, pi, flat
+
+    def eam_rho_fp(self, ghosts=False):
+        nl, ng = self.counts()
+        n = nl + (ng if ghosts else 0)
+        rho, fp = np.zeros(n), np.zeros(n)
+        self._chk(self.L.b200_get_eam_rho_fp(self.h, C.c_int(1 if ghosts else 0), _p(rho), _p(fp)))
+        return rho, fp
+
+    def profiling(self, on=True):
+        self._chk(self.L.b200_set_profiling(self.h, C.c_int(1 if on else 0)))
+
+    def phase_times(self) -> dict:
+        ms = np.zeros(NPHASE)
+        calls = np.zeros(NPHASE, np.int64)
+        self._chk(self.L.b200_get_phase_times(self.h, _p(ms), _p(calls)))
+        return {PHASES[k]: (float(ms[k]), int(calls[k])) for k in range(NPHASE)}
+
+    # ------------------------------------------------------------ thermo (host arithmetic)
+    def thermo_row(self, raw) -> dict:
+        """Temp / E_pair / TotEng / Press as thermo.cpp prints them, from the raw tallies.
+        compute_temp.cpp:57-97 (dof = 3N-3), compute_pressure.cpp:254-259, thermo norm."""
+        u = self.units
+        n = self.natoms_total
+        dof = 3.0 * n - 3.0
+        tfactor = u.mvv2e / (dof * u.boltz)
+        temp = raw[1] * tfactor
+        vol = float(np.prod(self.boxhi - self.boxlo))
+        press = (dof * u.boltz * temp + raw[3] + raw[4] + raw[5]) / 3.0 / vol * u.nktv2p
+        ke = 0.5 * dof * u.boltz * temp
+        pe = raw[2]
+        norm = n if u.normalize else 1
+        return {"step": int(raw[0]), "temp": temp, "e_pair": pe / norm,
+                "toteng": (pe + ke) / norm, "press": press}
