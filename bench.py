@@ -1,0 +1,374 @@
+#!/usr/bin/env python3
+"""bench.py -- atom-timesteps/s of the B200-native short-range MD hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload lj32m|lj4m|lj32k|eam16m|eam2m|eam32k] [--precision double|mixed]
+
+A "step" is ONE MD timestep of the hot path (fix nve + ghost halo + pair forces, with the
+neighbour list rebuilt on the reference's own schedule) over all atoms of a synthetic LJ-melt /
+Cu-EAM FCC lattice built exactly like bench/in.lj / bench/in.eam of the reference.
+
+Default workload (BASELINE.json config the target is quoted on): LJ melt, 32,000,000 atoms,
+lj/cut 2.5 sigma, skin 0.3, rebuild every 20 steps, NVE -- strong-scaled over N GPUs.
+
+Prints ONE JSON line (see the keys at the bottom).  `value` is device-resident steady-state
+throughput (CUDA events around K timesteps, max over ranks); `e2e` is the same metric through
+the C ABI with HOST buffers: upload from pinned host memory, Verlet setup, K timesteps with the
+thermo read-back, download of x/v/f -- all inside the timed region.
+
+--impl reference times the UNMODIFIED reference (oracle/_ref/lmp_ref, built by
+oracle/build_ref.py) on the host cores with its OPENMP package on a bounded sample of the
+same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (kind, cells per edge at N=1, scaling)
+    "lj32m": ("lj", 200, "strong"),
+    "lj4m": ("lj", 100, "strong"),
+    "lj32k": ("lj", 20, "strong"),
+    "eam16m": ("eam", 160, "strong"),
+    "eam2m": ("eam", 80, "weak"),
+    "eam32k": ("eam", 20, "strong"),
+}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_system(kind, cells):
+    from lammps_b200 import eam as eam_mod
+    from lammps_b200 import lattice, pair_lj
+    if kind == "lj":
+        x, lo, hi = lattice.fcc_block("lj", 0.8442, cells)
+        mass = np.array([0.0, 1.0])
+        typ = np.ones(len(x), np.int32)
+        v = lattice.velocity_create(x, typ, mass, 1.44, 87287, "lj")
+        return dict(kind="lj", units="lj", x=x, v=v, type=typ, mass=mass, lo=lo, hi=hi, skin=0.3,
+                    every=20, delay=0, check=False, dt=0.005,
+                    tables=pair_lj.lj_cut_tables(1, {(1, 1): (1.0, 1.0, 2.5)}, 2.5))
+    d = np.load(ROOT / "lammps_b200" / "data" / "Cu_u3_funcfl.npz")
+    f = eam_mod.Funcfl(float(d["mass"]), int(d["nrho"]), float(d["drho"]), int(d["nr"]),
+                       float(d["dr"]), float(d["cut"]), d["frho"], d["zr"], d["rhor"])
+    T = eam_mod.funcfl_tables([f], [0])
+    x, lo, hi = lattice.fcc_block("metal", 3.615, cells)
+    typ = np.ones(len(x), np.int32)
+    v = lattice.velocity_create(x, typ, T.mass, 1600.0, 376847, "metal")
+    return dict(kind="eam", units="metal", x=x, v=v, type=typ, mass=T.mass, lo=lo, hi=hi, skin=1.0,
+                every=1, delay=5, check=True, dt=0.005, tables=T.as_dict())
+
+
+def configure(e, s, x, v, typ, tag, natoms_total):
+    e.set_box(s["lo"], s["hi"])
+    e.set_atoms(x, v, typ, tag, s["mass"], natoms_total=natoms_total)
+    e.neighbor(s["skin"], every=s["every"], delay=s["delay"], check=s["check"])
+    e.fix_nve(s["dt"])
+    (e.pair_lj_cut if s["kind"] == "lj" else e.pair_eam)(s["tables"])
+
+
+# algorithmic bytes/flops per atom-step of the dominant (pair) kernel, SURVEY.md 8(d):
+#   LJ : list 4*Ps + x_i,type 32 + f_i write 24 + f clear 24 ; flops 8*Ps + 20*Pc
+#   EAM: 2 passes over the list, rho/fp traffic
+def pair_algorithmic(kind, ps, pc):
+    if kind == "lj":
+        return 4.0 * ps + 32 + 24 + 24, 8.0 * ps + 20.0 * pc
+    return 2 * 4.0 * ps + 2 * 32 + 8 * 3 + 24 + 24, 2 * 8.0 * ps + 24.0 * pc + 45.0 * pc
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from lammps_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    kind, cells1, scaling = WORKLOADS[args.workload]
+
+    from lammps_b200 import decomp
+    grid = decomp.proc_grid(world, (1.0, 1.0, 1.0))
+    if scaling == "weak":
+        cells = tuple(cells1 * g for g in grid)
+    else:
+        cells = (cells1,) * 3
+    t0 = time.time()
+    s = build_system(kind, cells)
+    natoms = len(s["x"])
+    tag = np.arange(1, natoms + 1, dtype=np.int32)
+    host_setup_s = time.time() - t0
+
+    e = Engine(local_rank, args.precision, s["units"])
+    if world > 1:
+        myloc = decomp.rank_to_loc(rank, grid)
+        sel = decomp.owned_mask(s["x"], s["lo"], s["hi"], grid, myloc)
+        xs, vs, ts, tg = s["x"][sel], s["v"][sel], s["type"][sel], tag[sel]
+        e.set_decomposition(grid, myloc)
+        decomp.init_comm(e, dist, rank, world)
+    else:
+        xs, vs, ts, tg = s["x"], s["v"], s["type"], tag
+    nown = len(xs)
+
+    # pinned host staging for the end-to-end leg
+    pin = {k: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+           for k, a in (("x", xs), ("v", vs), ("type", ts), ("tag", tg))}
+    hx, hv, ht, hg = (pin[k].numpy() for k in ("x", "v", "type", "tag"))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(val):
+        if world == 1:
+            return val
+        t = torch.tensor([val], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident leg
+    configure(e, s, hx, hv, ht, hg, natoms)
+    e.setup(1, 1)
+    e.run(args.warmup, 0)
+    launches0 = e.stats()["launches"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e.profiling(True)
+    barrier()
+    t0 = time.perf_counter()
+    e.run(args.steps, 0)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = maxreduce(e.last_run_ms())
+    ph = e.phase_times()
+    e.profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    st = e.stats()
+    launches = st["launches"] - launches0
+    value = natoms * args.steps / (dev_ms * 1e-3)
+
+    # ---------------- end-to-end leg through the C ABI with host buffers
+    e2e_steps = args.steps
+    out = {"x": np.empty((nown * 2, 3)), "v": np.empty((nown * 2, 3)), "f": np.empty((nown * 2, 3))}
+    barrier()
+    t0 = time.perf_counter()
+    e.step = 0
+    configure(e, s, hx, hv, ht, hg, natoms)       # H2D: x,v (24 B each), type, tag (4 B each)
+    e.setup(1, 1)
+    th = e.run(e2e_steps, 100)                    # thermo tallies read back every 100 steps
+    got = e.get_atoms(fields=("x", "v", "f"))      # D2H: x,v,f
+    barrier()
+    e2e_s = maxreduce(time.perf_counter() - t0)
+    e2e_value = natoms * e2e_steps / e2e_s
+    h2d = nown * (24 + 24 + 4 + 4)
+    d2h = len(got["x"]) * 72 + len(th) * 80
+
+    # ---------------- roofline of the dominant kernel (pair)
+    hbm_peak, peak_src = peaks()
+    pair_ms, pair_calls = ph["pair"]
+    ps = st["npairs"] / max(nown, 1)
+    pc = ps * (27.54 / 37.59 if kind == "lj" else 21.99 / 37.74)   # in-cutoff fraction, SURVEY 8(a)
+    bytes_atom, flops_atom = pair_algorithmic(kind, ps, pc)
+    pair_s = pair_ms * 1e-3 / max(pair_calls, 1)
+    achieved = bytes_atom * nown / pair_s / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_pair_lj" if kind == "lj" else "k_eam_rho+k_eam_force",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "peak_source": peak_src, "traffic": None,
+                "bytes_per_atom": bytes_atom, "pairs_stored_per_atom": ps,
+                "us_per_launch": pair_s * 1e6, "flop_per_atom": flops_atom,
+                "tflops": flops_atom * nown / pair_s / 1e12,
+                "share_of_step": pair_ms / max(dev_ms, 1e-9)}
+    phases = {k: {"ms": round(t, 3), "calls": c} for k, (t, c) in ph.items() if c}
+
+    if rank != 0:
+        return
+    res = {
+        "metric": "atom-timesteps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f64" if args.precision == "double" else "f32 pair math / f64 accumulate",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {kind} {'LJ melt' if kind == 'lj' else 'Cu EAM'} "
+                               f"{natoms} atoms, fcc {cells[0]}x{cells[1]}x{cells[2]} cells, NVE, "
+                               f"skin {s['skin']}, neigh every {s['every']} delay {s['delay']} "
+                               f"check {'yes' if s['check'] else 'no'}",
+                   "natoms": natoms, "proc_grid": list(grid), "precision": args.precision,
+                   "l2": "working set (>= 100 B/atom x natoms) exceeds the 126 MB L2; no flush"
+                         if natoms >= 2_000_000 else "working set fits L2 (small reference case)",
+                   "rebuilds_in_timed_region": ph["neigh"][1]},
+        "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d / e2e_steps,
+                "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps,
+                "includes": "pinned-host upload, Verlet setup (ghosts+list+forces), run, thermo "
+                            "read-back, x/v/f download"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "phases": phases,
+        "wall_s_timed_region": wall,
+        "host_setup_s": host_setup_s,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        res["cpu_baseline"] = cpu_baseline(kind, budget_s=20.0)
+    print(json.dumps(res))
+
+
+# ----------------------------------------------------------------------------- reference
+def lmp_script(kind, cells, warm, steps):
+    from oracle import ref_harness as R
+    if kind == "lj":
+        return R.lj_input(run=warm, cells=cells) + f"\nrun {steps}\n"
+    return R.eam_input(run=warm, cells=cells) + f"\nrun {steps}\n"
+
+
+def run_lmp_ref(kind, cells, warm, steps, threads):
+    from oracle import ref_harness as R
+    if not R.EXE.exists():
+        return None
+    out = R.run_exe(lmp_script(kind, cells, warm, steps), threads=threads,
+                    suffix="omp" if threads > 1 else None)
+    loops = re.findall(r"Loop time of ([0-9.eE+-]+) on \d+ procs for (\d+) steps with (\d+) atoms", out)
+    t, nst, nat = loops[-1]
+    return float(t), int(nst), int(nat)
+
+
+def cpu_baseline(kind, budget_s=20.0):
+    """The reference's CPU path (oracle/_ref, kind "reference") on a bounded sample."""
+    cores = os.cpu_count() or 1
+    rate_guess = 1.2e6 * cores if kind == "lj" else 0.45e6 * cores
+    steps = 100
+    natoms = rate_guess * budget_s / steps
+    cells = int(max(10, min(120, round((natoms / 4.0) ** (1 / 3)))))
+    r = run_lmp_ref(kind, cells, 0, steps, cores)
+    if r is None:
+        return {"value": None, "unit": "atom-steps/s", "cores": cores, "kind": "reference",
+                "sample": "oracle/_ref/lmp_ref not built"}
+    t, nst, nat = r
+    return {"value": nat * nst / t, "unit": "atom-steps/s", "cores": cores, "kind": "reference",
+            "sample": f"lmp_ref -sf omp -pk omp {cores}: {kind} {nat} atoms x {nst} steps "
+                      f"(loop time {t:.2f} s, setup excluded as in finish.cpp)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, cells1, scaling = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    rate_guess = 1.2e6 * cores if kind == "lj" else 0.45e6 * cores
+    natoms = rate_guess * 90.0 / max(total, 1)
+    cells = int(max(10, min(cells1, round((natoms / 4.0) ** (1 / 3)))))
+    r = run_lmp_ref(kind, cells, args.warmup, args.steps, cores)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/lmp_ref is not built"}))
+        return
+    t, nst, nat = r
+    val = nat * nst / t
+    sample = (f"lmp_ref -sf omp -pk omp {cores}: {kind} {nat} atoms x {nst} steps after {args.warmup} "
+              f"warm-up steps (bounded sample of {args.workload})")
+    print(json.dumps({
+        "impl": "reference", "metric": "atom-timesteps/s", "value": val, "unit": "atom-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t / nst * 1e3, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload} (sample: {nat} atoms)", "natoms": nat},
+        "cpu_baseline": {"value": val, "unit": "atom-steps/s", "cores": cores, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "atom-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="lj32m", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="double", choices=["double", "mixed"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -94,6 +94,9 @@ int b200_fix_nve(b200_ctx *ctx, double dtv, double dtf, int groupbit);
  *                        10 doubles {step, sum(m v^2), eng_vdwl, virial[0..5], 0}.
  */
 int b200_setup(b200_ctx *ctx, int eflag, int vflag);
+/* device time of the last b200_run: CUDA events recorded on the context's stream before the
+ * first and after the last kernel of the run (the "Loop time" of finish.cpp:117-160) */
+int b200_last_run_ms(b200_ctx *ctx, double *ms);
 int b200_run(b200_ctx *ctx, int nsteps, int64_t first_step, int thermo_every,
              double *thermo_out, int max_thermo, int *n_thermo);
 

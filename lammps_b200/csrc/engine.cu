@@ -100,6 +100,8 @@ struct b200_ctx {
   int *h_flags = nullptr; // pinned [32]
   double eng_vdwl = 0, virial[6] = {0, 0, 0, 0, 0, 0};
   bool setup_done = false;
+  cudaEvent_t run_a = nullptr, run_b = nullptr;
+  double last_run_ms = 0;
   // profiling
   bool profiling = false;
   std::vector<PhaseRec> recs;
@@ -1030,6 +1032,11 @@ int b200_run(b200_ctx *ctx, int nsteps, int64_t first_step, int thermo_every, do
   if (!ctx->setup_done) return ctx->fail(B200_EARG, "b200_run before b200_setup");
   CK(cudaSetDevice(ctx->device));
   int nout = 0;
+  if (!ctx->run_a) {
+    CK(cudaEventCreate(&ctx->run_a));
+    CK(cudaEventCreate(&ctx->run_b));
+  }
+  CK(cudaEventRecord(ctx->run_a, ctx->stream));
   for (int sidx = 1; sidx <= nsteps; sidx++) {
     const int64_t step = first_step + sidx;
     const int ev = (thermo_every > 0 && step % thermo_every == 0) || sidx == nsteps;
@@ -1062,8 +1069,20 @@ int b200_run(b200_ctx *ctx, int nsteps, int64_t first_step, int thermo_every, do
       }
     }
   }
+  CK(cudaEventRecord(ctx->run_b, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->run_a, ctx->run_b));
+    ctx->last_run_ms = ms;
+  }
   if (n_thermo) *n_thermo = nout;
+  return B200_OK;
+}
+
+int b200_last_run_ms(b200_ctx *ctx, double *ms) {
+  if (!ctx || !ms) return B200_EARG;
+  *ms = ctx->last_run_ms;
   return B200_OK;
 }
 

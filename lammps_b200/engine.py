@@ -25,7 +25,7 @@ EXPORTS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_set_box",
     "b200_set_decomposition", "b200_set_neighbor", "b200_set_atoms", "b200_get_atoms",
     "b200_get_counts", "b200_pair_lj_cut", "b200_pair_eam", "b200_fix_nve", "b200_setup",
-    "b200_run", "b200_initial_integrate", "b200_final_integrate", "b200_decide",
+    "b200_run", "b200_last_run_ms", "b200_initial_integrate", "b200_final_integrate", "b200_decide",
     "b200_forward_comm", "b200_reverse_comm", "b200_reneighbor", "b200_force_clear",
     "b200_pair_compute", "b200_get_tallies", "b200_ke_sum", "b200_get_stats",
     "b200_get_neighbor_list", "b200_get_eam_rho_fp", "b200_set_profiling",
@@ -173,6 +173,11 @@ class Engine:
         self._chk(rc)
         self.step += nsteps
         return out[:n.value]
+
+    def last_run_ms(self) -> float:
+        ms = C.c_double(0)
+        self._chk(self.L.b200_last_run_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def initial_integrate(self):
         self._chk(self.L.b200_initial_integrate(self.h))
