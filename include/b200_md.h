@@ -51,6 +51,9 @@ int b200_device_count(void);
 int b200_set_box(b200_ctx *ctx, const double boxlo[3], const double boxhi[3],
                  const int periodicity[3]);
 int b200_set_decomposition(b200_ctx *ctx, const int procgrid[3], const int myloc[3]);
+/*      optional: which rank owns grid location (ix,iy,iz), n = px*py*pz entries indexed
+ *      (ix*py+iy)*pz+iz -- Comm::grid2proc (comm.h); default = that index itself (MPI_Cart order) */
+int b200_set_rank_grid(b200_ctx *ctx, const int *grid2rank, int n);
 
 /* ---- neighbor / neigh_modify (neighbor.cpp:2680-2940): skin, every, delay, check, one.
  *      cutneighsq = (sqrt(cutsq)+skin)^2 is derived from the pair style's cutsq
@@ -100,7 +103,11 @@ int b200_last_run_ms(b200_ctx *ctx, double *ms);
 int b200_run(b200_ctx *ctx, int nsteps, int64_t first_step, int thermo_every,
              double *thermo_out, int max_thermo, int *n_thermo);
 
-/*      step-granular entry points (what verlet/b200 calls when other fixes interleave) */
+/*      one iteration of Verlet::run (verlet.cpp:246-355) minus output: what run_style verlet/b200
+ *      calls every timestep.  Asynchronous unless dist_check needs the rebuild vote or
+ *      eflag/vflag ask for tallies (then eng_vdwl/virial are current for b200_get_tallies). */
+int b200_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt);
+/*      stage-granular entry points (the same stages, one call each) */
 int b200_initial_integrate(b200_ctx *ctx);            /* FixNVE::initial_integrate fix_nve.cpp:68 */
 int b200_final_integrate(b200_ctx *ctx);              /* FixNVE::final_integrate  fix_nve.cpp:112 */
 int b200_decide(b200_ctx *ctx, int *rebuild);         /* Neighbor::decide neighbor.cpp:2408 */
@@ -157,10 +164,22 @@ int b200_set_profiling(b200_ctx *ctx, int on);
 /* accumulated since the last call (which resets them): milliseconds and launch counts */
 int b200_get_phase_times(b200_ctx *ctx, double ms[B200_NPHASE], int64_t calls[B200_NPHASE]);
 
-/* ---- multi-GPU: one context per GPU/process; halo exchange over NCCL send/recv.
- *      b200_comm_unique_id fills a 128-byte ncclUniqueId on rank 0 (to be broadcast by the
- *      host, e.g. torch.distributed); b200_comm_init joins the communicator. */
+/* ---- multi-GPU: one context per GPU/process = one brick sub-domain (CommBrick,
+ *      comm_brick.cpp:172-430).  The ghost halo (forward x, reverse f, EAM rho/fp), border
+ *      construction and atom migration run as grouped ncclSend/ncclRecv between the 26
+ *      neighbour sub-domains, from device buffers.  b200_comm_unique_id fills a 128-byte
+ *      ncclUniqueId on rank 0 (the host broadcasts it: MPI_Bcast in a LAMMPS+MPI build,
+ *      torch.distributed in bench.py); b200_comm_init joins the communicator.  Call order:
+ *      b200_create, b200_comm_init, b200_set_box, b200_set_decomposition, b200_set_atoms
+ *      (atoms this rank owns: sublo <= x < subhi), ... */
 int b200_comm_unique_id(void *id128);
+/*      host-only helper (no GPU needed): rank of the neighbour sub-domain in each of the 27
+ *      directions dir = (dz+1)*9 + (dy+1)*3 + (dx+1); ranks are numbered like MPI_Cart_create
+ *      does for the reference (last dimension fastest, procmap.cpp:361-374); -1 = no
+ *      neighbour beyond a non-periodic boundary.  Messages between two ranks are issued in
+ *      ascending direction order on both sides. */
+int b200_neighbor_ranks(const int procgrid[3], const int myloc[3], const int periodicity[3],
+                        int nbr[27]);
 int b200_comm_init(b200_ctx *ctx, int nranks, int rank, const void *id128);
 
 #ifdef __cplusplus

@@ -10,9 +10,13 @@
 //   neigh  int32[maxneigh][nstride] transposed half list, numneigh int32[nlocal]
 //   gsrc   int32[nghost], gdir uint8[nghost]: owner index and direction of every ghost
 #include "common.cuh"
+#include "kernels_halo.cuh"
 #include "kernels_neigh.cuh"
 #include "kernels_pair.cuh"
 #include "kernels_step.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -70,12 +74,26 @@ struct b200_ctx {
   int cur = 0;  // which of the ping-pong buffers holds the live atoms
   // bins
   DBuf<int> ostart, gstart, tilesum;
-  // ghosts
-  DBuf<int> sendlist, gsrc, gbin, gslot;
-  DBuf<unsigned char> gdir, gdir_tmp;
+  // ghosts (index spaces p / q / g: see kernels_halo.cuh)
+  DBuf<int> sendlist, gsrc, gbin, gslot, gtag_tmp, gsrc_tmp;
+  DBuf<unsigned char> senddir, gdir, gdir_tmp;
   DBuf<double4> gtmp;
-  int *dircount = nullptr;   // [27] device
-  int *diroffset = nullptr;  // [28] device
+  int *counts = nullptr;      // [32] device: per-direction counters [0,27), [27] error flags
+  int *diroffset = nullptr;   // [28] device: send-order segment offsets
+  int *recvoffset = nullptr;  // [28] device: recv-order segment offsets
+  int nsend = 0;
+  int sendoff[NDIR + 1] = {0}, recvoff[NDIR + 1] = {0};
+  // multi-GPU halo: one sub-domain per rank, NCCL send/recv between the 26 neighbours
+  ncclComm_t nccl = nullptr;
+  int nranks = 1, rank = 0;
+  int nbr[NDIR];             // rank of the neighbour sub-domain in each direction (-1: none)
+  std::vector<int> rankmap;  // optional grid location -> rank map supplied by the host
+  unsigned remote_mask = 0;  // directions whose neighbour is another rank
+  Owner owner;
+  DBuf<double> sbuf, rbuf;   // halo staging in send order / recv order (up to 4 doubles per atom)
+  DBuf<double> mig_send, mig_recv;
+  int *allcounts = nullptr;  // [nranks*32] device (all-gathered counters)
+  int *h_counts = nullptr;   // pinned [nranks*32]
   // list
   DBuf<int> neigh, numneigh;
   int maxneigh = 0, nstride = 0, max_numneigh = 0;
@@ -202,6 +220,110 @@ static void ph_collect(b200_ctx *ctx) {
   ctx->recs.clear();
 }
 
+
+// ------------------------------------------------------------------ NCCL (loaded on demand)
+// libnccl.so.2 is dlopen'ed only when b200_comm_init is called, so a single-GPU process has no
+// NCCL dependency.  Inside a process that already loaded NCCL (torch) the same copy is reused.
+namespace {
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+} g_nccl;
+
+bool load_nccl(std::string &why) {
+  if (g_nccl.ok) return true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  if (!g_nccl.handle) {
+    why = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+    return false;
+  }
+#define SYM(field, name)                                               \
+  *(void **)(&g_nccl.field) = dlsym(g_nccl.handle, name);              \
+  if (!g_nccl.field) {                                                 \
+    why = std::string("libnccl lacks ") + name;                        \
+    return false;                                                      \
+  }
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(AllGather, "ncclAllGather")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.ok = true;
+  return true;
+}
+}  // namespace
+
+#define NK(call)                                                                           \
+  do {                                                                                     \
+    ncclResult_t r_ = (call);                                                              \
+    if (r_ != ncclSuccess)                                                                 \
+      return ctx->fail(B200_ECUDA, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, \
+                       __LINE__);                                                          \
+  } while (0)
+
+// One grouped exchange between the 26 neighbours.  forward: segment `dir` of the send-order
+// buffer goes to nbr[dir]; segment `dir` of the recv-order buffer comes from nbr[26-dir] (the
+// rank that sent in direction dir).  reverse: the same segments travel the other way.  Both
+// sides walk the directions in ascending order, so several messages between one pair of ranks
+// (2 ranks along a dimension) match up in issue order.
+static int halo_exchange(b200_ctx *ctx, const double *src, const int *srcoff, double *dst,
+                         const int *dstoff, int width, bool reverse) {
+  if (ctx->nranks == 1 || !ctx->remote_mask) return B200_OK;
+  NK(g_nccl.GroupStart());
+  for (int dir = 0; dir < NDIR; dir++) {
+    if (!((ctx->remote_mask >> dir) & 1u)) continue;
+    const int to = reverse ? ctx->nbr[NDIR - 1 - dir] : ctx->nbr[dir];
+    const int from = reverse ? ctx->nbr[dir] : ctx->nbr[NDIR - 1 - dir];
+    const size_t ns = (size_t)(srcoff[dir + 1] - srcoff[dir]) * width;
+    const size_t nr = (size_t)(dstoff[dir + 1] - dstoff[dir]) * width;
+    if (ns && to >= 0)
+      NK(g_nccl.Send(src + (size_t)srcoff[dir] * width, ns, ncclDouble, to, ctx->nccl, ctx->stream));
+    if (nr && from >= 0)
+      NK(g_nccl.Recv(dst + (size_t)dstoff[dir] * width, nr, ncclDouble, from, ctx->nccl, ctx->stream));
+  }
+  NK(g_nccl.GroupEnd());
+  return B200_OK;
+}
+
+// The 32 device counters of every rank, on the host: [r*32 + dir] and the error word [r*32+27].
+// One all-gather + one D2H copy + one stream sync (rebuild steps only).
+static int sync_counts(b200_ctx *ctx) {
+  if (ctx->nranks > 1) {
+    NK(g_nccl.AllGather(ctx->counts, ctx->allcounts, 32, ncclInt, ctx->nccl, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_counts, ctx->allcounts, sizeof(int) * 32 * ctx->nranks,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  } else
+    CK(cudaMemcpyAsync(ctx->h_counts, ctx->counts, sizeof(int) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+static int global_err(const b200_ctx *ctx) {
+  int e = 0;
+  for (int r = 0; r < ctx->nranks; r++) e |= ctx->h_counts[r * 32 + 27];
+  return e;
+}
+
 // ------------------------------------------------------------------ per-atom storage
 static int alloc_atoms(b200_ctx *ctx, int nmax) {
   // (re)allocate every per-atom array for nmax atoms; live data is copied over
@@ -232,7 +354,7 @@ static int alloc_atoms(b200_ctx *ctx, int nmax) {
     TRY(regrow(ctx->f[d], nmax, keep, sizeof(double)));
     TRY(regrow(ctx->xh[d], nmax, keep, sizeof(double)));
   }
-  TRY(regrow(ctx->slot, nmax, 0, sizeof(int)));
+  TRY(regrow(ctx->slot, nmax, keep, sizeof(int)));
   TRY(regrow(ctx->rho, nmax, keep, sizeof(double)));
   TRY(regrow(ctx->fp, nmax, keep, sizeof(double)));
   ctx->nmax = nmax;
@@ -300,6 +422,46 @@ static int setup_geometry(b200_ctx *ctx) {
       if (dv[d] < 0 && ctx->myloc[d] == 0) s = 1 * ctx->prd[d];
       if (dv[d] > 0 && ctx->myloc[d] == ctx->procgrid[d] - 1) s = -1 * ctx->prd[d];
       g.shift[dir][d] = s;
+    }
+  }
+  // ---- neighbour sub-domains: rank numbering as MPI_Cart (last dimension fastest,
+  //      procmap.cpp:361-374), periodic wrap of the grid location, -1 beyond an open boundary
+  {
+    const int *P = ctx->procgrid, *me = ctx->myloc;
+    int np = P[0] * P[1] * P[2];
+    if (np != ctx->nranks)
+      return ctx->fail(B200_EARG, "decomposition %dx%dx%d needs %d ranks but the communicator has %d",
+                       P[0], P[1], P[2], np, ctx->nranks);
+    b200_neighbor_ranks(P, me, ctx->periodic, ctx->nbr);
+    if (!ctx->rankmap.empty()) {  // host-supplied grid -> rank map (Comm::grid2proc)
+      if ((int)ctx->rankmap.size() != np)
+        return ctx->fail(B200_EARG, "rank grid has %d entries, decomposition needs %d",
+                         (int)ctx->rankmap.size(), np);
+      for (int dir = 0; dir < NDIR; dir++)
+        if (ctx->nbr[dir] >= 0) ctx->nbr[dir] = ctx->rankmap[ctx->nbr[dir]];
+    }
+    ctx->remote_mask = 0;
+    for (int dir = 0; dir < NDIR; dir++)
+      if (dir != 13 && ctx->nbr[dir] >= 0 && ctx->nbr[dir] != ctx->rank) ctx->remote_mask |= 1u << dir;
+    Owner &o = ctx->owner;
+    memset(&o, 0, sizeof o);
+    auto bounds = [&](int d, int l, double &lo, double &hi) {
+      lo = ctx->boxlo[d] + ctx->prd[d] * (l * 1.0 / P[d]);
+      hi = (l < P[d] - 1) ? ctx->boxlo[d] + ctx->prd[d] * ((l + 1) * 1.0 / P[d]) : ctx->boxhi[d];
+    };
+    for (int d = 0; d < 3; d++) {
+      bounds(d, me[d], o.lo[d][0], o.hi[d][0]);
+      o.has[d][0] = 1;
+      for (int side = 1; side <= 2; side++) {
+        int l = me[d] + (side == 1 ? -1 : 1);
+        if (l < 0 || l >= P[d]) {
+          if (!ctx->periodic[d]) continue;
+          l = (l + P[d]) % P[d];
+        }
+        if (l == me[d]) continue;  // one rank along this dimension: nobody else can own it
+        bounds(d, l, o.lo[d][side], o.hi[d][side]);
+        o.has[d][side] = 1;
+      }
     }
   }
   // ---- bins
@@ -454,72 +616,154 @@ static int reneighbor(b200_ctx *ctx) {
   if (!ctx->geom_ready) TRY(setup_geometry(ctx));
   const int ph2 = ph_begin(ctx, B200_PH_NEIGH);
   const Geom &g = ctx->geom;
-  const int nl = ctx->nlocal;
+  const bool multi = ctx->nranks > 1;
+  const int nl0 = ctx->nlocal;
   int c = ctx->cur;
   cudaStream_t s = ctx->stream;
+  ctx->nghost = 0;  // the ghost region holds nothing worth keeping from here on
   CK(cudaMemsetAsync(ctx->ostart.p, 0, sizeof(int) * (g.mbins + 1), s));
   CK(cudaMemsetAsync(ctx->gstart.p, 0, sizeof(int) * (g.mbins + 1), s));
   CK(cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), s));
-  CK(cudaMemsetAsync(ctx->dircount, 0, NDIR * sizeof(int), s));
-  if (nl > 0) {
-    k_pbc_bin<<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], ctx->image[c], g, ctx->atombin[c],
-                                            ctx->slot, ctx->ostart.p, ctx->flags + 1);
+  CK(cudaMemsetAsync(ctx->counts, 0, 32 * sizeof(int), s));
+  int *err = ctx->counts + 27;
+  // ---- Domain::pbc + coord2bin (+ CommBrick::exchange classification)
+  if (nl0 > 0) {
+    if (multi)
+      k_pbc_bin<true><<<cdiv(nl0, 256), 256, 0, s>>>(nl0, ctx->xt[c], ctx->image[c], g, ctx->owner,
+                                                     ctx->atombin[c], ctx->slot, ctx->ostart.p,
+                                                     ctx->counts, err);
+    else
+      k_pbc_bin<false><<<cdiv(nl0, 256), 256, 0, s>>>(nl0, ctx->xt[c], ctx->image[c], g, ctx->owner,
+                                                      ctx->atombin[c], ctx->slot, ctx->ostart.p,
+                                                      ctx->counts, err);
     ctx->launches++;
+    LAUNCH_CHECK();
   }
+  int ntot = nl0, nl = nl0;
+  if (multi) {
+    // ---- CommBrick::exchange: ship leavers to the sub-domain that owns them now
+    TRY(sync_counts(ctx));
+    TRY(check_err_flags(ctx, global_err(ctx)));
+    int moff[NDIR + 1], aoff[NDIR + 1];
+    moff[0] = aoff[0] = 0;
+    for (int dir = 0; dir < NDIR; dir++) {
+      const bool rem = (ctx->remote_mask >> dir) & 1u;
+      const int from = ctx->nbr[NDIR - 1 - dir];
+      moff[dir + 1] = moff[dir] + (rem ? ctx->h_counts[ctx->rank * 32 + dir] : 0);
+      aoff[dir + 1] = aoff[dir] + ((rem && from >= 0) ? ctx->h_counts[from * 32 + dir] : 0);
+      if (!rem && ctx->h_counts[ctx->rank * 32 + dir] && dir != 13)
+        return ctx->fail(B200_ELOST, "atom left the sub-domain towards a direction without neighbour");
+    }
+    const int nleave = moff[NDIR], narrive = aoff[NDIR];
+    if (nl0 + narrive > ctx->nmax) {
+      ctx->nlocal = nl0;
+      TRY(alloc_atoms(ctx, (int)((nl0 + narrive) * 1.2) + 1024));
+    }
+    TRY(reserve(ctx, ctx->mig_send, (size_t)nleave * MIG_W));
+    TRY(reserve(ctx, ctx->mig_recv, (size_t)narrive * MIG_W));
+    CK(cudaMemcpyAsync(ctx->diroffset, moff, (NDIR + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (nleave > 0) {
+      k_pack_migrate<<<cdiv(nl0, 256), 256, 0, s>>>(nl0, ctx->atombin[c], ctx->slot, ctx->diroffset,
+                                                    ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2],
+                                                    ctx->tag[c], ctx->mask[c], ctx->image[c],
+                                                    ctx->mig_send.p);
+      ctx->launches++;
+    }
+    TRY(halo_exchange(ctx, ctx->mig_send.p, moff, ctx->mig_recv.p, aoff, MIG_W, false));
+    if (narrive > 0) {
+      k_unpack_migrate<<<cdiv(narrive, 256), 256, 0, s>>>(
+          narrive, nl0, ctx->mig_recv.p, g, ctx->owner, ctx->xt[c], ctx->v[c][0], ctx->v[c][1],
+          ctx->v[c][2], ctx->tag[c], ctx->mask[c], ctx->image[c], ctx->atombin[c], ctx->slot,
+          ctx->ostart.p, err);
+      ctx->launches++;
+    }
+    LAUNCH_CHECK();
+    ntot = nl0 + narrive;
+    nl = nl0 - nleave + narrive;
+    CK(cudaMemsetAsync(ctx->counts, 0, 27 * sizeof(int), s));
+  }
+  // ---- counting sort of the owned atoms by bin (+ xhold)
   TRY(scan_inplace(ctx, ctx->ostart.p, g.mbins));
-  if (nl > 0) {
-    k_permute_owned<<<cdiv(nl, 256), 256, 0, s>>>(
-        nl, ctx->atombin[c], ctx->slot, ctx->ostart.p, ctx->xt[c], ctx->xt[c ^ 1], ctx->v[c][0],
+  if (ntot > 0) {
+    k_permute_owned<<<cdiv(ntot, 256), 256, 0, s>>>(
+        ntot, ctx->atombin[c], ctx->slot, ctx->ostart.p, ctx->xt[c], ctx->xt[c ^ 1], ctx->v[c][0],
         ctx->v[c][1], ctx->v[c][2], ctx->v[c ^ 1][0], ctx->v[c ^ 1][1], ctx->v[c ^ 1][2], ctx->tag[c],
         ctx->tag[c ^ 1], ctx->mask[c], ctx->mask[c ^ 1], ctx->image[c], ctx->image[c ^ 1],
         ctx->atombin[c ^ 1], ctx->xh[0], ctx->xh[1], ctx->xh[2]);
     ctx->launches++;
-    c ^= 1;
-    ctx->cur = c;
-    // borders, count pass
-    k_border<0><<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], g, ctx->dircount, ctx->diroffset, nullptr);
+  }
+  c ^= 1;
+  ctx->cur = c;
+  ctx->nlocal = nl;
+  // ---- CommBrick::borders: count per direction, exchange the counts, fill, ship, place
+  if (nl > 0) {
+    k_border<0><<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], g, ctx->counts, ctx->diroffset, nullptr,
+                                              nullptr);
     ctx->launches++;
   }
   LAUNCH_CHECK();
-  CK(cudaMemcpyAsync(ctx->h_flags + 4, ctx->dircount, NDIR * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  TRY(check_err_flags(ctx, ctx->h_flags[1]));
-  int off[NDIR + 1];
-  off[0] = 0;
-  for (int d = 0; d < NDIR; d++) off[d + 1] = off[d] + ctx->h_flags[4 + d];
-  const int ng = off[NDIR];
-  ctx->nghost = 0;  // the ghost region holds nothing worth keeping across a regrow
+  TRY(sync_counts(ctx));
+  TRY(check_err_flags(ctx, global_err(ctx)));
+  ctx->sendoff[0] = ctx->recvoff[0] = 0;
+  for (int dir = 0; dir < NDIR; dir++) {
+    const bool rem = (ctx->remote_mask >> dir) & 1u;
+    const int from = ctx->nbr[NDIR - 1 - dir];
+    const int mine = ctx->h_counts[ctx->rank * 32 + dir];
+    const int theirs = rem ? (from >= 0 ? ctx->h_counts[from * 32 + dir] : 0) : mine;
+    ctx->sendoff[dir + 1] = ctx->sendoff[dir] + mine;
+    ctx->recvoff[dir + 1] = ctx->recvoff[dir] + theirs;
+  }
+  const int nsend = ctx->sendoff[NDIR], ng = ctx->recvoff[NDIR];
+  ctx->nsend = nsend;
   if (nl + ng > ctx->nmax) {
     TRY(alloc_atoms(ctx, (int)((nl + ng) * 1.1) + 1024));
     c = ctx->cur;
   }
   ctx->nghost = ng;
-  TRY(reserve(ctx, ctx->sendlist, (size_t)ng));
+  TRY(reserve(ctx, ctx->sendlist, (size_t)nsend));
+  TRY(reserve(ctx, ctx->senddir, (size_t)nsend));
   TRY(reserve(ctx, ctx->gsrc, (size_t)ng));
   TRY(reserve(ctx, ctx->gbin, (size_t)ng));
   TRY(reserve(ctx, ctx->gslot, (size_t)ng));
+  TRY(reserve(ctx, ctx->gtag_tmp, (size_t)ng));
+  TRY(reserve(ctx, ctx->gsrc_tmp, (size_t)ng));
   TRY(reserve(ctx, ctx->gdir, (size_t)ng));
   TRY(reserve(ctx, ctx->gdir_tmp, (size_t)ng));
   TRY(reserve(ctx, ctx->gtmp, (size_t)ng));
-  CK(cudaMemcpyAsync(ctx->diroffset, off, (NDIR + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
-  CK(cudaMemsetAsync(ctx->dircount, 0, NDIR * sizeof(int), s));
+  if (multi) {
+    TRY(reserve(ctx, ctx->sbuf, (size_t)nsend * 4));
+    TRY(reserve(ctx, ctx->rbuf, (size_t)ng * 4));
+  }
+  CK(cudaMemcpyAsync(ctx->diroffset, ctx->sendoff, (NDIR + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->recvoffset, ctx->recvoff, (NDIR + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(ctx->counts, 0, 27 * sizeof(int), s));
+  if (nsend > 0) {
+    k_border<1><<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], g, ctx->counts, ctx->diroffset,
+                                              ctx->sendlist.p, ctx->senddir.p);
+    ctx->launches++;
+    if (multi) {
+      k_pack_border<<<cdiv(nsend, 256), 256, 0, s>>>(nsend, ctx->sendlist.p, ctx->senddir.p,
+                                                     ctx->remote_mask, g, ctx->xt[c], ctx->tag[c],
+                                                     reinterpret_cast<double4 *>(ctx->sbuf.p));
+      ctx->launches++;
+    }
+  }
+  LAUNCH_CHECK();
+  TRY(halo_exchange(ctx, ctx->sbuf.p, ctx->sendoff, ctx->rbuf.p, ctx->recvoff, 4, false));
   if (ng > 0) {
-    k_border<1><<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], g, ctx->dircount, ctx->diroffset,
-                                              ctx->sendlist.p);
-    k_ghost_make<<<cdiv(ng, 256), 256, 0, s>>>(ng, ctx->sendlist.p, ctx->diroffset, g, ctx->xt[c],
-                                               ctx->gtmp.p, ctx->gbin.p, ctx->gslot.p,
-                                               ctx->gdir_tmp.p, ctx->gstart.p, ctx->flags + 1);
-    ctx->launches += 2;
+    k_ghost_make<<<cdiv(ng, 256), 256, 0, s>>>(
+        ng, ctx->recvoffset, ctx->diroffset, ctx->remote_mask, ctx->sendlist.p, g, ctx->xt[c],
+        ctx->tag[c], reinterpret_cast<const double4 *>(ctx->rbuf.p), ctx->gtmp.p, ctx->gtag_tmp.p,
+        ctx->gsrc_tmp.p, ctx->gbin.p, ctx->gslot.p, ctx->gdir_tmp.p, ctx->gstart.p, ctx->flags + 1);
+    ctx->launches++;
   }
   TRY(scan_inplace(ctx, ctx->gstart.p, g.mbins));
   if (ng > 0) {
-    k_ghost_place<<<cdiv(ng, 256), 256, 0, s>>>(ng, nl, ctx->sendlist.p, ctx->gtmp.p, ctx->gbin.p,
-                                                ctx->gslot.p, ctx->gdir_tmp.p, ctx->gstart.p,
-                                                ctx->tag[c], ctx->xt[c], ctx->tag[c], ctx->gsrc.p,
-                                                ctx->gdir.p);
-    k_ghost_type_copy<<<cdiv(ng, 256), 256, 0, s>>>(ng, nl, ctx->gsrc.p, ctx->mask[c], ctx->mask[c]);
-    ctx->launches += 2;
+    k_ghost_place<<<cdiv(ng, 256), 256, 0, s>>>(ng, nl, ctx->gtmp.p, ctx->gtag_tmp.p, ctx->gsrc_tmp.p,
+                                                ctx->gbin.p, ctx->gslot.p, ctx->gdir_tmp.p,
+                                                ctx->gstart.p, ctx->xt[c], ctx->tag[c], ctx->mask[c],
+                                                ctx->gsrc.p, ctx->gdir.p);
+    ctx->launches++;
   }
   LAUNCH_CHECK();
   TRY(build_list(ctx));
@@ -542,25 +786,64 @@ static int force_clear(b200_ctx *ctx) {
 
 static int forward_comm(b200_ctx *ctx) {
   const int ph4 = ph_begin(ctx, B200_PH_FORWARD);
-  if (ctx->nghost > 0) {
-    k_forward_self<<<cdiv(ctx->nghost, 256), 256, 0, ctx->stream>>>(
-        ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->geom, ctx->xt[ctx->cur]);
+  const int c = ctx->cur;
+  if (ctx->remote_mask && ctx->nsend > 0) {
+    k_pack_forward<<<cdiv(ctx->nsend, 256), 256, 0, ctx->stream>>>(
+        ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->remote_mask, ctx->geom, ctx->xt[c],
+        ctx->sbuf.p);
     ctx->launches++;
-    LAUNCH_CHECK();
   }
+  TRY(halo_exchange(ctx, ctx->sbuf.p, ctx->sendoff, ctx->rbuf.p, ctx->recvoff, 3, false));
+  if (ctx->nghost > 0) {
+    k_unpack_forward<<<cdiv(ctx->nghost, 256), 256, 0, ctx->stream>>>(
+        ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->geom, ctx->rbuf.p, ctx->xt[c]);
+    ctx->launches++;
+  }
+  LAUNCH_CHECK();
   ph_end(ctx, ph4);
+  return B200_OK;
+}
+
+// reverse halo of W per-atom doubles held in SoA arrays a[0..W)
+template <int W>
+static int reverse_halo(b200_ctx *ctx, Vec3Ptr a) {
+  if (ctx->nghost > 0) {
+    k_pack_reverse<W><<<cdiv(ctx->nghost, 256), 256, 0, ctx->stream>>>(ctx->nghost, ctx->nlocal,
+                                                                      ctx->gsrc.p, a, ctx->rbuf.p);
+    ctx->launches++;
+  }
+  TRY(halo_exchange(ctx, ctx->rbuf.p, ctx->recvoff, ctx->sbuf.p, ctx->sendoff, W, true));
+  if (ctx->remote_mask && ctx->nsend > 0) {
+    k_unpack_reverse<W><<<cdiv(ctx->nsend, 256), 256, 0, ctx->stream>>>(
+        ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->remote_mask, ctx->sbuf.p, a);
+    ctx->launches++;
+  }
+  LAUNCH_CHECK();
   return B200_OK;
 }
 
 static int reverse_comm(b200_ctx *ctx) {
   const int ph5 = ph_begin(ctx, B200_PH_REVERSE);
-  if (ctx->nghost > 0) {
-    k_reverse_self<<<cdiv(ctx->nghost, 256), 256, 0, ctx->stream>>>(
-        ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->f[0], ctx->f[1], ctx->f[2]);
-    ctx->launches++;
-    LAUNCH_CHECK();
-  }
+  Vec3Ptr f{{ctx->f[0], ctx->f[1], ctx->f[2]}};
+  TRY(reverse_halo<3>(ctx, f));
   ph_end(ctx, ph5);
+  return B200_OK;
+}
+
+// EAM: PairEAM::pack/unpack_forward_comm of fp (pair_eam.cpp:1600-1621)
+static int forward_scalar(b200_ctx *ctx, double *a) {
+  if (ctx->remote_mask && ctx->nsend > 0) {
+    k_pack_forward_scalar<<<cdiv(ctx->nsend, 256), 256, 0, ctx->stream>>>(
+        ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->remote_mask, a, ctx->sbuf.p);
+    ctx->launches++;
+  }
+  TRY(halo_exchange(ctx, ctx->sbuf.p, ctx->sendoff, ctx->rbuf.p, ctx->recvoff, 1, false));
+  if (ctx->nghost > 0) {
+    k_unpack_forward_scalar<<<cdiv(ctx->nghost, 256), 256, 0, ctx->stream>>>(
+        ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->rbuf.p, a);
+    ctx->launches++;
+  }
+  LAUNCH_CHECK();
   return B200_OK;
 }
 
@@ -598,20 +881,21 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag) {
     }
   } else if (ctx->pair_style == 2) {
     CK(cudaMemsetAsync(ctx->rho, 0, sizeof(double) * (nl + ng), s));
-    if (nl > 0) {
-      const int grid = cdiv(nl, 128);
+    {  // every rank walks the same sequence of halo calls, even one without atoms
+      const int grid = cdiv(std::max(nl, 1), 128);
       k_eam_rho<<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p, ctx->neigh.p,
                                      ctx->eam, ctx->rho);
-      if (ng > 0)
-        k_reverse_scalar_self<<<cdiv(ng, 256), 256, 0, s>>>(ng, nl, ctx->gsrc.p, ctx->rho);
+      {
+        Vec3Ptr r{{ctx->rho, nullptr, nullptr}};
+        TRY(reverse_halo<1>(ctx, r));
+      }
       if (eflag)
-        k_eam_embed<true><<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], ctx->eam, ctx->rho, ctx->fp,
+        k_eam_embed<true><<<cdiv(std::max(nl, 1), 256), 256, 0, s>>>(nl, ctx->xt[c], ctx->eam, ctx->rho, ctx->fp,
                                                         ctx->ev, ctx->flags + 1);
       else
-        k_eam_embed<false><<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], ctx->eam, ctx->rho, ctx->fp,
+        k_eam_embed<false><<<cdiv(std::max(nl, 1), 256), 256, 0, s>>>(nl, ctx->xt[c], ctx->eam, ctx->rho, ctx->fp,
                                                          ctx->ev, ctx->flags + 1);
-      if (ng > 0)
-        k_forward_scalar_self<<<cdiv(ng, 256), 256, 0, s>>>(ng, nl, ctx->gsrc.p, ctx->fp);
+      TRY(forward_scalar(ctx, ctx->fp));
       if (eflag)
         k_eam_force<true><<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
                                                ctx->neigh.p, ctx->eam, ctx->fp, ctx->f[0], ctx->f[1],
@@ -620,7 +904,7 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag) {
         k_eam_force<false><<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
                                                 ctx->neigh.p, ctx->eam, ctx->fp, ctx->f[0], ctx->f[1],
                                                 ctx->f[2], ctx->ev);
-      ctx->launches += 3 + (ng > 0 ? 2 : 0);
+      ctx->launches += 3;
     }
   } else
     return ctx->fail(B200_EARG, "no pair style set");
@@ -677,6 +961,9 @@ static int decide(b200_ctx *ctx, int *rebuild) {
       *rebuild = 1;
       return B200_OK;
     }
+    // Neighbor::check_distance: MPI_Allreduce(MAX) of the moved flag (neighbor.cpp:2487)
+    if (ctx->nranks > 1)
+      NK(g_nccl.AllReduce(ctx->flags, ctx->flags, 1, ncclInt, ncclMax, ctx->nccl, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_flags[0]) {
@@ -706,6 +993,9 @@ static int ke_reduce(b200_ctx *ctx) {
 }
 
 static int fetch_ev(b200_ctx *ctx) {
+  // MPI_Allreduce(SUM) of compute_pe / compute_pressure virial / compute_temp
+  if (ctx->nranks > 1)
+    NK(g_nccl.AllReduce(ctx->ev, ctx->ev, 8, ncclDouble, ncclSum, ctx->nccl, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_ev, ctx->ev, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->eng_vdwl = ctx->h_ev[0];
@@ -739,7 +1029,12 @@ int b200_create(b200_ctx **out, int device, int precision) {
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   TRY(dalloc(ctx, &ctx->ev, 8));
   TRY(dalloc(ctx, &ctx->flags, 4));
-  TRY(dalloc(ctx, &ctx->dircount, NDIR));
+  TRY(dalloc(ctx, &ctx->counts, 32));
+  TRY(dalloc(ctx, &ctx->recvoffset, NDIR + 1));
+  TRY(dalloc(ctx, &ctx->allcounts, 32));
+  CK(cudaMallocHost((void **)&ctx->h_counts, 32 * sizeof(int)));
+  for (int d = 0; d < NDIR; d++) ctx->nbr[d] = 0;
+  memset(&ctx->owner, 0, sizeof ctx->owner);
   TRY(dalloc(ctx, &ctx->diroffset, NDIR + 1));
   TRY(dalloc(ctx, &ctx->cnt64, 1));
   CK(cudaMallocHost((void **)&ctx->h_ev, 8 * sizeof(double)));
@@ -765,7 +1060,12 @@ void b200_destroy(b200_ctx *ctx) {
   F(ctx->slot); F(ctx->rho); F(ctx->fp);
   F(ctx->cutneighsq_d.p); F(ctx->mass_d.p); F(ctx->ostart.p); F(ctx->gstart.p); F(ctx->tilesum.p);
   F(ctx->sendlist.p); F(ctx->gsrc.p); F(ctx->gbin.p); F(ctx->gslot.p); F(ctx->gdir.p);
-  F(ctx->gdir_tmp.p); F(ctx->gtmp.p); F(ctx->dircount); F(ctx->diroffset); F(ctx->neigh.p);
+  F(ctx->gdir_tmp.p); F(ctx->gtmp.p); F(ctx->counts); F(ctx->diroffset); F(ctx->recvoffset); F(ctx->allcounts);
+  F(ctx->senddir.p); F(ctx->gtag_tmp.p); F(ctx->gsrc_tmp.p); F(ctx->sbuf.p); F(ctx->rbuf.p);
+  F(ctx->mig_send.p); F(ctx->mig_recv.p);
+  if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  if (ctx->nccl && g_nccl.ok) g_nccl.CommDestroy(ctx->nccl);
+  F(ctx->neigh.p);
   F(ctx->numneigh.p); F(ctx->lj_tab.p); F(ctx->eam_i.p); F(ctx->eam_d.p); F(ctx->ev); F(ctx->flags);
   F(ctx->cnt64);
   if (ctx->h_ev) cudaFreeHost(ctx->h_ev);
@@ -800,6 +1100,13 @@ int b200_set_decomposition(b200_ctx *ctx, const int procgrid[3], const int myloc
     ctx->procgrid[d] = procgrid[d];
     ctx->myloc[d] = myloc[d];
   }
+  ctx->geom_ready = false;
+  return B200_OK;
+}
+
+int b200_set_rank_grid(b200_ctx *ctx, const int *grid2rank, int n) {
+  if (!ctx || n < 0 || (n > 0 && !grid2rank)) return B200_EARG;
+  ctx->rankmap.assign(grid2rank, grid2rank + n);
   ctx->geom_ready = false;
   return B200_OK;
 }
@@ -1026,6 +1333,33 @@ int b200_pair_compute(b200_ctx *ctx, int eflag, int vflag) {
   return B200_OK;
 }
 
+// one iteration of Verlet::run (verlet.cpp:246-355) without the output stage
+static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt) {
+  const int chk = check_due_next(ctx) ? 1 : 0;
+  if (chk) CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
+  TRY(initial_integrate(ctx, chk));
+  int nflag = 0;
+  TRY(decide(ctx, &nflag));
+  if (!nflag)
+    TRY(forward_comm(ctx));
+  else
+    TRY(reneighbor(ctx));
+  TRY(force_clear(ctx));
+  TRY(pair_compute(ctx, eflag, vflag));
+  TRY(reverse_comm(ctx));
+  TRY(final_integrate(ctx));
+  if (rebuilt) *rebuilt = nflag;
+  return B200_OK;
+}
+
+int b200_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt) {
+  if (!ctx) return B200_EARG;
+  if (!ctx->setup_done) return ctx->fail(B200_EARG, "b200_step before b200_setup");
+  TRY(one_step(ctx, eflag, vflag, rebuilt));
+  if (eflag || vflag) TRY(fetch_ev(ctx));  // the host is about to read eng_vdwl / virial
+  return B200_OK;
+}
+
 int b200_run(b200_ctx *ctx, int nsteps, int64_t first_step, int thermo_every, double *thermo_out,
              int max_thermo, int *n_thermo) {
   if (!ctx) return B200_EARG;
@@ -1040,19 +1374,8 @@ int b200_run(b200_ctx *ctx, int nsteps, int64_t first_step, int thermo_every, do
   for (int sidx = 1; sidx <= nsteps; sidx++) {
     const int64_t step = first_step + sidx;
     const int ev = (thermo_every > 0 && step % thermo_every == 0) || sidx == nsteps;
-    const int chk = check_due_next(ctx) ? 1 : 0;
-    if (chk) CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
-    TRY(initial_integrate(ctx, chk));
     int nflag = 0;
-    TRY(decide(ctx, &nflag));
-    if (!nflag)
-      TRY(forward_comm(ctx));
-    else
-      TRY(reneighbor(ctx));
-    TRY(force_clear(ctx));
-    TRY(pair_compute(ctx, ev, ev));
-    TRY(reverse_comm(ctx));
-    TRY(final_integrate(ctx));
+    TRY(one_step(ctx, ev, ev, &nflag));
     if (ev) {
       const int ph10 = ph_begin(ctx, B200_PH_THERMO);
       TRY(ke_reduce(ctx));
@@ -1096,6 +1419,8 @@ int b200_get_tallies(b200_ctx *ctx, double *eng_vdwl, double virial[6]) {
 int b200_ke_sum(b200_ctx *ctx, double *mv2) {
   if (!ctx || !mv2) return B200_EARG;
   TRY(ke_reduce(ctx));
+  if (ctx->nranks > 1)
+    NK(g_nccl.AllReduce(ctx->ev + 7, ctx->ev + 7, 1, ncclDouble, ncclSum, ctx->nccl, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_ev + 7, ctx->ev + 7, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   *mv2 = ctx->h_ev[7];
@@ -1182,9 +1507,58 @@ int b200_get_phase_times(b200_ctx *ctx, double ms[B200_NPHASE], int64_t calls[B2
   return B200_OK;
 }
 
-int b200_comm_unique_id(void *) { return B200_EARG; }
-int b200_comm_init(b200_ctx *ctx, int, int, const void *) {
-  return ctx ? ctx->fail(B200_EARG, "multi-GPU halo is not built into this library yet") : B200_EARG;
+int b200_neighbor_ranks(const int procgrid[3], const int myloc[3], const int periodicity[3],
+                        int nbr[27]) {
+  if (!procgrid || !myloc || !periodicity || !nbr) return B200_EARG;
+  for (int dir = 0; dir < NDIR; dir++) {
+    const int dv[3] = {dir % 3 - 1, (dir / 3) % 3 - 1, dir / 9 - 1};
+    int loc[3];
+    bool exists = true;
+    for (int d = 0; d < 3; d++) {
+      loc[d] = myloc[d] + dv[d];
+      if (loc[d] < 0 || loc[d] >= procgrid[d]) {
+        if (periodicity[d]) loc[d] = (loc[d] + procgrid[d]) % procgrid[d];
+        else exists = false;
+      }
+    }
+    nbr[dir] = exists ? (loc[0] * procgrid[1] + loc[1]) * procgrid[2] + loc[2] : -1;
+  }
+  return B200_OK;
+}
+
+int b200_comm_unique_id(void *id128) {
+  if (!id128) return B200_EARG;
+  std::string why;
+  if (!load_nccl(why)) return B200_ECUDA;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return B200_ECUDA;
+  memcpy(id128, &id, sizeof id);
+  return B200_OK;
+}
+
+int b200_comm_init(b200_ctx *ctx, int nranks, int rank, const void *id128) {
+  if (!ctx) return B200_EARG;
+  if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !id128))
+    return ctx->fail(B200_EARG, "b200_comm_init: bad arguments");
+  if (ctx->nccl) return ctx->fail(B200_EARG, "b200_comm_init called twice");
+  ctx->nranks = nranks;
+  ctx->rank = rank;
+  ctx->geom_ready = false;
+  if (nranks == 1) return B200_OK;
+  CK(cudaSetDevice(ctx->device));
+  std::string why;
+  if (!load_nccl(why)) return ctx->fail(B200_ECUDA, "%s", why.c_str());
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NK(g_nccl.CommInitRank(&ctx->nccl, nranks, id, rank));
+  cudaFree(ctx->allcounts);
+  cudaFreeHost(ctx->h_counts);
+  ctx->allcounts = nullptr;
+  ctx->h_counts = nullptr;
+  TRY(dalloc(ctx, &ctx->allcounts, (size_t)32 * nranks));
+  CK(cudaMallocHost((void **)&ctx->h_counts, sizeof(int) * 32 * nranks));
+  return B200_OK;
 }
 
 }  // extern "C"

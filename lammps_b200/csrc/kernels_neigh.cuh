@@ -3,6 +3,7 @@
 // streaming or gather kernels; no tensor-core work exists on this path.
 #pragma once
 #include "common.cuh"
+#include "kernels_halo.cuh"
 
 // ---------------------------------------------------------------------------------------
 // exclusive scan of int32 (bin counts -> bin starts), 3 launches, hand-written.
@@ -92,10 +93,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(int *__restrict__ out
 // counting sort.  One thread per owned atom.  32 B read + 32 B write of position, 4+4 B image.
 // err[0] |= 1 non-finite coordinate, |= 2 atom outside the local bin grid (lost).
 // ---------------------------------------------------------------------------------------
+template <bool MULTI>
 __global__ void __launch_bounds__(256) k_pbc_bin(int nlocal, double4 *__restrict__ xt,
-                                                 int *__restrict__ image, Geom g,
+                                                 int *__restrict__ image, Geom g, Owner own,
                                                  int *__restrict__ atombin, int *__restrict__ slot,
-                                                 int *__restrict__ bincount, int *__restrict__ err) {
+                                                 int *__restrict__ bincount,
+                                                 int *__restrict__ dircount, int *__restrict__ err) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlocal) return;
   double4 p = xt[i];
@@ -148,6 +151,22 @@ __global__ void __launch_bounds__(256) k_pbc_bin(int nlocal, double4 *__restrict
   }
   xt[i] = p;
   image[i] = img;
+  if (MULTI) {
+    // CommBrick::exchange: an atom outside [sublo,subhi) leaves to the sub-domain owning it
+    const int ox = owner_dim(own, 0, p.x), oy = owner_dim(own, 1, p.y), oz = owner_dim(own, 2, p.z);
+    if (ox | oy | oz) {
+      if (ox == 2 || oy == 2 || oz == 2) {
+        atomicOr(err, 2);
+        atombin[i] = -1 - 13;
+        slot[i] = 0;
+        return;
+      }
+      const int dir = (oz + 1) * 9 + (oy + 1) * 3 + (ox + 1);
+      atombin[i] = -1 - dir;
+      slot[i] = atomicAdd(&dircount[dir], 1);
+      return;
+    }
+  }
   int b = coord2bin(g, p.x, p.y, p.z);
   if (b < 0) {
     atomicOr(err, 2);
@@ -172,6 +191,7 @@ __global__ void __launch_bounds__(256) k_permute_owned(
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlocal) return;
   const int b = atombin[i];
+  if (b < 0) return;  // left for another sub-domain (k_pack_migrate shipped it)
   const int d = binstart[b] + slot[i];
   const double4 p = xt_in[i];
   xt_out[d] = p;
@@ -200,7 +220,8 @@ template <int FILL>
 __global__ void __launch_bounds__(256) k_border(int nlocal, const double4 *__restrict__ xt, Geom g,
                                                 int *__restrict__ dircount /*[27]*/,
                                                 const int *__restrict__ diroffset /*[28]*/,
-                                                int *__restrict__ sendlist) {
+                                                int *__restrict__ sendlist,
+                                                unsigned char *__restrict__ senddir) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
@@ -227,62 +248,13 @@ __global__ void __launch_bounds__(256) k_border(int nlocal, const double4 *__res
     if (lane == leader) base = atomicAdd(&dircount[dir], __popc(m));
     if (FILL) {
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (ok) sendlist[diroffset[dir] + base + __popc(m & ((1u << lane) - 1u))] = i;
+      if (ok) {
+        const int p = diroffset[dir] + base + __popc(m & ((1u << lane) - 1u));
+        sendlist[p] = i;
+        senddir[p] = (unsigned char)dir;
+      }
     }
   }
-}
-
-// Ghost creation, pass 1: pack_border/unpack_border (atom_vec.cpp:796-830, 1026-1042):
-// position = owner + pbc shift, tag/type copied; then bin the ghost and take a slot.
-__global__ void __launch_bounds__(256) k_ghost_make(int nghost, const int *__restrict__ sendlist,
-                                                    const int *__restrict__ diroffset, Geom g,
-                                                    const double4 *__restrict__ xt,
-                                                    double4 *__restrict__ gtmp,
-                                                    int *__restrict__ gbin, int *__restrict__ gslot,
-                                                    unsigned char *__restrict__ gdir_tmp,
-                                                    int *__restrict__ gbincount,
-                                                    int *__restrict__ err) {
-  __shared__ int soff[NDIR + 1];
-  if (threadIdx.x <= NDIR) soff[threadIdx.x] = diroffset[threadIdx.x];
-  __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= nghost) return;
-  int dir = 0;
-#pragma unroll 1
-  while (dir < NDIR - 1 && p >= soff[dir + 1]) dir++;
-  const int src = sendlist[p];
-  double4 q = xt[src];
-  q.x = q.x + g.shift[dir][0];
-  q.y = q.y + g.shift[dir][1];
-  q.z = q.z + g.shift[dir][2];
-  int b = coord2bin(g, q.x, q.y, q.z);
-  if (b < 0) {
-    atomicOr(err, 2);
-    b = 0;
-  }
-  gtmp[p] = q;
-  gbin[p] = b;
-  gdir_tmp[p] = (unsigned char)dir;
-  gslot[p] = atomicAdd(&gbincount[b], 1);
-}
-
-// Ghost creation, pass 2: place ghosts sorted by bin behind the owned atoms and remember for
-// every ghost its source atom and direction (this is sendlist/firstrecv of comm_brick in
-// receiver order, reused by forward/reverse comm every step).
-__global__ void __launch_bounds__(256) k_ghost_place(
-    int nghost, int nlocal, const int *__restrict__ sendlist, const double4 *__restrict__ gtmp,
-    const int *__restrict__ gbin, const int *__restrict__ gslot,
-    const unsigned char *__restrict__ gdir_tmp, const int *__restrict__ gstart,
-    const int *tag_owned, double4 *__restrict__ xt, int *tag,
-    int *__restrict__ gsrc, unsigned char *__restrict__ gdir) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= nghost) return;
-  const int gidx = gstart[gbin[p]] + gslot[p];
-  const int src = sendlist[p];
-  xt[nlocal + gidx] = gtmp[p];
-  tag[nlocal + gidx] = tag_owned[src];
-  gsrc[gidx] = src;
-  gdir[gidx] = gdir_tmp[p];
 }
 
 // ---------------------------------------------------------------------------------------

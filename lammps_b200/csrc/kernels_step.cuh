@@ -55,53 +55,6 @@ __global__ void __launch_bounds__(256) k_nve_final(
   }
 }
 
-// CommBrick::forward_comm + AtomVec::pack_comm (comm_brick.cpp:485-538, atom_vec.cpp:354-440)
-// for ghosts whose owner lives on this device: ghost = owner + pbc shift of its direction.
-__global__ void __launch_bounds__(256) k_forward_self(int nghost, int nlocal,
-                                                      const int *__restrict__ gsrc,
-                                                      const unsigned char *__restrict__ gdir,
-                                                      Geom g, double4 *__restrict__ xt) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nghost) return;
-  const int dir = gdir[k];
-  double4 q = xt[gsrc[k]];
-  q.x = q.x + g.shift[dir][0];
-  q.y = q.y + g.shift[dir][1];
-  q.z = q.z + g.shift[dir][2];
-  xt[nlocal + k] = q;
-}
-
-// CommBrick::reverse_comm + unpack_reverse (comm_brick.cpp:545-586, atom_vec.cpp:729):
-// owner force += ghost force.  An owner can have up to 7 images -> atomics.
-__global__ void __launch_bounds__(256) k_reverse_self(int nghost, int nlocal,
-                                                      const int *__restrict__ gsrc,
-                                                      double *__restrict__ fx,
-                                                      double *__restrict__ fy,
-                                                      double *__restrict__ fz) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nghost) return;
-  const int s = gsrc[k];
-  atomicAdd(&fx[s], fx[nlocal + k]);
-  atomicAdd(&fy[s], fy[nlocal + k]);
-  atomicAdd(&fz[s], fz[nlocal + k]);
-}
-
-// scalar versions for the EAM halo: reverse (rho, pair_eam.cpp:1625-1646) and forward (fp, :1600-1621)
-__global__ void __launch_bounds__(256) k_reverse_scalar_self(int nghost, int nlocal,
-                                                             const int *__restrict__ gsrc,
-                                                             double *__restrict__ a) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nghost) return;
-  atomicAdd(&a[gsrc[k]], a[nlocal + k]);
-}
-__global__ void __launch_bounds__(256) k_forward_scalar_self(int nghost, int nlocal,
-                                                             const int *__restrict__ gsrc,
-                                                             double *__restrict__ a) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nghost) return;
-  a[nlocal + k] = a[gsrc[k]];
-}
-
 // ComputeTemp::compute_scalar numerator (compute_temp.cpp:73-97): ev[7] += sum m v^2
 __global__ void __launch_bounds__(256) k_ke(int nlocal, const double4 *__restrict__ xt,
                                             const double *__restrict__ vx,
@@ -153,11 +106,4 @@ __global__ void __launch_bounds__(256) k_soa_to_aos(int n, const double *__restr
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   a3[3 * (size_t)i] = x[i]; a3[3 * (size_t)i + 1] = y[i]; a3[3 * (size_t)i + 2] = z[i];
-}
-__global__ void __launch_bounds__(256) k_ghost_type_copy(int nghost, int nlocal,
-                                                         const int *__restrict__ gsrc,
-                                                         const int *a_in, int *a) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nghost) return;
-  a[nlocal + k] = a_in[gsrc[k]];
 }

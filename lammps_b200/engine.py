@@ -23,13 +23,13 @@ PHASES = ("initial_integrate", "final_integrate", "forward_comm", "reverse_comm"
 
 EXPORTS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_set_box",
-    "b200_set_decomposition", "b200_set_neighbor", "b200_set_atoms", "b200_get_atoms",
+    "b200_set_decomposition", "b200_set_rank_grid", "b200_set_neighbor", "b200_set_atoms", "b200_get_atoms",
     "b200_get_counts", "b200_pair_lj_cut", "b200_pair_eam", "b200_fix_nve", "b200_setup",
-    "b200_run", "b200_last_run_ms", "b200_initial_integrate", "b200_final_integrate", "b200_decide",
+    "b200_run", "b200_step", "b200_last_run_ms", "b200_initial_integrate", "b200_final_integrate", "b200_decide",
     "b200_forward_comm", "b200_reverse_comm", "b200_reneighbor", "b200_force_clear",
     "b200_pair_compute", "b200_get_tallies", "b200_ke_sum", "b200_get_stats",
     "b200_get_neighbor_list", "b200_get_eam_rho_fp", "b200_set_profiling",
-    "b200_get_phase_times", "b200_comm_unique_id", "b200_comm_init",
+    "b200_get_phase_times", "b200_comm_unique_id", "b200_comm_init", "b200_neighbor_ranks",
 ]
 
 

@@ -1,0 +1,36 @@
+/* -*- c++ -*- ----------------------------------------------------------
+   B200 package for LAMMPS: host-side glue between LAMMPS styles and the
+   C ABI of libb200md (include/b200_md.h).  New code, not derived from the
+   GPU or KOKKOS packages.
+------------------------------------------------------------------------- */
+
+#ifndef LMP_B200_LMP_H
+#define LMP_B200_LMP_H
+
+#include "b200_md.h"
+
+namespace LAMMPS_NS {
+
+class LAMMPS;
+
+// bit for Pair::suffix_flag (next free bit after Suffix::KOKKOS, src/suffix.h)
+enum { B200_SUFFIX_BIT = 1 << 5 };
+
+// implemented by every pair style of the package: hand the finished coefficient tables
+// (products of init_one() / array2spline()) to the device context
+class B200PairStyle {
+ public:
+  virtual ~B200PairStyle() noexcept(false) {}
+  virtual int b200_upload(b200_ctx *ctx) = 0;
+};
+
+// marker for the time-integration fix verlet/b200 knows how to run on the device
+class B200NVEFix {
+ public:
+  virtual ~B200NVEFix() noexcept(false) {}
+  virtual void b200_params(double &dtv, double &dtf, int &groupbit) = 0;
+};
+
+}    // namespace LAMMPS_NS
+
+#endif

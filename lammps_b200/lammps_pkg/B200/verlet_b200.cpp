@@ -1,0 +1,285 @@
+/* ----------------------------------------------------------------------
+   run_style verlet/b200
+
+   Same sequence of stages as Verlet::setup()/run() (src/verlet.cpp), but
+   every stage of a timestep -- fix nve half-kicks and drift, the rebuild
+   decision, ghost halo or pbc/exchange/borders/list build, force clear,
+   pair forces with energy/virial tallies, reverse halo -- executes on the
+   device through the C ABI of libb200md.  Host arrays (atom->x/v/f,
+   pair->eng_vdwl/virial, neighbor statistics) are refreshed only when host
+   code needs them: on output steps and at the end of a run.
+------------------------------------------------------------------------- */
+
+#include "verlet_b200.h"
+
+#include "atom.h"
+#include "atom_vec.h"
+#include "comm.h"
+#include "domain.h"
+#include "error.h"
+#include "fix.h"
+#include "fix_b200.h"
+#include "force.h"
+#include "memory.h"
+#include "modify.h"
+#include "neigh_list.h"
+#include "neighbor.h"
+#include "output.h"
+#include "pair.h"
+#include "timer.h"
+#include "update.h"
+
+#include <cstring>
+
+using namespace LAMMPS_NS;
+using namespace FixConst;
+
+VerletB200::VerletB200(LAMMPS *lmp, int narg, char **arg) :
+    Verlet(lmp, narg, arg), pkg(nullptr), ctx(nullptr), bpair(nullptr), bnve(nullptr), resident(0), joined(0)
+{
+}
+
+/* ---------------------------------------------------------------------- */
+
+void VerletB200::init()
+{
+  Verlet::init();
+
+  pkg = FixB200::instance(lmp);
+  ctx = pkg->context();
+
+  if (domain->triclinic) error->all(FLERR, "run_style verlet/b200 requires an orthogonal box");
+  if (domain->dimension != 3) error->all(FLERR, "run_style verlet/b200 requires a 3d system");
+  if (atom->molecular != Atom::ATOMIC || atom->rmass_flag)
+    error->all(FLERR, "run_style verlet/b200 requires atom_style atomic with per-type masses");
+  if (force->kspace || force->bond || force->angle || force->dihedral || force->improper)
+    error->all(FLERR, "run_style verlet/b200 supports pairwise short-range forces only");
+  if (!force->newton_pair) error->all(FLERR, "run_style verlet/b200 requires newton pair on");
+  if (domain->box_change) error->all(FLERR, "run_style verlet/b200 requires a fixed box");
+
+  bpair = dynamic_cast<B200PairStyle *>(force->pair);
+  if (!bpair)
+    error->all(FLERR, "run_style verlet/b200 requires a /b200 pair style (lj/cut/b200, eam/b200)");
+
+  // the only fixes that may act during a timestep are nve/b200 instances (one device group)
+  const int stepmask = INITIAL_INTEGRATE | POST_INTEGRATE | PRE_EXCHANGE | PRE_NEIGHBOR |
+      POST_NEIGHBOR | PRE_FORCE | PRE_REVERSE | POST_FORCE | FINAL_INTEGRATE | END_OF_STEP;
+  bnve = nullptr;
+  for (auto &fix : modify->get_fix_list()) {
+    auto *nve = dynamic_cast<B200NVEFix *>(fix);
+    if (nve) {
+      if (bnve) error->all(FLERR, "run_style verlet/b200 supports a single fix nve/b200");
+      bnve = nve;
+      continue;
+    }
+    if (modify->get_fix_mask(fix) & stepmask)
+      error->all(FLERR, "Fix {} (style {}) acts during the timestep and has no /b200 version", fix->id,
+                 fix->style);
+  }
+  if (!bnve) error->all(FLERR, "run_style verlet/b200 requires fix nve/b200");
+  resident = 0;
+
+  // one MPI rank = one GPU = one brick sub-domain: join the NCCL communicator once.  The
+  // ncclUniqueId travels over MPI; afterwards all halo traffic is device-to-device NCCL.
+  if (comm->nprocs > 1 && !joined) {
+    char id[128];
+    memset(id, 0, sizeof id);
+    if (comm->me == 0) B200_CHECK(pkg, b200_comm_unique_id(id));
+    MPI_Bcast(id, 128, MPI_CHAR, 0, world);
+    B200_CHECK(pkg, b200_comm_init(ctx, comm->nprocs, comm->me, id));
+    joined = 1;
+  }
+}
+
+/* ----------------------------------------------------------------------
+   host state -> device: box, decomposition, neighbor settings, atoms,
+   pair coefficients, integrator constants
+------------------------------------------------------------------------- */
+
+void VerletB200::upload()
+{
+  B200_CHECK(pkg, b200_set_box(ctx, domain->boxlo, domain->boxhi, domain->periodicity));
+  B200_CHECK(pkg, b200_set_decomposition(ctx, comm->procgrid, comm->myloc));
+  if (comm->nprocs > 1)
+    B200_CHECK(pkg,
+               b200_set_rank_grid(ctx, &comm->grid2proc[0][0][0],
+                                  comm->procgrid[0] * comm->procgrid[1] * comm->procgrid[2]));
+  B200_CHECK(pkg,
+             b200_set_neighbor(ctx, neighbor->skin, neighbor->every, neighbor->delay,
+                               neighbor->dist_check, neighbor->oneatom));
+  const int nlocal = atom->nlocal;
+  B200_CHECK(pkg,
+             b200_set_atoms(ctx, nlocal, atom->ntypes, atom->mass, nlocal ? &atom->x[0][0] : nullptr,
+                            nlocal ? &atom->v[0][0] : nullptr, atom->type, atom->tag, atom->mask,
+                            atom->image));
+  B200_CHECK(pkg, bpair->b200_upload(ctx));
+  double dtv, dtf;
+  int groupbit;
+  bnve->b200_params(dtv, dtf, groupbit);
+  B200_CHECK(pkg, b200_fix_nve(ctx, dtv, dtf, groupbit));
+}
+
+/* ----------------------------------------------------------------------
+   device -> host arrays; atoms come back in device (bin-sorted) order,
+   which is as legitimate a local order as any Atom::sort() leaves
+------------------------------------------------------------------------- */
+
+void VerletB200::download(int with_ghosts)
+{
+  int nlocal, nghost;
+  B200_CHECK(pkg, b200_get_counts(ctx, &nlocal, &nghost));
+  const int nall = nlocal + (with_ghosts ? nghost : 0);
+  while (nall > atom->nmax) atom->avec->grow(0);
+  atom->nlocal = nlocal;
+  atom->nghost = with_ghosts ? nghost : 0;
+  if (nall == 0) return;
+  B200_CHECK(pkg,
+             b200_get_atoms(ctx, with_ghosts, &atom->x[0][0], &atom->v[0][0], &atom->f[0][0], atom->type,
+                            atom->tag, atom->mask, atom->image));
+}
+
+void VerletB200::fetch_tallies()
+{
+  Pair *pair = force->pair;
+  B200_CHECK(pkg, b200_get_tallies(ctx, &pair->eng_vdwl, pair->virial));
+  pair->eng_coul = 0.0;
+}
+
+/* ---------------------------------------------------------------------- */
+
+void VerletB200::device_setup(int flag, int output_flag)
+{
+  update->setupflag = 1;
+
+  // host side: what must happen before atoms are handed over (same calls as Verlet::setup
+  // up to the point where ghosts would be created -- ghosts and lists are device business)
+  if (flag) {
+    atom->setup();
+    modify->setup_pre_exchange();
+    domain->pbc();
+    domain->reset_box();
+    comm->setup();
+    if (neighbor->style) neighbor->setup_bins();
+    comm->exchange();
+  }
+  force->setup();
+  ev_set(update->ntimestep);
+
+  // device side: ghosts, bins, half list, forces (+ tallies)
+  upload();
+  B200_CHECK(pkg, b200_set_profiling(ctx, pkg->profile()));
+  B200_CHECK(pkg, b200_setup(ctx, eflag ? 1 : 0, vflag ? 1 : 0));
+  resident = 1;
+  download(0);
+  if (eflag || vflag) fetch_tallies();
+  neighbor->ncalls = 0;
+  neighbor->ndanger = 0;
+
+  modify->setup(vflag);
+  if (output_flag >= 0) output->setup(output_flag);
+  update->setupflag = 0;
+}
+
+void VerletB200::setup(int flag)
+{
+  if (comm->me == 0 && screen) {
+    fputs("Setting up Verlet/B200 run ...\n", screen);
+    if (flag) {
+      utils::print(screen, "  Unit style    : {}\n  Current step  : {}\n  Time step     : {}\n",
+                   update->unit_style, update->ntimestep, update->dt);
+      timer->print_timeout(screen);
+    }
+  }
+  device_setup(1, flag);
+}
+
+void VerletB200::setup_minimal(int flag)
+{
+  device_setup(flag, -1);
+}
+
+void VerletB200::reset_dt()
+{
+  // fix nve/b200::reset_dt() forwards the new dtv/dtf itself
+}
+
+/* ----------------------------------------------------------------------
+   run for N steps
+------------------------------------------------------------------------- */
+
+void VerletB200::run(int n)
+{
+  bigint ntimestep;
+
+  for (int i = 0; i < n; i++) {
+    if (timer->check_timeout(i)) {
+      update->nsteps = i;
+      break;
+    }
+
+    ntimestep = ++update->ntimestep;
+    ev_set(ntimestep);
+
+    // one whole timestep on the device; asynchronous unless the rebuild vote or a tally
+    // needs a word back (verlet.cpp:229-360 is the sequence it implements)
+    timer->stamp();
+    int rebuilt = 0;
+    B200_CHECK(pkg, b200_step(ctx, eflag ? 1 : 0, vflag ? 1 : 0, &rebuilt));
+    resident = 1;
+
+    if (ntimestep == output->next) {
+      download(0);
+      if (eflag || vflag) fetch_tallies();
+      timer->stamp(Timer::PAIR);
+      output->write(ntimestep);
+      timer->stamp(Timer::OUTPUT);
+    }
+  }
+}
+
+/* ----------------------------------------------------------------------
+   neighbor statistics for Finish (finish.cpp): builds, dangerous builds and
+   the stored-pair count through the pair style's NeighList
+------------------------------------------------------------------------- */
+
+void VerletB200::publish_neighbor_stats()
+{
+  b200_stats st;
+  B200_CHECK(pkg, b200_get_stats(ctx, &st));
+  neighbor->ncalls = st.nbuilds;
+  neighbor->ndanger = st.ndanger;
+  neighbor->ago = (int) st.ago;
+  NeighList *list = force->pair ? force->pair->list : nullptr;
+  if (list) {
+    const int nlocal = atom->nlocal;
+    list->grow(nlocal, nlocal + atom->nghost);
+    int64_t npairs = 0;
+    B200_CHECK(pkg, b200_get_neighbor_list(ctx, list->numneigh, nullptr, 0, &npairs));
+    for (int i = 0; i < nlocal; i++) list->ilist[i] = i;
+    list->inum = nlocal;
+    list->gnum = 0;
+  }
+}
+
+void VerletB200::cleanup()
+{
+  if (resident) {
+    // the device timed everything up to here: one sync so "Loop time" covers all queued work
+    download(1);
+    publish_neighbor_stats();
+    if (pkg->profile() && comm->me == 0) {
+      double ms[B200_NPHASE];
+      int64_t calls[B200_NPHASE];
+      B200_CHECK(pkg, b200_get_phase_times(ctx, ms, calls));
+      static const char *names[B200_NPHASE] = {"nve initial", "nve final", "halo forward",
+                                               "halo reverse", "pair", "neigh (all)",
+                                               "neigh list build", "force clear", "tallies"};
+      std::string mesg = "B200 device time by phase (CUDA events):\n";
+      for (int k = 0; k < B200_NPHASE; k++)
+        if (calls[k])
+          mesg += fmt::format("  {:18s} {:10.3f} ms  {:8d} calls\n", names[k], ms[k], calls[k]);
+      utils::logmesg(lmp, mesg);
+    }
+  }
+  Verlet::cleanup();
+}

@@ -1,0 +1,49 @@
+/* -*- c++ -*- ----------------------------------------------------------
+   run_style verlet/b200 -- the velocity-Verlet timestep loop with every
+   per-step stage resident on the device (selected automatically by
+   "-sf b200", like verlet/kk is by "-sf kk").
+------------------------------------------------------------------------- */
+
+#ifdef INTEGRATE_CLASS
+// clang-format off
+IntegrateStyle(verlet/b200,VerletB200);
+// clang-format on
+#else
+
+#ifndef LMP_VERLET_B200_H
+#define LMP_VERLET_B200_H
+
+#include "b200_lmp.h"
+#include "verlet.h"
+
+namespace LAMMPS_NS {
+
+class VerletB200 : public Verlet {
+ public:
+  VerletB200(class LAMMPS *, int, char **);
+  void init() override;
+  void setup(int flag) override;
+  void setup_minimal(int) override;
+  void run(int) override;
+  void cleanup() override;
+  void reset_dt() override;
+
+ protected:
+  class FixB200 *pkg;
+  b200_ctx *ctx;
+  B200PairStyle *bpair;
+  B200NVEFix *bnve;
+  int resident;    // 1 while the device copy of the atoms is newer than the host copy
+  int joined;      // 1 once this rank joined the NCCL communicator of the package
+
+  void upload();                  // host atom arrays + all parameters -> device
+  void download(int with_ghosts); // device -> host atom arrays (x, v, f, type, tag, mask, image)
+  void fetch_tallies();           // eng_vdwl / virial -> force->pair
+  void device_setup(int flag, int output_flag);
+  void publish_neighbor_stats();
+};
+
+}    // namespace LAMMPS_NS
+
+#endif
+#endif

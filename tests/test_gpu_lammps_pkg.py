@@ -1,0 +1,133 @@
+"""The drop-in boundary end to end: the reference's UNMODIFIED bench inputs (bench/in.lj,
+bench/in.eam, copied untouched to lammps_pkg/bench_inputs by lammps_pkg/build_pkg.py) run by
+lmp_b200 -- the reference LAMMPS with the B200 package compiled in -- with nothing but
+`-sf b200` on the command line.  The thermo output must reproduce the reference's own golden
+logs (bench/log.15Jul25.{lj,eam}.fixed.g++.1, digits committed in tests/golden/*.json) and
+its neighbour statistics."""
+import json
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+EXE = ROOT / "lammps_b200" / "lammps_pkg" / "lmp_b200"
+BENCH = ROOT / "lammps_b200" / "lammps_pkg" / "bench_inputs"
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def run_lmp(args, cwd=BENCH):
+    assert EXE.exists(), "lmp_b200 not built (python lammps_b200/lammps_pkg/build_pkg.py)"
+    r = subprocess.run([str(EXE), *args], cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+def thermo_rows(out):
+    """[step, temp, e_pair, toteng, press] per thermo line (columns picked by header name)"""
+    rows, cols = [], None
+    for ln in out.splitlines():
+        if re.match(r"\s*Step\s+Temp\s+E_pair", ln):
+            names = ln.split()
+            cols = [names.index(k) for k in ("Step", "Temp", "E_pair", "TotEng", "Press")]
+            continue
+        if ln.startswith("Loop time"):
+            cols = None
+        if cols:
+            f = ln.split()
+            if len(f) > max(cols) and re.fullmatch(r"\d+", f[0]):
+                rows.append([float(f[k]) for k in cols])
+    return rows
+
+
+def close_to_printed(val, printed):
+    """equal to the golden log at its printed precision (8 significant digits), +-1 ulp of it"""
+    if printed == 0:
+        return abs(val) < 1e-7
+    return abs(val - printed) <= 1.5e-8 * max(abs(printed), 1e-300) * 10
+
+
+@pytest.mark.parametrize("name,pair,golden", [("in.lj", "lj/cut/b200", "ref_lj_32k.json"),
+                                              ("in.eam", "eam/b200", "ref_eam_32k.json")])
+def test_unmodified_bench_input_with_sf_b200(name, pair, golden):
+    out = run_lmp(["-sf", "b200", "-in", name])
+    g = json.loads((GOLDEN / golden).read_text())["published_log"]
+    assert "B200 package: device" in out
+    assert "Setting up Verlet/B200 run" in out
+    rows = thermo_rows(out)
+    assert [int(r[0]) for r in rows] == [int(r[0]) for r in g["thermo"]]
+    for got, ref in zip(rows, g["thermo"]):
+        for a, b in zip(got[1:], ref[1:]):
+            assert close_to_printed(a, b), f"{name} step {int(ref[0])}: {got} vs golden {ref}"
+    m = re.search(r"Neighbor list builds = (\d+)", out)
+    assert m and int(m.group(1)) == g["builds"]
+    m = re.search(r"Dangerous builds = (\d+)", out)
+    assert (m and int(m.group(1)) == 0) or "Dangerous builds not checked" in out
+    m = re.search(r"Total # of neighbors = (\d+)", out)
+    assert m
+    if name == "in.lj":  # the EAM trajectory's last-digit noise moves a few skin-shell pairs
+        assert int(m.group(1)) == g["neighbors"]
+    else:
+        assert abs(int(m.group(1)) - g["neighbors"]) <= 200
+    assert re.search(r"Loop time of [0-9.e+-]+ on 1 procs for 100 steps with 32000 atoms", out)
+
+
+def test_package_command_and_explicit_styles(tmp_path):
+    """`package b200` + explicit /b200 style names instead of the -sf switch; two runs in a
+    row (host <-> device round trip of the atoms between runs)."""
+    script = tmp_path / "in.explicit"
+    script.write_text("""
+package b200 prec double profile yes
+units lj
+atom_style atomic
+lattice fcc 0.8442
+region box block 0 10 0 10 0 10
+create_box 1 box
+create_atoms 1 box
+mass 1 1.0
+velocity all create 1.44 87287 loop geom
+pair_style lj/cut/b200 2.5
+pair_coeff 1 1 1.0 1.0 2.5
+neighbor 0.3 bin
+neigh_modify delay 0 every 20 check no
+fix 1 all nve/b200
+run_style verlet/b200
+thermo 50
+run 50
+run 50
+""")
+    out = run_lmp(["-in", str(script)], cwd=tmp_path)
+    ref = tmp_path / "in.ref"
+    ref.write_text(script.read_text().replace("package b200 prec double profile yes\n", "")
+                   .replace("/b200", ""))
+    refexe = ROOT / "oracle" / "_ref" / "lmp_ref"
+    r = subprocess.run([str(refexe), "-in", str(ref)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0
+    a, b = thermo_rows(out), thermo_rows(r.stdout)
+    assert len(a) == len(b) == 4
+    for x, y in zip(a, b):
+        for u, v in zip(x, y):
+            assert abs(u - v) <= 2e-7 * max(1.0, abs(v)), (x, y)
+    assert "B200 device time by phase" in out
+
+
+def test_foreign_integrator_is_refused(tmp_path):
+    """no silent CPU fallback: a /b200 pair style under plain run_style verlet must error out"""
+    script = tmp_path / "in.bad"
+    script.write_text("""
+units lj
+lattice fcc 0.8442
+region box block 0 4 0 4 0 4
+create_box 1 box
+create_atoms 1 box
+mass 1 1.0
+pair_style lj/cut/b200 2.5
+pair_coeff 1 1 1.0 1.0 2.5
+fix 1 all nve
+run 1
+""")
+    r = subprocess.run([str(EXE), "-in", str(script)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "requires run_style verlet/b200" in (r.stdout + r.stderr)
