@@ -13,6 +13,7 @@
 #include "kernels_halo.cuh"
 #include "kernels_neigh.cuh"
 #include "kernels_pair.cuh"
+#include "kernels_pair_mixed.cuh"
 #include "kernels_step.cuh"
 
 #include <dlfcn.h>
@@ -102,6 +103,11 @@ struct b200_ctx {
   std::vector<double> cutsq_h;
   LJOne lj_one;
   DBuf<double> lj_tab;
+  LJOneF lj_onef;
+  DBuf<float> lj_tabf;   // mixed mode: lj1..lj4, offset as float tables
+  EAMParamsF eamf;
+  DBuf<float> eam_f;     // mixed mode: rhor / z2r splines, 8 floats per knot
+  float4 *ff = nullptr;  // mixed mode: float4 Newton-scatter force array [nmax]
   EAMParams eam;
   DBuf<int> eam_i;
   DBuf<double> eam_d;
@@ -355,6 +361,7 @@ static int alloc_atoms(b200_ctx *ctx, int nmax) {
     TRY(regrow(ctx->xh[d], nmax, keep, sizeof(double)));
   }
   TRY(regrow(ctx->slot, nmax, keep, sizeof(int)));
+  TRY(regrow(ctx->ff, nmax, 0, sizeof(float4)));
   TRY(regrow(ctx->rho, nmax, keep, sizeof(double)));
   TRY(regrow(ctx->fp, nmax, keep, sizeof(double)));
   ctx->nmax = nmax;
@@ -779,7 +786,10 @@ static int reneighbor(b200_ctx *ctx) {
 static int force_clear(b200_ctx *ctx) {
   const int ph3 = ph_begin(ctx, B200_PH_CLEAR);
   const int nall = ctx->nlocal + ctx->nghost;
-  for (int d = 0; d < 3; d++) CK(cudaMemsetAsync(ctx->f[d], 0, sizeof(double) * nall, ctx->stream));
+  // mixed mode: the pair kernel stores f_i and k_merge_ff writes the ghosts; only the float4
+  // scatter array is cleared (inside pair_compute)
+  if (ctx->prec != B200_PREC_MIXED)
+    for (int d = 0; d < 3; d++) CK(cudaMemsetAsync(ctx->f[d], 0, sizeof(double) * nall, ctx->stream));
   ph_end(ctx, ph3);
   return B200_OK;
 }
@@ -851,69 +861,79 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag) {
   const int nl = ctx->nlocal, ng = ctx->nghost, c = ctx->cur;
   cudaStream_t s = ctx->stream;
   const bool ev = eflag || vflag;
+  const bool mixed = ctx->prec == B200_PREC_MIXED;
   if (ev) CK(cudaMemsetAsync(ctx->ev, 0, 7 * sizeof(double), s));
   const int ph6 = ph_begin(ctx, B200_PH_PAIR);
+  const int grid = cdiv(std::max(nl, 1), 128);
+  double4 *xt = ctx->xt[c];
+  const int *nn = ctx->numneigh.p, *nb = ctx->neigh.p;
+  double *fx = ctx->f[0], *fy = ctx->f[1], *fz = ctx->f[2];
+  if (mixed) CK(cudaMemsetAsync(ctx->ff, 0, sizeof(float4) * (nl + ng), s));
   if (ctx->pair_style == 1) {
-    if (nl > 0) {
-      const int grid = cdiv(nl, 128);
-      if (ctx->ntypes == 1) {
-        if (eflag)
-          k_pair_lj<true, true><<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
-                                                     ctx->neigh.p, ctx->f[0], ctx->f[1], ctx->f[2],
-                                                     ctx->lj_one, nullptr, 1, ctx->ev);
-        else
-          k_pair_lj<false, true><<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
-                                                      ctx->neigh.p, ctx->f[0], ctx->f[1], ctx->f[2],
-                                                      ctx->lj_one, nullptr, 1, ctx->ev);
-      } else {
-        const int n1 = ctx->ntypes + 1;
-        const size_t sm = sizeof(double) * 6 * n1 * n1;
-        if (eflag)
-          k_pair_lj<true, false><<<grid, 128, sm, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
-                                                       ctx->neigh.p, ctx->f[0], ctx->f[1], ctx->f[2],
-                                                       ctx->lj_one, ctx->lj_tab.p, ctx->ntypes, ctx->ev);
-        else
-          k_pair_lj<false, false><<<grid, 128, sm, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
-                                                        ctx->neigh.p, ctx->f[0], ctx->f[1], ctx->f[2],
-                                                        ctx->lj_one, ctx->lj_tab.p, ctx->ntypes, ctx->ev);
-      }
-      ctx->launches++;
+    const int n1 = ctx->ntypes + 1, n2 = n1 * n1;
+    const bool one = ctx->ntypes == 1;
+    if (!mixed) {
+      const size_t sm = one ? 0 : sizeof(double) * 6 * n2;
+      const double *tab = one ? nullptr : ctx->lj_tab.p;
+#define LJ_LAUNCH(EV, ONE) \
+  k_pair_lj<EV, ONE><<<grid, 128, sm, s>>>(nl, ctx->nstride, xt, nn, nb, fx, fy, fz, ctx->lj_one, tab, ctx->ntypes, ctx->ev)
+      if (one) { if (eflag) LJ_LAUNCH(true, true); else LJ_LAUNCH(false, true); }
+      else     { if (eflag) LJ_LAUNCH(true, false); else LJ_LAUNCH(false, false); }
+#undef LJ_LAUNCH
+    } else {
+      const size_t sm = one ? 0 : sizeof(double) * n2 + sizeof(float) * 5 * n2;
+#define LJ_LAUNCH(EV, ONE)                                                                        \
+  k_pair_lj_mixed<EV, ONE><<<grid, 128, sm, s>>>(nl, ctx->nstride, xt, nn, nb, fx, fy, fz, ctx->ff,  \
+                                                 ctx->lj_one.cutsq, ctx->lj_onef, ctx->lj_tab.p,   \
+                                                 ctx->lj_tabf.p, ctx->ntypes, ctx->ev)
+      if (one) { if (eflag) LJ_LAUNCH(true, true); else LJ_LAUNCH(false, true); }
+      else     { if (eflag) LJ_LAUNCH(true, false); else LJ_LAUNCH(false, false); }
+#undef LJ_LAUNCH
     }
+    ctx->launches++;
   } else if (ctx->pair_style == 2) {
+    // every rank walks the same sequence of halo calls, even one without atoms
     CK(cudaMemsetAsync(ctx->rho, 0, sizeof(double) * (nl + ng), s));
-    {  // every rank walks the same sequence of halo calls, even one without atoms
-      const int grid = cdiv(std::max(nl, 1), 128);
-      k_eam_rho<<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p, ctx->neigh.p,
-                                     ctx->eam, ctx->rho);
-      {
-        Vec3Ptr r{{ctx->rho, nullptr, nullptr}};
-        TRY(reverse_halo<1>(ctx, r));
-      }
-      if (eflag)
-        k_eam_embed<true><<<cdiv(std::max(nl, 1), 256), 256, 0, s>>>(nl, ctx->xt[c], ctx->eam, ctx->rho, ctx->fp,
-                                                        ctx->ev, ctx->flags + 1);
-      else
-        k_eam_embed<false><<<cdiv(std::max(nl, 1), 256), 256, 0, s>>>(nl, ctx->xt[c], ctx->eam, ctx->rho, ctx->fp,
-                                                         ctx->ev, ctx->flags + 1);
-      TRY(forward_scalar(ctx, ctx->fp));
-      if (eflag)
-        k_eam_force<true><<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
-                                               ctx->neigh.p, ctx->eam, ctx->fp, ctx->f[0], ctx->f[1],
-                                               ctx->f[2], ctx->ev);
-      else
-        k_eam_force<false><<<grid, 128, 0, s>>>(nl, ctx->nstride, ctx->xt[c], ctx->numneigh.p,
-                                                ctx->neigh.p, ctx->eam, ctx->fp, ctx->f[0], ctx->f[1],
-                                                ctx->f[2], ctx->ev);
-      ctx->launches += 3;
+    if (mixed)
+      k_eam_rho_mixed<<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eamf, ctx->rho);
+    else
+      k_eam_rho<<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->rho);
+    {
+      Vec3Ptr r{{ctx->rho, nullptr, nullptr}};
+      TRY(reverse_halo<1>(ctx, r));
     }
+    const int g2 = cdiv(std::max(nl, 1), 256);
+    if (eflag)
+      k_eam_embed<true><<<g2, 256, 0, s>>>(nl, xt, ctx->eam, ctx->rho, ctx->fp, ctx->ev, ctx->flags + 1);
+    else
+      k_eam_embed<false><<<g2, 256, 0, s>>>(nl, xt, ctx->eam, ctx->rho, ctx->fp, ctx->ev, ctx->flags + 1);
+    TRY(forward_scalar(ctx, ctx->fp));
+    if (mixed) {
+      if (eflag)
+        k_eam_force_mixed<true><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eamf,
+                                                     ctx->fp, fx, fy, fz, ctx->ff, ctx->ev);
+      else
+        k_eam_force_mixed<false><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eamf,
+                                                      ctx->fp, fx, fy, fz, ctx->ff, ctx->ev);
+    } else {
+      if (eflag)
+        k_eam_force<true><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->fp, fx, fy, fz, ctx->ev);
+      else
+        k_eam_force<false><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->fp, fx, fy, fz, ctx->ev);
+    }
+    ctx->launches += 3;
   } else
     return ctx->fail(B200_EARG, "no pair style set");
+  if (mixed && nl + ng > 0) {
+    k_merge_ff<<<cdiv(nl + ng, 256), 256, 0, s>>>(nl + ng, nl, ctx->ff, fx, fy, fz);
+    ctx->launches++;
+  }
   LAUNCH_CHECK();
   ph_end(ctx, ph6);
   if (vflag && nl + ng > 0) {
     const int ph7 = ph_begin(ctx, B200_PH_THERMO);
-    const int grid = std::min(cdiv(nl + ng, 256), 148 * 8);
-    k_virial_fdotr<<<grid, 256, 0, s>>>(nl + ng, ctx->xt[c], ctx->f[0], ctx->f[1], ctx->f[2], ctx->ev);
+    const int gv = std::min(cdiv(nl + ng, 256), 148 * 8);
+    k_virial_fdotr<<<gv, 256, 0, s>>>(nl + ng, xt, fx, fy, fz, ctx->ev);
     ctx->launches++;
     LAUNCH_CHECK();
     ph_end(ctx, ph7);
@@ -1057,7 +1077,7 @@ void b200_destroy(b200_ctx *ctx) {
     F(ctx->tag[b]); F(ctx->mask[b]); F(ctx->image[b]); F(ctx->atombin[b]);
   }
   for (int d = 0; d < 3; d++) { F(ctx->f[d]); F(ctx->xh[d]); }
-  F(ctx->slot); F(ctx->rho); F(ctx->fp);
+  F(ctx->slot); F(ctx->rho); F(ctx->fp); F(ctx->ff); F(ctx->lj_tabf.p); F(ctx->eam_f.p);
   F(ctx->cutneighsq_d.p); F(ctx->mass_d.p); F(ctx->ostart.p); F(ctx->gstart.p); F(ctx->tilesum.p);
   F(ctx->sendlist.p); F(ctx->gsrc.p); F(ctx->gbin.p); F(ctx->gslot.p); F(ctx->gdir.p);
   F(ctx->gdir_tmp.p); F(ctx->gtmp.p); F(ctx->counts); F(ctx->diroffset); F(ctx->recvoffset); F(ctx->allcounts);
@@ -1244,6 +1264,15 @@ int b200_pair_lj_cut(b200_ctx *ctx, int ntypes, const double *cutsq, const doubl
   CK(cudaStreamSynchronize(ctx->stream));
   const int k = n1 + 1;  // [1][1]
   ctx->lj_one = LJOne{cutsq[k], lj1[k], lj2[k], lj3[k], lj4[k], offset[k]};
+  ctx->lj_onef = LJOneF{(float)lj1[k], (float)lj2[k], (float)lj3[k], (float)lj4[k], (float)offset[k]};
+  {
+    std::vector<float> tf(5 * (size_t)n2);
+    const double *srcf[5] = {lj1, lj2, lj3, lj4, offset};
+    for (int t = 0; t < 5; t++)
+      for (int q = 0; q < n2; q++) tf[(size_t)t * n2 + q] = (float)srcf[t][q];
+    TRY(reserve(ctx, ctx->lj_tabf, tf.size()));
+    CK(cudaMemcpy(ctx->lj_tabf.p, tf.data(), sizeof(float) * tf.size(), cudaMemcpyHostToDevice));
+  }
   ctx->geom_ready = false;
   return B200_OK;
 }
@@ -1286,6 +1315,19 @@ int b200_pair_eam(b200_ctx *ctx, int ntypes, int nr, int nrho, double rdr, doubl
   P.frho = ctx->eam_d.p + n2;
   P.rhor = ctx->eam_d.p + n2 + nf;
   P.z2r = ctx->eam_d.p + n2 + nf + nh;
+  {  // mixed mode: float copies of the r-space splines, one 32-byte sector per knot
+    const size_t kh = (size_t)nrhor * (nr + 1), kz = (size_t)nz2r * (nr + 1);
+    std::vector<float> tf((kh + kz) * 8, 0.0f);
+    for (size_t q = 0; q < kh; q++)
+      for (int t = 0; t < 7; t++) tf[q * 8 + t] = (float)rhor_spline[q * 7 + t];
+    for (size_t q = 0; q < kz; q++)
+      for (int t = 0; t < 7; t++) tf[(kh + q) * 8 + t] = (float)z2r_spline[q * 7 + t];
+    TRY(reserve(ctx, ctx->eam_f, tf.size()));
+    CK(cudaMemcpy(ctx->eam_f.p, tf.data(), sizeof(float) * tf.size(), cudaMemcpyHostToDevice));
+    ctx->eamf.rhor = ctx->eam_f.p;
+    ctx->eamf.z2r = ctx->eam_f.p + kh * 8;
+    ctx->eamf.rdr = (float)rdr;
+  }
   ctx->geom_ready = false;
   return B200_OK;
 }
