@@ -46,6 +46,18 @@ struct Stencil {
 __device__ __forceinline__ int d2type(double w) { return (int)__double_as_longlong(w); }
 __device__ __forceinline__ double type2d(int t) { return __longlong_as_double((long long)t); }
 
+// One atom record {x,y,z,type} = 32 bytes = one sector.  sm_100a has a 256-bit global load
+// (LDG.E.ENL2.256): the gather of a neighbour costs ONE load instruction / one L1 wavefront set
+// instead of the two LDG.128 a plain double4 read compiles to.  Read-only (.nc) path: positions
+// are never written by a kernel that gathers them.
+__device__ __forceinline__ double4 ld_xt(const double4 *p) {
+  double4 r;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+               : "l"(p));
+  return r;
+}
+
 // NBin::coord2bin, nbin.cpp:141-173 (three branches per dimension, truncating casts)
 __device__ __forceinline__ int coord2bin_dim(double x, double lo, double hi, double bininv,
                                              int nbin) {

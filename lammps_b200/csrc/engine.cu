@@ -98,6 +98,7 @@ struct b200_ctx {
   // list
   DBuf<int> neigh, numneigh;
   int maxneigh = 0, nstride = 0, max_numneigh = 0;
+  int tpa = 2;  // lanes per atom in the pair kernels = interleave factor of the list (1,2,4,8)
   // pair
   int pair_style = 0;  // 1 lj/cut, 2 eam
   std::vector<double> cutsq_h;
@@ -116,6 +117,7 @@ struct b200_ctx {
   double dtv = 0, dtf = 0;
   int groupbit = 1;
   bool have_nve = false;
+  bool pending_final = false;  // final_integrate of the last step is deferred (fused into the next initial)
   // tallies / flags
   double *ev = nullptr;   // [8] device: eng, virial[6], ke
   int *flags = nullptr;   // [4] device: moved, err, maxcount, grand_total
@@ -584,6 +586,7 @@ static int build_list(b200_ctx *ctx) {
   if (ctx->maxneigh == 0) ctx->maxneigh = 96;
   for (int attempt = 0; attempt < 4; attempt++) {
     ctx->nstride = cdiv(std::max(nl, 1), 32) * 32;
+    ctx->maxneigh = cdiv(ctx->maxneigh, 8) * 8;  // whole slot groups for every tpa
     TRY(reserve(ctx, ctx->neigh, (size_t)ctx->maxneigh * ctx->nstride));
     TRY(reserve(ctx, ctx->numneigh, (size_t)nl));
     CK(cudaMemsetAsync(ctx->flags + 2, 0, sizeof(int), ctx->stream));
@@ -592,12 +595,12 @@ static int build_list(b200_ctx *ctx) {
       const int n1 = ctx->ntypes + 1;
       if (ctx->ntypes == 1)
         k_build_half<true><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
-            nl, ctx->nstride, ctx->maxneigh, ctx->xt[c], ctx->atombin[c], ctx->ostart.p,
+            nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->atombin[c], ctx->ostart.p,
             ctx->gstart.p, ctx->stencil, ctx->cutneighsq_h[n1 + 1], ctx->cutneighsq_d.p,
             ctx->ntypes, ctx->numneigh.p, ctx->neigh.p, ctx->flags + 2);
       else
         k_build_half<false><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
-            nl, ctx->nstride, ctx->maxneigh, ctx->xt[c], ctx->atombin[c], ctx->ostart.p,
+            nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->atombin[c], ctx->ostart.p,
             ctx->gstart.p, ctx->stencil, 0.0, ctx->cutneighsq_d.p, ctx->ntypes, ctx->numneigh.p,
             ctx->neigh.p, ctx->flags + 2);
       ctx->launches++;
@@ -864,40 +867,56 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag) {
   const bool mixed = ctx->prec == B200_PREC_MIXED;
   if (ev) CK(cudaMemsetAsync(ctx->ev, 0, 7 * sizeof(double), s));
   const int ph6 = ph_begin(ctx, B200_PH_PAIR);
-  const int grid = cdiv(std::max(nl, 1), 128);
   double4 *xt = ctx->xt[c];
   const int *nn = ctx->numneigh.p, *nb = ctx->neigh.p;
   double *fx = ctx->f[0], *fy = ctx->f[1], *fz = ctx->f[2];
+  const int T = ctx->tpa;
+  const int grid = cdiv(std::max(nl, 1) * T, 128);  // T lanes per atom
   if (mixed) CK(cudaMemsetAsync(ctx->ff, 0, sizeof(float4) * (nl + ng), s));
+// instantiate a kernel launch for the run-time lanes-per-atom value
+#define TPA_SWITCH(LAUNCH)        \
+  switch (T) {                    \
+    case 1: { LAUNCH(1); } break; \
+    case 4: { LAUNCH(4); } break; \
+    case 8: { LAUNCH(8); } break; \
+    default: { LAUNCH(2); } break; \
+  }
   if (ctx->pair_style == 1) {
     const int n1 = ctx->ntypes + 1, n2 = n1 * n1;
     const bool one = ctx->ntypes == 1;
     if (!mixed) {
       const size_t sm = one ? 0 : sizeof(double) * 6 * n2;
       const double *tab = one ? nullptr : ctx->lj_tab.p;
-#define LJ_LAUNCH(EV, ONE) \
-  k_pair_lj<EV, ONE><<<grid, 128, sm, s>>>(nl, ctx->nstride, xt, nn, nb, fx, fy, fz, ctx->lj_one, tab, ctx->ntypes, ctx->ev)
-      if (one) { if (eflag) LJ_LAUNCH(true, true); else LJ_LAUNCH(false, true); }
-      else     { if (eflag) LJ_LAUNCH(true, false); else LJ_LAUNCH(false, false); }
-#undef LJ_LAUNCH
+#define LJ_K(EV, ONE, TT) \
+  k_pair_lj<EV, ONE, TT><<<grid, 128, sm, s>>>(nl, ctx->nstride, xt, nn, nb, fx, fy, fz, ctx->lj_one, tab, ctx->ntypes, ctx->ev)
+#define LJ_L(TT)                                                         \
+  if (one) { if (eflag) LJ_K(true, true, TT); else LJ_K(false, true, TT); } \
+  else     { if (eflag) LJ_K(true, false, TT); else LJ_K(false, false, TT); }
+      TPA_SWITCH(LJ_L)
+#undef LJ_L
+#undef LJ_K
     } else {
       const size_t sm = one ? 0 : sizeof(double) * n2 + sizeof(float) * 5 * n2;
-#define LJ_LAUNCH(EV, ONE)                                                                        \
-  k_pair_lj_mixed<EV, ONE><<<grid, 128, sm, s>>>(nl, ctx->nstride, xt, nn, nb, fx, fy, fz, ctx->ff,  \
-                                                 ctx->lj_one.cutsq, ctx->lj_onef, ctx->lj_tab.p,   \
-                                                 ctx->lj_tabf.p, ctx->ntypes, ctx->ev)
-      if (one) { if (eflag) LJ_LAUNCH(true, true); else LJ_LAUNCH(false, true); }
-      else     { if (eflag) LJ_LAUNCH(true, false); else LJ_LAUNCH(false, false); }
-#undef LJ_LAUNCH
+#define LJ_K(EV, ONE, TT)                                                                             \
+  k_pair_lj_mixed<EV, ONE, TT><<<grid, 128, sm, s>>>(nl, ctx->nstride, xt, nn, nb, fx, fy, fz, ctx->ff, \
+                                                     ctx->lj_one.cutsq, ctx->lj_onef, ctx->lj_tab.p,  \
+                                                     ctx->lj_tabf.p, ctx->ntypes, ctx->ev)
+#define LJ_L(TT)                                                         \
+  if (one) { if (eflag) LJ_K(true, true, TT); else LJ_K(false, true, TT); } \
+  else     { if (eflag) LJ_K(true, false, TT); else LJ_K(false, false, TT); }
+      TPA_SWITCH(LJ_L)
+#undef LJ_L
+#undef LJ_K
     }
     ctx->launches++;
   } else if (ctx->pair_style == 2) {
     // every rank walks the same sequence of halo calls, even one without atoms
     CK(cudaMemsetAsync(ctx->rho, 0, sizeof(double) * (nl + ng), s));
-    if (mixed)
-      k_eam_rho_mixed<<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eamf, ctx->rho);
-    else
-      k_eam_rho<<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->rho);
+#define RHO_L(TT)                                                                                       \
+  if (mixed) k_eam_rho_mixed<TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eamf, ctx->rho); \
+  else k_eam_rho<TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->rho);
+    TPA_SWITCH(RHO_L)
+#undef RHO_L
     {
       Vec3Ptr r{{ctx->rho, nullptr, nullptr}};
       TRY(reverse_halo<1>(ctx, r));
@@ -908,22 +927,20 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag) {
     else
       k_eam_embed<false><<<g2, 256, 0, s>>>(nl, xt, ctx->eam, ctx->rho, ctx->fp, ctx->ev, ctx->flags + 1);
     TRY(forward_scalar(ctx, ctx->fp));
-    if (mixed) {
-      if (eflag)
-        k_eam_force_mixed<true><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eamf,
-                                                     ctx->fp, fx, fy, fz, ctx->ff, ctx->ev);
-      else
-        k_eam_force_mixed<false><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eamf,
-                                                      ctx->fp, fx, fy, fz, ctx->ff, ctx->ev);
-    } else {
-      if (eflag)
-        k_eam_force<true><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->fp, fx, fy, fz, ctx->ev);
-      else
-        k_eam_force<false><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->fp, fx, fy, fz, ctx->ev);
-    }
+#define FORCE_L(TT)                                                                                        \
+  if (mixed) {                                                                                             \
+    if (eflag) k_eam_force_mixed<true, TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eamf, ctx->fp, fx, fy, fz, ctx->ff, ctx->ev); \
+    else k_eam_force_mixed<false, TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eamf, ctx->fp, fx, fy, fz, ctx->ff, ctx->ev); \
+  } else {                                                                                                 \
+    if (eflag) k_eam_force<true, TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->fp, fx, fy, fz, ctx->ev); \
+    else k_eam_force<false, TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->fp, fx, fy, fz, ctx->ev); \
+  }
+    TPA_SWITCH(FORCE_L)
+#undef FORCE_L
     ctx->launches += 3;
   } else
     return ctx->fail(B200_EARG, "no pair style set");
+#undef TPA_SWITCH
   if (mixed && nl + ng > 0) {
     k_merge_ff<<<cdiv(nl + ng, 256), 256, 0, s>>>(nl + ng, nl, ctx->ff, fx, fy, fz);
     ctx->launches++;
@@ -946,13 +963,20 @@ static int initial_integrate(b200_ctx *ctx, int do_check) {
   const int ph8 = ph_begin(ctx, B200_PH_INITIAL);
   const int nl = ctx->nlocal, c = ctx->cur;
   if (nl > 0) {
-    k_nve_initial<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(
-        nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->f[0], ctx->f[1], ctx->f[2],
-        ctx->mask[c], ctx->mass_d.p, ctx->dtv, ctx->dtf, ctx->groupbit, do_check, ctx->xh[0],
-        ctx->xh[1], ctx->xh[2], ctx->triggersq, ctx->flags);
+    if (ctx->pending_final)  // deferred final_integrate(n) + initial_integrate(n+1), one pass
+      k_nve_final_initial<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(
+          nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->f[0], ctx->f[1], ctx->f[2],
+          ctx->mask[c], ctx->mass_d.p, ctx->dtv, ctx->dtf, ctx->groupbit, do_check, ctx->xh[0],
+          ctx->xh[1], ctx->xh[2], ctx->triggersq, ctx->flags);
+    else
+      k_nve_initial<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(
+          nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->f[0], ctx->f[1], ctx->f[2],
+          ctx->mask[c], ctx->mass_d.p, ctx->dtv, ctx->dtf, ctx->groupbit, do_check, ctx->xh[0],
+          ctx->xh[1], ctx->xh[2], ctx->triggersq, ctx->flags);
     ctx->launches++;
     LAUNCH_CHECK();
   }
+  ctx->pending_final = false;
   ph_end(ctx, ph8);
   return B200_OK;
 }
@@ -970,6 +994,13 @@ static int final_integrate(b200_ctx *ctx) {
   }
   ph_end(ctx, ph9);
   return B200_OK;
+}
+
+// A deferred final_integrate must be applied before anything reads or replaces v.
+static int flush_final(b200_ctx *ctx) {
+  if (!ctx->pending_final) return B200_OK;
+  ctx->pending_final = false;
+  return final_integrate(ctx);
 }
 
 // Neighbor::decide (neighbor.cpp:2408-2424); `moved` is the device vote of check_distance
@@ -1043,6 +1074,10 @@ int b200_create(b200_ctx **out, int device, int precision) {
   b200_ctx *ctx = new b200_ctx();
   ctx->device = device;
   ctx->prec = precision;
+  if (const char *e = getenv("B200_TPA")) {  // tuning knob: lanes per atom in the pair kernels
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) ctx->tpa = v;
+  }
   *out = ctx;
   if (precision != B200_PREC_DOUBLE && precision != B200_PREC_MIXED)
     return ctx->fail(B200_EARG, "unknown precision mode %d", precision);
@@ -1175,23 +1210,23 @@ int b200_set_atoms(b200_ctx *ctx, int nlocal, int ntypes, const double *mass, co
     CK(cudaMemcpyAsync(ctx->tag[0], tag, sizeof(int) * n, cudaMemcpyHostToDevice, s));
     if (mask)
       CK(cudaMemcpyAsync(ctx->mask[0], mask, sizeof(int) * n, cudaMemcpyHostToDevice, s));
-    else {
-      std::vector<int> ones(n, 1);
-      CK(cudaMemcpyAsync(ctx->mask[0], ones.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
-      CK(cudaStreamSynchronize(s));
+    else {  // group `all` (bit 0) for every atom
+      k_fill_int<<<cdiv(n, 256), 256, 0, s>>>(n, 1, ctx->mask[0]);
+      ctx->launches++;
     }
     if (image)
       CK(cudaMemcpyAsync(ctx->image[0], image, sizeof(int) * n, cudaMemcpyHostToDevice, s));
-    else {
+    else {  // image flags 0 0 0 (biased by IMGMAX = 512, lmptype.h)
       const int img0 = (512 << IMG2BITS) | (512 << IMGBITS) | 512;
-      std::vector<int> im(n, img0);
-      CK(cudaMemcpyAsync(ctx->image[0], im.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
-      CK(cudaStreamSynchronize(s));
+      k_fill_int<<<cdiv(n, 256), 256, 0, s>>>(n, img0, ctx->image[0]);
+      ctx->launches++;
     }
+    LAUNCH_CHECK();
     for (int d = 0; d < 3; d++) CK(cudaMemsetAsync(ctx->f[d], 0, sizeof(double) * n, s));
   }
   CK(cudaStreamSynchronize(s));
   ctx->nlocal = n;
+  ctx->pending_final = false;
   ctx->setup_done = false;
   ctx->geom_ready = false;
   return B200_OK;
@@ -1209,6 +1244,7 @@ int b200_get_atoms(b200_ctx *ctx, int with_ghosts, double *x, double *v, double 
   if (!ctx) return B200_EARG;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
+  TRY(flush_final(ctx));
   const int c = ctx->cur, nl = ctx->nlocal, n = nl + (with_ghosts ? ctx->nghost : 0);
   if (n == 0) return B200_OK;
   double *stage = reinterpret_cast<double *>(ctx->xt[c ^ 1]);
@@ -1334,6 +1370,7 @@ int b200_pair_eam(b200_ctx *ctx, int ntypes, int nr, int nrho, double rdr, doubl
 
 int b200_fix_nve(b200_ctx *ctx, double dtv, double dtf, int groupbit) {
   if (!ctx) return B200_EARG;
+  TRY(flush_final(ctx));  // a pending half-kick belongs to the old dtf
   ctx->dtv = dtv;
   ctx->dtf = dtf;
   ctx->groupbit = groupbit;
@@ -1344,6 +1381,7 @@ int b200_fix_nve(b200_ctx *ctx, double dtv, double dtf, int groupbit) {
 int b200_setup(b200_ctx *ctx, int eflag, int vflag) {
   if (!ctx) return B200_EARG;
   CK(cudaSetDevice(ctx->device));
+  TRY(flush_final(ctx));
   TRY(setup_geometry(ctx));
   TRY(reneighbor(ctx));
   ctx->nbuilds = 0;  // Verlet::setup: neighbor->ncalls = 0 (verlet.cpp:131)
@@ -1359,10 +1397,15 @@ int b200_setup(b200_ctx *ctx, int eflag, int vflag) {
 
 int b200_initial_integrate(b200_ctx *ctx) {
   if (!ctx) return B200_EARG;
+  TRY(flush_final(ctx));
   CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
   return initial_integrate(ctx, check_due_next(ctx) ? 1 : 0);
 }
-int b200_final_integrate(b200_ctx *ctx) { return ctx ? final_integrate(ctx) : B200_EARG; }
+int b200_final_integrate(b200_ctx *ctx) {
+  if (!ctx) return B200_EARG;
+  TRY(flush_final(ctx));
+  return final_integrate(ctx);
+}
 int b200_decide(b200_ctx *ctx, int *rebuild) { return (ctx && rebuild) ? decide(ctx, rebuild) : B200_EARG; }
 int b200_forward_comm(b200_ctx *ctx) { return ctx ? forward_comm(ctx) : B200_EARG; }
 int b200_reverse_comm(b200_ctx *ctx) { return ctx ? reverse_comm(ctx) : B200_EARG; }
@@ -1389,7 +1432,12 @@ static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt) {
   TRY(force_clear(ctx));
   TRY(pair_compute(ctx, eflag, vflag));
   TRY(reverse_comm(ctx));
-  TRY(final_integrate(ctx));
+  // FixNVE::final_integrate: on steps whose velocities nobody reads (no tallies) it is deferred
+  // and fused with the next step's initial_integrate (k_nve_final_initial)
+  if (eflag || vflag)
+    TRY(final_integrate(ctx));
+  else
+    ctx->pending_final = true;
   if (rebuilt) *rebuilt = nflag;
   return B200_OK;
 }
@@ -1434,6 +1482,7 @@ int b200_run(b200_ctx *ctx, int nsteps, int64_t first_step, int thermo_every, do
       }
     }
   }
+  TRY(flush_final(ctx));  // normally a no-op: the last step of a run tallies
   CK(cudaEventRecord(ctx->run_b, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   {
@@ -1460,6 +1509,7 @@ int b200_get_tallies(b200_ctx *ctx, double *eng_vdwl, double virial[6]) {
 
 int b200_ke_sum(b200_ctx *ctx, double *mv2) {
   if (!ctx || !mv2) return B200_EARG;
+  TRY(flush_final(ctx));
   TRY(ke_reduce(ctx));
   if (ctx->nranks > 1)
     NK(g_nccl.AllReduce(ctx->ev + 7, ctx->ev + 7, 1, ncclDouble, ncclSum, ctx->nccl, ctx->stream));
@@ -1511,7 +1561,7 @@ int b200_get_neighbor_list(b200_ctx *ctx, int *numneigh, int *neigh, int64_t cap
   CK(cudaMalloc((void **)&dfirst, sizeof(long long) * (nl + 1)));
   CK(cudaMalloc((void **)&dflat, sizeof(int) * first[nl]));
   CK(cudaMemcpy(dfirst, first.data(), sizeof(long long) * (nl + 1), cudaMemcpyHostToDevice));
-  k_export_csr<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->nstride, ctx->numneigh.p, ctx->neigh.p,
+  k_export_csr<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->nstride, ctx->tpa, ctx->numneigh.p, ctx->neigh.p,
                                                        dfirst, dflat);
   ctx->launches++;
   CK(cudaStreamSynchronize(ctx->stream));

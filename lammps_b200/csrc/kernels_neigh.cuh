@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_halo.cuh"
+#include "kernels_pair.cuh"
 
 // ---------------------------------------------------------------------------------------
 // exclusive scan of int32 (bin counts -> bin starts), 3 launches, hand-written.
@@ -265,12 +266,13 @@ __global__ void __launch_bounds__(256) k_border(int nlocal, const double4 *__res
 // and [gstart[b0], gstart[b1+1]) of ghosts.  Own bin: owned j > i (list position), ghosts only
 // if "above/right" by exact (z,y,x) compare (npair_bin.cpp:156-171).  Distance test in FP64
 // with `rsq <= cutneighsq[itype][jtype]` (npair_bin.cpp:219) -> bit-exact pair set.
-// Output: transposed list neigh[k*nstride + i]; numneigh[i] = full count even when it
+// Output: slot-major list, entry n of atom i at list_index(n, i, nstride, T) (kernels_pair.cuh);
+// numneigh[i] = full count even when it
 // exceeds maxneigh (then nothing past maxneigh is written and the host regrows the list).
 // ---------------------------------------------------------------------------------------
 template <bool ONETYPE>
 __global__ void __launch_bounds__(128) k_build_half(
-    int nlocal, int nstride, int maxneigh, const double4 *__restrict__ xt,
+    int nlocal, int nstride, int maxneigh, int T, const double4 *__restrict__ xt,
     const int *__restrict__ atombin, const int *__restrict__ ostart,
     const int *__restrict__ gstart, Stencil st, double cutneighsq_one,
     const double *__restrict__ cutneighsq, int ntypes, int *__restrict__ numneigh,
@@ -282,15 +284,14 @@ __global__ void __launch_bounds__(128) k_build_half(
     const int itype = d2type(pi.w);
     const int b = atombin[i];
     const double *cut_i = ONETYPE ? nullptr : cutneighsq + (size_t)itype * (ntypes + 1);
-    int *out = neigh + i;
 
     auto test = [&](int j) {
-      const double4 pj = xt[j];
+      const double4 pj = ld_xt(xt + j);
       const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
       const double rsq = rsq_ref(delx, dely, delz);
       const double c = ONETYPE ? cutneighsq_one : cut_i[d2type(pj.w)];
       if (rsq <= c) {
-        if (n < maxneigh) out[(size_t)n * nstride] = j;
+        if (n < maxneigh) neigh[list_index(n, i, nstride, T)] = j;
         n++;
       }
     };
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(128) k_build_half(
         const int gown_end = gstart[b + 1];
         for (int gj = gstart[b]; gj < gown_end; gj++) {
           const int j = nlocal + gj;
-          const double4 pj = xt[j];
+          const double4 pj = ld_xt(xt + j);
           if (pj.z < pi.z) continue;
           if (pj.z == pi.z) {
             if (pj.y < pi.y) continue;
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(256) k_sum_int(int n, const int *__restrict__ 
 }
 
 // CSR export of the transposed list (test hook b200_get_neighbor_list)
-__global__ void __launch_bounds__(256) k_export_csr(int nlocal, int nstride,
+__global__ void __launch_bounds__(256) k_export_csr(int nlocal, int nstride, int T,
                                                     const int *__restrict__ numneigh,
                                                     const int *__restrict__ neigh,
                                                     const long long *__restrict__ first,
@@ -347,5 +348,5 @@ __global__ void __launch_bounds__(256) k_export_csr(int nlocal, int nstride,
   if (i >= nlocal) return;
   const int n = numneigh[i];
   long long o = first[i];
-  for (int k = 0; k < n; k++) flat[o + k] = neigh[(size_t)k * nstride + i];
+  for (int k = 0; k < n; k++) flat[o + k] = neigh[list_index(k, i, nstride, T)];
 }

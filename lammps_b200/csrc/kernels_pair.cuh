@@ -1,20 +1,39 @@
 // kernels_pair.cuh -- pair force/energy kernels over the half (Newton on) Verlet list.
 //   lj/cut : PairLJCut::compute                pair_lj_cut.cpp:71-141
 //   eam    : PairEAM::compute (3 phases)       pair_eam.cpp:124-327, 338-366, pair_eam.h:146-169
-// Layout: positions+type are one 32-byte record double4{x,y,z,type} per atom (one sector per
-// gather); forces are SoA fx/fy/fz so the Newton scatter (RED.ADD.F64) of spatially adjacent
-// j lands in shared sectors; the list is transposed (neigh[k*nstride+i]) so a warp reads one
-// coalesced 128-byte row per neighbour slot.  f_i is accumulated in registers and added once.
+//
+// Layout: positions+type are one 32-byte record double4{x,y,z,type} per atom (one sector, one
+// 256-bit load per gather); forces are SoA fx/fy/fz.  T lanes share one atom ("threads per
+// atom"): lane t walks neighbours t, t+T, t+2T, ... and the T partial sums of f_i are combined
+// with warp shuffles; only the Newton scatter onto atom j uses atomics (RED.ADD.F64).
+// Why T > 1: these kernels are bound by L1 wavefronts -- the number of distinct cache lines a
+// warp-wide gather / scatter touches (profiles/r01c_*).  With one atom per lane the 32 lanes
+// gather 32 unrelated atoms; with T lanes per atom the T neighbours fetched together are
+// consecutive list entries, i.e. mostly consecutive atoms of one bin row, and share lines.
+// The list is stored so that a warp reads 32 consecutive ints per slot group:
+//   entry n of atom i lives at neigh[((n / T) * nstride + i) * T + n % T].
 // No tensor cores: nothing here is a dense contraction.
 #pragma once
 #include "common.cuh"
+
+__host__ __device__ __forceinline__ size_t list_index(int n, int i, int nstride, int T) {
+  return ((size_t)(n / T) * nstride + i) * T + (n % T);
+}
+
+// sum over the T lanes that share an atom (T a power of two <= 32, lanes contiguous)
+template <int T>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = T / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
 struct LJOne {  // single-type fast path: coefficients travel as kernel arguments
   double cutsq, lj1, lj2, lj3, lj4, offset;
 };
 
 // ev[0] += eng_vdwl (only when EV)
-template <bool EV, bool ONETYPE>
+template <bool EV, bool ONETYPE, int T>
 __global__ void __launch_bounds__(128) k_pair_lj(int nlocal, int nstride,
                                                  const double4 *__restrict__ xt,
                                                  const int *__restrict__ numneigh,
@@ -29,18 +48,18 @@ __global__ void __launch_bounds__(128) k_pair_lj(int nlocal, int nstride,
     for (int k = threadIdx.x; k < 6 * n2; k += blockDim.x) stab[k] = tab[k];
     __syncthreads();
   }
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double evdwl = 0.0;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / T, t = tid % T;
+  double evdwl = 0.0, fxi = 0.0, fyi = 0.0, fzi = 0.0;
   if (i < nlocal) {
     const double4 pi = xt[i];
     const int itype = d2type(pi.w);
     const int jnum = numneigh[i];
-    const int *jl = neigh + i;
-    double fxi = 0.0, fyi = 0.0, fzi = 0.0;
+    const int *jl = neigh + (size_t)i * T + t;
 #pragma unroll 4
-    for (int k = 0; k < jnum; k++) {
-      const int j = jl[(size_t)k * nstride] & NEIGHMASK;
-      const double4 pj = xt[j];
+    for (int n = t, kk = 0; n < jnum; n += T, kk++) {
+      const int j = jl[(size_t)kk * nstride * T] & NEIGHMASK;
+      const double4 pj = ld_xt(xt + j);
       const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
       const double rsq = rsq_ref(delx, dely, delz);
       double cutsq, lj1, lj2;
@@ -70,6 +89,13 @@ __global__ void __launch_bounds__(128) k_pair_lj(int nlocal, int nstride,
         }
       }
     }
+  }
+  if (T > 1) {
+    fxi = group_sum<T>(fxi);
+    fyi = group_sum<T>(fyi);
+    fzi = group_sum<T>(fzi);
+  }
+  if (i < nlocal && t == 0) {
     atomicAdd(&fx[i], fxi);
     atomicAdd(&fy[i], fyi);
     atomicAdd(&fz[i], fzi);
@@ -113,44 +139,48 @@ struct EAMParams {
 };
 
 // phase 1, pair_eam.cpp:163-211: rho_i += rho_j(r), rho_j += rho_i(r) for rsq < cutforcesq
+template <int T>
 __global__ void __launch_bounds__(128) k_eam_rho(int nlocal, int nstride,
                                                  const double4 *__restrict__ xt,
                                                  const int *__restrict__ numneigh,
                                                  const int *__restrict__ neigh, EAMParams P,
                                                  double *__restrict__ rho) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nlocal) return;
-  const double4 pi = xt[i];
-  const int itype = d2type(pi.w), n1 = P.ntypes + 1;
-  const int jnum = numneigh[i];
-  const int *jl = neigh + i;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / T, t = tid % T;
   double rhoi = 0.0;
+  if (i < nlocal) {
+    const double4 pi = xt[i];
+    const int itype = d2type(pi.w), n1 = P.ntypes + 1;
+    const int jnum = numneigh[i];
+    const int *jl = neigh + (size_t)i * T + t;
 #pragma unroll 4
-  for (int k = 0; k < jnum; k++) {
-    const int j = jl[(size_t)k * nstride] & NEIGHMASK;
-    const double4 pj = xt[j];
-    const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
-    const double rsq = rsq_ref(delx, dely, delz);
-    if (rsq < P.cutforcesq) {
-      const int jtype = d2type(pj.w);
-      double p = sqrt(rsq) * P.rdr + 1.0;
-      int m = (int)p;
-      m = min(m, P.nr - 1);
-      p -= m;
-      p = fmin(p, 1.0);
-      const int tji = P.type2rhor[jtype * n1 + itype], tij = P.type2rhor[itype * n1 + jtype];
-      const double *c = P.rhor + ((size_t)tji * (P.nr + 1) + m) * 7;
-      const double rj = ((__ldg(c + 3) * p + __ldg(c + 4)) * p + __ldg(c + 5)) * p + __ldg(c + 6);
-      rhoi += rj;
-      double ri = rj;
-      if (tij != tji) {
-        c = P.rhor + ((size_t)tij * (P.nr + 1) + m) * 7;
-        ri = ((__ldg(c + 3) * p + __ldg(c + 4)) * p + __ldg(c + 5)) * p + __ldg(c + 6);
+    for (int n = t, kk = 0; n < jnum; n += T, kk++) {
+      const int j = jl[(size_t)kk * nstride * T] & NEIGHMASK;
+      const double4 pj = ld_xt(xt + j);
+      const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
+      const double rsq = rsq_ref(delx, dely, delz);
+      if (rsq < P.cutforcesq) {
+        const int jtype = d2type(pj.w);
+        double p = sqrt(rsq) * P.rdr + 1.0;
+        int m = (int)p;
+        m = min(m, P.nr - 1);
+        p -= m;
+        p = fmin(p, 1.0);
+        const int tji = P.type2rhor[jtype * n1 + itype], tij = P.type2rhor[itype * n1 + jtype];
+        const double *c = P.rhor + ((size_t)tji * (P.nr + 1) + m) * 7;
+        const double rj = ((__ldg(c + 3) * p + __ldg(c + 4)) * p + __ldg(c + 5)) * p + __ldg(c + 6);
+        rhoi += rj;
+        double ri = rj;
+        if (tij != tji) {
+          c = P.rhor + ((size_t)tij * (P.nr + 1) + m) * 7;
+          ri = ((__ldg(c + 3) * p + __ldg(c + 4)) * p + __ldg(c + 5)) * p + __ldg(c + 6);
+        }
+        atomicAdd(&rho[j], ri);
       }
-      atomicAdd(&rho[j], ri);
     }
   }
-  atomicAdd(&rho[i], rhoi);
+  if (T > 1) rhoi = group_sum<T>(rhoi);
+  if (i < nlocal && t == 0) atomicAdd(&rho[i], rhoi);
 }
 
 // phase 2, compute_embedding<0> (pair_eam.cpp:338-366) + embedding_index<0> (pair_eam.h:146-169)
@@ -191,7 +221,7 @@ __global__ void __launch_bounds__(256) k_eam_embed(int nlocal, const double4 *__
 }
 
 // phase 3, pair_eam.cpp:233-314: force from fp_i, fp_j, rho', z2r
-template <bool EV>
+template <bool EV, int T>
 __global__ void __launch_bounds__(128) k_eam_force(int nlocal, int nstride,
                                                    const double4 *__restrict__ xt,
                                                    const int *__restrict__ numneigh,
@@ -199,19 +229,19 @@ __global__ void __launch_bounds__(128) k_eam_force(int nlocal, int nstride,
                                                    const double *__restrict__ fp,
                                                    double *__restrict__ fx, double *__restrict__ fy,
                                                    double *__restrict__ fz, double *__restrict__ ev) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double evdwl = 0.0;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / T, t = tid % T;
+  double evdwl = 0.0, fxi = 0.0, fyi = 0.0, fzi = 0.0;
   if (i < nlocal) {
     const double4 pi = xt[i];
     const int itype = d2type(pi.w), n1 = P.ntypes + 1;
     const int jnum = numneigh[i];
-    const int *jl = neigh + i;
+    const int *jl = neigh + (size_t)i * T + t;
     const double fpi = fp[i];
-    double fxi = 0.0, fyi = 0.0, fzi = 0.0;
 #pragma unroll 2
-    for (int k = 0; k < jnum; k++) {
-      const int j = jl[(size_t)k * nstride] & NEIGHMASK;
-      const double4 pj = xt[j];
+    for (int n = t, kk = 0; n < jnum; n += T, kk++) {
+      const int j = jl[(size_t)kk * nstride * T] & NEIGHMASK;
+      const double4 pj = ld_xt(xt + j);
       const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
       const double rsq = rsq_ref(delx, dely, delz);
       if (rsq < P.cutforcesq) {
@@ -248,6 +278,13 @@ __global__ void __launch_bounds__(128) k_eam_force(int nlocal, int nstride,
         if (EV) evdwl += sc * phi;
       }
     }
+  }
+  if (T > 1) {
+    fxi = group_sum<T>(fxi);
+    fyi = group_sum<T>(fyi);
+    fzi = group_sum<T>(fzi);
+  }
+  if (i < nlocal && t == 0) {
     atomicAdd(&fx[i], fxi);
     atomicAdd(&fy[i], fyi);
     atomicAdd(&fz[i], fzi);

@@ -13,13 +13,20 @@
 #include "common.cuh"
 #include "kernels_pair.cuh"
 
+template <int T>
+__device__ __forceinline__ float group_sumf(float v) {
+#pragma unroll
+  for (int o = T / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 struct LJOneF {
   float lj1, lj2, lj3, lj4, offset;
 };
 
 // PairLJCut::compute (pair_lj_cut.cpp:71-141), FP32 pair math.
 // tabf: 5 float tables lj1, lj2, lj3, lj4, offset [(ntypes+1)^2 each]; cutsq stays double (tabd).
-template <bool EV, bool ONETYPE>
+template <bool EV, bool ONETYPE, int T>
 __global__ void __launch_bounds__(128) k_pair_lj_mixed(
     int nlocal, int nstride, const double4 *__restrict__ xt, const int *__restrict__ numneigh,
     const int *__restrict__ neigh, double *__restrict__ fx, double *__restrict__ fy,
@@ -35,18 +42,19 @@ __global__ void __launch_bounds__(128) k_pair_lj_mixed(
     for (int k = threadIdx.x; k < 5 * n2; k += blockDim.x) stab[k] = tabf[k];
     __syncthreads();
   }
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / T, t = tid % T;
   double evdwl = 0.0;
+  float fxi = 0.0f, fyi = 0.0f, fzi = 0.0f;  // < 64 terms: FP32 is ample for the 1e-5 bound
   if (i < nlocal) {
     const double4 pi = xt[i];
     const int itype = d2type(pi.w);
     const int jnum = numneigh[i];
-    const int *jl = neigh + i;
-    float fxi = 0.0f, fyi = 0.0f, fzi = 0.0f;  // < 64 terms: FP32 is ample for the 1e-5 bound
+    const int *jl = neigh + (size_t)i * T + t;
 #pragma unroll 4
-    for (int k = 0; k < jnum; k++) {
-      const int j = jl[(size_t)k * nstride] & NEIGHMASK;
-      const double4 pj = xt[j];
+    for (int n = t, kk = 0; n < jnum; n += T, kk++) {
+      const int j = jl[(size_t)kk * nstride * T] & NEIGHMASK;
+      const double4 pj = ld_xt(xt + j);
       const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
       const double rsq = rsq_ref(delx, dely, delz);
       int tij = 0;
@@ -74,6 +82,13 @@ __global__ void __launch_bounds__(128) k_pair_lj_mixed(
         }
       }
     }
+  }
+  if (T > 1) {
+    fxi = group_sumf<T>(fxi);
+    fyi = group_sumf<T>(fyi);
+    fzi = group_sumf<T>(fzi);
+  }
+  if (i < nlocal && t == 0) {
     fx[i] = (double)fxi;  // the scatter half of f_i arrives through ff (k_merge_ff)
     fy[i] = (double)fyi;
     fz[i] = (double)fzi;
@@ -114,22 +129,24 @@ struct EAMParamsF {
 };
 
 // phase 1 (pair_eam.cpp:163-211): FP32 spline evaluation, FP64 rho accumulators / reductions
+template <int T>
 __global__ void __launch_bounds__(128) k_eam_rho_mixed(int nlocal, int nstride,
                                                        const double4 *__restrict__ xt,
                                                        const int *__restrict__ numneigh,
                                                        const int *__restrict__ neigh, EAMParams P,
                                                        EAMParamsF F, double *__restrict__ rho) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nlocal) return;
-  const double4 pi = xt[i];
-  const int itype = d2type(pi.w), n1 = P.ntypes + 1;
-  const int jnum = numneigh[i];
-  const int *jl = neigh + i;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / T, t = tid % T;
   double rhoi = 0.0;
+  const bool active = i < nlocal;
+  const double4 pi = active ? xt[i] : make_double4(0, 0, 0, 0);
+  const int itype = d2type(pi.w), n1 = P.ntypes + 1;
+  const int jnum = active ? numneigh[i] : 0;
+  const int *jl = neigh + (size_t)i * T + t;
 #pragma unroll 4
-  for (int k = 0; k < jnum; k++) {
-    const int j = jl[(size_t)k * nstride] & NEIGHMASK;
-    const double4 pj = xt[j];
+  for (int n = t, kk = 0; n < jnum; n += T, kk++) {
+    const int j = jl[(size_t)kk * nstride * T] & NEIGHMASK;
+    const double4 pj = ld_xt(xt + j);
     const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
     const double rsq = rsq_ref(delx, dely, delz);
     if (rsq < P.cutforcesq) {
@@ -153,29 +170,31 @@ __global__ void __launch_bounds__(128) k_eam_rho_mixed(int nlocal, int nstride,
       atomicAdd(&rho[j], (double)ri);
     }
   }
-  atomicAdd(&rho[i], rhoi);
+  if (T > 1) rhoi = group_sum<T>(rhoi);
+  if (active && t == 0) atomicAdd(&rho[i], rhoi);
 }
 
 // phase 3 (pair_eam.cpp:233-314): FP32 force evaluation, one RED.ADD.F32x4 per pair
-template <bool EV>
+template <bool EV, int T>
 __global__ void __launch_bounds__(128) k_eam_force_mixed(
     int nlocal, int nstride, const double4 *__restrict__ xt, const int *__restrict__ numneigh,
     const int *__restrict__ neigh, EAMParams P, EAMParamsF F, const double *__restrict__ fp,
     double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
     float4 *__restrict__ ff, double *__restrict__ ev) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / T, t = tid % T;
   double evdwl = 0.0;
+  float fxi = 0.0f, fyi = 0.0f, fzi = 0.0f;  // < 64 terms: FP32 is ample for the 1e-5 bound
   if (i < nlocal) {
     const double4 pi = xt[i];
     const int itype = d2type(pi.w), n1 = P.ntypes + 1;
     const int jnum = numneigh[i];
-    const int *jl = neigh + i;
+    const int *jl = neigh + (size_t)i * T + t;
     const float fpi = (float)fp[i];
-    float fxi = 0.0f, fyi = 0.0f, fzi = 0.0f;  // < 64 terms: FP32 is ample for the 1e-5 bound
 #pragma unroll 2
-    for (int k = 0; k < jnum; k++) {
-      const int j = jl[(size_t)k * nstride] & NEIGHMASK;
-      const double4 pj = xt[j];
+    for (int n = t, kk = 0; n < jnum; n += T, kk++) {
+      const int j = jl[(size_t)kk * nstride * T] & NEIGHMASK;
+      const double4 pj = ld_xt(xt + j);
       const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
       const double rsq = rsq_ref(delx, dely, delz);
       if (rsq < P.cutforcesq) {
@@ -213,6 +232,13 @@ __global__ void __launch_bounds__(128) k_eam_force_mixed(
         if (EV) evdwl += (double)(sc * phi);
       }
     }
+  }
+  if (T > 1) {
+    fxi = group_sumf<T>(fxi);
+    fyi = group_sumf<T>(fyi);
+    fzi = group_sumf<T>(fzi);
+  }
+  if (i < nlocal && t == 0) {
     fx[i] = (double)fxi;
     fy[i] = (double)fyi;
     fz[i] = (double)fzi;

@@ -55,6 +55,46 @@ __global__ void __launch_bounds__(256) k_nve_final(
   }
 }
 
+// final_integrate of step n immediately followed by initial_integrate of step n+1 in ONE pass
+// over the atoms (both use the same forces f(n)): v += dtfm*f ; v += dtfm*f ; x += dtv*v, each
+// operation rounded separately exactly like the two reference loops.  Used whenever nothing
+// on the host needs the full-step velocities in between; saves the 84 B/atom of a separate
+// final_integrate pass (x 32r+32w, v 24r+24w, f 24r, mask 4r = 140 B for both half-kicks).
+__global__ void __launch_bounds__(256) k_nve_final_initial(
+    int nlocal, double4 *__restrict__ xt, double *__restrict__ vx, double *__restrict__ vy,
+    double *__restrict__ vz, const double *__restrict__ fx, const double *__restrict__ fy,
+    const double *__restrict__ fz, const int *__restrict__ mask, const double *__restrict__ mass,
+    double dtv, double dtf, int groupbit, int do_check, const double *__restrict__ xhx,
+    const double *__restrict__ xhy, const double *__restrict__ xhz, double triggersq,
+    int *__restrict__ moved) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  double4 p = xt[i];
+  if (mask[i] & groupbit) {
+    const double dtfm = dtf / mass[d2type(p.w)];
+    const double ka = __dmul_rn(dtfm, fx[i]), kb = __dmul_rn(dtfm, fy[i]), kc = __dmul_rn(dtfm, fz[i]);
+    double a = vx[i], b = vy[i], c = vz[i];
+    a = __dadd_rn(__dadd_rn(a, ka), ka);  // final_integrate(n), then the half-kick of n+1
+    b = __dadd_rn(__dadd_rn(b, kb), kb);
+    c = __dadd_rn(__dadd_rn(c, kc), kc);
+    vx[i] = a; vy[i] = b; vz[i] = c;
+    p.x = __dadd_rn(p.x, __dmul_rn(dtv, a));
+    p.y = __dadd_rn(p.y, __dmul_rn(dtv, b));
+    p.z = __dadd_rn(p.z, __dmul_rn(dtv, c));
+    xt[i] = p;
+  }
+  if (do_check) {
+    const double dx = p.x - xhx[i], dy = p.y - xhy[i], dz = p.z - xhz[i];
+    const double rsq = rsq_ref(dx, dy, dz);
+    if (rsq > triggersq) *moved = 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_fill_int(int n, int value, int *__restrict__ a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = value;
+}
+
 // ComputeTemp::compute_scalar numerator (compute_temp.cpp:73-97): ev[7] += sum m v^2
 __global__ void __launch_bounds__(256) k_ke(int nlocal, const double4 *__restrict__ xt,
                                             const double *__restrict__ vx,

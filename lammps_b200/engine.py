@@ -211,17 +211,24 @@ class Engine:
         self._chk(self.L.b200_get_counts(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def get_atoms(self, ghosts=False, fields=("x", "v", "f", "type", "tag", "image")):
+    def get_atoms(self, ghosts=False, fields=("x", "v", "f", "type", "tag", "image"), into=None):
+        """Download per-atom arrays in current device order.  `into` may hold preallocated
+        (e.g. pinned) C-contiguous host buffers of sufficient length per field; the returned
+        arrays are then views of them."""
         nl, ng = self.counts()
         n = nl + (ng if ghosts else 0)
+        shapes = {"x": ((n, 3), np.float64), "v": ((nl, 3), np.float64), "f": ((n, 3), np.float64),
+                  "type": ((n,), np.int32), "tag": ((n,), np.int32), "mask": ((n,), np.int32),
+                  "image": ((nl,), np.int32)}
         out = {}
-        if "x" in fields: out["x"] = np.zeros((n, 3))
-        if "v" in fields: out["v"] = np.zeros((nl, 3))
-        if "f" in fields: out["f"] = np.zeros((n, 3))
-        if "type" in fields: out["type"] = np.zeros(n, np.int32)
-        if "tag" in fields: out["tag"] = np.zeros(n, np.int32)
-        if "mask" in fields: out["mask"] = np.zeros(n, np.int32)
-        if "image" in fields: out["image"] = np.zeros(nl, np.int32)
+        for k in fields:
+            shape, dt = shapes[k]
+            if into is not None and k in into:
+                buf = into[k]
+                assert buf.dtype == dt and buf.flags.c_contiguous and buf.shape[0] >= shape[0]
+                out[k] = buf[:shape[0]]
+            else:
+                out[k] = np.zeros(shape, dt)
         g = lambda k: _p(out[k]) if k in out else None  # noqa: E731
         self._chk(self.L.b200_get_atoms(self.h, C.c_int(1 if ghosts else 0), g("x"), g("v"),
                                         g("f"), g("type"), g("tag"), g("mask"), g("image")))
