@@ -92,6 +92,21 @@ struct b200_ctx {
   unsigned remote_mask = 0;  // directions whose neighbour is another rank
   Owner owner;
   DBuf<double> sbuf, rbuf;   // halo staging in send order / recv order (up to 4 doubles per atom)
+  // peer-memory halo (CUDA IPC over NVLink): sbuf/rbuf live in one arena that neighbours map
+  bool p2p = false;               // transport of the per-step halo: peer stores (true) or NCCL
+  char *arena = nullptr;          // [sbuf | rbuf], one cudaMalloc, exported through IPC
+  size_t arena_bytes = 0, arena_roff = 0;
+  unsigned arena_gen = 0;         // bumped at every (re)allocation
+  long long *pflags = nullptr;    // [4][32] own flags: arrival F, arrival R, ack F, ack R
+  unsigned *p2p_counter = nullptr;  // [4] last-block counters
+  std::vector<char *> peer_arena;   // per rank: mapping of its arena (nullptr = not mapped)
+  std::vector<void *> peer_base;    // per rank: what cudaIpcOpenMemHandle returned (to close it)
+  std::vector<long long *> peer_flags;
+  std::vector<size_t> peer_roff;
+  std::vector<unsigned> peer_gen;
+  std::vector<int> peer_off;        // per rank: sendoff[28] then recvoff[28]
+  P2PMap fwdP, revP;
+  long long seqF = 0, seqR = 0;
   DBuf<double> mig_send, mig_recv;
   int *allcounts = nullptr;  // [nranks*32] device (all-gathered counters)
   int *h_counts = nullptr;   // pinned [nranks*32]
@@ -323,13 +338,212 @@ static int sync_counts(b200_ctx *ctx) {
                        cudaMemcpyDeviceToHost, ctx->stream));
   } else
     CK(cudaMemcpyAsync(ctx->h_counts, ctx->counts, sizeof(int) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->p2p)
+    CK(cudaMemcpyAsync(ctx->h_flags + 40, ctx->p2p_counter + 4, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->p2p && ctx->h_flags[40])
+    return ctx->fail(B200_ECUDA, "peer-memory halo timed out waiting for a neighbour");
   return B200_OK;
 }
 static int global_err(const b200_ctx *ctx) {
   int e = 0;
   for (int r = 0; r < ctx->nranks; r++) e |= ctx->h_counts[r * 32 + 27];
   return e;
+}
+
+
+// ------------------------------------------------------------------ peer-memory halo (host side)
+namespace {
+struct PeerInfo {  // what every rank publishes at a border build (all-gathered, 512 bytes)
+  int sendoff[NDIR + 1], recvoff[NDIR + 1];
+  unsigned gen;
+  int ok;
+  unsigned long long arena_delta;  // arena pointer minus the base of its cudaMalloc allocation
+  unsigned long long roff;         // byte offset of rbuf inside the arena
+  cudaIpcMemHandle_t arena;
+  char pad[512 - 2 * (NDIR + 1) * 4 - 8 - 16 - sizeof(cudaIpcMemHandle_t)];
+};
+static_assert(sizeof(PeerInfo) == 512, "PeerInfo is one 512-byte record");
+
+// offset of p inside the cudaMalloc allocation that contains it (IPC handles name allocations)
+size_t alloc_delta(const void *p) {
+  typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+  static range_fn fn = nullptr;
+  if (!fn) {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) == cudaSuccess) fn = (range_fn)f;
+  }
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (fn && fn(&base, &size, (unsigned long long)(uintptr_t)p) == 0) return (size_t)((uintptr_t)p - base);
+  return 0;
+}
+}  // namespace
+
+// all-gather `bytes` per rank from a host record (through device staging) back to the host
+static int allgather_host(b200_ctx *ctx, const void *mine, void *all, size_t bytes) {
+  char *stage = nullptr;
+  CK(cudaMalloc((void **)&stage, bytes * (ctx->nranks + 1)));
+  CK(cudaMemcpyAsync(stage, mine, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  NK(g_nccl.AllGather(stage, stage + bytes, bytes, ncclChar, ctx->nccl, ctx->stream));
+  CK(cudaMemcpyAsync(all, stage + bytes, bytes * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(stage);
+  return B200_OK;
+}
+
+// once, at b200_comm_init: flags + counters, IPC-map every rank's flags; decides ctx->p2p
+static int p2p_init(b200_ctx *ctx) {
+  const char *mode = getenv("B200_HALO");
+  const bool want = !(mode && strcmp(mode, "nccl") == 0);
+  const size_t fbytes = 2u << 20;  // own allocation (>= 1 MiB) so the IPC handle names just it
+  CK(cudaMalloc((void **)&ctx->pflags, fbytes));
+  CK(cudaMemset(ctx->pflags, 0, fbytes));
+  CK(cudaMalloc((void **)&ctx->p2p_counter, 8 * sizeof(unsigned)));  // [0..3] counters, [4] error word
+  CK(cudaMemset(ctx->p2p_counter, 0, 8 * sizeof(unsigned)));
+  struct FlagInfo {
+    cudaIpcMemHandle_t h;
+    unsigned long long delta;
+    int ok, pad;
+  } mine, *all;
+  memset(&mine, 0, sizeof mine);
+  mine.ok = want && cudaIpcGetMemHandle(&mine.h, ctx->pflags) == cudaSuccess;
+  mine.delta = alloc_delta(ctx->pflags);
+  std::vector<FlagInfo> allv(ctx->nranks);
+  all = allv.data();
+  TRY(allgather_host(ctx, &mine, all, sizeof(FlagInfo)));
+  ctx->peer_flags.assign(ctx->nranks, nullptr);
+  ctx->peer_arena.assign(ctx->nranks, nullptr);
+  ctx->peer_base.assign(ctx->nranks, nullptr);
+  ctx->peer_roff.assign(ctx->nranks, 0);
+  ctx->peer_gen.assign(ctx->nranks, 0);
+  ctx->peer_off.assign((size_t)ctx->nranks * 2 * (NDIR + 1), 0);
+  int ok = 1;
+  for (int r = 0; r < ctx->nranks; r++) ok &= all[r].ok;
+  if (ok)
+    for (int r = 0; r < ctx->nranks && ok; r++) {
+      if (r == ctx->rank) {
+        ctx->peer_flags[r] = ctx->pflags;
+        continue;
+      }
+      void *m = nullptr;
+      if (cudaIpcOpenMemHandle(&m, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        break;
+      }
+      ctx->peer_flags[r] = (long long *)((char *)m + all[r].delta);
+    }
+  // every rank must take the same transport
+  int *d_ok = ctx->counts + 28;
+  CK(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NK(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, ctx->nccl, ctx->stream));
+  CK(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->p2p = ok != 0;
+  return B200_OK;
+}
+
+// sbuf/rbuf capacity (doubles) inside the arena; (re)allocates when too small
+static int ensure_arena(b200_ctx *ctx, size_t ns, size_t nr) {
+  const size_t need_s = (ns * sizeof(double) + 4095) / 4096 * 4096;
+  const size_t need_r = (nr * sizeof(double) + 4095) / 4096 * 4096;
+  if (ctx->arena && ctx->sbuf.cap >= ns && ctx->rbuf.cap >= nr) return B200_OK;
+  const size_t cap_s = need_s + need_s / 4 + (1u << 20), cap_r = need_r + need_r / 4 + (1u << 20);
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->arena) {
+    cudaFree(ctx->arena);
+    ctx->dev_bytes -= std::min(ctx->dev_bytes, ctx->arena_bytes);
+  }
+  ctx->arena_bytes = cap_s + cap_r;
+  CK(cudaMalloc((void **)&ctx->arena, ctx->arena_bytes));
+  ctx->dev_bytes += ctx->arena_bytes;
+  ctx->arena_roff = cap_s;
+  ctx->sbuf.p = (double *)ctx->arena;
+  ctx->sbuf.cap = cap_s / sizeof(double);
+  ctx->rbuf.p = (double *)(ctx->arena + cap_s);
+  ctx->rbuf.cap = cap_r / sizeof(double);
+  ctx->arena_gen++;
+  return B200_OK;
+}
+
+// at every border build: publish offsets + arena, (re)map neighbours whose arena moved, and
+// lay out the per-direction tables the pack/unpack kernels take by value
+static int p2p_publish_borders(b200_ctx *ctx) {
+  if (!ctx->p2p) return B200_OK;
+  PeerInfo mine;
+  memset(&mine, 0, sizeof mine);
+  memcpy(mine.sendoff, ctx->sendoff, sizeof mine.sendoff);
+  memcpy(mine.recvoff, ctx->recvoff, sizeof mine.recvoff);
+  mine.gen = ctx->arena_gen;
+  mine.roff = ctx->arena_roff;
+  mine.arena_delta = alloc_delta(ctx->arena);
+  mine.ok = cudaIpcGetMemHandle(&mine.arena, ctx->arena) == cudaSuccess;
+  std::vector<PeerInfo> all(ctx->nranks);
+  TRY(allgather_host(ctx, &mine, all.data(), sizeof(PeerInfo)));
+  const int W2 = 2 * (NDIR + 1);
+  for (int r = 0; r < ctx->nranks; r++) {
+    memcpy(&ctx->peer_off[(size_t)r * W2], all[r].sendoff, sizeof(int) * (NDIR + 1));
+    memcpy(&ctx->peer_off[(size_t)r * W2 + NDIR + 1], all[r].recvoff, sizeof(int) * (NDIR + 1));
+    if (!all[r].ok) return ctx->fail(B200_ECUDA, "rank %d cannot export its halo arena through CUDA IPC", r);
+  }
+  // map (or re-map) the arenas of the ranks I talk to
+  for (int dir = 0; dir < NDIR; dir++) {
+    if (!((ctx->remote_mask >> dir) & 1u)) continue;
+    const int r = ctx->nbr[dir];
+    if (r < 0 || r == ctx->rank) continue;
+    if (ctx->peer_arena[r] && ctx->peer_gen[r] == all[r].gen) continue;
+    if (ctx->peer_base[r]) {
+      cudaIpcCloseMemHandle(ctx->peer_base[r]);
+      ctx->peer_base[r] = nullptr;
+      ctx->peer_arena[r] = nullptr;
+    }
+    void *m = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&m, all[r].arena, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+      return ctx->fail(B200_ECUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+    ctx->peer_base[r] = m;
+    ctx->peer_arena[r] = (char *)m + all[r].arena_delta;
+    ctx->peer_gen[r] = all[r].gen;
+    ctx->peer_roff[r] = (size_t)all[r].roff;
+  }
+  // tables
+  P2PMap &F = ctx->fwdP, &R = ctx->revP;
+  memset(&F, 0, sizeof F);
+  memset(&R, 0, sizeof R);
+  long long *own = ctx->pflags;
+  F.flag_in = own + 0 * 32;  // arrival F
+  R.flag_in = own + 1 * 32;  // arrival R
+  F.ack_in = own + 2 * 32;   // ack F
+  R.ack_in = own + 3 * 32;   // ack R
+  for (int dir = 0; dir < NDIR; dir++) {
+    if (!((ctx->remote_mask >> dir) & 1u)) continue;
+    const int to = ctx->nbr[dir], from = ctx->nbr[NDIR - 1 - dir];
+    const int nsend = ctx->sendoff[dir + 1] - ctx->sendoff[dir];
+    const int nrecv = ctx->recvoff[dir + 1] - ctx->recvoff[dir];
+    if (nsend > 0 && to >= 0) {
+      // forward: my send segment dir lands in `to`'s rbuf at its recvoff[dir]
+      F.out_mask |= 1u << dir;
+      F.dst[dir] = (double *)(ctx->peer_arena[to] + ctx->peer_roff[to]);
+      F.dstoff[dir] = ctx->peer_off[(size_t)to * W2 + NDIR + 1 + dir];
+      F.flag_out[dir] = ctx->peer_flags[to] + 0 * 32 + dir;
+      // reverse: `to` returns that segment into my sbuf; I acknowledge to it
+      R.in_mask |= 1u << dir;
+      R.ack_out[dir] = ctx->peer_flags[to] + 3 * 32 + dir;
+    }
+    if (nrecv > 0 && from >= 0) {
+      // forward: I receive segment dir from `from` and acknowledge to it
+      F.in_mask |= 1u << dir;
+      F.ack_out[dir] = ctx->peer_flags[from] + 2 * 32 + dir;
+      // reverse: my recv segment dir goes back into `from`'s sbuf at its sendoff[dir]
+      R.out_mask |= 1u << dir;
+      R.dst[dir] = (double *)ctx->peer_arena[from];
+      R.dstoff[dir] = ctx->peer_off[(size_t)from * W2 + dir];
+      R.flag_out[dir] = ctx->peer_flags[from] + 1 * 32 + dir;
+    }
+  }
+  return B200_OK;
 }
 
 // ------------------------------------------------------------------ per-atom storage
@@ -577,6 +791,7 @@ static int scan_inplace(b200_ctx *ctx, int *a, int n) {
 static int check_err_flags(b200_ctx *ctx, int e) {
   if (e & 1) return ctx->fail(B200_ENONFINITE, "Non-numeric atom coords - simulation unstable");
   if (e & 2) return ctx->fail(B200_ELOST, "atom outside the local bin grid (lost atom)");
+  if (e & 8) return ctx->fail(B200_ECUDA, "peer-memory halo timed out waiting for a neighbour");
   return B200_OK;
 }
 
@@ -741,8 +956,8 @@ static int reneighbor(b200_ctx *ctx) {
   TRY(reserve(ctx, ctx->gdir_tmp, (size_t)ng));
   TRY(reserve(ctx, ctx->gtmp, (size_t)ng));
   if (multi) {
-    TRY(reserve(ctx, ctx->sbuf, (size_t)nsend * 4));
-    TRY(reserve(ctx, ctx->rbuf, (size_t)ng * 4));
+    TRY(ensure_arena(ctx, (size_t)nsend * 4, (size_t)ng * 4));
+    TRY(p2p_publish_borders(ctx));
   }
   CK(cudaMemcpyAsync(ctx->diroffset, ctx->sendoff, (NDIR + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->recvoffset, ctx->recvoff, (NDIR + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -800,17 +1015,31 @@ static int force_clear(b200_ctx *ctx) {
 static int forward_comm(b200_ctx *ctx) {
   const int ph4 = ph_begin(ctx, B200_PH_FORWARD);
   const int c = ctx->cur;
-  if (ctx->remote_mask && ctx->nsend > 0) {
-    k_pack_forward<<<cdiv(ctx->nsend, 256), 256, 0, ctx->stream>>>(
-        ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->remote_mask, ctx->geom, ctx->xt[c],
-        ctx->sbuf.p);
-    ctx->launches++;
-  }
-  TRY(halo_exchange(ctx, ctx->sbuf.p, ctx->sendoff, ctx->rbuf.p, ctx->recvoff, 3, false));
-  if (ctx->nghost > 0) {
-    k_unpack_forward<<<cdiv(ctx->nghost, 256), 256, 0, ctx->stream>>>(
-        ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->geom, ctx->rbuf.p, ctx->xt[c]);
-    ctx->launches++;
+  cudaStream_t s = ctx->stream;
+  if (ctx->p2p && ctx->remote_mask) {
+    // pack + transfer in one kernel: records are stored straight into the neighbours' rbuf
+    const long long seq = ++ctx->seqF;
+    k_p2p_pack_forward<0><<<cdiv(std::max(ctx->nsend, 1), 256), 256, 0, s>>>(
+        ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->diroffset, ctx->geom, ctx->xt[c], nullptr,
+        ctx->fwdP, seq, ctx->p2p_counter + 0, (int *)ctx->p2p_counter + 4);
+    k_p2p_unpack_forward<0><<<cdiv(std::max(ctx->nghost, 1), 256), 256, 0, s>>>(
+        ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->geom, ctx->rbuf.p, ctx->xt[c], nullptr,
+        ctx->fwdP, seq, ctx->p2p_counter + 1, (int *)ctx->p2p_counter + 4);
+    ctx->launches += 2;
+  } else {
+    if (ctx->remote_mask && ctx->nsend > 0) {
+      k_pack_forward<<<cdiv(ctx->nsend, 256), 256, 0, s>>>(ctx->nsend, ctx->sendlist.p, ctx->senddir.p,
+                                                         ctx->remote_mask, ctx->geom, ctx->xt[c],
+                                                         ctx->sbuf.p);
+      ctx->launches++;
+    }
+    TRY(halo_exchange(ctx, ctx->sbuf.p, ctx->sendoff, ctx->rbuf.p, ctx->recvoff, 3, false));
+    if (ctx->nghost > 0) {
+      k_unpack_forward<<<cdiv(ctx->nghost, 256), 256, 0, s>>>(ctx->nghost, ctx->nlocal, ctx->gsrc.p,
+                                                             ctx->gdir.p, ctx->geom, ctx->rbuf.p,
+                                                             ctx->xt[c]);
+      ctx->launches++;
+    }
   }
   LAUNCH_CHECK();
   ph_end(ctx, ph4);
@@ -820,15 +1049,29 @@ static int forward_comm(b200_ctx *ctx) {
 // reverse halo of W per-atom doubles held in SoA arrays a[0..W)
 template <int W>
 static int reverse_halo(b200_ctx *ctx, Vec3Ptr a) {
+  cudaStream_t s = ctx->stream;
+  if (ctx->p2p && ctx->remote_mask) {
+    const long long seq = ++ctx->seqR;
+    k_p2p_pack_reverse<W><<<cdiv(std::max(ctx->nghost, 1), 256), 256, 0, s>>>(
+        ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->recvoffset, a, ctx->revP, seq,
+        ctx->p2p_counter + 2, (int *)ctx->p2p_counter + 4);
+    k_p2p_unpack_reverse<W><<<cdiv(std::max(ctx->nsend, 1), 256), 256, 0, s>>>(
+        ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->sbuf.p, a, ctx->revP, seq,
+        ctx->p2p_counter + 3, (int *)ctx->p2p_counter + 4);
+    ctx->launches += 2;
+    LAUNCH_CHECK();
+    return B200_OK;
+  }
   if (ctx->nghost > 0) {
-    k_pack_reverse<W><<<cdiv(ctx->nghost, 256), 256, 0, ctx->stream>>>(ctx->nghost, ctx->nlocal,
-                                                                      ctx->gsrc.p, a, ctx->rbuf.p);
+    k_pack_reverse<W><<<cdiv(ctx->nghost, 256), 256, 0, s>>>(ctx->nghost, ctx->nlocal, ctx->gsrc.p, a,
+                                                           ctx->rbuf.p);
     ctx->launches++;
   }
   TRY(halo_exchange(ctx, ctx->rbuf.p, ctx->recvoff, ctx->sbuf.p, ctx->sendoff, W, true));
   if (ctx->remote_mask && ctx->nsend > 0) {
-    k_unpack_reverse<W><<<cdiv(ctx->nsend, 256), 256, 0, ctx->stream>>>(
-        ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->remote_mask, ctx->sbuf.p, a);
+    k_unpack_reverse<W><<<cdiv(ctx->nsend, 256), 256, 0, s>>>(ctx->nsend, ctx->sendlist.p,
+                                                            ctx->senddir.p, ctx->remote_mask,
+                                                            ctx->sbuf.p, a);
     ctx->launches++;
   }
   LAUNCH_CHECK();
@@ -845,15 +1088,29 @@ static int reverse_comm(b200_ctx *ctx) {
 
 // EAM: PairEAM::pack/unpack_forward_comm of fp (pair_eam.cpp:1600-1621)
 static int forward_scalar(b200_ctx *ctx, double *a) {
+  cudaStream_t s = ctx->stream;
+  if (ctx->p2p && ctx->remote_mask) {
+    const long long seq = ++ctx->seqF;
+    k_p2p_pack_forward<1><<<cdiv(std::max(ctx->nsend, 1), 256), 256, 0, s>>>(
+        ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->diroffset, ctx->geom, nullptr, a, ctx->fwdP,
+        seq, ctx->p2p_counter + 0, (int *)ctx->p2p_counter + 4);
+    k_p2p_unpack_forward<1><<<cdiv(std::max(ctx->nghost, 1), 256), 256, 0, s>>>(
+        ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->geom, ctx->rbuf.p, nullptr, a,
+        ctx->fwdP, seq, ctx->p2p_counter + 1, (int *)ctx->p2p_counter + 4);
+    ctx->launches += 2;
+    LAUNCH_CHECK();
+    return B200_OK;
+  }
   if (ctx->remote_mask && ctx->nsend > 0) {
-    k_pack_forward_scalar<<<cdiv(ctx->nsend, 256), 256, 0, ctx->stream>>>(
-        ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->remote_mask, a, ctx->sbuf.p);
+    k_pack_forward_scalar<<<cdiv(ctx->nsend, 256), 256, 0, s>>>(ctx->nsend, ctx->sendlist.p,
+                                                              ctx->senddir.p, ctx->remote_mask, a,
+                                                              ctx->sbuf.p);
     ctx->launches++;
   }
   TRY(halo_exchange(ctx, ctx->sbuf.p, ctx->sendoff, ctx->rbuf.p, ctx->recvoff, 1, false));
   if (ctx->nghost > 0) {
-    k_unpack_forward_scalar<<<cdiv(ctx->nghost, 256), 256, 0, ctx->stream>>>(
-        ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->rbuf.p, a);
+    k_unpack_forward_scalar<<<cdiv(ctx->nghost, 256), 256, 0, s>>>(ctx->nghost, ctx->nlocal,
+                                                                  ctx->gsrc.p, ctx->rbuf.p, a);
     ctx->launches++;
   }
   LAUNCH_CHECK();
@@ -1116,7 +1373,7 @@ void b200_destroy(b200_ctx *ctx) {
   F(ctx->cutneighsq_d.p); F(ctx->mass_d.p); F(ctx->ostart.p); F(ctx->gstart.p); F(ctx->tilesum.p);
   F(ctx->sendlist.p); F(ctx->gsrc.p); F(ctx->gbin.p); F(ctx->gslot.p); F(ctx->gdir.p);
   F(ctx->gdir_tmp.p); F(ctx->gtmp.p); F(ctx->counts); F(ctx->diroffset); F(ctx->recvoffset); F(ctx->allcounts);
-  F(ctx->senddir.p); F(ctx->gtag_tmp.p); F(ctx->gsrc_tmp.p); F(ctx->sbuf.p); F(ctx->rbuf.p);
+  F(ctx->senddir.p); F(ctx->gtag_tmp.p); F(ctx->gsrc_tmp.p); F(ctx->arena); F(ctx->pflags); F(ctx->p2p_counter);
   F(ctx->mig_send.p); F(ctx->mig_recv.p);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   if (ctx->nccl && g_nccl.ok) g_nccl.CommDestroy(ctx->nccl);
@@ -1650,6 +1907,7 @@ int b200_comm_init(b200_ctx *ctx, int nranks, int rank, const void *id128) {
   ctx->h_counts = nullptr;
   TRY(dalloc(ctx, &ctx->allcounts, (size_t)32 * nranks));
   CK(cudaMallocHost((void **)&ctx->h_counts, sizeof(int) * 32 * nranks));
+  TRY(p2p_init(ctx));
   return B200_OK;
 }
 

@@ -295,3 +295,174 @@ __global__ void __launch_bounds__(256) k_unpack_forward_scalar(int nghost, int n
   const int src = gsrc[k];
   a[nlocal + k] = src >= 0 ? a[src] : rbuf[-1 - src];
 }
+
+// =======================================================================================
+// Peer-memory halo (NVLink / NVSwitch): the pack kernel stores straight into the neighbour's
+// staging buffer (a CUDA-IPC mapping of the peer's arena) and raises an arrival flag there;
+// the neighbour's unpack kernel waits for its arrival flags, reads, and acknowledges.  One
+// kernel does "pack + transfer", no send/recv rendezvous, no intermediate copy.  NCCL
+// (halo_exchange) stays for the rebuild-time traffic and as the fallback transport.
+//
+// Protocol, per direction and per buffer class (F: messages into peers' rbuf, R: into sbuf):
+//   sender  : wait ack_in[dir]  >= seq-1   (peer consumed my previous message)
+//             store records; __threadfence_system(); last block: flag_out[dir] = seq
+//   receiver: wait flag_in[dir] >= seq; read; last block: ack_out[dir] = seq
+// seq advances identically on every rank (all ranks execute the same halo sequence).  Spins
+// give up after P2P_SPIN_LIMIT cycles and raise err |= 8 instead of hanging the GPU.
+// =======================================================================================
+#define P2P_SPIN_LIMIT (4000000000ll)
+
+struct P2PMap {
+  double *dst[NDIR];          // peer staging buffer (base of the peer's rbuf or sbuf)
+  int dstoff[NDIR];           // first record of my message inside it
+  long long *flag_out[NDIR];  // peer's arrival flag for my message
+  long long *ack_out[NDIR];   // peer's ack flag for the message I consume
+  const long long *flag_in;   // own arrival flags [32]
+  const long long *ack_in;    // own ack flags [32]
+  unsigned out_mask, in_mask; // directions with data to send / to receive
+};
+
+__device__ __forceinline__ long long ld_relaxed_sys(const long long *p) {
+  long long v;
+  asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(long long *p, long long v) {
+  asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// lanes 0..26 of the block poll one direction each until flags[dir] >= need, then one
+// system-scope fence orders the flag reads before the data reads of the whole block
+__device__ __forceinline__ void p2p_wait(const long long *flags, unsigned mask, long long need,
+                                         int *err) {
+  if (need > 0 && threadIdx.x < NDIR && ((mask >> threadIdx.x) & 1u)) {
+    const long long t0 = clock64();
+    while (ld_relaxed_sys(flags + threadIdx.x) < need) {
+      if (clock64() - t0 > P2P_SPIN_LIMIT) {
+        atomicOr(err, 8);
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
+// the last block to get here publishes `value` to out[dir] for every dir in mask: every
+// thread fences its own stores (system scope) before the block is counted, the last block
+// fences once more and then lanes 0..26 store one flag each
+__device__ __forceinline__ void p2p_publish(long long *const *out, unsigned mask, long long value,
+                                            unsigned *counter) {
+  __shared__ int s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(counter, 1u);
+    s_last = (done == gridDim.x - 1);
+    if (s_last) *counter = 0;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < NDIR && ((mask >> threadIdx.x) & 1u)) {
+    __threadfence_system();
+    st_relaxed_sys(out[threadIdx.x], value);
+  }
+}
+
+// forward: MODE 0 = positions (3 doubles, + periodic shift), MODE 1 = one scalar per atom
+template <int MODE>
+__global__ void __launch_bounds__(256) k_p2p_pack_forward(
+    int nsend, const int *__restrict__ sendlist, const unsigned char *__restrict__ senddir,
+    const int *__restrict__ sendoffset, Geom g, const double4 *__restrict__ xt,
+    const double *__restrict__ a, P2PMap pm, long long seq, unsigned *counter, int *err) {
+  p2p_wait(pm.ack_in, pm.out_mask, seq - 1, err);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nsend) {
+    const int dir = senddir[p];
+    if ((pm.out_mask >> dir) & 1u) {
+      const size_t q = (size_t)pm.dstoff[dir] + (p - sendoffset[dir]);
+      if (MODE == 0) {
+        const double4 r = xt[sendlist[p]];
+        double *o = pm.dst[dir] + 3 * q;
+        o[0] = r.x + g.shift[dir][0];
+        o[1] = r.y + g.shift[dir][1];
+        o[2] = r.z + g.shift[dir][2];
+      } else {
+        pm.dst[dir][q] = a[sendlist[p]];
+      }
+    }
+  }
+  p2p_publish(pm.flag_out, pm.out_mask, seq, counter);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_p2p_unpack_forward(
+    int nghost, int nlocal, const int *__restrict__ gsrc, const unsigned char *__restrict__ gdir,
+    Geom g, const double *__restrict__ rbuf, double4 *__restrict__ xt, double *__restrict__ a,
+    P2PMap pm, long long seq, unsigned *counter, int *err) {
+  p2p_wait(pm.flag_in, pm.in_mask, seq, err);
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nghost) {
+    const int src = gsrc[k];
+    if (MODE == 0) {
+      double *o = reinterpret_cast<double *>(xt + nlocal + k);
+      if (src >= 0) {
+        const int dir = gdir[k];
+        const double4 q = xt[src];
+        o[0] = q.x + g.shift[dir][0];
+        o[1] = q.y + g.shift[dir][1];
+        o[2] = q.z + g.shift[dir][2];
+      } else {
+        const double *r = rbuf + 3 * (size_t)(-1 - src);
+        o[0] = __ldcv(r);
+        o[1] = __ldcv(r + 1);
+        o[2] = __ldcv(r + 2);
+      }
+    } else {
+      a[nlocal + k] = src >= 0 ? a[src] : __ldcv(rbuf + (-1 - src));
+    }
+  }
+  p2p_publish(pm.ack_out, pm.in_mask, seq, counter);
+}
+
+// reverse: ghost contributions of W SoA arrays; local images are added to their owner at
+// once, ghosts owned elsewhere are stored into the owner's sbuf (send order of the owner)
+template <int W>
+__global__ void __launch_bounds__(256) k_p2p_pack_reverse(
+    int nghost, int nlocal, const int *__restrict__ gsrc, const unsigned char *__restrict__ gdir,
+    const int *__restrict__ recvoffset, Vec3Ptr f, P2PMap pm, long long seq, unsigned *counter,
+    int *err) {
+  p2p_wait(pm.ack_in, pm.out_mask, seq - 1, err);
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nghost) {
+    const int src = gsrc[k];
+    if (src >= 0) {
+#pragma unroll
+      for (int d = 0; d < W; d++) atomicAdd(&f.a[d][src], f.a[d][nlocal + k]);
+    } else {
+      const int dir = gdir[k];
+      const size_t q = (size_t)pm.dstoff[dir] + ((-1 - src) - recvoffset[dir]);
+      double *o = pm.dst[dir] + (size_t)W * q;
+#pragma unroll
+      for (int d = 0; d < W; d++) o[d] = f.a[d][nlocal + k];
+    }
+  }
+  p2p_publish(pm.flag_out, pm.out_mask, seq, counter);
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) k_p2p_unpack_reverse(
+    int nsend, const int *__restrict__ sendlist, const unsigned char *__restrict__ senddir,
+    const double *__restrict__ sbuf, Vec3Ptr f, P2PMap pm, long long seq, unsigned *counter,
+    int *err) {
+  p2p_wait(pm.flag_in, pm.in_mask, seq, err);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nsend) {
+    if ((pm.in_mask >> senddir[p]) & 1u) {
+      const int i = sendlist[p];
+      const double *r = sbuf + (size_t)W * p;
+#pragma unroll
+      for (int d = 0; d < W; d++) atomicAdd(&f.a[d][i], __ldcv(r + d));
+    }
+  }
+  p2p_publish(pm.ack_out, pm.in_mask, seq, counter);
+}
