@@ -247,13 +247,28 @@ def run_b200(args):
     bytes_atom, flops_atom = pair_algorithmic(kind, ps, pc)
     pair_s = pair_ms * 1e-3 / max(pair_calls, 1)
     achieved = bytes_atom * nown / pair_s / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_pair_lj" if kind == "lj" else "k_eam_rho+k_eam_force",
+    # DRAM traffic per launch from the committed `ncu --set full` capture of the same kernel
+    # (dram__bytes_read.sum + dram__bytes_write.sum per atom, profiles/ncu_traffic.json), scaled
+    # to this launch's atom count; null when no capture exists for this kernel / precision
+    traffic, traffic_src = None, None
+    tj = ROOT / "profiles" / "ncu_traffic.json"
+    if tj.exists():
+        t = json.loads(tj.read_text()).get(f"{kind}_{args.precision}")
+        if t:
+            traffic = t["dram_bytes_per_atom"] * nown
+            traffic_src = t["source"]
+    kern = {"lj_double": "k_pair_lj", "lj_mixed": "k_pair_lj_mixed+k_merge_ff",
+            "eam_double": "k_eam_rho+k_eam_embed+k_eam_force (+ rho/fp halo)",
+            "eam_mixed": "k_eam_rho_mixed+k_eam_embed+k_eam_force_mixed+k_merge_ff (+ rho/fp halo)"}
+    roofline = {"bound": "hbm", "kernel": kern[f"{kind}_{args.precision}"],
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                 "bytes_per_atom": bytes_atom, "pairs_stored_per_atom": ps,
                 "us_per_launch": pair_s * 1e6, "flop_per_atom": flops_atom,
                 "tflops": flops_atom * nown / pair_s / 1e12,
-                "share_of_step": pair_ms / max(dev_ms, 1e-9)}
+                "share_of_step": pair_ms / max(dev_ms, 1e-9),
+                "note": "the pair kernels are bound by the L1TEX data pipe (one 32-byte sector "
+                        "per gathered atom and per RED), not by DRAM: see DESIGN.md section 4"}
     phases = {k: {"ms": round(t, 3), "calls": c} for k, (t, c) in ph.items() if c}
 
     if rank != 0:
@@ -271,7 +286,12 @@ def run_b200(args):
                    "natoms": natoms, "proc_grid": list(grid), "precision": args.precision,
                    "l2": "working set (>= 100 B/atom x natoms) exceeds the 126 MB L2; no flush"
                          if natoms >= 2_000_000 else "working set fits L2 (small reference case)",
-                   "rebuilds_in_timed_region": ph["neigh"][1]},
+                   "rebuilds_in_timed_region": ph["neigh"][1],
+                   "halo": {0: "none (one sub-domain, periodic self images)",
+                            1: "NCCL send/recv between the 26 neighbour sub-domains",
+                            2: "peer-memory stores over NVLink (CUDA IPC) + arrival/ack flags"}[
+                                st["halo_transport"]],
+                   "lanes_per_atom": st["lanes_per_atom"]},
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d / e2e_steps,
                 "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps,
                 "includes": "pinned-host upload, Verlet setup (ghosts+list+forces), run, thermo "

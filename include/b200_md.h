@@ -135,6 +135,8 @@ typedef struct {
   int64_t nstencil;
   int64_t launches;     /* kernels launched since create */
   double  device_bytes; /* device memory currently allocated */
+  int64_t halo_transport; /* per-step halo: 0 none (one rank), 1 NCCL send/recv, 2 peer-memory stores */
+  int64_t lanes_per_atom; /* lanes sharing one atom in the pair kernels (B200_TPA) */
 } b200_stats;
 int b200_get_stats(b200_ctx *ctx, b200_stats *out);
 

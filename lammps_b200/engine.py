@@ -41,7 +41,8 @@ class Stats(C.Structure):
     _fields_ = [("nbuilds", C.c_int64), ("ndanger", C.c_int64), ("ago", C.c_int64),
                 ("npairs", C.c_int64), ("maxneigh", C.c_int64), ("max_numneigh", C.c_int64),
                 ("nbins", C.c_int64 * 3), ("mbins", C.c_int64), ("nstencil", C.c_int64),
-                ("launches", C.c_int64), ("device_bytes", C.c_double)]
+                ("launches", C.c_int64), ("device_bytes", C.c_double),
+                ("halo_transport", C.c_int64), ("lanes_per_atom", C.c_int64)]
 
 
 _lib = None

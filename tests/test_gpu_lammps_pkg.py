@@ -131,3 +131,98 @@ run 1
     r = subprocess.run([str(EXE), "-in", str(script)], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode != 0
     assert "requires run_style verlet/b200" in (r.stdout + r.stderr)
+
+
+def _both(tmp_path, body, nsteps_dump):
+    """run the same script with lmp_ref (plain styles) and lmp_b200 (-sf b200); returns the two
+    thermo tables and the two id-sorted force dumps of the last step"""
+    refexe = ROOT / "oracle" / "_ref" / "lmp_ref"
+    outs = {}
+    for tag, exe, extra in (("ref", refexe, []), ("b200", EXE, ["-sf", "b200"])):
+        d = tmp_path / tag
+        d.mkdir()
+        (d / "in.t").write_text(body.replace("POT", str(ROOT / "oracle" / "_ref" / "potentials")))
+        r = subprocess.run([str(exe), *extra, "-in", "in.t"], cwd=d, capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        rows = []
+        blocks = (d / "f.dump").read_text().split("ITEM: TIMESTEP")[1:]
+        last = blocks[-1].splitlines()
+        assert int(last[1]) == nsteps_dump
+        k = last.index([ln for ln in last if ln.startswith("ITEM: ATOMS")][0])
+        for ln in last[k + 1:]:
+            if ln.strip():
+                rows.append([float(t) for t in ln.split()])
+        outs[tag] = (thermo_rows(r.stdout), rows)
+    return outs
+
+
+def _compare(outs, ftol, ttol):
+    import numpy as np
+    (ta, fa), (tb, fb) = outs["ref"], outs["b200"]
+    assert len(ta) == len(tb) > 1
+    for x, y in zip(ta, tb):
+        for u, v in zip(x, y):
+            assert abs(u - v) <= ttol * max(1.0, abs(u)), (x, y)
+    fa, fb = np.array(fa), np.array(fb)
+    assert fa.shape == fb.shape and np.array_equal(fa[:, 0], fb[:, 0])
+    err = np.abs(fa[:, 1:] - fb[:, 1:]).max() / np.abs(fa[:, 1:]).max()
+    assert err <= ftol, f"force error vs the reference executable: {err:.2e}"
+
+
+def test_two_element_eam_matches_reference_executable(tmp_path):
+    """Al + Cu funcfl files (the reference's own unit-test pairing, atomic-pair-eam.yaml):
+    exercises the per-type-pair rho / z2r table mixing against lmp_ref, forces by atom id
+    (the dump prints 10 significant digits, so 1e-8 is the comparison's resolution)."""
+    body = """
+units metal
+lattice fcc 3.8
+region box block 0 6 0 6 0 6
+create_box 2 box
+create_atoms 1 box
+set type 1 type/fraction 2 0.4 12345
+mass 1 63.55
+mass 2 26.98
+velocity all create 1200.0 4928459 loop geom
+pair_style eam
+pair_coeff 1 1 POT/Cu_u3.eam
+pair_coeff 2 2 POT/Al_jnp.eam
+neighbor 1.0 bin
+neigh_modify every 1 delay 5 check yes
+fix 1 all nve
+thermo 20
+thermo_modify format float %.12g
+dump 1 all custom 40 f.dump id type fx fy fz
+dump_modify 1 sort id format float %.10g
+run 40
+"""
+    _compare(_both(tmp_path, body, 40), ftol=1e-8, ttol=1e-9)
+
+
+def test_nve_on_a_sub_group_matches_reference_executable(tmp_path):
+    """`fix nve` applied to a group only (mask & groupbit, fix_nve.cpp:86) -- the frozen slab
+    must not move, the rest follows the reference trajectory."""
+    body = """
+units lj
+lattice fcc 0.8442
+region box block 0 8 0 8 0 8
+create_box 1 box
+create_atoms 1 box
+mass 1 1.0
+velocity all create 1.44 87287 loop geom
+region slab block INF INF INF INF 0 2
+group frozen region slab
+group mobile subtract all frozen
+velocity frozen set 0.0 0.0 0.0
+pair_style lj/cut 2.5
+pair_coeff 1 1 1.0 1.0 2.5
+neighbor 0.3 bin
+neigh_modify every 10 delay 0 check no
+fix 1 mobile nve
+thermo 25
+thermo_modify format float %.12g
+dump 1 all custom 50 f.dump id x y z fx
+dump_modify 1 sort id format float %.10g
+run 50
+"""
+    _compare(_both(tmp_path, body, 50), ftol=1e-8, ttol=1e-9)
