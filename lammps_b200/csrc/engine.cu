@@ -7,7 +7,9 @@
 //   v      3 x double[nmax] SoA,  f 3 x double[nmax] SoA (owned + ghost, Newton on)
 //   tag/mask/image int32[nmax], xhold 3 x double[nmax]
 //   ostart/gstart  int32[mbins+1]  bin -> first owned / first ghost index (counting sort)
-//   neigh  int32[maxneigh][nstride] transposed half list, numneigh int32[nlocal]
+//   tile list (default): uint16 entries into the shared-memory staging of a bin tile, 8 per
+//          16-byte word, [slot/8][list row]; see kernels_tile.cuh
+//   neigh  (B200_LIST=flat) int32[maxneigh][nstride] transposed half list, numneigh int32[nlocal]
 //   gsrc   int32[nghost], gdir uint8[nghost]: owner index and direction of every ghost
 #include "common.cuh"
 #include "kernels_halo.cuh"
@@ -15,6 +17,7 @@
 #include "kernels_pair.cuh"
 #include "kernels_pair_mixed.cuh"
 #include "kernels_step.cuh"
+#include "kernels_tile.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -114,6 +117,20 @@ struct b200_ctx {
   DBuf<int> neigh, numneigh;
   int maxneigh = 0, nstride = 0, max_numneigh = 0;
   int tpa = 2;  // lanes per atom in the pair kernels = interleave factor of the list (1,2,4,8)
+  // bin-tile list (kernels_tile.cuh): the default; B200_LIST=flat selects the flat int32 list
+  bool use_tiles = true;
+  int list_mode = 0;            // B200_LIST: 0 auto (tiles for lj/cut, flat for eam), 1 tile, 2 flat
+  bool tiles_active = false;    // the current list is the tile list
+  int tile_req[3] = {0, 0, 0};  // B200_TILE=tx,ty,tz override of the tile size
+  int tile_level = -1;
+  TileGeom tg;
+  FullStencil fst;
+  int ibin_lo[3] = {0, 0, 0}, ibin_n[3] = {0, 0, 0};  // local bins that can hold owned atoms
+  DBuf<int> tile_ibase;
+  DBuf<unsigned short> tl_iloc, tl_num;
+  DBuf<uint4> tl_list;
+  int *tflags = nullptr;  // [8] device: max staged, max owned/tile, max entries, max FWD, owned total, overflow
+  int tile_NI = 0, tile_scap = 0, tile_slots = 0, tile_threads = 256, tile_maxfull = 0;
   // pair
   int pair_style = 0;  // 1 lj/cut, 2 eam
   std::vector<double> cutsq_h;
@@ -769,6 +786,49 @@ static int setup_geometry(b200_ctx *ctx) {
         st.nrows++;
       }
     }
+  // ---- bin tiles (kernels_tile.cuh): every (dy,dz) row of the stencil, both halves, and the
+  //      range of local bins that can hold an owned atom (sublo <= x < subhi)
+  {
+    FullStencil &fs = ctx->fst;
+    memset(&fs, 0, sizeof fs);
+    bool ok = s[0] <= 3 && s[1] <= 3 && s[2] <= 3;
+    for (int k = -s[2]; ok && k <= s[2]; k++)
+      for (int j = -s[1]; j <= s[1]; j++) {
+        int lo = 1 << 30, hi = -(1 << 30), cnt = 0;
+        for (int i = -s[0]; i <= s[0]; i++)
+          if (bin_distance(i, j, k) < ctx->cutneighmaxsq) {
+            lo = std::min(lo, i);
+            hi = std::max(hi, i);
+            cnt++;
+          }
+        if (!cnt) continue;
+        if (cnt != hi - lo + 1 || lo != -hi || fs.nrows >= FST_MAXROWS) {
+          ok = false;
+          break;
+        }
+        fs.dy[fs.nrows] = (signed char)j;
+        fs.dz[fs.nrows] = (signed char)k;
+        fs.dxlo[fs.nrows] = (signed char)lo;
+        fs.dxhi[fs.nrows] = (signed char)hi;
+        fs.nrows++;
+      }
+    if (!ok) ctx->use_tiles = false;  // unusual stencil: the flat list handles it
+    auto host_bin = [&](double x, int d) {  // NBin::coord2bin, nbin.cpp:141-173
+      int ix;
+      if (x >= g.boxhi[d]) ix = (int)((x - g.boxhi[d]) * g.bininv[d]) + g.nbin[d];
+      else if (x >= g.boxlo[d]) ix = std::min((int)((x - g.boxlo[d]) * g.bininv[d]), g.nbin[d] - 1);
+      else ix = (int)((x - g.boxlo[d]) * g.bininv[d]) - 1;
+      return ix - g.mbinlo[d];
+    };
+    for (int d = 0; d < 3; d++) {
+      const int lo = std::max(host_bin(ctx->sublo[d], d), 0);
+      const int hi = std::min(host_bin(std::nextafter(ctx->subhi[d], -1.0e300), d), g.mbin[d] - 1);
+      ctx->ibin_lo[d] = lo;
+      ctx->ibin_n[d] = std::max(hi - lo + 1, 1);
+      ctx->tg.s[d] = s[d];
+    }
+    ctx->tile_level = -1;
+  }
   TRY(reserve(ctx, ctx->ostart, (size_t)g.mbins + 2));
   TRY(reserve(ctx, ctx->gstart, (size_t)g.mbins + 2));
   TRY(reserve(ctx, ctx->tilesum, (size_t)cdiv(g.mbins + 1, SCAN_TILE) + 2));
@@ -795,9 +855,165 @@ static int check_err_flags(b200_ctx *ctx, int e) {
   return B200_OK;
 }
 
+// ------------------------------------------------------------------ list build (bin tiles)
+static const int TILE_MENU[][3] = {{8, 4, 4}, {4, 4, 4}, {4, 4, 2}, {4, 2, 2},
+                                   {2, 2, 2}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}};
+static const int TILE_NMENU = sizeof(TILE_MENU) / sizeof(TILE_MENU[0]);
+static const size_t TILE_SMEM_MAX = 227 * 1024;      // opt-in limit per CTA on sm_100
+static const size_t TILE_SMEM_TWO = 113 * 1024;      // two CTAs per SM fit below this
+
+static void set_tile_geom(b200_ctx *ctx, const int t[3]) {
+  TileGeom &G = ctx->tg;
+  G.ntiles = 1;
+  for (int d = 0; d < 3; d++) {
+    G.t[d] = std::max(1, std::min(t[d], ctx->ibin_n[d]));
+    G.nt[d] = cdiv(ctx->ibin_n[d], G.t[d]);
+    G.ilo[d] = ctx->ibin_lo[d];
+    G.mbin[d] = ctx->geom.mbin[d];
+    G.ntiles *= G.nt[d];
+  }
+  G.srow_y = G.t[1] + 2 * G.s[1];
+  G.srow_z = G.t[2] + 2 * G.s[2];
+  G.sbx = G.t[0] + 2 * G.s[0];
+}
+
+template <class K>
+static int tile_attr(b200_ctx *ctx, K kernel) {
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_MAX));
+  return B200_OK;
+}
+
+static int tile_kernel_attrs(b200_ctx *ctx) {
+  TRY(tile_attr(ctx, k_tile_build<true>));
+  TRY(tile_attr(ctx, k_tile_build<false>));
+  TRY(tile_attr(ctx, k_tile_export));
+#define A3(K) \
+  TRY(tile_attr(ctx, K<false, false, false>)); TRY(tile_attr(ctx, K<false, false, true>)); \
+  TRY(tile_attr(ctx, K<false, true, false>));  TRY(tile_attr(ctx, K<false, true, true>));  \
+  TRY(tile_attr(ctx, K<true, false, false>));  TRY(tile_attr(ctx, K<true, false, true>));  \
+  TRY(tile_attr(ctx, K<true, true, false>));   TRY(tile_attr(ctx, K<true, true, true>));
+  A3(k_tile_lj)
+#undef A3
+  TRY(tile_attr(ctx, k_tile_eam_rho<false>));
+  TRY(tile_attr(ctx, k_tile_eam_rho<true>));
+  TRY(tile_attr(ctx, k_tile_eam_force<false, false>));
+  TRY(tile_attr(ctx, k_tile_eam_force<false, true>));
+  TRY(tile_attr(ctx, k_tile_eam_force<true, false>));
+  TRY(tile_attr(ctx, k_tile_eam_force<true, true>));
+  return B200_OK;
+}
+
+// rc: B200_OK with ctx->tiles_active set, or tiles_active == false when no tile size fits
+static int build_tiles(b200_ctx *ctx) {
+  const int nl = ctx->nlocal, c = ctx->cur;
+  cudaStream_t s = ctx->stream;
+  ctx->tiles_active = false;
+  const bool eam = ctx->pair_style == 2;
+  if (ctx->tile_level < 0) {
+    // first build for this geometry: the largest tile that still gives every SM several CTAs
+    int lvl = 0;
+    for (; lvl < TILE_NMENU - 1; lvl++) {
+      set_tile_geom(ctx, TILE_MENU[lvl]);
+      if (ctx->tg.ntiles >= 2 * 148) break;
+    }
+    ctx->tile_level = lvl;
+  }
+  int h[8] = {0};
+  for (;;) {
+    if (ctx->tile_req[0] > 0) set_tile_geom(ctx, ctx->tile_req);
+    else set_tile_geom(ctx, TILE_MENU[ctx->tile_level]);
+    const TileGeom &G = ctx->tg;
+    bool fits = G.srow_y * G.srow_z <= TILE_MAXROWS && G.t[1] * G.t[2] <= TILE_MAXRUNS;
+    if (fits) {
+      TRY(reserve(ctx, ctx->tile_ibase, (size_t)G.ntiles + 2));
+      TRY(reserve(ctx, ctx->tilesum, (size_t)cdiv(std::max(G.ntiles, ctx->geom.mbins) + 1, SCAN_TILE) + 2));
+      CK(cudaMemsetAsync(ctx->tflags, 0, 8 * sizeof(int), s));
+      k_tile_count<<<G.ntiles, 128, 0, s>>>(G, ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tflags);
+      ctx->launches++;
+      LAUNCH_CHECK();
+      TRY(scan_inplace(ctx, ctx->tile_ibase.p, G.ntiles));
+      CK(cudaMemcpyAsync(ctx->h_flags + 8, ctx->tflags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(ctx->h_flags + 16, ctx->flags + 3, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      memcpy(h, ctx->h_flags + 8, sizeof h);
+      if (h[4] != nl)
+        return ctx->fail(B200_ELOST, "bin tiles cover %d of %d owned atoms", h[4], nl);
+      ctx->tile_NI = ctx->h_flags[16];
+      ctx->tile_scap = cdiv(std::max(h[0], 1), 64) * 64;
+      const size_t need = std::max(tile_smem_bytes(ctx->tile_scap, G.srow_y * G.srow_z, G.sbx, true, false),
+                                   tile_smem_bytes(ctx->tile_scap, G.srow_y * G.srow_z, G.sbx, false, eam));
+      const bool last = ctx->tile_req[0] > 0 || ctx->tile_level == TILE_NMENU - 1;
+      fits = h[0] <= TILE_MAXSTAGE && need <= (last ? TILE_SMEM_MAX : TILE_SMEM_TWO);
+    }
+    if (fits) break;
+    if (ctx->tile_req[0] > 0 || ctx->tile_level == TILE_NMENU - 1) return B200_OK;  // flat list instead
+    ctx->tile_level++;
+  }
+  const TileGeom &G = ctx->tg;
+  const int rows = G.srow_y * G.srow_z;
+  // one thread per owned atom of the fullest tile; very full tiles take two passes
+  int thr = cdiv(std::max(h[1], 1), 32) * 32;
+  if (thr > 384) thr = cdiv(cdiv(h[1], cdiv(h[1], 384)), 32) * 32;
+  ctx->tile_threads = std::min(std::max(thr, 64), 384);
+  if (ctx->tile_slots == 0) ctx->tile_slots = 112;
+  const int n1 = ctx->ntypes + 1;
+  const size_t smem = tile_smem_bytes(ctx->tile_scap, rows, G.sbx, true, false);
+  for (int attempt = 0; attempt < 4; attempt++) {
+    ctx->tile_slots = cdiv(ctx->tile_slots, 8) * 8;
+    const size_t NI = (size_t)std::max(ctx->tile_NI, 32);
+    TRY(reserve(ctx, ctx->tl_list, NI * (ctx->tile_slots / 8)));
+    TRY(reserve(ctx, ctx->tl_iloc, NI));
+    TRY(reserve(ctx, ctx->tl_num, NI));
+    TRY(reserve(ctx, ctx->numneigh, (size_t)std::max(nl, 1)));
+    CK(cudaMemsetAsync(ctx->tflags + 2, 0, 2 * sizeof(int), s));
+    CK(cudaMemsetAsync(ctx->tflags + 5, 0, sizeof(int), s));
+    const int ph1 = ph_begin(ctx, B200_PH_BUILD);
+    if (ctx->ntypes == 1)
+      k_tile_build<true><<<G.ntiles, ctx->tile_threads, smem, s>>>(
+          G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,
+          ctx->tile_NI, ctx->tile_slots, ctx->cutneighsq_h[n1 + 1], ctx->cutneighsq_d.p, ctx->ntypes,
+          ctx->tl_iloc.p, ctx->tl_num.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags);
+    else
+      k_tile_build<false><<<G.ntiles, ctx->tile_threads, smem, s>>>(
+          G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,
+          ctx->tile_NI, ctx->tile_slots, 0.0, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,
+          ctx->tl_num.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags);
+    ctx->launches++;
+    LAUNCH_CHECK();
+    ph_end(ctx, ph1);
+    CK(cudaMemcpyAsync(ctx->h_flags + 8, ctx->tflags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    TRY(check_err_flags(ctx, ctx->h_flags[1]));
+    if (ctx->h_flags[8 + 5])
+      return ctx->fail(B200_ECAPACITY, "bin tile stages %d atoms, capacity %d", ctx->h_flags[8 + 5], ctx->tile_scap);
+    ctx->tile_maxfull = ctx->h_flags[8 + 2];
+    ctx->max_numneigh = ctx->h_flags[8 + 3];
+    if (ctx->max_numneigh > ctx->one)
+      return ctx->fail(B200_ECAPACITY, "Neighbor list overflow, boost neigh_modify one (%d > %d)",
+                       ctx->max_numneigh, ctx->one);
+    if (ctx->tile_maxfull <= ctx->tile_slots) {
+      ctx->tiles_active = true;
+      ctx->maxneigh = ctx->tile_slots;
+      return B200_OK;
+    }
+    ctx->tile_slots = (ctx->tile_maxfull * 9 / 8 + 8) / 8 * 8;
+  }
+  return ctx->fail(B200_ECAPACITY, "neighbor list did not converge");
+}
+
 // ------------------------------------------------------------------ list build
 static int build_list(b200_ctx *ctx) {
   const int nl = ctx->nlocal, c = ctx->cur;
+  // eam evaluates an expensive pair function: computing every owned-owned pair from both sides
+  // costs more there than the Newton scatter it removes (profiles/r01g_probe_eam_*), so the
+  // flat half list stays the default for it
+  const bool want_tiles = ctx->list_mode == 1 || (ctx->list_mode == 0 && ctx->pair_style == 1);
+  if (ctx->use_tiles && want_tiles && nl > 0) {
+    TRY(build_tiles(ctx));
+    if (ctx->tiles_active) return B200_OK;
+  }
+  ctx->tiles_active = false;
   if (ctx->maxneigh == 0) ctx->maxneigh = 96;
   for (int attempt = 0; attempt < 4; attempt++) {
     ctx->nstride = cdiv(std::max(nl, 1), 32) * 32;
@@ -1006,7 +1222,12 @@ static int force_clear(b200_ctx *ctx) {
   const int nall = ctx->nlocal + ctx->nghost;
   // mixed mode: the pair kernel stores f_i and k_merge_ff writes the ghosts; only the float4
   // scatter array is cleared (inside pair_compute)
-  if (ctx->prec != B200_PREC_MIXED)
+  if (ctx->tiles_active) {
+    // tile kernels store f of every owned atom; only the ghosts (Newton scatter targets) are cleared
+    if (ctx->nghost > 0)
+      for (int d = 0; d < 3; d++)
+        CK(cudaMemsetAsync(ctx->f[d] + ctx->nlocal, 0, sizeof(double) * ctx->nghost, ctx->stream));
+  } else if (ctx->prec != B200_PREC_MIXED)
     for (int d = 0; d < 3; d++) CK(cudaMemsetAsync(ctx->f[d], 0, sizeof(double) * nall, ctx->stream));
   ph_end(ctx, ph3);
   return B200_OK;
@@ -1129,6 +1350,69 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag) {
   double *fx = ctx->f[0], *fy = ctx->f[1], *fz = ctx->f[2];
   const int T = ctx->tpa;
   const int grid = cdiv(std::max(nl, 1) * T, 128);  // T lanes per atom
+  if (ctx->tiles_active) {
+    const TileGeom &G = ctx->tg;
+    const int rows = G.srow_y * G.srow_z, thr = ctx->tile_threads;
+    const int *ib = ctx->tile_ibase.p;
+    const unsigned short *il = ctx->tl_iloc.p, *tn = ctx->tl_num.p;
+    const uint4 *tl = ctx->tl_list.p;
+    const int NI = ctx->tile_NI, slots = ctx->tile_slots, scap = ctx->tile_scap;
+    if (ctx->pair_style == 1) {
+      const size_t sm = tile_smem_bytes(scap, rows, G.sbx, false, false);
+      const bool one = ctx->ntypes == 1;
+#define TLJ(EV, ONE, MX)                                                                              \
+  k_tile_lj<EV, ONE, MX><<<G.ntiles, thr, sm, s>>>(G, nl, xt, ctx->ostart.p, ctx->gstart.p, ib, NI,   \
+                                                   slots, il, tn, tl, fx, fy, fz, ctx->lj_one,        \
+                                                   ctx->lj_onef, ctx->lj_tab.p, ctx->lj_tabf.p,       \
+                                                   ctx->ntypes, ctx->ev, scap, ctx->tflags)
+#define TLJ2(EV, ONE) if (mixed) TLJ(EV, ONE, true); else TLJ(EV, ONE, false)
+      if (one) { if (eflag) { TLJ2(true, true); } else { TLJ2(false, true); } }
+      else     { if (eflag) { TLJ2(true, false); } else { TLJ2(false, false); } }
+#undef TLJ2
+#undef TLJ
+      ctx->launches++;
+    } else if (ctx->pair_style == 2) {
+      const size_t sm1 = tile_smem_bytes(scap, rows, G.sbx, false, false);
+      const size_t sm3 = tile_smem_bytes(scap, rows, G.sbx, false, true);
+      if (ng > 0) CK(cudaMemsetAsync(ctx->rho + nl, 0, sizeof(double) * ng, s));
+      if (mixed)
+        k_tile_eam_rho<true><<<G.ntiles, thr, sm1, s>>>(G, nl, xt, ctx->ostart.p, ctx->gstart.p, ib, NI, slots,
+                                                        il, tn, tl, ctx->eam, ctx->eamf, ctx->rho, scap, ctx->tflags);
+      else
+        k_tile_eam_rho<false><<<G.ntiles, thr, sm1, s>>>(G, nl, xt, ctx->ostart.p, ctx->gstart.p, ib, NI, slots,
+                                                         il, tn, tl, ctx->eam, ctx->eamf, ctx->rho, scap, ctx->tflags);
+      {
+        Vec3Ptr r{{ctx->rho, nullptr, nullptr}};
+        TRY(reverse_halo<1>(ctx, r));
+      }
+      const int g2 = cdiv(std::max(nl, 1), 256);
+      if (eflag)
+        k_eam_embed<true><<<g2, 256, 0, s>>>(nl, xt, ctx->eam, ctx->rho, ctx->fp, ctx->ev, ctx->flags + 1);
+      else
+        k_eam_embed<false><<<g2, 256, 0, s>>>(nl, xt, ctx->eam, ctx->rho, ctx->fp, ctx->ev, ctx->flags + 1);
+      TRY(forward_scalar(ctx, ctx->fp));
+#define TEF(EV, MX)                                                                                    \
+  k_tile_eam_force<EV, MX><<<G.ntiles, thr, sm3, s>>>(G, nl, xt, ctx->ostart.p, ctx->gstart.p, ib, NI, \
+                                                      slots, il, tn, tl, ctx->eam, ctx->eamf, ctx->fp, \
+                                                      fx, fy, fz, ctx->ev, scap, ctx->tflags)
+      if (eflag) { if (mixed) TEF(true, true); else TEF(true, false); }
+      else       { if (mixed) TEF(false, true); else TEF(false, false); }
+#undef TEF
+      ctx->launches += 3;
+    } else
+      return ctx->fail(B200_EARG, "no pair style set");
+    LAUNCH_CHECK();
+    ph_end(ctx, ph6);
+    if (vflag && nl + ng > 0) {
+      const int ph7 = ph_begin(ctx, B200_PH_THERMO);
+      const int gv = std::min(cdiv(nl + ng, 256), 148 * 8);
+      k_virial_fdotr<<<gv, 256, 0, s>>>(nl + ng, xt, fx, fy, fz, ctx->ev);
+      ctx->launches++;
+      LAUNCH_CHECK();
+      ph_end(ctx, ph7);
+    }
+    return B200_OK;
+  }
   if (mixed) CK(cudaMemsetAsync(ctx->ff, 0, sizeof(float4) * (nl + ng), s));
 // instantiate a kernel launch for the run-time lanes-per-atom value
 #define TPA_SWITCH(LAUNCH)        \
@@ -1335,12 +1619,21 @@ int b200_create(b200_ctx **out, int device, int precision) {
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8) ctx->tpa = v;
   }
+  if (const char *e = getenv("B200_LIST"))  // "flat": int32 half list + RED scatter kernels
+    ctx->list_mode = strcmp(e, "flat") == 0 ? 2 : (strcmp(e, "tile") == 0 ? 1 : 0);
+  if (const char *e = getenv("B200_TILE")) {  // tuning knob: tile size in bins "tx,ty,tz"
+    int t[3];
+    if (sscanf(e, "%d,%d,%d", &t[0], &t[1], &t[2]) == 3 && t[0] > 0 && t[1] > 0 && t[2] > 0)
+      for (int d = 0; d < 3; d++) ctx->tile_req[d] = t[d];
+  }
   *out = ctx;
   if (precision != B200_PREC_DOUBLE && precision != B200_PREC_MIXED)
     return ctx->fail(B200_EARG, "unknown precision mode %d", precision);
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   TRY(dalloc(ctx, &ctx->ev, 8));
   TRY(dalloc(ctx, &ctx->flags, 4));
+  TRY(dalloc(ctx, &ctx->tflags, 8));
+  TRY(tile_kernel_attrs(ctx));
   TRY(dalloc(ctx, &ctx->counts, 32));
   TRY(dalloc(ctx, &ctx->recvoffset, NDIR + 1));
   TRY(dalloc(ctx, &ctx->allcounts, 32));
@@ -1380,6 +1673,7 @@ void b200_destroy(b200_ctx *ctx) {
   F(ctx->neigh.p);
   F(ctx->numneigh.p); F(ctx->lj_tab.p); F(ctx->eam_i.p); F(ctx->eam_d.p); F(ctx->ev); F(ctx->flags);
   F(ctx->cnt64);
+  F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p);
   if (ctx->h_ev) cudaFreeHost(ctx->h_ev);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   for (auto &r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -1822,8 +2116,15 @@ int b200_get_neighbor_list(b200_ctx *ctx, int *numneigh, int *neigh, int64_t cap
   CK(cudaMalloc((void **)&dfirst, sizeof(long long) * (nl + 1)));
   CK(cudaMalloc((void **)&dflat, sizeof(int) * first[nl]));
   CK(cudaMemcpy(dfirst, first.data(), sizeof(long long) * (nl + 1), cudaMemcpyHostToDevice));
-  k_export_csr<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->nstride, ctx->tpa, ctx->numneigh.p, ctx->neigh.p,
-                                                       dfirst, dflat);
+  if (ctx->tiles_active) {
+    const TileGeom &G = ctx->tg;
+    const size_t sm = TILE_HDR_BYTES + (size_t)ctx->tile_scap * sizeof(int);
+    k_tile_export<<<G.ntiles, 256, sm, ctx->stream>>>(G, nl, ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p,
+                                                     ctx->tile_NI, ctx->tile_slots, ctx->tl_num.p,
+                                                     ctx->tl_list.p, dfirst, dflat, ctx->tile_scap);
+  } else
+    k_export_csr<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->nstride, ctx->tpa, ctx->numneigh.p,
+                                                         ctx->neigh.p, dfirst, dflat);
   ctx->launches++;
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(neigh, dflat, sizeof(int) * first[nl], cudaMemcpyDeviceToHost));

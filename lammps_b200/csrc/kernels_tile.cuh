@@ -1,0 +1,851 @@
+// kernels_tile.cuh -- bin-tile kernels: the Verlet list and the pair loops with the
+// neighbourhood of a tile of bins staged in shared memory.
+//
+// Why: the flat kernels (kernels_pair.cuh) gather every neighbour record through L1TEX and
+// scatter every Newton partner force with a global RED; ncu shows them pinned at ~1 L1TEX
+// wavefront per cycle per SM (profiles/r01d_ncu_full_k_pair_lj*.txt), not at DRAM or the FP
+// pipes.  Here one CTA owns a tile of tx*ty*tz bins.  Atoms are bin-sorted, so the atoms of the
+// tile and of its +-s bin halo are (ty+2s)*(tz+2s) runs of consecutive records (an owned run and a
+// ghost run per x-row), read coalesced once per CTA and stored as SoA x[],y[],z[],type[] in
+// shared memory.  Neighbour reads are then three LDS.64, and list entries are 16-bit indices into
+// the staged tile (half the list traffic of int32 indices).
+// (A first version staged the 32-byte AoS records with cp.async.bulk: correct, but a 32-byte
+// stride maps every record onto 4 of the 8 16-byte bank groups and ncu counted 232.9 M conflict
+// wavefronts on 66 M ideal ones -- profiles/r01e_ncu_full_k_tile_lj_aos.txt.  SoA doubles give
+// 16 distinct bank pairs for 16 consecutive atoms.)
+//
+// The list: for owned atom i every partner within the neighbour cutoff is stored once in i's row.
+// An entry carries two flags:
+//   FWD   the pair (i,j) is a member of the reference's half/Newton-on list of atom i
+//         (NPairBin<1,1,0,0,1>::build, npair_bin.cpp:52-253: same bin -> j after i, ghosts by
+//         the (z,y,x) rule; other bins -> upper half stencil).  The FWD entries ARE that list:
+//         b200_get_neighbor_list exports exactly them and the parity tests compare them
+//         bit-for-bit with the reference's pair set.
+//   GHOST j is a ghost atom (only FWD entries can be ghosts).
+// Entries without FWD are the transposed copy of an owned-owned pair (the member (j,i) of j's
+// half list).  With them atom i accumulates ALL of its pair forces in registers and stores f_i
+// once: no atomics between owned atoms.  Only a FWD|GHOST entry scatters (RED.ADD.F64) onto
+// the ghost, which the reverse halo returns to its owner exactly as the reference does with
+// Newton on.  Energy is tallied on FWD entries only, so every pair counts once; the virial
+// uses the f.x form over owned+ghost atoms as before (pair.cpp:1809-1825).
+// rsq uses the reference's operation order (rsq_ref) in the build and in the pair kernels, in
+// both precisions, so list membership and cutoff decisions are those of the CPU path.
+// No tensor cores: nothing here is a dense contraction.
+#pragma once
+#include "common.cuh"
+#include "kernels_pair.cuh"
+#include "kernels_pair_mixed.cuh"
+
+#define TILE_MAXROWS 160  // staged x-rows of one tile: (ty+2sy)*(tz+2sz)
+#define TILE_MAXRUNS 64   // x-rows of the tile itself: ty*tz
+#define FST_MAXROWS 49    // (dy,dz) rows of the full stencil: (2sy+1)*(2sz+1), s <= 3
+#define TILE_FWD 0x8000u
+#define TILE_GHOST 0x4000u
+#define TILE_IDX 0x3fffu
+#define TILE_MAXSTAGE 16384
+#define TILE_NOATOM 0xffffu
+
+struct TileGeom {
+  int t[3];     // tile size in bins
+  int nt[3];    // tiles per dimension
+  int ilo[3];   // first local bin (per dim) that can hold an owned atom
+  int s[3];     // stencil half width in bins (NStencil::sx,sy,sz, nstencil.cpp:203-237)
+  int mbin[3];  // local bin grid
+  int ntiles, srow_y, srow_z, sbx;  // staged rows along y and z, staged bins per row
+};
+
+// all (dy,dz) rows of the stencil, both halves: bins with bin_distance < cutneighmaxsq
+struct FullStencil {
+  int nrows;
+  signed char dy[FST_MAXROWS], dz[FST_MAXROWS], dxlo[FST_MAXROWS], dxhi[FST_MAXROWS];
+};
+
+struct TileHdr {
+  unsigned long long pad0;
+  int S, ni, nrows, nruns;
+  int rowbase[TILE_MAXROWS + 1];  // staged index of the first atom of each row
+  int row_o0[TILE_MAXROWS], row_no[TILE_MAXROWS], row_g0[TILE_MAXROWS], row_ng[TILE_MAXROWS];
+  int runpre[TILE_MAXRUNS + 1];   // exclusive prefix of the owned-atom counts of the tile's rows
+  int run_o0[TILE_MAXRUNS];       // global index of the first owned atom of each of them
+};
+#define TILE_HDR_BYTES ((sizeof(TileHdr) + 127) / 128 * 128)
+
+__host__ __device__ __forceinline__ size_t tile_smem_bytes(int scap, int rows, int sbx, bool build,
+                                                          bool with_fp) {
+  size_t b = TILE_HDR_BYTES + (size_t)scap * (3 * sizeof(double) + 2 * sizeof(int));
+  if (with_fp) b += (size_t)scap * sizeof(double);
+  if (build) b += (size_t)2 * rows * (sbx + 1) * sizeof(unsigned short);
+  return (b + 127) / 128 * 128;
+}
+
+// the staged tile in shared memory
+struct TileS {
+  double *x, *y, *z, *fp;
+  int *type, *gmap;
+  unsigned short *tail;  // build only: bin tables
+};
+__device__ __forceinline__ TileS tile_carve(unsigned char *tsm, int scap, bool with_fp) {
+  TileS T;
+  T.x = reinterpret_cast<double *>(tsm + TILE_HDR_BYTES);
+  T.y = T.x + scap;
+  T.z = T.y + scap;
+  T.fp = T.z + scap;
+  T.type = reinterpret_cast<int *>(T.fp + (with_fp ? scap : 0));
+  T.gmap = T.type + scap;
+  T.tail = reinterpret_cast<unsigned short *>(T.gmap + scap);
+  return T;
+}
+
+struct TilePos {
+  int tx0, ty0, tz0;
+};
+
+__device__ __forceinline__ TilePos tile_pos(const TileGeom &G, int tile) {
+  TilePos p;
+  p.tx0 = G.ilo[0] + (tile % G.nt[0]) * G.t[0];
+  p.ty0 = G.ilo[1] + ((tile / G.nt[0]) % G.nt[1]) * G.t[1];
+  p.tz0 = G.ilo[2] + (tile / (G.nt[0] * G.nt[1])) * G.t[2];
+  return p;
+}
+
+// x-extent [xa,xb) of the staged bins of a row, clamped to the local grid
+__device__ __forceinline__ void tile_xrange(const TileGeom &G, const TilePos &P, int &xa, int &xb) {
+  xa = max(P.tx0 - G.s[0], 0);
+  xb = min(P.tx0 + G.t[0] + G.s[0], G.mbin[0]);
+  if (xb < xa) xb = xa;
+}
+
+// Row tables of a tile: which runs of atom records make up the staged neighbourhood.
+// Returns the staged atom count S (uniform over the CTA).  Ends with a __syncthreads.
+__device__ __forceinline__ int tile_rows(const TileGeom &G, const TilePos &P,
+                                         const int *__restrict__ ostart,
+                                         const int *__restrict__ gstart, TileHdr *H) {
+  const int tid = threadIdx.x, bd = blockDim.x, lane = tid & 31;
+  const int nrows = G.srow_y * G.srow_z, nruns = G.t[1] * G.t[2];
+  int xa, xb;
+  tile_xrange(G, P, xa, xb);
+  for (int r = tid; r < nrows; r += bd) {
+    const int y = P.ty0 - G.s[1] + r % G.srow_y, z = P.tz0 - G.s[2] + r / G.srow_y;
+    int o0 = 0, no = 0, g0 = 0, ng = 0;
+    if (y >= 0 && y < G.mbin[1] && z >= 0 && z < G.mbin[2] && xb > xa) {
+      const int b = (z * G.mbin[1] + y) * G.mbin[0];
+      o0 = ostart[b + xa];
+      no = ostart[b + xb] - o0;
+      g0 = gstart[b + xa];
+      ng = gstart[b + xb] - g0;
+    }
+    H->row_o0[r] = o0;
+    H->row_no[r] = no;
+    H->row_g0[r] = g0;
+    H->row_ng[r] = ng;
+  }
+  // the tile's own rows: owned atoms of bins [tx0, tx0+tx) (bins past the sub-domain hold none)
+  const int oxa = min(P.tx0, G.mbin[0]), oxb = min(P.tx0 + G.t[0], G.mbin[0]);
+  for (int q = tid; q < nruns; q += bd) {
+    const int y = P.ty0 + q % G.t[1], z = P.tz0 + q / G.t[1];
+    int o0 = 0, no = 0;
+    if (y < G.mbin[1] && z < G.mbin[2]) {
+      const int b = (z * G.mbin[1] + y) * G.mbin[0];
+      o0 = ostart[b + oxa];
+      no = ostart[b + oxb] - o0;
+    }
+    H->run_o0[q] = o0;
+    H->runpre[q + 1] = no;  // count for now, prefix below
+  }
+  if (tid == 0) {
+    H->nrows = nrows;
+    H->nruns = nruns;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    int carry = 0;
+    for (int base = 0; base < nrows; base += 32) {
+      const int r = base + lane;
+      const int c = r < nrows ? H->row_no[r] + H->row_ng[r] : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (r < nrows) H->rowbase[r] = carry + incl - c;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      H->rowbase[nrows] = carry;
+      H->S = carry;
+    }
+    carry = 0;
+    for (int base = 0; base < nruns; base += 32) {
+      const int q = base + lane;
+      const int c = q < nruns ? H->runpre[q + 1] : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      __syncwarp();
+      if (q < nruns) H->runpre[q + 1] = carry + incl;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      H->runpre[0] = 0;
+      H->ni = carry;
+    }
+  }
+  __syncthreads();
+  return H->S;
+}
+
+__device__ __forceinline__ double3 tile_pos3(const TileS &T, int s) {
+  return make_double3(T.x[s], T.y[s], T.z[s]);
+}
+
+// Stage the tile: one coalesced pass over the S records of its runs (LDG.256 of {x,y,z,type},
+// SoA stores) plus the staged->global index map.  Precondition: tile_rows() done, S <= scap.
+template <bool WITH_FP>
+__device__ __forceinline__ void tile_stage(int nlocal, const double4 *__restrict__ xt,
+                                           const double *__restrict__ fp, const TileHdr *H,
+                                           const TileS &T) {
+  const int S = H->S, nrows = H->nrows;
+#pragma unroll 4
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    int lo = 0, hi = nrows;  // row r with rowbase[r] <= s < rowbase[r+1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (H->rowbase[mid] <= s) lo = mid; else hi = mid;
+    }
+    const int k = s - H->rowbase[lo], no = H->row_no[lo];
+    const int src = k < no ? H->row_o0[lo] + k : nlocal + H->row_g0[lo] + (k - no);
+    const double4 p = ld_xt(xt + src);
+    T.x[s] = p.x;
+    T.y[s] = p.y;
+    T.z[s] = p.z;
+    T.type[s] = d2type(p.w);
+    T.gmap[s] = src;
+    if (WITH_FP) T.fp[s] = fp[src];
+  }
+  __syncthreads();
+}
+
+// thread ti of a tile -> staged index of its owned atom (and the atom's global index)
+__device__ __forceinline__ int tile_own_atom(const TileGeom &G, const TileHdr *H, int ti, int &gi) {
+  int lo = 0, hi = H->nruns;  // find run q with runpre[q] <= ti < runpre[q+1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (H->runpre[mid] <= ti) lo = mid; else hi = mid;
+  }
+  const int q = lo, k = ti - H->runpre[q];
+  const int row = (q % G.t[1] + G.s[1]) + (q / G.t[1] + G.s[2]) * G.srow_y;
+  gi = H->run_o0[q] + k;
+  return H->rowbase[row] + (gi - H->row_o0[row]);
+}
+
+
+// Reciprocal and square root without the IEEE special-case paths the compiler emits for `1.0/x`
+// and `sqrt(x)` (a slow-path call per use that also stops it interleaving neighbouring pairs):
+// MUFU seed + Newton steps, <= 1 ulp for the normal, positive arguments a pair distance can be.
+__device__ __forceinline__ double rcp_nr(double a) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  e = fma(e, e, e);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  return fma(x, e, x);
+}
+__device__ __forceinline__ double sqrt_nr(double a, double &rinv) {  // returns sqrt(a), rinv ~ 1/sqrt(a)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  const double d = fma(-g, g, a);
+  g = fma(d, h, g);
+  rinv = h + h;
+  return g;
+}
+__device__ __forceinline__ float rcp_f(float a) {
+  float x;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(a));
+  return x;
+}
+
+// Walk the n entries of list row g: 8 entries per 16-byte word, next word prefetched.
+// body(e, valid) must be branch-free (entries past n are zero padding -> valid = false): the
+// eight bodies of a word then interleave in the instruction stream.  ghost(e) runs only for
+// FWD|GHOST entries, behind one test per word.
+template <int ILP, class Body, class Ghost>
+__device__ __forceinline__ void tile_walk(const uint4 *__restrict__ list, int g, int n, int NI,
+                                          Body &&body, Ghost &&ghost) {
+  const uint4 *lp = list + g;
+  uint4 q = n > 0 ? __ldg(lp) : make_uint4(0, 0, 0, 0);
+  for (int k0 = 0; k0 < n; k0 += 8) {
+    const uint4 c = q;
+    if (k0 + 8 < n) q = __ldg(lp + (size_t)((k0 >> 3) + 1) * NI);
+    // ILP entries at a time (2 in FP64, 4 in FP32 pair math): enough independent chains to
+    // cover the pipe latency without the register cost of all eight
+    if (ILP == 4) {
+#pragma unroll 1
+      for (int h = 0; h < 2; h++) {
+        const unsigned w0 = h ? c.z : c.x, w1 = h ? c.w : c.y;
+        const int kb = k0 + 4 * h;
+        body(w0 & 0xffffu, kb < n);
+        body(w0 >> 16, kb + 1 < n);
+        body(w1 & 0xffffu, kb + 2 < n);
+        body(w1 >> 16, kb + 3 < n);
+        if ((w0 | w1) & (TILE_GHOST | (TILE_GHOST << 16))) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const unsigned e = ((k & 2 ? w1 : w0) >> ((k & 1) * 16)) & 0xffffu;
+            if ((e & TILE_GHOST) && kb + k < n) ghost(e);
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int h = 0; h < 4; h++) {
+        const unsigned w0 = (h & 2) ? ((h & 1) ? c.w : c.z) : ((h & 1) ? c.y : c.x);
+        const int kb = k0 + 2 * h;
+        body(w0 & 0xffffu, kb < n);
+        body(w0 >> 16, kb + 1 < n);
+        if (w0 & (TILE_GHOST | (TILE_GHOST << 16))) {
+          if ((w0 & TILE_GHOST) && kb < n) ghost(w0 & 0xffffu);
+          if ((w0 & (TILE_GHOST << 16)) && kb + 1 < n) ghost(w0 >> 16);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// per-tile counts: owned atoms (padded to a warp) and staged atoms; sizes the list and the
+// shared-memory request.  tflags: [0] max staged, [1] max owned per tile, [4] owned total.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_tile_count(TileGeom G, const int *__restrict__ ostart,
+                                                    const int *__restrict__ gstart,
+                                                    int *__restrict__ tile_ibase,
+                                                    int *__restrict__ tflags) {
+  __shared__ TileHdr H;
+  const TilePos P = tile_pos(G, blockIdx.x);
+  const int S = tile_rows(G, P, ostart, gstart, &H);
+  if (threadIdx.x == 0) {
+    const int ni = H.ni;
+    tile_ibase[blockIdx.x] = (ni + 31) / 32 * 32;
+    atomicMax(&tflags[0], S);
+    atomicMax(&tflags[1], ni);
+    atomicAdd(&tflags[4], ni);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// List build.  One CTA per tile, one thread per owned atom; candidates are read from the staged
+// tile in the reference's bin order.  Eight 16-bit entries are packed into one 16-byte store:
+// entry n of list row g lives in word (n/8)*NI + g (uint4), lane-contiguous for a warp.
+// tflags: [2] max entries per atom, [3] max FWD entries per atom, [5] tile overflow.
+// ---------------------------------------------------------------------------------------
+template <bool ONETYPE>
+__global__ void __launch_bounds__(512) k_tile_build(
+    TileGeom G, FullStencil F, int nlocal, const double4 *__restrict__ xt,
+    const int *__restrict__ ostart, const int *__restrict__ gstart,
+    const int *__restrict__ atombin, const int *__restrict__ tile_ibase, int NI, int maxslots,
+    double cut1, const double *__restrict__ cutneighsq, int ntypes,
+    unsigned short *__restrict__ iloc, unsigned short *__restrict__ tnum, uint4 *__restrict__ list,
+    int *__restrict__ numneigh_half, int scap, int *__restrict__ tflags) {
+  extern __shared__ __align__(128) unsigned char tsm[];
+  TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
+  const TileS T = tile_carve(tsm, scap, false);
+  unsigned short *sbo = T.tail;
+  const int ncol = G.sbx + 1;
+  unsigned short *sbg = sbo + (size_t)G.srow_y * G.srow_z * ncol;
+
+  const int tile = blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
+  const TilePos P = tile_pos(G, tile);
+  const int S = tile_rows(G, P, ostart, gstart, H);
+  if (S > scap || S > TILE_MAXSTAGE) {
+    if (tid == 0) atomicMax(&tflags[5], S);
+    return;
+  }
+  // staged index of the first owned / first ghost atom of every staged bin (+ end sentinel)
+  {
+    int xa, xb;
+    tile_xrange(G, P, xa, xb);
+    const int xs = P.tx0 - G.s[0], nrows = H->nrows;
+    for (int e = tid; e < nrows * ncol; e += bd) {
+      const int r = e / ncol, c = e % ncol;
+      const int y = P.ty0 - G.s[1] + r % G.srow_y, z = P.tz0 - G.s[2] + r / G.srow_y;
+      int so = H->rowbase[r], sg = so + H->row_no[r];
+      if (y >= 0 && y < G.mbin[1] && z >= 0 && z < G.mbin[2] && xb > xa) {
+        const int b = (z * G.mbin[1] + y) * G.mbin[0];
+        const int xc = min(max(xs + c, xa), xb);
+        so += ostart[b + xc] - H->row_o0[r];
+        sg += gstart[b + xc] - H->row_g0[r];
+      }
+      sbo[e] = (unsigned short)so;
+      sbg[e] = (unsigned short)sg;
+    }
+  }
+  tile_stage<false>(nlocal, xt, nullptr, H, T);
+
+  const int ni = H->ni, ibase = tile_ibase[tile], nipad = (ni + 31) / 32 * 32;
+  const int n1 = ntypes + 1;
+  const int xs = P.tx0 - G.s[0], ys = P.ty0 - G.s[1], zs = P.tz0 - G.s[2];
+  int wmax = 0, wmaxf = 0;
+  for (int ti = tid; ti < nipad; ti += bd) {
+    const int g = ibase + ti;
+    int n = 0, nf = 0;
+    if (ti < ni) {
+      int gi;
+      const int li = tile_own_atom(G, H, ti, gi);
+      const double3 pi = tile_pos3(T, li);
+      const double *cut_i = ONETYPE ? nullptr : cutneighsq + (size_t)T.type[li] * n1;
+      const int b = atombin[gi];
+      const int bx = b % G.mbin[0], by = (b / G.mbin[0]) % G.mbin[1], bz = b / (G.mbin[0] * G.mbin[1]);
+      unsigned long long qlo = 0, qhi = 0;
+      auto test = [&](int s, unsigned flags) {
+        const double3 pj = tile_pos3(T, s);
+        const double rsq = rsq_ref(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+        const double c = ONETYPE ? cut1 : __ldg(cut_i + T.type[s]);
+        if (rsq <= c) {
+          const unsigned long long e = (unsigned)s | flags;
+          qlo = (qlo >> 16) | (qhi << 48);
+          qhi = (qhi >> 16) | (e << 48);
+          n++;
+          nf += flags >> 15;
+          if ((n & 7) == 0 && n <= maxslots)
+            list[(size_t)((n >> 3) - 1) * NI + g] = make_uint4((unsigned)qlo, (unsigned)(qlo >> 32),
+                                                             (unsigned)qhi, (unsigned)(qhi >> 32));
+        }
+      };
+      for (int r = 0; r < F.nrows; r++) {
+        const int dy = F.dy[r], dz = F.dz[r];
+        const int srow = (by + dy - ys) + (bz + dz - zs) * G.srow_y;
+        const unsigned short *bo = sbo + srow * ncol, *bg = sbg + srow * ncol;
+        const int ca = bx + F.dxlo[r] - xs, cb = bx + F.dxhi[r] + 1 - xs;
+        if (dz > 0 || (dz == 0 && dy > 0)) {  // upper half stencil: members of i's half list
+          for (int s = bo[ca]; s < bo[cb]; s++) test(s, TILE_FWD);
+          for (int s = bg[ca]; s < bg[cb]; s++) test(s, TILE_FWD | TILE_GHOST);
+        } else if (dz < 0 || dy < 0) {        // lower half: owned j holds (j,i) in ITS half list
+          for (int s = bo[ca]; s < bo[cb]; s++) test(s, 0u);
+        } else {
+          // row (0,0): bins left of own bin -> transposed; own bin -> by list position;
+          // right -> members.  Owned atoms of a row are staged in index order, so that is s > li.
+          for (int s = bo[ca]; s < bo[cb]; s++)
+            if (s != li) test(s, s > li ? TILE_FWD : 0u);
+          const int c0 = bx - xs;
+          for (int s = bg[c0]; s < bg[c0 + 1]; s++) {  // own-bin ghosts: npair_bin.cpp:156-171
+            const double3 pj = tile_pos3(T, s);
+            if (pj.z < pi.z) continue;
+            if (pj.z == pi.z) {
+              if (pj.y < pi.y) continue;
+              if (pj.y == pi.y && pj.x < pi.x) continue;
+            }
+            test(s, TILE_FWD | TILE_GHOST);
+          }
+          for (int s = bg[c0 + 1]; s < bg[cb]; s++) test(s, TILE_FWD | TILE_GHOST);
+        }
+      }
+      if ((n & 7) && (n >> 3) < (maxslots >> 3)) {
+        for (int k = n & 7; k < 8; k++) {
+          qlo = (qlo >> 16) | (qhi << 48);
+          qhi >>= 16;
+        }
+        list[(size_t)(n >> 3) * NI + g] = make_uint4((unsigned)qlo, (unsigned)(qlo >> 32),
+                                                   (unsigned)qhi, (unsigned)(qhi >> 32));
+      }
+      iloc[g] = (unsigned short)li;
+      numneigh_half[gi] = nf;
+    } else {
+      iloc[g] = (unsigned short)TILE_NOATOM;
+    }
+    tnum[g] = (unsigned short)min(n, 65535);
+    wmax = max(wmax, n);
+    wmaxf = max(wmaxf, nf);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    wmaxf = max(wmaxf, __shfl_xor_sync(0xffffffffu, wmaxf, o));
+  }
+  if ((tid & 31) == 0 && wmax > 0) {
+    atomicMax(&tflags[2], wmax);
+    atomicMax(&tflags[3], wmaxf);
+  }
+}
+
+// half list (FWD entries) as CSR over the owned atoms in global indices (test hook)
+__global__ void __launch_bounds__(512) k_tile_export(
+    TileGeom G, int nlocal, const int *__restrict__ ostart, const int *__restrict__ gstart,
+    const int *__restrict__ tile_ibase, int NI, int maxslots, const unsigned short *__restrict__ tnum,
+    const uint4 *__restrict__ list, const long long *__restrict__ first, int *__restrict__ flat,
+    int scap) {
+  extern __shared__ __align__(128) unsigned char tsm[];
+  TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
+  int *gmap = reinterpret_cast<int *>(tsm + TILE_HDR_BYTES);
+  const int tile = blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
+  const TilePos P = tile_pos(G, tile);
+  const int S = tile_rows(G, P, ostart, gstart, H);
+  if (S > scap) return;
+  for (int r = tid >> 5; r < H->nrows; r += bd >> 5) {
+    const int base = H->rowbase[r], no = H->row_no[r], n = no + H->row_ng[r];
+    const int o0 = H->row_o0[r], g0 = nlocal + H->row_g0[r] - no;
+    for (int k = tid & 31; k < n; k += 32) gmap[base + k] = k < no ? o0 + k : g0 + k;
+  }
+  __syncthreads();
+  const int ni = H->ni, ibase = tile_ibase[tile];
+  for (int ti = tid; ti < ni; ti += bd) {
+    const int g = ibase + ti;
+    int gi;
+    tile_own_atom(G, H, ti, gi);
+    const int n = min((int)tnum[g], maxslots);
+    long long o = first[gi];
+    for (int k = 0; k < n; k++) {
+      const uint4 q = list[(size_t)(k >> 3) * NI + g];
+      const unsigned w = (k & 4) ? ((k & 2) ? q.w : q.z) : ((k & 2) ? q.y : q.x);
+      const unsigned e = (w >> ((k & 1) * 16)) & 0xffffu;
+      if (e & TILE_FWD) flat[o++] = gmap[e & TILE_IDX];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// lj/cut over a tile.  PairLJCut::compute (pair_lj_cut.cpp:71-141); MIXED evaluates the pair
+// function in FP32 (del, rsq and the cutoff test stay FP64) like k_pair_lj_mixed.
+// ---------------------------------------------------------------------------------------
+template <bool EV, bool ONETYPE, bool MIXED>
+__global__ void __launch_bounds__(384, 2) k_tile_lj(
+    TileGeom G, int nlocal, const double4 *__restrict__ xt, const int *__restrict__ ostart,
+    const int *__restrict__ gstart, const int *__restrict__ tile_ibase, int NI, int maxslots,
+    const unsigned short *__restrict__ iloc, const unsigned short *__restrict__ tnum,
+    const uint4 *__restrict__ list, double *__restrict__ fx, double *__restrict__ fy,
+    double *__restrict__ fz, LJOne one, LJOneF onef, const double *__restrict__ tab,
+    const float *__restrict__ tabf, int ntypes, double *__restrict__ ev, int scap,
+    int *__restrict__ tflags) {
+  extern __shared__ __align__(128) unsigned char tsm[];
+  TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
+  const TileS T = tile_carve(tsm, scap, false);
+  const int tile = blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
+  const TilePos P = tile_pos(G, tile);
+  const int S = tile_rows(G, P, ostart, gstart, H);
+  if (S > scap) {  // cannot happen between rebuilds (the rows are those the build staged)
+    if (tid == 0) atomicMax(&tflags[5], S);
+    return;
+  }
+  tile_stage<false>(nlocal, xt, nullptr, H, T);
+  const int ni = H->ni, ibase = tile_ibase[tile];
+  const int n1 = ntypes + 1, n2 = n1 * n1;
+  double evdwl = 0.0;
+  for (int ti = tid; ti < ni; ti += bd) {
+    const int g = ibase + ti;
+    const int li = iloc[g];
+    const int n = min((int)tnum[g], maxslots);
+    const double3 pi = tile_pos3(T, li);
+    const int gi = T.gmap[li];
+    const int itype = T.type[li];
+    double fxi = 0.0, fyi = 0.0, fzi = 0.0;
+    float gxi = 0.0f, gyi = 0.0f, gzi = 0.0f;
+    // pair force of one entry (times del gives the force on i); 0 outside the cutoff
+    auto pair = [&](unsigned e, bool valid, double &delx, double &dely, double &delz, double &fp64,
+                    float &fp32, double &epair) {
+      const int j = e & TILE_IDX;
+      const double3 pj = tile_pos3(T, j);
+      delx = pi.x - pj.x; dely = pi.y - pj.y; delz = pi.z - pj.z;
+      const double rsq = rsq_ref(delx, dely, delz);
+      int tij = 0;
+      double cutsq = one.cutsq;
+      if (!ONETYPE) {
+        tij = itype * n1 + T.type[j];
+        cutsq = __ldg(tab + tij);
+      }
+      const bool in = valid && rsq < cutsq;
+      if (MIXED) {
+        const float lj1 = ONETYPE ? onef.lj1 : __ldg(tabf + tij);
+        const float lj2 = ONETYPE ? onef.lj2 : __ldg(tabf + n2 + tij);
+        const float r2inv = rcp_f((float)rsq);
+        const float r6inv = r2inv * r2inv * r2inv;
+        fp32 = in ? r6inv * (lj1 * r6inv - lj2) * r2inv : 0.0f;
+        if (EV) {
+          const float lj3 = ONETYPE ? onef.lj3 : __ldg(tabf + 2 * n2 + tij);
+          const float lj4 = ONETYPE ? onef.lj4 : __ldg(tabf + 3 * n2 + tij);
+          const float off = ONETYPE ? onef.offset : __ldg(tabf + 4 * n2 + tij);
+          epair = (in && (e & TILE_FWD)) ? (double)(r6inv * (lj3 * r6inv - lj4) - off) : 0.0;
+        }
+      } else {
+        const double lj1 = ONETYPE ? one.lj1 : __ldg(tab + n2 + tij);
+        const double lj2 = ONETYPE ? one.lj2 : __ldg(tab + 2 * n2 + tij);
+        const double r2inv = rcp_nr(rsq);
+        const double r6inv = r2inv * r2inv * r2inv;
+        fp64 = in ? r6inv * (lj1 * r6inv - lj2) * r2inv : 0.0;
+        if (EV) {
+          const double lj3 = ONETYPE ? one.lj3 : __ldg(tab + 3 * n2 + tij);
+          const double lj4 = ONETYPE ? one.lj4 : __ldg(tab + 4 * n2 + tij);
+          const double off = ONETYPE ? one.offset : __ldg(tab + 5 * n2 + tij);
+          epair = (in && (e & TILE_FWD)) ? r6inv * (lj3 * r6inv - lj4) - off : 0.0;
+        }
+      }
+    };
+    tile_walk<MIXED ? 4 : 2>(
+        list, g, n, NI,
+        [&](unsigned e, bool valid) {
+          double delx, dely, delz, f64 = 0.0, ep = 0.0;
+          float f32 = 0.0f;
+          pair(e, valid, delx, dely, delz, f64, f32, ep);
+          if (MIXED) {
+            gxi += (float)delx * f32; gyi += (float)dely * f32; gzi += (float)delz * f32;
+          } else {
+            fxi += delx * f64; fyi += dely * f64; fzi += delz * f64;
+          }
+          if (EV) evdwl += ep;
+        },
+        [&](unsigned e) {  // Newton scatter onto a ghost; the reverse halo returns it to the owner
+          double delx, dely, delz, f64 = 0.0, ep = 0.0;
+          float f32 = 0.0f;
+          pair(e, true, delx, dely, delz, f64, f32, ep);
+          const int gj = T.gmap[e & TILE_IDX];
+          if (MIXED) {
+            atomicAdd(&fx[gj], -(double)((float)delx * f32));
+            atomicAdd(&fy[gj], -(double)((float)dely * f32));
+            atomicAdd(&fz[gj], -(double)((float)delz * f32));
+          } else {
+            atomicAdd(&fx[gj], -(delx * f64));
+            atomicAdd(&fy[gj], -(dely * f64));
+            atomicAdd(&fz[gj], -(delz * f64));
+          }
+        });
+    if (MIXED) {
+      fxi = (double)gxi; fyi = (double)gyi; fzi = (double)gzi;
+    }
+    fx[gi] = fxi;
+    fy[gi] = fyi;
+    fz[gi] = fzi;
+  }
+  if (EV) {
+    double v[1] = {evdwl};
+    __syncthreads();
+    block_sum<1>(v, T.x);
+    if (tid == 0) atomicAdd(&ev[0], v[0]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// eam over a tile, PairEAM::compute (pair_eam.cpp:124-327).  Phase 1: rho_i from every entry of
+// the row (stored, not accumulated); a FWD|GHOST entry also adds this atom's density onto the
+// ghost (RED), which the rho reverse halo returns to its owner (pair_eam.cpp:215,1625-1646).
+// ---------------------------------------------------------------------------------------
+template <bool MIXED>
+__global__ void __launch_bounds__(384, 2) k_tile_eam_rho(
+    TileGeom G, int nlocal, const double4 *__restrict__ xt, const int *__restrict__ ostart,
+    const int *__restrict__ gstart, const int *__restrict__ tile_ibase, int NI, int maxslots,
+    const unsigned short *__restrict__ iloc, const unsigned short *__restrict__ tnum,
+    const uint4 *__restrict__ list, EAMParams P, EAMParamsF F, double *__restrict__ rho, int scap,
+    int *__restrict__ tflags) {
+  extern __shared__ __align__(128) unsigned char tsm[];
+  TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
+  const TileS T = tile_carve(tsm, scap, false);
+  const int tile = blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
+  const TilePos Tp = tile_pos(G, tile);
+  const int S = tile_rows(G, Tp, ostart, gstart, H);
+  if (S > scap) {
+    if (tid == 0) atomicMax(&tflags[5], S);
+    return;
+  }
+  tile_stage<false>(nlocal, xt, nullptr, H, T);
+  const int ni = H->ni, ibase = tile_ibase[tile], n1 = P.ntypes + 1;
+  const bool onetype = P.ntypes == 1;
+  for (int ti = tid; ti < ni; ti += bd) {
+    const int g = ibase + ti;
+    const int li = iloc[g];
+    const int n = min((int)tnum[g], maxslots);
+    const double3 pi = tile_pos3(T, li);
+    const int itype = T.type[li];
+    double rhoi = 0.0;
+    // density of type `from` felt at distance sqrt(rsq) by type `to`; 0 outside the cutoff
+    auto dens = [&](double rsq, bool valid, int from, int to) -> double {
+      const bool in = valid && rsq < P.cutforcesq;
+      const int tr = onetype ? P.type2rhor[n1 + 1] : P.type2rhor[from * n1 + to];
+      if (MIXED) {
+        float p = sqrtf((float)rsq) * F.rdr + 1.0f;
+        int m = (int)p;
+        m = min(m, P.nr - 1);
+        p -= (float)m;
+        p = fminf(p, 1.0f);
+        // knot = {c0,c1,c2,c3 | c4,c5,c6,pad}: the value cubic is c3..c6
+        const float4 *kc = reinterpret_cast<const float4 *>(F.rhor + ((size_t)tr * (P.nr + 1) + m) * 8);
+        const float4 c0 = __ldg(kc), c1 = __ldg(kc + 1);
+        return in ? (double)(((c0.w * p + c1.x) * p + c1.y) * p + c1.z) : 0.0;
+      } else {
+        double rinv;
+        double p = sqrt_nr(fmax(rsq, 1.0e-300), rinv) * P.rdr + 1.0;
+        int m = (int)p;
+        m = min(m, P.nr - 1);
+        p -= m;
+        p = fmin(p, 1.0);
+        const double *c = P.rhor + ((size_t)tr * (P.nr + 1) + m) * 7;
+        return in ? ((__ldg(c + 3) * p + __ldg(c + 4)) * p + __ldg(c + 5)) * p + __ldg(c + 6) : 0.0;
+      }
+    };
+    tile_walk<MIXED ? 4 : 2>(
+        list, g, n, NI,
+        [&](unsigned e, bool valid) {
+          const int j = e & TILE_IDX;
+          const double3 pj = tile_pos3(T, j);
+          const double rsq = rsq_ref(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+          rhoi += dens(rsq, valid, onetype ? 1 : T.type[j], itype);
+        },
+        [&](unsigned e) {
+          const int j = e & TILE_IDX;
+          const double3 pj = tile_pos3(T, j);
+          const double rsq = rsq_ref(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+          if (rsq < P.cutforcesq) atomicAdd(&rho[T.gmap[j]], dens(rsq, true, itype, T.type[j]));
+        });
+    rho[T.gmap[li]] = rhoi;
+  }
+}
+
+// Phase 3 (pair_eam.cpp:233-314).  fp of the staged atoms rides along in shared memory.
+template <bool EV, bool MIXED>
+__global__ void __launch_bounds__(384, 2) k_tile_eam_force(
+    TileGeom G, int nlocal, const double4 *__restrict__ xt, const int *__restrict__ ostart,
+    const int *__restrict__ gstart, const int *__restrict__ tile_ibase, int NI, int maxslots,
+    const unsigned short *__restrict__ iloc, const unsigned short *__restrict__ tnum,
+    const uint4 *__restrict__ list, EAMParams P, EAMParamsF F, const double *__restrict__ fp,
+    double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
+    double *__restrict__ ev, int scap, int *__restrict__ tflags) {
+  extern __shared__ __align__(128) unsigned char tsm[];
+  TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
+  const TileS T = tile_carve(tsm, scap, true);
+  const double *sfp = T.fp;
+  const int tile = blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
+  const TilePos Tp = tile_pos(G, tile);
+  const int S = tile_rows(G, Tp, ostart, gstart, H);
+  if (S > scap) {
+    if (tid == 0) atomicMax(&tflags[5], S);
+    return;
+  }
+  tile_stage<true>(nlocal, xt, fp, H, T);
+  const int ni = H->ni, ibase = tile_ibase[tile], n1 = P.ntypes + 1;
+  const bool onetype = P.ntypes == 1;
+  const int t11 = n1 + 1;
+  double evdwl = 0.0;
+  for (int ti = tid; ti < ni; ti += bd) {
+    const int g = ibase + ti;
+    const int li = iloc[g];
+    const int n = min((int)tnum[g], maxslots);
+    const double3 pi = tile_pos3(T, li);
+    const int gi = T.gmap[li];
+    const int itype = T.type[li];
+    const double fpi = sfp[li];
+    double fxi = 0.0, fyi = 0.0, fzi = 0.0;
+    float gxi = 0.0f, gyi = 0.0f, gzi = 0.0f;
+    // fpair of one entry (times del gives the force on i) and its pair energy; 0 outside the cutoff
+    auto pair = [&](unsigned e, bool valid, double &delx, double &dely, double &delz, double &f64,
+                    float &f32, double &epair) {
+      const int j = e & TILE_IDX;
+      const double3 pj = tile_pos3(T, j);
+      delx = pi.x - pj.x; dely = pi.y - pj.y; delz = pi.z - pj.z;
+      const double rsq = rsq_ref(delx, dely, delz);
+      const bool in = valid && rsq < P.cutforcesq;
+      const int jtype = onetype ? 1 : T.type[j];
+      const int tt = onetype ? t11 : itype * n1 + jtype;
+      const int tij = P.type2rhor[tt], tji = onetype ? tij : P.type2rhor[jtype * n1 + itype];
+      const int tz = P.type2z2r[tt];
+      const double fpj = sfp[j];
+      if (MIXED) {
+        const float r = sqrtf((float)rsq);
+        float p = r * F.rdr + 1.0f;
+        int m = (int)p;
+        m = min(m, P.nr - 1);
+        p -= (float)m;
+        p = fminf(p, 1.0f);
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(F.rhor + ((size_t)tij * (P.nr + 1) + m) * 8));
+        const float rhoip = (a.x * p + a.y) * p + a.z;
+        float rhojp = rhoip;
+        if (tji != tij) {
+          const float4 b = __ldg(reinterpret_cast<const float4 *>(F.rhor + ((size_t)tji * (P.nr + 1) + m) * 8));
+          rhojp = (b.x * p + b.y) * p + b.z;
+        }
+        const float4 *zc = reinterpret_cast<const float4 *>(F.z2r + ((size_t)tz * (P.nr + 1) + m) * 8);
+        const float4 z0 = __ldg(zc), z1 = __ldg(zc + 1);
+        const float z2p = (z0.x * p + z0.y) * p + z0.z;
+        const float z2 = ((z0.w * p + z1.x) * p + z1.y) * p + z1.z;
+        const float recip = rcp_f(r);
+        const float phi = z2 * recip;
+        const float phip = z2p * recip - phi * recip;
+        const float psip = (float)fpi * rhojp + (float)fpj * rhoip + phip;
+        const float sc = (float)P.scale[tt];
+        f32 = in ? -sc * psip * recip : 0.0f;
+        if (EV) epair = (in && (e & TILE_FWD)) ? (double)(sc * phi) : 0.0;
+      } else {
+        double recip;
+        const double r = sqrt_nr(fmax(rsq, 1.0e-300), recip);
+        recip = fma(recip, fma(-r, recip, 1.0), recip);  // one Newton step: 1/r to <= 1 ulp
+        double p = r * P.rdr + 1.0;
+        int m = (int)p;
+        m = min(m, P.nr - 1);
+        p -= m;
+        p = fmin(p, 1.0);
+        const double *c = P.rhor + ((size_t)tij * (P.nr + 1) + m) * 7;
+        const double rhoip = (__ldg(c) * p + __ldg(c + 1)) * p + __ldg(c + 2);
+        double rhojp = rhoip;
+        if (tji != tij) {
+          c = P.rhor + ((size_t)tji * (P.nr + 1) + m) * 7;
+          rhojp = (__ldg(c) * p + __ldg(c + 1)) * p + __ldg(c + 2);
+        }
+        c = P.z2r + ((size_t)tz * (P.nr + 1) + m) * 7;
+        const double z2p = (__ldg(c) * p + __ldg(c + 1)) * p + __ldg(c + 2);
+        const double z2 = ((__ldg(c + 3) * p + __ldg(c + 4)) * p + __ldg(c + 5)) * p + __ldg(c + 6);
+        const double phi = z2 * recip;
+        const double phip = z2p * recip - phi * recip;
+        const double psip = fpi * rhojp + fpj * rhoip + phip;
+        const double sc = P.scale[tt];
+        f64 = in ? -sc * psip * recip : 0.0;
+        if (EV) epair = (in && (e & TILE_FWD)) ? sc * phi : 0.0;
+      }
+    };
+    tile_walk<MIXED ? 4 : 2>(
+        list, g, n, NI,
+        [&](unsigned e, bool valid) {
+          double delx, dely, delz, f64 = 0.0, ep = 0.0;
+          float f32 = 0.0f;
+          pair(e, valid, delx, dely, delz, f64, f32, ep);
+          if (MIXED) {
+            gxi += (float)delx * f32; gyi += (float)dely * f32; gzi += (float)delz * f32;
+          } else {
+            fxi += delx * f64; fyi += dely * f64; fzi += delz * f64;
+          }
+          if (EV) evdwl += ep;
+        },
+        [&](unsigned e) {
+          double delx, dely, delz, f64 = 0.0, ep = 0.0;
+          float f32 = 0.0f;
+          pair(e, true, delx, dely, delz, f64, f32, ep);
+          const int gj = T.gmap[e & TILE_IDX];
+          if (MIXED) {
+            atomicAdd(&fx[gj], -(double)((float)delx * f32));
+            atomicAdd(&fy[gj], -(double)((float)dely * f32));
+            atomicAdd(&fz[gj], -(double)((float)delz * f32));
+          } else {
+            atomicAdd(&fx[gj], -(delx * f64));
+            atomicAdd(&fy[gj], -(dely * f64));
+            atomicAdd(&fz[gj], -(delz * f64));
+          }
+        });
+    if (MIXED) {
+      fxi = (double)gxi; fyi = (double)gyi; fzi = (double)gzi;
+    }
+    fx[gi] = fxi;
+    fy[gi] = fyi;
+    fz[gi] = fzi;
+  }
+  if (EV) {
+    double v[1] = {evdwl};
+    __syncthreads();
+    block_sum<1>(v, T.x);
+    if (tid == 0) atomicAdd(&ev[0], v[0]);
+  }
+}
