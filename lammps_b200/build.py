@@ -9,9 +9,10 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-LIB = HERE / "libb200md.so"
+LIB = Path(os.environ.get("B200_LIB_OUT", HERE / "libb200md.so"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+EXTRA = os.environ.get("B200_NVCC_EXTRA", "").split()
+FLAGS = [*EXTRA, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 

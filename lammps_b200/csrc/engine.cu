@@ -856,7 +856,7 @@ static int check_err_flags(b200_ctx *ctx, int e) {
 }
 
 // ------------------------------------------------------------------ list build (bin tiles)
-static const int TILE_MENU[][3] = {{8, 4, 4}, {4, 4, 4}, {4, 4, 2}, {4, 2, 2},
+static const int TILE_MENU[][3] = {{8, 8, 4}, {8, 4, 4}, {4, 4, 4}, {4, 4, 2}, {4, 2, 2},
                                    {2, 2, 2}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}};
 static const int TILE_NMENU = sizeof(TILE_MENU) / sizeof(TILE_MENU[0]);
 static const size_t TILE_SMEM_MAX = 227 * 1024;      // opt-in limit per CTA on sm_100
@@ -953,8 +953,8 @@ static int build_tiles(b200_ctx *ctx) {
   const int rows = G.srow_y * G.srow_z;
   // one thread per owned atom of the fullest tile; very full tiles take two passes
   int thr = cdiv(std::max(h[1], 1), 32) * 32;
-  if (thr > 384) thr = cdiv(cdiv(h[1], cdiv(h[1], 384)), 32) * 32;
-  ctx->tile_threads = std::min(std::max(thr, 64), 384);
+  if (thr > 352) thr = cdiv(cdiv(h[1], cdiv(h[1], 352)), 32) * 32;
+  ctx->tile_threads = std::min(std::max(thr, 64), 352);
   if (ctx->tile_slots == 0) ctx->tile_slots = 112;
   const int n1 = ctx->ntypes + 1;
   const size_t smem = tile_smem_bytes(ctx->tile_scap, rows, G.sbx, true, false);

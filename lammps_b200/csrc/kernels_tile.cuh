@@ -6,7 +6,7 @@
 // wavefront per cycle per SM (profiles/r01d_ncu_full_k_pair_lj*.txt), not at DRAM or the FP
 // pipes.  Here one CTA owns a tile of tx*ty*tz bins.  Atoms are bin-sorted, so the atoms of the
 // tile and of its +-s bin halo are (ty+2s)*(tz+2s) runs of consecutive records (an owned run and a
-// ghost run per x-row), read coalesced once per CTA and stored as SoA x[],y[],z[],type[] in
+// ghost run per x-row), copied once per CTA with cp.async (LDGSTS) into SoA x[],y[],z[],type[] in
 // shared memory.  Neighbour reads are then three LDS.64, and list entries are 16-bit indices into
 // the staged tile (half the list traffic of int32 indices).
 // (A first version staged the 32-byte AoS records with cp.async.bulk: correct, but a 32-byte
@@ -44,6 +44,9 @@
 #define TILE_IDX 0x3fffu
 #define TILE_MAXSTAGE 16384
 #define TILE_NOATOM 0xffffu
+#ifndef TILE_MINB
+#define TILE_MINB 2  // CTAs per SM the pair kernels are register-budgeted for
+#endif
 
 struct TileGeom {
   int t[3];     // tile size in bins
@@ -202,30 +205,43 @@ __device__ __forceinline__ double3 tile_pos3(const TileS &T, int s) {
   return make_double3(T.x[s], T.y[s], T.z[s]);
 }
 
-// Stage the tile: one coalesced pass over the S records of its runs (LDG.256 of {x,y,z,type},
-// SoA stores) plus the staged->global index map.  Precondition: tile_rows() done, S <= scap.
+// cp.async (LDGSTS): global -> shared without a register round trip, so a warp keeps the copies
+// of all its rows in flight at once
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)),
+               "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)),
+               "l"(src)
+               : "memory");
+}
+
+// Stage the tile: one warp per run of records, {x,y,z,type} of each record copied into the SoA
+// arrays with cp.async, plus the staged->global index map.  Precondition: tile_rows() done,
+// S <= scap.  Ends with a __syncthreads after the copies have landed.
 template <bool WITH_FP>
 __device__ __forceinline__ void tile_stage(int nlocal, const double4 *__restrict__ xt,
                                            const double *__restrict__ fp, const TileHdr *H,
                                            const TileS &T) {
-  const int S = H->S, nrows = H->nrows;
-#pragma unroll 4
-  for (int s = threadIdx.x; s < S; s += blockDim.x) {
-    int lo = 0, hi = nrows;  // row r with rowbase[r] <= s < rowbase[r+1]
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (H->rowbase[mid] <= s) lo = mid; else hi = mid;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nrows = H->nrows;
+  for (int r = warp; r < nrows; r += nwarp) {
+    const int base = H->rowbase[r], no = H->row_no[r], n = no + H->row_ng[r];
+    const int o0 = H->row_o0[r], g0 = nlocal + H->row_g0[r] - no;
+    for (int k = lane; k < n; k += 32) {
+      const int src = k < no ? o0 + k : g0 + k, s = base + k;
+      const double *p = reinterpret_cast<const double *>(xt + src);
+      cp_async8(T.x + s, p);
+      cp_async8(T.y + s, p + 1);
+      cp_async8(T.z + s, p + 2);
+      cp_async4(T.type + s, p + 3);  // low word of the int64 type field (little endian)
+      if (WITH_FP) cp_async8(T.fp + s, fp + src);
+      T.gmap[s] = src;
     }
-    const int k = s - H->rowbase[lo], no = H->row_no[lo];
-    const int src = k < no ? H->row_o0[lo] + k : nlocal + H->row_g0[lo] + (k - no);
-    const double4 p = ld_xt(xt + src);
-    T.x[s] = p.x;
-    T.y[s] = p.y;
-    T.z[s] = p.z;
-    T.type[s] = d2type(p.w);
-    T.gmap[s] = src;
-    if (WITH_FP) T.fp[s] = fp[src];
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 }
 
@@ -288,38 +304,43 @@ __device__ __forceinline__ void tile_walk(const uint4 *__restrict__ list, int g,
   for (int k0 = 0; k0 < n; k0 += 8) {
     const uint4 c = q;
     if (k0 + 8 < n) q = __ldg(lp + (size_t)((k0 >> 3) + 1) * NI);
-    // ILP entries at a time (2 in FP64, 4 in FP32 pair math): enough independent chains to
-    // cover the pipe latency without the register cost of all eight
+    // ILP entries at a time (2 in FP64, 4 with FP32 pair math): enough independent chains to
+    // cover the pipe latency without the register cost of all eight.  The empty asm statements
+    // keep the compiler from hoisting the next step's shared-memory reads above this step.
+    auto step2 = [&](unsigned w, int kb) {
+      body(w & 0xffffu, kb < n);
+      body(w >> 16, kb + 1 < n);
+      if (w & (TILE_GHOST | (TILE_GHOST << 16))) {
+        if ((w & TILE_GHOST) && kb < n) ghost(w & 0xffffu);
+        if ((w & (TILE_GHOST << 16)) && kb + 1 < n) ghost(w >> 16);
+      }
+    };
+    auto step4 = [&](unsigned w0, unsigned w1, int kb) {
+      body(w0 & 0xffffu, kb < n);
+      body(w0 >> 16, kb + 1 < n);
+      body(w1 & 0xffffu, kb + 2 < n);
+      body(w1 >> 16, kb + 3 < n);
+      if ((w0 | w1) & (TILE_GHOST | (TILE_GHOST << 16))) {
+        if ((w0 & TILE_GHOST) && kb < n) ghost(w0 & 0xffffu);
+        if ((w0 & (TILE_GHOST << 16)) && kb + 1 < n) ghost(w0 >> 16);
+        if ((w1 & TILE_GHOST) && kb + 2 < n) ghost(w1 & 0xffffu);
+        if ((w1 & (TILE_GHOST << 16)) && kb + 3 < n) ghost(w1 >> 16);
+      }
+    };
     if (ILP == 4) {
-#pragma unroll 1
-      for (int h = 0; h < 2; h++) {
-        const unsigned w0 = h ? c.z : c.x, w1 = h ? c.w : c.y;
-        const int kb = k0 + 4 * h;
-        body(w0 & 0xffffu, kb < n);
-        body(w0 >> 16, kb + 1 < n);
-        body(w1 & 0xffffu, kb + 2 < n);
-        body(w1 >> 16, kb + 3 < n);
-        if ((w0 | w1) & (TILE_GHOST | (TILE_GHOST << 16))) {
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const unsigned e = ((k & 2 ? w1 : w0) >> ((k & 1) * 16)) & 0xffffu;
-            if ((e & TILE_GHOST) && kb + k < n) ghost(e);
-          }
-        }
-      }
+      step4(c.x, c.y, k0);
+      asm volatile("" ::: "memory");
+      step4(c.z, c.w, k0 + 4);
     } else {
-#pragma unroll 1
-      for (int h = 0; h < 4; h++) {
-        const unsigned w0 = (h & 2) ? ((h & 1) ? c.w : c.z) : ((h & 1) ? c.y : c.x);
-        const int kb = k0 + 2 * h;
-        body(w0 & 0xffffu, kb < n);
-        body(w0 >> 16, kb + 1 < n);
-        if (w0 & (TILE_GHOST | (TILE_GHOST << 16))) {
-          if ((w0 & TILE_GHOST) && kb < n) ghost(w0 & 0xffffu);
-          if ((w0 & (TILE_GHOST << 16)) && kb + 1 < n) ghost(w0 >> 16);
-        }
-      }
+      step2(c.x, k0);
+      asm volatile("" ::: "memory");
+      step2(c.y, k0 + 2);
+      asm volatile("" ::: "memory");
+      step2(c.z, k0 + 4);
+      asm volatile("" ::: "memory");
+      step2(c.w, k0 + 6);
     }
+    asm volatile("" ::: "memory");
   }
 }
 
@@ -518,7 +539,7 @@ __global__ void __launch_bounds__(512) k_tile_export(
 // function in FP32 (del, rsq and the cutoff test stay FP64) like k_pair_lj_mixed.
 // ---------------------------------------------------------------------------------------
 template <bool EV, bool ONETYPE, bool MIXED>
-__global__ void __launch_bounds__(384, 2) k_tile_lj(
+__global__ void __launch_bounds__(352, TILE_MINB) k_tile_lj(
     TileGeom G, int nlocal, const double4 *__restrict__ xt, const int *__restrict__ ostart,
     const int *__restrict__ gstart, const int *__restrict__ tile_ibase, int NI, int maxslots,
     const unsigned short *__restrict__ iloc, const unsigned short *__restrict__ tnum,
@@ -638,7 +659,7 @@ __global__ void __launch_bounds__(384, 2) k_tile_lj(
 // ghost (RED), which the rho reverse halo returns to its owner (pair_eam.cpp:215,1625-1646).
 // ---------------------------------------------------------------------------------------
 template <bool MIXED>
-__global__ void __launch_bounds__(384, 2) k_tile_eam_rho(
+__global__ void __launch_bounds__(352, TILE_MINB) k_tile_eam_rho(
     TileGeom G, int nlocal, const double4 *__restrict__ xt, const int *__restrict__ ostart,
     const int *__restrict__ gstart, const int *__restrict__ tile_ibase, int NI, int maxslots,
     const unsigned short *__restrict__ iloc, const unsigned short *__restrict__ tnum,
@@ -709,7 +730,7 @@ __global__ void __launch_bounds__(384, 2) k_tile_eam_rho(
 
 // Phase 3 (pair_eam.cpp:233-314).  fp of the staged atoms rides along in shared memory.
 template <bool EV, bool MIXED>
-__global__ void __launch_bounds__(384, 2) k_tile_eam_force(
+__global__ void __launch_bounds__(352, TILE_MINB) k_tile_eam_force(
     TileGeom G, int nlocal, const double4 *__restrict__ xt, const int *__restrict__ ostart,
     const int *__restrict__ gstart, const int *__restrict__ tile_ibase, int NI, int maxslots,
     const unsigned short *__restrict__ iloc, const unsigned short *__restrict__ tnum,

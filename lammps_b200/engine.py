@@ -8,6 +8,7 @@ no CUDA device is visible, construction raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
@@ -52,6 +53,9 @@ def load_library():
     """dlopen libb200md.so; raises if it has not been built (never falls back)."""
     global _lib
     if _lib is None:
+        global LIBPATH
+        if os.environ.get("B200_LIBPATH"):  # development: an alternative build of the same ABI
+            LIBPATH = Path(os.environ["B200_LIBPATH"])
         if not LIBPATH.exists():
             raise B200Error(f"{LIBPATH} not found: run `python -m lammps_b200.build` "
                             "(there is no CPU fallback)")
