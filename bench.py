@@ -138,6 +138,10 @@ def configure(e, s, x, v, typ, tag, natoms_total):
 # algorithmic bytes/flops per atom-step of the dominant (pair) kernel, SURVEY.md 8(d):
 #   LJ : list 4*Ps + x_i,type 32 + f_i write 24 + f clear 24 ; flops 8*Ps + 20*Pc
 #   EAM: 2 passes over the list, rho/fp traffic
+# Ps = stored half-list pairs per atom (measured from the list), Pc = in-cutoff pairs.
+# The bin-tile list moves the same list bytes in another shape (2 B x 2*Ps entries instead of
+# 4 B x Ps) and needs no force clear, but evaluates owned-owned pairs from both sides; the
+# roofline keeps SURVEY's half-list figures so that numbers stay comparable between rounds.
 def pair_algorithmic(kind, ps, pc):
     if kind == "lj":
         return 4.0 * ps + 32 + 24 + 24, 8.0 * ps + 20.0 * pc
@@ -251,24 +255,34 @@ def run_b200(args):
     # (dram__bytes_read.sum + dram__bytes_write.sum per atom, profiles/ncu_traffic.json), scaled
     # to this launch's atom count; null when no capture exists for this kernel / precision
     traffic, traffic_src = None, None
+    tiled = st["list_kind"] == 1
+    key = f"{kind}_{args.precision}" + ("_tile" if tiled else "")
     tj = ROOT / "profiles" / "ncu_traffic.json"
     if tj.exists():
-        t = json.loads(tj.read_text()).get(f"{kind}_{args.precision}")
+        t = json.loads(tj.read_text()).get(key)
         if t:
             traffic = t["dram_bytes_per_atom"] * nown
             traffic_src = t["source"]
     kern = {"lj_double": "k_pair_lj", "lj_mixed": "k_pair_lj_mixed+k_merge_ff",
+            "lj_double_tile": "k_tile_lj<EV,ONETYPE,MIXED=0>", "lj_mixed_tile": "k_tile_lj<EV,ONETYPE,MIXED=1>",
             "eam_double": "k_eam_rho+k_eam_embed+k_eam_force (+ rho/fp halo)",
-            "eam_mixed": "k_eam_rho_mixed+k_eam_embed+k_eam_force_mixed+k_merge_ff (+ rho/fp halo)"}
-    roofline = {"bound": "hbm", "kernel": kern[f"{kind}_{args.precision}"],
+            "eam_mixed": "k_eam_rho_mixed+k_eam_embed+k_eam_force_mixed+k_merge_ff (+ rho/fp halo)",
+            "eam_double_tile": "k_tile_eam_rho+k_eam_embed+k_tile_eam_force (+ rho/fp halo)",
+            "eam_mixed_tile": "k_tile_eam_rho+k_eam_embed+k_tile_eam_force (+ rho/fp halo)"}
+    note = ("the tile pair kernel is bound by shared-memory load wavefronts (3 LDS.64 per list entry, "
+            "~2.7x bank-conflict replay on scattered neighbours) and then by the FP64 pipe; its DRAM "
+            "traffic equals the algorithmic bytes: see DESIGN.md section 4" if tiled else
+            "the flat pair kernels are bound by the L1TEX data pipe (one 32-byte sector per gathered "
+            "atom and per RED), not by DRAM: see DESIGN.md section 4")
+    roofline = {"bound": "hbm", "kernel": kern[key],
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                 "bytes_per_atom": bytes_atom, "pairs_stored_per_atom": ps,
+                "list_entries_per_atom": st["list_entries"] / max(nown, 1),
                 "us_per_launch": pair_s * 1e6, "flop_per_atom": flops_atom,
                 "tflops": flops_atom * nown / pair_s / 1e12,
                 "share_of_step": pair_ms / max(dev_ms, 1e-9),
-                "note": "the pair kernels are bound by the L1TEX data pipe (one 32-byte sector "
-                        "per gathered atom and per RED), not by DRAM: see DESIGN.md section 4"}
+                "note": note}
     phases = {k: {"ms": round(t, 3), "calls": c} for k, (t, c) in ph.items() if c}
 
     if rank != 0:
@@ -291,7 +305,10 @@ def run_b200(args):
                             1: "NCCL send/recv between the 26 neighbour sub-domains",
                             2: "peer-memory stores over NVLink (CUDA IPC) + arrival/ack flags"}[
                                 st["halo_transport"]],
-                   "lanes_per_atom": st["lanes_per_atom"]},
+                   "list": (f"bin tiles {st['tile'][0]}x{st['tile'][1]}x{st['tile'][2]} bins, 16-bit entries, "
+                            f"<= {st['tile_stage_max']} atoms staged in shared memory per tile")
+                           if st["list_kind"] == 1 else
+                           f"flat int32 half list, {st['lanes_per_atom']} lanes per atom"},
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d / e2e_steps,
                 "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps,
                 "includes": "pinned-host upload, Verlet setup (ghosts+list+forces), run, thermo "
@@ -388,7 +405,12 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_b200(args)
+        try:
+            run_b200(args)
+        finally:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -136,9 +136,20 @@ typedef struct {
   int64_t launches;     /* kernels launched since create */
   double  device_bytes; /* device memory currently allocated */
   int64_t halo_transport; /* per-step halo: 0 none (one rank), 1 NCCL send/recv, 2 peer-memory stores */
-  int64_t lanes_per_atom; /* lanes sharing one atom in the pair kernels (B200_TPA) */
+  int64_t lanes_per_atom; /* lanes sharing one atom in the flat pair kernels (B200_TPA) */
+  int64_t list_kind;      /* 0 flat int32 half list (RED scatter), 1 bin-tile list (kernels_tile.cuh) */
+  int64_t tile[3];        /* bin-tile size in bins (tx,ty,tz); 0 for the flat list */
+  int64_t list_entries;   /* entries stored per build: the half-list pairs (npairs) plus, for the
+                             tile list, the transposed copies of owned-owned pairs */
+  int64_t tile_stage_max; /* most atoms one tile stages in shared memory */
 } b200_stats;
 int b200_get_stats(b200_ctx *ctx, b200_stats *out);
+
+/* ---- list layout.  Default: the bin-tile list for lj/cut (16-bit entries into a shared-memory
+ *      staging of a tile of bins; every owned-owned pair is stored in both atoms' rows so forces
+ *      need no atomics; the entries flagged FWD are exactly the reference's half/Newton-on list)
+ *      and the flat int32 half list for eam.  Environment B200_LIST=flat|tile overrides,
+ *      B200_TILE=tx,ty,tz sets the tile size in bins. */
 
 /* ---- test hooks: the half list as CSR over current owned order.  j indexes
  *      owned [0,nlocal) or ghost [nlocal, nlocal+nghost) atoms, as NeighList does

@@ -871,6 +871,7 @@ static void set_tile_geom(b200_ctx *ctx, const int t[3]) {
     G.ilo[d] = ctx->ibin_lo[d];
     G.mbin[d] = ctx->geom.mbin[d];
     G.ntiles *= G.nt[d];
+
   }
   G.srow_y = G.t[1] + 2 * G.s[1];
   G.srow_z = G.t[2] + 2 * G.s[2];
@@ -2097,6 +2098,21 @@ int b200_get_stats(b200_ctx *ctx, b200_stats *out) {
   out->device_bytes = (double)ctx->dev_bytes;
   out->halo_transport = ctx->nranks > 1 ? (ctx->p2p ? 2 : 1) : 0;
   out->lanes_per_atom = ctx->tpa;
+  out->list_kind = ctx->tiles_active ? 1 : 0;
+  out->list_entries = out->npairs;
+  if (ctx->tiles_active) {
+    for (int d = 0; d < 3; d++) out->tile[d] = ctx->tg.t[d];
+    out->tile_stage_max = ctx->tile_scap;
+    // entries = sum of the list-row lengths (FWD members + transposed copies)
+    CK(cudaMemsetAsync(ctx->cnt64, 0, sizeof(unsigned long long), ctx->stream));
+    k_sum_u16<<<std::min(cdiv(ctx->tile_NI, 256), 1184), 256, 0, ctx->stream>>>(ctx->tile_NI, ctx->tl_num.p,
+                                                                            ctx->cnt64);
+    ctx->launches++;
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, ctx->cnt64, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    out->list_entries = (int64_t)h;
+  }
   return B200_OK;
 }
 

@@ -338,6 +338,15 @@ __global__ void __launch_bounds__(256) k_sum_int(int n, const int *__restrict__ 
   if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
+__global__ void __launch_bounds__(256) k_sum_u16(int n, const unsigned short *__restrict__ a,
+                                                 unsigned long long *__restrict__ out) {
+  unsigned long long s = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += a[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
 // CSR export of the transposed list (test hook b200_get_neighbor_list)
 __global__ void __launch_bounds__(256) k_export_csr(int nlocal, int nstride, int T,
                                                     const int *__restrict__ numneigh,

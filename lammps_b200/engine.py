@@ -43,7 +43,9 @@ class Stats(C.Structure):
                 ("npairs", C.c_int64), ("maxneigh", C.c_int64), ("max_numneigh", C.c_int64),
                 ("nbins", C.c_int64 * 3), ("mbins", C.c_int64), ("nstencil", C.c_int64),
                 ("launches", C.c_int64), ("device_bytes", C.c_double),
-                ("halo_transport", C.c_int64), ("lanes_per_atom", C.c_int64)]
+                ("halo_transport", C.c_int64), ("lanes_per_atom", C.c_int64),
+                ("list_kind", C.c_int64), ("tile", C.c_int64 * 3), ("list_entries", C.c_int64),
+                ("tile_stage_max", C.c_int64)]
 
 
 _lib = None
@@ -253,8 +255,9 @@ class Engine:
     def stats(self) -> dict:
         s = Stats()
         self._chk(self.L.b200_get_stats(self.h, C.byref(s)))
-        d = {k: getattr(s, k) for k, _ in Stats._fields_ if k != "nbins"}
+        d = {k: getattr(s, k) for k, _ in Stats._fields_ if k not in ("nbins", "tile")}
         d["nbins"] = list(s.nbins)
+        d["tile"] = list(s.tile)
         return d
 
     def neighbor_list(self):

@@ -106,7 +106,8 @@ def build(jobs: int = 8) -> Path:
     objdir = BUILD / "obj"
     patched = patched_core()
     restyle = [R.SRC / n for n in ("force.cpp", "update.cpp")]
-    new_objs = R.compile_all(pkg_cpp + patched + restyle, inc, objdir, jobs)
+    new_objs = R.compile_all(pkg_cpp + patched + restyle, inc, objdir, jobs,
+                             deps=[*pkg_h, REPO / "include" / "b200_md.h"])
     replaced = {"core__force.o", "core__modify.o", "core__update.o", "core__input.o", "core__lammps.o"}
     ref_objs = [o for o in all_ref_objs if o.name not in replaced]
     newest = max(o.stat().st_mtime for o in new_objs + [lib])

@@ -99,14 +99,17 @@ def _write_if_changed(p: Path, s: str) -> None:
 
 
 def compile_all(files: list[Path], incs: list[Path], objdir: Path, jobs: int,
-                extra_flags: list[str] = ()) -> list[Path]:
+                extra_flags: list[str] = (), deps: list[Path] = ()) -> list[Path]:
+    """Compile `files` into objdir; an object is stale when its source or any of `deps`
+    (headers outside the reference tree, e.g. the C ABI) is newer."""
     objdir.mkdir(parents=True, exist_ok=True)
     objs, todo = [], []
+    dep_time = max((d.stat().st_mtime for d in deps), default=0.0)
     for f in files:
         tag = f.parent.name if f.parent != SRC else "core"
         o = objdir / f"{tag}__{f.stem}.o"
         objs.append(o)
-        if not o.exists() or o.stat().st_mtime < f.stat().st_mtime:
+        if not o.exists() or o.stat().st_mtime < max(f.stat().st_mtime, dep_time):
             todo.append((f, o))
     inc_flags = [f"-I{i}" for i in incs]
 
