@@ -142,6 +142,10 @@ typedef struct {
   int64_t list_entries;   /* entries stored per build: the half-list pairs (npairs) plus, for the
                              tile list, the transposed copies of owned-owned pairs */
   int64_t tile_stage_max; /* most atoms one tile stages in shared memory */
+  int64_t tiles_interior; /* tiles that touch owned atoms only ... */
+  int64_t tiles_boundary; /* ... and tiles that stage ghosts or own atoms the reverse halo adds to */
+  int64_t halo_overlap;   /* 1: interior tiles run on a second stream beside the forward halo, the
+                             boundary tiles and the reverse halo (multi-GPU, tile list, B200_OVERLAP) */
 } b200_stats;
 int b200_get_stats(b200_ctx *ctx, b200_stats *out);
 

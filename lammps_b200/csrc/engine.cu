@@ -131,6 +131,13 @@ struct b200_ctx {
   DBuf<uint4> tl_list;
   int *tflags = nullptr;  // [8] device: max staged, max owned/tile, max entries, max FWD, owned total, overflow
   int tile_NI = 0, tile_scap = 0, tile_slots = 0, tile_threads = 256, tile_maxfull = 0;
+  // halo/compute overlap (multi-GPU, tile list): tiles that stage no ghost ("interior") run on
+  // stream2 while the forward halo, the boundary tiles and the reverse halo run on `stream`
+  DBuf<int> tile_bflag, tile_bpos, tile_ids;
+  int tile_nint = 0, tile_nbnd = 0;
+  bool overlap = true;  // B200_OVERLAP=0 disables
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // pair
   int pair_style = 0;  // 1 lj/cut, 2 eam
   std::vector<double> cutsq_h;
@@ -869,6 +876,7 @@ static void set_tile_geom(b200_ctx *ctx, const int t[3]) {
     G.t[d] = std::max(1, std::min(t[d], ctx->ibin_n[d]));
     G.nt[d] = cdiv(ctx->ibin_n[d], G.t[d]);
     G.ilo[d] = ctx->ibin_lo[d];
+    G.nib[d] = ctx->ibin_n[d];
     G.mbin[d] = ctx->geom.mbin[d];
     G.ntiles *= G.nt[d];
 
@@ -929,13 +937,27 @@ static int build_tiles(b200_ctx *ctx) {
       TRY(reserve(ctx, ctx->tile_ibase, (size_t)G.ntiles + 2));
       TRY(reserve(ctx, ctx->tilesum, (size_t)cdiv(std::max(G.ntiles, ctx->geom.mbins) + 1, SCAN_TILE) + 2));
       CK(cudaMemsetAsync(ctx->tflags, 0, 8 * sizeof(int), s));
-      k_tile_count<<<G.ntiles, 128, 0, s>>>(G, ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tflags);
+      TRY(reserve(ctx, ctx->tile_bflag, (size_t)G.ntiles + 2));
+      TRY(reserve(ctx, ctx->tile_bpos, (size_t)G.ntiles + 2));
+      TRY(reserve(ctx, ctx->tile_ids, (size_t)G.ntiles + 2));
+      k_tile_count<<<G.ntiles, 128, 0, s>>>(G, ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p,
+                                            ctx->tile_bflag.p, ctx->tflags);
       ctx->launches++;
       LAUNCH_CHECK();
       TRY(scan_inplace(ctx, ctx->tile_ibase.p, G.ntiles));
-      CK(cudaMemcpyAsync(ctx->h_flags + 8, ctx->tflags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
       CK(cudaMemcpyAsync(ctx->h_flags + 16, ctx->flags + 3, sizeof(int), cudaMemcpyDeviceToHost, s));
+      // interior / boundary split of the tile ids (exclusive scan of the boundary flags)
+      CK(cudaMemcpyAsync(ctx->tile_bpos.p, ctx->tile_bflag.p, sizeof(int) * G.ntiles, cudaMemcpyDeviceToDevice, s));
+      TRY(scan_inplace(ctx, ctx->tile_bpos.p, G.ntiles));
+      k_tile_split<<<cdiv(G.ntiles, 256), 256, 0, s>>>(G.ntiles, ctx->tile_bflag.p, ctx->tile_bpos.p,
+                                                      ctx->tile_ids.p);
+      ctx->launches++;
+      LAUNCH_CHECK();
+      CK(cudaMemcpyAsync(ctx->h_flags + 17, ctx->flags + 3, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(ctx->h_flags + 8, ctx->tflags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
+      ctx->tile_nbnd = ctx->h_flags[17];
+      ctx->tile_nint = G.ntiles - ctx->tile_nbnd;
       memcpy(h, ctx->h_flags + 8, sizeof h);
       if (h[4] != nl)
         return ctx->fail(B200_ELOST, "bin tiles cover %d of %d owned atoms", h[4], nl);
@@ -1339,11 +1361,69 @@ static int forward_scalar(b200_ctx *ctx, double *a) {
   return B200_OK;
 }
 
-static int pair_compute(b200_ctx *ctx, int eflag, int vflag) {
+// lj/cut over `ntiles` tiles of the tile list (ids == nullptr: all tiles in order) on stream s
+static int launch_tile_lj(b200_ctx *ctx, cudaStream_t s, int eflag, const int *ids, int ntiles) {
+  if (ntiles <= 0) return B200_OK;
+  const TileGeom &G = ctx->tg;
+  const int nl = ctx->nlocal, c = ctx->cur, thr = ctx->tile_threads, scap = ctx->tile_scap;
+  const size_t sm = tile_smem_bytes(scap, G.srow_y * G.srow_z, G.sbx, false, false);
+  const bool one = ctx->ntypes == 1, mixed = ctx->prec == B200_PREC_MIXED;
+#define TLJ(EV, ONE, MX)                                                                            \
+  k_tile_lj<EV, ONE, MX><<<ntiles, thr, sm, s>>>(                                                   \
+      G, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tile_NI,             \
+      ctx->tile_slots, ctx->tl_iloc.p, ctx->tl_num.p, ctx->tl_list.p, ctx->f[0], ctx->f[1],         \
+      ctx->f[2], ctx->lj_one, ctx->lj_onef, ctx->lj_tab.p, ctx->lj_tabf.p, ctx->ntypes, ctx->ev,    \
+      scap, ctx->tflags, ids)
+#define TLJ2(EV, ONE) if (mixed) TLJ(EV, ONE, true); else TLJ(EV, ONE, false)
+  if (one) { if (eflag) { TLJ2(true, true); } else { TLJ2(false, true); } }
+  else     { if (eflag) { TLJ2(true, false); } else { TLJ2(false, false); } }
+#undef TLJ2
+#undef TLJ
+  ctx->launches++;
+  LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// Can this step run the interior tiles beside the halo?  (per-phase profiling times one stream,
+// so it keeps everything on it)
+static bool overlap_active(const b200_ctx *ctx) {
+  return ctx->overlap && ctx->tiles_active && ctx->pair_style == 1 && ctx->remote_mask &&
+         !ctx->profiling && ctx->tile_nint > 0 && ctx->tile_nbnd > 0;
+}
+
+// fork: interior tiles on stream2, after everything enqueued on `stream` so far
+static int pair_interior_async(b200_ctx *ctx, int eflag, int vflag) {
+  if (eflag || vflag) CK(cudaMemsetAsync(ctx->ev, 0, 7 * sizeof(double), ctx->stream));
+  CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+  TRY(launch_tile_lj(ctx, ctx->stream2, eflag, ctx->tile_ids.p, ctx->tile_nint));
+  CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+  return B200_OK;
+}
+
+// part 0: the whole pair computation on `stream`; part 1: boundary tiles only (the interior
+// tiles were forked by pair_interior_async, which also cleared the tallies); the join happens
+// before the virial (it reads every force) or is left to the caller (*joined = false)
+static int pair_compute(b200_ctx *ctx, int eflag, int vflag, int part = 0, bool *joined = nullptr) {
   const int nl = ctx->nlocal, ng = ctx->nghost, c = ctx->cur;
   cudaStream_t s = ctx->stream;
   const bool ev = eflag || vflag;
   const bool mixed = ctx->prec == B200_PREC_MIXED;
+  if (joined) *joined = true;
+  if (part == 1) {
+    const int ph6 = ph_begin(ctx, B200_PH_PAIR);
+    TRY(launch_tile_lj(ctx, s, eflag, ctx->tile_ids.p + ctx->tile_nint, ctx->tile_nbnd));
+    ph_end(ctx, ph6);
+    if (vflag && nl + ng > 0) {
+      CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+      const int gv = std::min(cdiv(nl + ng, 256), 148 * 8);
+      k_virial_fdotr<<<gv, 256, 0, s>>>(nl + ng, ctx->xt[c], ctx->f[0], ctx->f[1], ctx->f[2], ctx->ev);
+      ctx->launches++;
+      LAUNCH_CHECK();
+    } else if (joined)
+      *joined = false;
+    return B200_OK;
+  }
   if (ev) CK(cudaMemsetAsync(ctx->ev, 0, 7 * sizeof(double), s));
   const int ph6 = ph_begin(ctx, B200_PH_PAIR);
   double4 *xt = ctx->xt[c];
@@ -1359,29 +1439,17 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag) {
     const uint4 *tl = ctx->tl_list.p;
     const int NI = ctx->tile_NI, slots = ctx->tile_slots, scap = ctx->tile_scap;
     if (ctx->pair_style == 1) {
-      const size_t sm = tile_smem_bytes(scap, rows, G.sbx, false, false);
-      const bool one = ctx->ntypes == 1;
-#define TLJ(EV, ONE, MX)                                                                              \
-  k_tile_lj<EV, ONE, MX><<<G.ntiles, thr, sm, s>>>(G, nl, xt, ctx->ostart.p, ctx->gstart.p, ib, NI,   \
-                                                   slots, il, tn, tl, fx, fy, fz, ctx->lj_one,        \
-                                                   ctx->lj_onef, ctx->lj_tab.p, ctx->lj_tabf.p,       \
-                                                   ctx->ntypes, ctx->ev, scap, ctx->tflags)
-#define TLJ2(EV, ONE) if (mixed) TLJ(EV, ONE, true); else TLJ(EV, ONE, false)
-      if (one) { if (eflag) { TLJ2(true, true); } else { TLJ2(false, true); } }
-      else     { if (eflag) { TLJ2(true, false); } else { TLJ2(false, false); } }
-#undef TLJ2
-#undef TLJ
-      ctx->launches++;
+      TRY(launch_tile_lj(ctx, s, eflag, nullptr, G.ntiles));
     } else if (ctx->pair_style == 2) {
       const size_t sm1 = tile_smem_bytes(scap, rows, G.sbx, false, false);
       const size_t sm3 = tile_smem_bytes(scap, rows, G.sbx, false, true);
       if (ng > 0) CK(cudaMemsetAsync(ctx->rho + nl, 0, sizeof(double) * ng, s));
       if (mixed)
         k_tile_eam_rho<true><<<G.ntiles, thr, sm1, s>>>(G, nl, xt, ctx->ostart.p, ctx->gstart.p, ib, NI, slots,
-                                                        il, tn, tl, ctx->eam, ctx->eamf, ctx->rho, scap, ctx->tflags);
+                                                        il, tn, tl, ctx->eam, ctx->eamf, ctx->rho, scap, ctx->tflags, nullptr);
       else
         k_tile_eam_rho<false><<<G.ntiles, thr, sm1, s>>>(G, nl, xt, ctx->ostart.p, ctx->gstart.p, ib, NI, slots,
-                                                         il, tn, tl, ctx->eam, ctx->eamf, ctx->rho, scap, ctx->tflags);
+                                                         il, tn, tl, ctx->eam, ctx->eamf, ctx->rho, scap, ctx->tflags, nullptr);
       {
         Vec3Ptr r{{ctx->rho, nullptr, nullptr}};
         TRY(reverse_halo<1>(ctx, r));
@@ -1395,7 +1463,7 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag) {
 #define TEF(EV, MX)                                                                                    \
   k_tile_eam_force<EV, MX><<<G.ntiles, thr, sm3, s>>>(G, nl, xt, ctx->ostart.p, ctx->gstart.p, ib, NI, \
                                                       slots, il, tn, tl, ctx->eam, ctx->eamf, ctx->fp, \
-                                                      fx, fy, fz, ctx->ev, scap, ctx->tflags)
+                                                      fx, fy, fz, ctx->ev, scap, ctx->tflags, nullptr)
       if (eflag) { if (mixed) TEF(true, true); else TEF(true, false); }
       else       { if (mixed) TEF(false, true); else TEF(false, false); }
 #undef TEF
@@ -1630,7 +1698,16 @@ int b200_create(b200_ctx **out, int device, int precision) {
   *out = ctx;
   if (precision != B200_PREC_DOUBLE && precision != B200_PREC_MIXED)
     return ctx->fail(B200_EARG, "unknown precision mode %d", precision);
-  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  {
+    // `stream` carries the step (and the halo); stream2 only ever runs interior tiles beside it
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, lo));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    if (const char *e = getenv("B200_OVERLAP")) ctx->overlap = atoi(e) != 0;
+  }
   TRY(dalloc(ctx, &ctx->ev, 8));
   TRY(dalloc(ctx, &ctx->flags, 4));
   TRY(dalloc(ctx, &ctx->tflags, 8));
@@ -1655,6 +1732,7 @@ int b200_create(b200_ctx **out, int device, int precision) {
 void b200_destroy(b200_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   auto F = [](auto *p) { if (p) cudaFree((void *)p); };
   for (int b = 0; b < 2; b++) {
@@ -1679,6 +1757,10 @@ void b200_destroy(b200_ctx *ctx) {
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   for (auto &r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->evpool) cudaEventDestroy(e);
+  F(ctx->tile_bflag.p); F(ctx->tile_bpos.p); F(ctx->tile_ids.p);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1979,13 +2061,22 @@ static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt) {
   TRY(initial_integrate(ctx, chk));
   int nflag = 0;
   TRY(decide(ctx, &nflag));
-  if (!nflag)
-    TRY(forward_comm(ctx));
-  else
-    TRY(reneighbor(ctx));
-  TRY(force_clear(ctx));
-  TRY(pair_compute(ctx, eflag, vflag));
-  TRY(reverse_comm(ctx));
+  if (nflag) TRY(reneighbor(ctx));
+  if (overlap_active(ctx)) {
+    // interior tiles start now; halo, boundary tiles and the reverse halo overlap with them
+    bool joined = false;
+    TRY(pair_interior_async(ctx, eflag, vflag));
+    if (!nflag) TRY(forward_comm(ctx));
+    TRY(force_clear(ctx));
+    TRY(pair_compute(ctx, eflag, vflag, 1, &joined));
+    TRY(reverse_comm(ctx));
+    if (!joined) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  } else {
+    if (!nflag) TRY(forward_comm(ctx));
+    TRY(force_clear(ctx));
+    TRY(pair_compute(ctx, eflag, vflag));
+    TRY(reverse_comm(ctx));
+  }
   // FixNVE::final_integrate: on steps whose velocities nobody reads (no tallies) it is deferred
   // and fused with the next step's initial_integrate (k_nve_final_initial)
   if (eflag || vflag)
@@ -2103,6 +2194,10 @@ int b200_get_stats(b200_ctx *ctx, b200_stats *out) {
   if (ctx->tiles_active) {
     for (int d = 0; d < 3; d++) out->tile[d] = ctx->tg.t[d];
     out->tile_stage_max = ctx->tile_scap;
+    out->tiles_interior = ctx->tile_nint;
+    out->tiles_boundary = ctx->tile_nbnd;
+    out->halo_overlap = ctx->overlap && ctx->pair_style == 1 && ctx->remote_mask && ctx->tile_nint > 0 &&
+                        ctx->tile_nbnd > 0;
     // entries = sum of the list-row lengths (FWD members + transposed copies)
     CK(cudaMemsetAsync(ctx->cnt64, 0, sizeof(unsigned long long), ctx->stream));
     k_sum_u16<<<std::min(cdiv(ctx->tile_NI, 256), 1184), 256, 0, ctx->stream>>>(ctx->tile_NI, ctx->tl_num.p,

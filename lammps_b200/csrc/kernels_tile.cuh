@@ -52,6 +52,7 @@ struct TileGeom {
   int t[3];     // tile size in bins
   int nt[3];    // tiles per dimension
   int ilo[3];   // first local bin (per dim) that can hold an owned atom
+  int nib[3];   // number of such bins per dim (the first and last may also hold ghosts)
   int s[3];     // stencil half width in bins (NStencil::sx,sy,sz, nstencil.cpp:203-237)
   int mbin[3];  // local bin grid
   int ntiles, srow_y, srow_z, sbx;  // staged rows along y and z, staged bins per row
@@ -351,17 +352,42 @@ __device__ __forceinline__ void tile_walk(const uint4 *__restrict__ list, int g,
 __global__ void __launch_bounds__(128) k_tile_count(TileGeom G, const int *__restrict__ ostart,
                                                     const int *__restrict__ gstart,
                                                     int *__restrict__ tile_ibase,
+                                                    int *__restrict__ tile_bflag,
                                                     int *__restrict__ tflags) {
   __shared__ TileHdr H;
   const TilePos P = tile_pos(G, blockIdx.x);
   const int S = tile_rows(G, P, ostart, gstart, &H);
+  // "boundary" tile: it stages a ghost (must wait for the forward halo) or its staged bins reach
+  // the first/last owned bin of a dimension -- then it may own atoms within the ghost cutoff of a
+  // face, whose forces the reverse halo adds to (2 bins >= cutghost, nbin_standard.cpp:82-214).
+  // Every other tile touches owned atoms only and can run beside the halo.
+  int ghosts = 0;
+  for (int r = threadIdx.x; r < H.nrows; r += blockDim.x) ghosts |= H.row_ng[r] > 0;
+  const int t0[3] = {P.tx0, P.ty0, P.tz0};
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+    ghosts |= (t0[d] - G.s[d] <= G.ilo[d]) || (t0[d] + G.t[d] - 1 + G.s[d] >= G.ilo[d] + G.nib[d] - 1);
+  ghosts = __syncthreads_or(ghosts);
   if (threadIdx.x == 0) {
+    tile_bflag[blockIdx.x] = ghosts ? 1 : 0;
     const int ni = H.ni;
     tile_ibase[blockIdx.x] = (ni + 31) / 32 * 32;
     atomicMax(&tflags[0], S);
     atomicMax(&tflags[1], ni);
     atomicAdd(&tflags[4], ni);
   }
+}
+
+// tile ids ordered interior first, boundary last (both ascending, i.e. still in spatial order);
+// bpos = exclusive scan of the boundary flags, bpos[ntiles] = number of boundary tiles
+__global__ void __launch_bounds__(256) k_tile_split(int ntiles, const int *__restrict__ bflag,
+                                                    const int *__restrict__ bpos,
+                                                    int *__restrict__ ids) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const int nint = ntiles - bpos[ntiles];
+  if (bflag[t]) ids[nint + bpos[t]] = t;
+  else ids[t - bpos[t]] = t;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -546,11 +572,12 @@ __global__ void __launch_bounds__(352, TILE_MINB) k_tile_lj(
     const uint4 *__restrict__ list, double *__restrict__ fx, double *__restrict__ fy,
     double *__restrict__ fz, LJOne one, LJOneF onef, const double *__restrict__ tab,
     const float *__restrict__ tabf, int ntypes, double *__restrict__ ev, int scap,
-    int *__restrict__ tflags) {
+    int *__restrict__ tflags,
+    const int *__restrict__ tile_ids) {
   extern __shared__ __align__(128) unsigned char tsm[];
   TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
   const TileS T = tile_carve(tsm, scap, false);
-  const int tile = blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
+  const int tile = tile_ids ? tile_ids[blockIdx.x] : blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
   const TilePos P = tile_pos(G, tile);
   const int S = tile_rows(G, P, ostart, gstart, H);
   if (S > scap) {  // cannot happen between rebuilds (the rows are those the build staged)
@@ -664,11 +691,12 @@ __global__ void __launch_bounds__(352, TILE_MINB) k_tile_eam_rho(
     const int *__restrict__ gstart, const int *__restrict__ tile_ibase, int NI, int maxslots,
     const unsigned short *__restrict__ iloc, const unsigned short *__restrict__ tnum,
     const uint4 *__restrict__ list, EAMParams P, EAMParamsF F, double *__restrict__ rho, int scap,
-    int *__restrict__ tflags) {
+    int *__restrict__ tflags,
+    const int *__restrict__ tile_ids) {
   extern __shared__ __align__(128) unsigned char tsm[];
   TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
   const TileS T = tile_carve(tsm, scap, false);
-  const int tile = blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
+  const int tile = tile_ids ? tile_ids[blockIdx.x] : blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
   const TilePos Tp = tile_pos(G, tile);
   const int S = tile_rows(G, Tp, ostart, gstart, H);
   if (S > scap) {
@@ -736,12 +764,13 @@ __global__ void __launch_bounds__(352, TILE_MINB) k_tile_eam_force(
     const unsigned short *__restrict__ iloc, const unsigned short *__restrict__ tnum,
     const uint4 *__restrict__ list, EAMParams P, EAMParamsF F, const double *__restrict__ fp,
     double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
-    double *__restrict__ ev, int scap, int *__restrict__ tflags) {
+    double *__restrict__ ev, int scap, int *__restrict__ tflags,
+    const int *__restrict__ tile_ids) {
   extern __shared__ __align__(128) unsigned char tsm[];
   TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
   const TileS T = tile_carve(tsm, scap, true);
   const double *sfp = T.fp;
-  const int tile = blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
+  const int tile = tile_ids ? tile_ids[blockIdx.x] : blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
   const TilePos Tp = tile_pos(G, tile);
   const int S = tile_rows(G, Tp, ostart, gstart, H);
   if (S > scap) {

@@ -45,7 +45,8 @@ class Stats(C.Structure):
                 ("launches", C.c_int64), ("device_bytes", C.c_double),
                 ("halo_transport", C.c_int64), ("lanes_per_atom", C.c_int64),
                 ("list_kind", C.c_int64), ("tile", C.c_int64 * 3), ("list_entries", C.c_int64),
-                ("tile_stage_max", C.c_int64)]
+                ("tile_stage_max", C.c_int64), ("tiles_interior", C.c_int64),
+                ("tiles_boundary", C.c_int64), ("halo_overlap", C.c_int64)]
 
 
 _lib = None
