@@ -136,6 +136,7 @@ struct b200_ctx {
   DBuf<int> tile_bflag, tile_bpos, tile_ids;
   int tile_nint = 0, tile_nbnd = 0;
   bool overlap = true;  // B200_OVERLAP=0 disables
+  bool mixed_fx = true; // mixed lj/cut on tiles: fixed-point staged positions (B200_MIXED_FX=0: FP64 staging)
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // pair
@@ -879,7 +880,17 @@ static void set_tile_geom(b200_ctx *ctx, const int t[3]) {
     G.nib[d] = ctx->ibin_n[d];
     G.mbin[d] = ctx->geom.mbin[d];
     G.ntiles *= G.nt[d];
+    G.bsize[d] = ctx->prd[d] / ctx->geom.nbin[d];
+    G.bin0[d] = ctx->boxlo[d] + ctx->geom.mbinlo[d] * G.bsize[d];
 
+  }
+  {
+    // fixed-point staging (k_tile_lj_fx): the staged bins plus a pad of one neighbour cutoff on
+    // either side must fit 31 bits; power-of-two scale so that (x - origin) * scale is exact
+    double ext = 0.0;
+    for (int d = 0; d < 3; d++) ext = std::max(ext, (G.t[d] + 2 * G.s[d]) * G.bsize[d]);
+    G.fxpad = ctx->cutneighmax;
+    G.fxscale = std::ldexp(1.0, (int)std::floor(std::log2(2147483000.0 / (ext + 2.0 * G.fxpad))));
   }
   G.srow_y = G.t[1] + 2 * G.s[1];
   G.srow_z = G.t[2] + 2 * G.s[2];
@@ -903,6 +914,10 @@ static int tile_kernel_attrs(b200_ctx *ctx) {
   TRY(tile_attr(ctx, K<true, true, false>));   TRY(tile_attr(ctx, K<true, true, true>));
   A3(k_tile_lj)
 #undef A3
+  TRY(tile_attr(ctx, k_tile_lj_fx<false, false>));
+  TRY(tile_attr(ctx, k_tile_lj_fx<false, true>));
+  TRY(tile_attr(ctx, k_tile_lj_fx<true, false>));
+  TRY(tile_attr(ctx, k_tile_lj_fx<true, true>));
   TRY(tile_attr(ctx, k_tile_eam_rho<false>));
   TRY(tile_attr(ctx, k_tile_eam_rho<true>));
   TRY(tile_attr(ctx, k_tile_eam_force<false, false>));
@@ -1374,10 +1389,17 @@ static int launch_tile_lj(b200_ctx *ctx, cudaStream_t s, int eflag, const int *i
       ctx->tile_slots, ctx->tl_iloc.p, ctx->tl_num.p, ctx->tl_list.p, ctx->f[0], ctx->f[1],         \
       ctx->f[2], ctx->lj_one, ctx->lj_onef, ctx->lj_tab.p, ctx->lj_tabf.p, ctx->ntypes, ctx->ev,    \
       scap, ctx->tflags, ids)
-#define TLJ2(EV, ONE) if (mixed) TLJ(EV, ONE, true); else TLJ(EV, ONE, false)
+#define TLJFX(EV, ONE)                                                                              \
+  k_tile_lj_fx<EV, ONE><<<ntiles, thr, tile_smem_bytes_fx(scap), s>>>(                              \
+      G, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tile_NI,             \
+      ctx->tile_slots, ctx->tl_iloc.p, ctx->tl_num.p, ctx->tl_list.p, ctx->f[0], ctx->f[1],         \
+      ctx->f[2], ctx->lj_one, ctx->lj_onef, ctx->lj_tab.p, ctx->lj_tabf.p, ctx->ntypes, ctx->ev,    \
+      scap, ctx->tflags, ids)
+#define TLJ2(EV, ONE) if (mixed && ctx->mixed_fx) TLJFX(EV, ONE); else if (mixed) TLJ(EV, ONE, true); else TLJ(EV, ONE, false)
   if (one) { if (eflag) { TLJ2(true, true); } else { TLJ2(false, true); } }
   else     { if (eflag) { TLJ2(true, false); } else { TLJ2(false, false); } }
 #undef TLJ2
+#undef TLJFX
 #undef TLJ
   ctx->launches++;
   LAUNCH_CHECK();
@@ -1707,6 +1729,7 @@ int b200_create(b200_ctx **out, int device, int precision) {
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     if (const char *e = getenv("B200_OVERLAP")) ctx->overlap = atoi(e) != 0;
+    if (const char *e = getenv("B200_MIXED_FX")) ctx->mixed_fx = atoi(e) != 0;
   }
   TRY(dalloc(ctx, &ctx->ev, 8));
   TRY(dalloc(ctx, &ctx->flags, 4));

@@ -56,6 +56,9 @@ struct TileGeom {
   int s[3];     // stencil half width in bins (NStencil::sx,sy,sz, nstencil.cpp:203-237)
   int mbin[3];  // local bin grid
   int ntiles, srow_y, srow_z, sbx;  // staged rows along y and z, staged bins per row
+  // fixed-point staging of the mixed-precision lj kernel: q = rn((x - origin) * fxscale),
+  // origin = lower corner of the tile's staged bins minus fxpad
+  double bin0[3], bsize[3], fxpad, fxscale;
 };
 
 // all (dy,dz) rows of the stencil, both halves: bins with bin_distance < cutneighmaxsq
@@ -896,6 +899,187 @@ __global__ void __launch_bounds__(352, TILE_MINB) k_tile_eam_force(
     double v[1] = {evdwl};
     __syncthreads();
     block_sum<1>(v, T.x);
+    if (tid == 0) atomicAdd(&ev[0], v[0]);
+  }
+}
+
+// tile_walk for the fixed-point kernel: four branch-free bodies per step; a body returns true
+// when its cutoff decision must be re-taken in FP64 (then `exact(e)` adds that entry's
+// contribution), FWD|GHOST entries additionally call `ghost(e)`.  Both are rare.
+template <class Body, class Exact, class Ghost>
+__device__ __forceinline__ void tile_walk_fx(const uint4 *__restrict__ list, int g, int n, int NI,
+                                             Body &&body, Exact &&exact, Ghost &&ghost) {
+  const uint4 *lp = list + g;
+  uint4 q = n > 0 ? __ldg(lp) : make_uint4(0, 0, 0, 0);
+  for (int k0 = 0; k0 < n; k0 += 8) {
+    const uint4 c = q;
+    if (k0 + 8 < n) q = __ldg(lp + (size_t)((k0 >> 3) + 1) * NI);
+    auto step4 = [&](unsigned w0, unsigned w1, int kb) {
+      const bool a0 = body(w0 & 0xffffu, kb < n), a1 = body(w0 >> 16, kb + 1 < n);
+      const bool a2 = body(w1 & 0xffffu, kb + 2 < n), a3 = body(w1 >> 16, kb + 3 < n);
+      if (a0 | a1 | a2 | a3) {
+        if (a0) exact(w0 & 0xffffu);
+        if (a1) exact(w0 >> 16);
+        if (a2) exact(w1 & 0xffffu);
+        if (a3) exact(w1 >> 16);
+      }
+      if ((w0 | w1) & (TILE_GHOST | (TILE_GHOST << 16))) {
+        if ((w0 & TILE_GHOST) && kb < n) ghost(w0 & 0xffffu);
+        if ((w0 & (TILE_GHOST << 16)) && kb + 1 < n) ghost(w0 >> 16);
+        if ((w1 & TILE_GHOST) && kb + 2 < n) ghost(w1 & 0xffffu);
+        if ((w1 & (TILE_GHOST << 16)) && kb + 3 < n) ghost(w1 >> 16);
+      }
+    };
+    step4(c.x, c.y, k0);
+    asm volatile("" ::: "memory");
+    step4(c.z, c.w, k0 + 4);
+    asm volatile("" ::: "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// lj/cut over a tile, mixed precision with fixed-point staging.
+// Positions are staged as int32 fixed point relative to the tile corner (resolution
+// 1/fxscale ~ 1.5e-8 sigma for 8x8x4 tiles: finer than an FP32 coordinate, and differences of
+// two staged coordinates are exact), 12 bytes per atom instead of 24: half the shared-memory
+// wavefronts that bound the FP64 kernel, and no FP64 instruction in the common path.
+// del = float(q_i - q_j) / fxscale, rsq and the pair function in FP32.  A cutoff decision
+// within 2e-6 (relative) of the cutoff is re-taken in FP64 from the global positions with the
+// reference's operation order, so the set of interacting pairs is still the CPU path's.
+// Tolerances (BASELINE.json): forces <= 1e-5 relative, energy/pressure <= 1e-6.
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ size_t tile_smem_bytes_fx(int scap) {
+  return (TILE_HDR_BYTES + (size_t)scap * 5 * sizeof(int) + 127) / 128 * 128;
+}
+
+#ifndef TILE_FX_MINB
+#define TILE_FX_MINB 2
+#endif
+template <bool EV, bool ONETYPE>
+__global__ void __launch_bounds__(352, TILE_FX_MINB) k_tile_lj_fx(
+    TileGeom G, int nlocal, const double4 *__restrict__ xt, const int *__restrict__ ostart,
+    const int *__restrict__ gstart, const int *__restrict__ tile_ibase, int NI, int maxslots,
+    const unsigned short *__restrict__ iloc, const unsigned short *__restrict__ tnum,
+    const uint4 *__restrict__ list, double *__restrict__ fx, double *__restrict__ fy,
+    double *__restrict__ fz, LJOne one, LJOneF onef, const double *__restrict__ tab,
+    const float *__restrict__ tabf, int ntypes, double *__restrict__ ev, int scap,
+    int *__restrict__ tflags, const int *__restrict__ tile_ids) {
+  extern __shared__ __align__(128) unsigned char tsm[];
+  TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
+  int *qx = reinterpret_cast<int *>(tsm + TILE_HDR_BYTES), *qy = qx + scap, *qz = qy + scap;
+  int *stype = qz + scap, *gmap = stype + scap;
+  const int tile = tile_ids ? tile_ids[blockIdx.x] : blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
+  const TilePos P = tile_pos(G, tile);
+  const int S = tile_rows(G, P, ostart, gstart, H);
+  if (S > scap) {
+    if (tid == 0) atomicMax(&tflags[5], S);
+    return;
+  }
+  {  // stage: one warp per run, LDG.256 of the record, fixed-point conversion, STS.32
+    const double ox = G.bin0[0] + (P.tx0 - G.s[0]) * G.bsize[0] - G.fxpad,
+                 oy = G.bin0[1] + (P.ty0 - G.s[1]) * G.bsize[1] - G.fxpad,
+                 oz = G.bin0[2] + (P.tz0 - G.s[2]) * G.bsize[2] - G.fxpad;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = bd >> 5, nrows = H->nrows;
+    for (int r = warp; r < nrows; r += nwarp) {
+      const int base = H->rowbase[r], no = H->row_no[r], n = no + H->row_ng[r];
+      const int o0 = H->row_o0[r], g0 = nlocal + H->row_g0[r] - no;
+      for (int k = lane; k < n; k += 32) {
+        const int src = k < no ? o0 + k : g0 + k, s = base + k;
+        const double4 p = ld_xt(xt + src);
+        qx[s] = __double2int_rn((p.x - ox) * G.fxscale);
+        qy[s] = __double2int_rn((p.y - oy) * G.fxscale);
+        qz[s] = __double2int_rn((p.z - oz) * G.fxscale);
+        stype[s] = d2type(p.w);
+        gmap[s] = src;
+      }
+    }
+    __syncthreads();
+  }
+  const int ni = H->ni, ibase = tile_ibase[tile];
+  const int n1 = ntypes + 1, n2 = n1 * n1;
+  const float inv = (float)(1.0 / G.fxscale);
+  double evdwl = 0.0;
+  for (int ti = tid; ti < ni; ti += bd) {
+    const int g = ibase + ti;
+    const int li = iloc[g];
+    const int n = min((int)tnum[g], maxslots);
+    const int xi = qx[li], yi = qy[li], zi = qz[li];
+    const int gi = gmap[li];
+    const int itype = stype[li];
+    float gxi = 0.0f, gyi = 0.0f, gzi = 0.0f, ei = 0.0f;
+    // FP32 pair function of entry e; `in` decided by the caller
+    auto lj = [&](float rsq, int tij, bool in, bool fwd, float &fpair, float &epair) {
+      const float lj1 = ONETYPE ? onef.lj1 : __ldg(tabf + tij);
+      const float lj2 = ONETYPE ? onef.lj2 : __ldg(tabf + n2 + tij);
+      const float r2inv = rcp_f(rsq);
+      const float r6inv = r2inv * r2inv * r2inv;
+      fpair = in ? r6inv * (lj1 * r6inv - lj2) * r2inv : 0.0f;
+      if (EV) {
+        const float lj3 = ONETYPE ? onef.lj3 : __ldg(tabf + 2 * n2 + tij);
+        const float lj4 = ONETYPE ? onef.lj4 : __ldg(tabf + 3 * n2 + tij);
+        const float off = ONETYPE ? onef.offset : __ldg(tabf + 4 * n2 + tij);
+        epair = (in && fwd) ? r6inv * (lj3 * r6inv - lj4) - off : 0.0f;
+      }
+    };
+    auto geom = [&](int j, float &delx, float &dely, float &delz, float &rsq, int &tij, float &cutsq) {
+      delx = (float)(xi - qx[j]) * inv;
+      dely = (float)(yi - qy[j]) * inv;
+      delz = (float)(zi - qz[j]) * inv;
+      rsq = delx * delx + dely * dely + delz * delz;
+      tij = 0;
+      cutsq = (float)one.cutsq;
+      if (!ONETYPE) {
+        tij = itype * n1 + stype[j];
+        cutsq = (float)__ldg(tab + tij);
+      }
+    };
+    // the reference's FP64 cutoff test, from the global positions (rare: |rsq - cutsq| tiny)
+    auto exact_in = [&](int j, int tij) -> bool {
+      const double4 a = ld_xt(xt + gi), b = ld_xt(xt + gmap[j]);
+      return rsq_ref(a.x - b.x, a.y - b.y, a.z - b.z) < (ONETYPE ? one.cutsq : __ldg(tab + tij));
+    };
+    tile_walk_fx(
+        list, g, n, NI,
+        [&](unsigned e, bool valid) -> bool {  // fast path; returns "too close to call"
+          float delx, dely, delz, rsq, cutsq, f32, ep = 0.0f;
+          int tij;
+          geom(e & TILE_IDX, delx, dely, delz, rsq, tij, cutsq);
+          const bool amb = valid && fabsf(rsq - cutsq) < 2.0e-6f * cutsq;
+          lj(rsq, tij, valid && !amb && rsq < cutsq, e & TILE_FWD, f32, ep);
+          gxi += delx * f32; gyi += dely * f32; gzi += delz * f32;
+          if (EV) ei += ep;
+          return amb;
+        },
+        [&](unsigned e) {  // an ambiguous entry: decide in FP64, then the same FP32 pair function
+          float delx, dely, delz, rsq, cutsq, f32, ep = 0.0f;
+          int tij;
+          geom(e & TILE_IDX, delx, dely, delz, rsq, tij, cutsq);
+          lj(rsq, tij, exact_in(e & TILE_IDX, tij), e & TILE_FWD, f32, ep);
+          gxi += delx * f32; gyi += dely * f32; gzi += delz * f32;
+          if (EV) ei += ep;
+        },
+        [&](unsigned e) {  // Newton scatter onto a ghost; the reverse halo returns it to the owner
+          float delx, dely, delz, rsq, cutsq, f32, ep = 0.0f;
+          int tij;
+          const int j = e & TILE_IDX;
+          geom(j, delx, dely, delz, rsq, tij, cutsq);
+          bool in = rsq < cutsq;
+          if (fabsf(rsq - cutsq) < 2.0e-6f * cutsq) in = exact_in(j, tij);
+          lj(rsq, tij, in, false, f32, ep);
+          const int gj = gmap[j];
+          atomicAdd(&fx[gj], -(double)(delx * f32));
+          atomicAdd(&fy[gj], -(double)(dely * f32));
+          atomicAdd(&fz[gj], -(double)(delz * f32));
+        });
+    fx[gi] = (double)gxi;
+    fy[gi] = (double)gyi;
+    fz[gi] = (double)gzi;
+    if (EV) evdwl += (double)ei;  // <= ~110 terms per atom in FP32, FP64 across atoms
+  }
+  if (EV) {
+    double v[1] = {evdwl};
+    __syncthreads();
+    block_sum<1>(v, reinterpret_cast<double *>(tsm + TILE_HDR_BYTES));
     if (tid == 0) atomicAdd(&ev[0], v[0]);
   }
 }

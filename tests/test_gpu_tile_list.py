@@ -87,3 +87,41 @@ def test_tile_list_mixed_precision(kind, cells):
     assert np.abs(fe - fo).max() <= 1e-5 * np.abs(fo).max()
     eng, vir = e.tallies()
     assert abs(eng - o.eng_vdwl) <= 1e-6 * abs(o.eng_vdwl)
+
+
+@pytest.mark.parametrize("env", [{"B200_MIXED_FX": "1"}, {"B200_MIXED_FX": "0"}, {"B200_LIST": "flat"}],
+                         ids=["tile-fixedpoint", "tile-fp64-staged", "flat"])
+def test_lj_mixed_variants_meet_the_mixed_tolerances(env):
+    """every mixed lj/cut kernel (fixed-point staged tile, FP64-staged tile, flat list) against the
+    FP64 oracle: same pair set, forces <= 1e-5 (norm-wise), energy <= 1e-6, and a 60-step run
+    that stays on the oracle's trajectory to 1e-4 sigma"""
+    s = melted(lj_system((11, 9, 10)), 40)
+    o = make_oracle(s)
+    o.setup(1, 1)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        e = make_engine(s, "mixed")
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    e.setup(1, 1)
+    assert e.stats()["npairs"] == o.nneigh
+    a = e.get_atoms(fields=("f", "tag"))
+    (fe,) = by_tag(a["tag"], a["f"])
+    (fo,) = by_tag(o.tag(), o.f())
+    assert np.abs(fe - fo).max() <= 1e-5 * np.abs(fo).max()
+    eng, _ = e.tallies()
+    assert abs(eng - o.eng_vdwl) <= 1e-6 * abs(o.eng_vdwl)
+    e.run(60, 0)
+    o.run(60, 0, 0)
+    a = e.get_atoms(fields=("x", "tag"))
+    (xe,) = by_tag(a["tag"], a["x"])
+    (xo,) = by_tag(o.tag(), o.x())
+    prd = np.asarray(s["hi"]) - np.asarray(s["lo"])
+    d = xe - xo
+    d -= prd * np.rint(d / prd)
+    assert np.abs(d).max() < 1e-4
