@@ -154,18 +154,10 @@ __global__ void __launch_bounds__(128) k_eam_rho(int nlocal, int nstride,
     const int itype = d2type(pi.w), n1 = P.ntypes + 1;
     const int jnum = numneigh[i];
     const int *jl = neigh + (size_t)i * T + t;
-    // software pipeline: the neighbour record of the NEXT slot is requested before this slot's
-    // math and reduction, because loads are not hoisted above the RED of the previous pair
-    const size_t step = (size_t)nstride * T;
-    int jn = t < jnum ? jl[0] & NEIGHMASK : 0;
-    double4 pn = ld_xt(xt + jn);
+#pragma unroll 4
     for (int n = t, kk = 0; n < jnum; n += T, kk++) {
-      const int j = jn;
-      const double4 pj = pn;
-      if (n + T < jnum) {
-        jn = jl[(size_t)(kk + 1) * step] & NEIGHMASK;
-        pn = ld_xt(xt + jn);
-      }
+      const int j = jl[(size_t)kk * nstride * T] & NEIGHMASK;
+      const double4 pj = ld_xt(xt + j);
       const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
       const double rsq = rsq_ref(delx, dely, delz);
       if (rsq < P.cutforcesq) {
@@ -247,21 +239,10 @@ __global__ void __launch_bounds__(128) k_eam_force(int nlocal, int nstride,
     const int jnum = numneigh[i];
     const int *jl = neigh + (size_t)i * T + t;
     const double fpi = fp[i];
-    // software pipeline (see k_eam_rho): record and fp of the next neighbour are in flight
-    // while this pair is evaluated and scattered
-    const size_t step = (size_t)nstride * T;
-    int jn = t < jnum ? jl[0] & NEIGHMASK : 0;
-    double4 pn = ld_xt(xt + jn);
-    double fpn = __ldg(fp + jn);
+#pragma unroll 2
     for (int n = t, kk = 0; n < jnum; n += T, kk++) {
-      const int j = jn;
-      const double4 pj = pn;
-      const double fpj = fpn;
-      if (n + T < jnum) {
-        jn = jl[(size_t)(kk + 1) * step] & NEIGHMASK;
-        pn = ld_xt(xt + jn);
-        fpn = __ldg(fp + jn);
-      }
+      const int j = jl[(size_t)kk * nstride * T] & NEIGHMASK;
+      const double4 pj = ld_xt(xt + j);
       const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
       const double rsq = rsq_ref(delx, dely, delz);
       if (rsq < P.cutforcesq) {
@@ -286,7 +267,7 @@ __global__ void __launch_bounds__(128) k_eam_force(int nlocal, int nstride,
         const double recip = 1.0 / r;
         const double phi = z2 * recip;
         const double phip = z2p * recip - phi * recip;
-        const double psip = fpi * rhojp + fpj * rhoip + phip;
+        const double psip = fpi * rhojp + fp[j] * rhoip + phip;
         const double sc = P.scale[itype * n1 + jtype];
         const double fpair = -sc * psip * recip;
         fxi += delx * fpair;
