@@ -136,6 +136,11 @@ struct b200_ctx {
   DBuf<int> tile_bflag, tile_bpos, tile_ids;
   int tile_nint = 0, tile_nbnd = 0;
   bool overlap = true;  // B200_OVERLAP=0 disables
+  // CUDA graph of one plain timestep (no rebuild, no tallies, one sub-domain): small systems
+  // are launch-bound (bench/in.lj: 32 k atoms, ~9 launches of a few microseconds each)
+  bool use_graph = true;  // B200_GRAPH=0 disables
+  cudaGraphExec_t step_graph = nullptr;
+  int graph_launches = 0;
   bool mixed_fx = true; // mixed lj/cut on tiles: fixed-point staged positions (B200_MIXED_FX=0: FP64 staging)
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1089,9 +1094,19 @@ static int build_list(b200_ctx *ctx) {
   return ctx->fail(B200_ECAPACITY, "neighbor list did not converge");
 }
 
+// The captured timestep bakes in atom counts, buffer addresses and every kernel argument:
+// anything that can change one of them drops it (it is re-captured on the next plain step).
+static void drop_step_graph(b200_ctx *ctx) {
+  if (ctx->step_graph) {
+    cudaGraphExecDestroy(ctx->step_graph);
+    ctx->step_graph = nullptr;
+  }
+}
+
 // ------------------------------------------------------------------ reneighbor
 // Verlet::run rebuild branch (verlet.cpp:268-297): pbc, exchange, borders, neighbor->build.
 static int reneighbor(b200_ctx *ctx) {
+  drop_step_graph(ctx);
   if (!ctx->geom_ready) TRY(setup_geometry(ctx));
   const int ph2 = ph_begin(ctx, B200_PH_NEIGH);
   const Geom &g = ctx->geom;
@@ -1729,6 +1744,7 @@ int b200_create(b200_ctx **out, int device, int precision) {
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     if (const char *e = getenv("B200_OVERLAP")) ctx->overlap = atoi(e) != 0;
+    if (const char *e = getenv("B200_GRAPH")) ctx->use_graph = atoi(e) != 0;
     if (const char *e = getenv("B200_MIXED_FX")) ctx->mixed_fx = atoi(e) != 0;
   }
   TRY(dalloc(ctx, &ctx->ev, 8));
@@ -1781,6 +1797,7 @@ void b200_destroy(b200_ctx *ctx) {
   for (auto &r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->evpool) cudaEventDestroy(e);
   F(ctx->tile_bflag.p); F(ctx->tile_bpos.p); F(ctx->tile_ids.p);
+  if (ctx->step_graph) cudaGraphExecDestroy(ctx->step_graph);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -1792,6 +1809,7 @@ const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->err.c_str()
 
 int b200_set_box(b200_ctx *ctx, const double boxlo[3], const double boxhi[3], const int per[3]) {
   if (!ctx) return B200_EARG;
+  drop_step_graph(ctx);
   for (int d = 0; d < 3; d++) {
     if (!(boxhi[d] > boxlo[d])) return ctx->fail(B200_EARG, "box hi <= lo in dim %d", d);
     ctx->boxlo[d] = boxlo[d];
@@ -1825,6 +1843,7 @@ int b200_set_rank_grid(b200_ctx *ctx, const int *grid2rank, int n) {
 
 int b200_set_neighbor(b200_ctx *ctx, double skin, int every, int delay, int dist_check, int one) {
   if (!ctx) return B200_EARG;
+  drop_step_graph(ctx);
   if (skin < 0 || every < 1 || delay < 0) return ctx->fail(B200_EARG, "Illegal neighbor settings");
   ctx->skin = skin;
   ctx->every = every;
@@ -1839,6 +1858,7 @@ int b200_set_atoms(b200_ctx *ctx, int nlocal, int ntypes, const double *mass, co
                    const double *v, const int *type, const int *tag, const int *mask,
                    const int *image) {
   if (!ctx) return B200_EARG;
+  drop_step_graph(ctx);
   if (nlocal < 0 || ntypes < 1 || !mass || (nlocal && (!x || !v || !type || !tag)))
     return ctx->fail(B200_EARG, "b200_set_atoms: bad arguments");
   CK(cudaSetDevice(ctx->device));
@@ -1939,6 +1959,7 @@ int b200_pair_lj_cut(b200_ctx *ctx, int ntypes, const double *cutsq, const doubl
                      const double *lj2, const double *lj3, const double *lj4,
                      const double *offset, const double special_lj[4]) {
   if (!ctx) return B200_EARG;
+  drop_step_graph(ctx);
   if (ntypes < 1 || !cutsq || !lj1 || !lj2 || !lj3 || !lj4 || !offset)
     return ctx->fail(B200_EARG, "b200_pair_lj_cut: bad arguments");
   if (ntypes > 15) return ctx->fail(B200_EARG, "lj/cut/b200 supports at most 15 atom types");
@@ -1975,6 +1996,7 @@ int b200_pair_eam(b200_ctx *ctx, int ntypes, int nr, int nrho, double rdr, doubl
                   const int *type2z2r, const double *scale, int nfrho, const double *frho_spline,
                   int nrhor, const double *rhor_spline, int nz2r, const double *z2r_spline) {
   if (!ctx) return B200_EARG;
+  drop_step_graph(ctx);
   if (ntypes < 1 || nr < 2 || nrho < 2 || !type2frho || !type2rhor || !type2z2r || !scale ||
       !frho_spline || !rhor_spline || !z2r_spline)
     return ctx->fail(B200_EARG, "b200_pair_eam: bad arguments");
@@ -2029,6 +2051,7 @@ int b200_pair_eam(b200_ctx *ctx, int ntypes, int nr, int nrho, double rdr, doubl
 
 int b200_fix_nve(b200_ctx *ctx, double dtv, double dtf, int groupbit) {
   if (!ctx) return B200_EARG;
+  drop_step_graph(ctx);
   TRY(flush_final(ctx));  // a pending half-kick belongs to the old dtf
   ctx->dtv = dtv;
   ctx->dtf = dtf;
@@ -2078,7 +2101,57 @@ int b200_pair_compute(b200_ctx *ctx, int eflag, int vflag) {
 }
 
 // one iteration of Verlet::run (verlet.cpp:246-355) without the output stage
+// A plain timestep: no tallies, no displacement check due, no rebuild due (known on the host
+// when the schedule is `check no`), one sub-domain, final_integrate of the previous step
+// pending so that the fused integrate kernel opens the step.
+static bool plain_step(const b200_ctx *ctx, int eflag, int vflag) {
+  // (`check yes` schedules rebuild irregularly and often; re-instantiating the graph after every
+  // rebuild then costs more than it saves -- measured on bench/in.eam)
+  if (!ctx->use_graph || eflag || vflag || ctx->profiling || ctx->nranks > 1 || ctx->remote_mask ||
+      !ctx->pending_final || ctx->nlocal <= 0 || ctx->dist_check)
+    return false;
+  const int64_t a = ctx->ago + 1;
+  const bool due = a >= ctx->delay && a % ctx->every == 0;  // Neighbor::decide
+  return !due;  // with `check yes` a due step needs the device vote; with `check no` it rebuilds
+}
+
+static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt);
+
+static int graph_step(b200_ctx *ctx) {
+  if (!ctx->step_graph) {
+    // capture this very step: the same host code path, recorded instead of launched
+    cudaGraph_t g = nullptr;
+    const int64_t l0 = ctx->launches;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = initial_integrate(ctx, 0);
+    if (rc == B200_OK) rc = forward_comm(ctx);
+    if (rc == B200_OK) rc = force_clear(ctx);
+    if (rc == B200_OK) rc = pair_compute(ctx, 0, 0);
+    if (rc == B200_OK) rc = reverse_comm(ctx);
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+    if (rc != B200_OK) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    CK(ce);
+    ctx->graph_launches = (int)(ctx->launches - l0);
+    ctx->launches = l0;
+    const cudaError_t ie = cudaGraphInstantiate(&ctx->step_graph, g, 0);
+    cudaGraphDestroy(g);
+    CK(ie);
+  }
+  CK(cudaGraphLaunch(ctx->step_graph, ctx->stream));
+  ctx->launches += ctx->graph_launches;
+  ctx->ago++;
+  ctx->pending_final = true;
+  return B200_OK;
+}
+
 static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt) {
+  if (plain_step(ctx, eflag, vflag)) {
+    if (rebuilt) *rebuilt = 0;
+    return graph_step(ctx);
+  }
   const int chk = check_due_next(ctx) ? 1 : 0;
   if (chk) CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
   TRY(initial_integrate(ctx, chk));
