@@ -48,3 +48,24 @@ def test_product_never_imports_oracle():
         assert "import oracle" not in t and "from oracle" not in t, p
     for p in (ROOT / "lammps_b200" / "csrc").glob("*"):
         assert "oracle" not in p.read_text()
+
+
+def test_stats_struct_layout_matches_the_header(tmp_path):
+    """engine.Stats (ctypes) and the LAMMPS package both mirror `b200_stats`; a C program
+    compiled against the header says what the library really writes (size and field offsets)"""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    fields = [n for n, _ in engine.Stats._fields_]
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "b200_md.h"}"',
+             'int main(void) {', '  printf("%zu\\n", sizeof(b200_stats));']
+    lines += [f'  printf("%zu\\n", offsetof(b200_stats, {n}));' for n in fields]
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-o", str(exe), str(src)])
+    out = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    assert out[0] == C.sizeof(engine.Stats)
+    assert out[1:] == [getattr(engine.Stats, n).offset for n in fields]

@@ -125,3 +125,29 @@ def test_lj_mixed_variants_meet_the_mixed_tolerances(env):
     d = xe - xo
     d -= prd * np.rint(d / prd)
     assert np.abs(d).max() < 1e-4
+
+
+def test_two_type_lj_on_tiles_matches_oracle_and_flat_list():
+    """the per-type-pair table path of the tile kernels (cutsq, lj1..lj4, offset looked up by
+    (itype, jtype)), FP64: forces <= 1e-12 against the oracle, same pair set as the flat list"""
+    from lammps_b200 import pair_lj
+    s = melted(lj_system((9, 8, 10)), 40)
+    s["type"] = (1 + (np.arange(len(s["x"])) % 2)).astype(np.int32)
+    s["mass"] = np.array([0.0, 1.0, 1.5])
+    s["tables"] = pair_lj.lj_cut_tables(2, {(1, 1): (1.0, 1.0, 2.5), (2, 2): (0.8, 1.1, 2.2),
+                                            (1, 2): (0.9, 1.05, 2.4)}, 2.5)
+    o = make_oracle(s)
+    o.setup(1, 1)
+    et, ef = _engine(s, "tile"), _engine(s, "flat")
+    for e in (et, ef):
+        e.setup(1, 1)
+    assert et.stats()["list_kind"] == 1
+    assert et.stats()["npairs"] == o.nneigh == ef.stats()["npairs"]
+    assert np.array_equal(_keys(et, s), _keys(ef, s))
+    a = et.get_atoms(fields=("f", "tag"))
+    (fe,) = by_tag(a["tag"], a["f"])
+    (fo,) = by_tag(o.tag(), o.f())
+    assert np.abs(fe - fo).max() <= 1e-12 * np.abs(fo).max()
+    eng, vir = et.tallies()
+    assert abs(eng - o.eng_vdwl) <= 1e-12 * abs(o.eng_vdwl)
+    assert np.abs(vir - o.virial).max() <= 1e-12 * np.abs(o.virial).max()
