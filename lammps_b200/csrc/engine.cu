@@ -155,6 +155,9 @@ struct b200_ctx {
   DBuf<float> eam_f;     // mixed mode: rhor / z2r splines, 8 floats per knot
   float4 *ff = nullptr;  // mixed mode: float4 Newton-scatter force array [nmax]
   EAMParams eam;
+  EAMFast eam_one;            // packed r-space tables of a single-element potential
+  DBuf<double> eam_one_d;
+  bool eam_one_ok = false;    // B200_EAM_ONE=0 disables
   DBuf<int> eam_i;
   DBuf<double> eam_d;
   double *rho = nullptr, *fp = nullptr;
@@ -1559,8 +1562,10 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag, int part = 0, bool 
   } else if (ctx->pair_style == 2) {
     // every rank walks the same sequence of halo calls, even one without atoms
     CK(cudaMemsetAsync(ctx->rho, 0, sizeof(double) * (nl + ng), s));
+    const bool fast1 = ctx->eam_one_ok && !mixed;
 #define RHO_L(TT)                                                                                       \
   if (mixed) k_eam_rho_mixed<TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eamf, ctx->rho); \
+  else if (fast1) k_eam_rho_one<TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eam_one, ctx->rho); \
   else k_eam_rho<TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->rho);
     TPA_SWITCH(RHO_L)
 #undef RHO_L
@@ -1578,6 +1583,9 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag, int part = 0, bool 
   if (mixed) {                                                                                             \
     if (eflag) k_eam_force_mixed<true, TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eamf, ctx->fp, fx, fy, fz, ctx->ff, ctx->ev); \
     else k_eam_force_mixed<false, TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eamf, ctx->fp, fx, fy, fz, ctx->ff, ctx->ev); \
+  } else if (fast1) {                                                                                      \
+    if (eflag) k_eam_force_one<true, TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eam_one, ctx->fp, fx, fy, fz, ctx->ev); \
+    else k_eam_force_one<false, TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->eam_one, ctx->fp, fx, fy, fz, ctx->ev); \
   } else {                                                                                                 \
     if (eflag) k_eam_force<true, TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->fp, fx, fy, fz, ctx->ev); \
     else k_eam_force<false, TT><<<grid, 128, 0, s>>>(nl, ctx->nstride, xt, nn, nb, ctx->eam, ctx->fp, fx, fy, fz, ctx->ev); \
@@ -1789,7 +1797,7 @@ void b200_destroy(b200_ctx *ctx) {
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   if (ctx->nccl && g_nccl.ok) g_nccl.CommDestroy(ctx->nccl);
   F(ctx->neigh.p);
-  F(ctx->numneigh.p); F(ctx->lj_tab.p); F(ctx->eam_i.p); F(ctx->eam_d.p); F(ctx->ev); F(ctx->flags);
+  F(ctx->numneigh.p); F(ctx->lj_tab.p); F(ctx->eam_i.p); F(ctx->eam_d.p); F(ctx->eam_one_d.p); F(ctx->ev); F(ctx->flags);
   F(ctx->cnt64);
   F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p);
   if (ctx->h_ev) cudaFreeHost(ctx->h_ev);
@@ -2033,6 +2041,29 @@ int b200_pair_eam(b200_ctx *ctx, int ntypes, int nr, int nrho, double rdr, doubl
   P.frho = ctx->eam_d.p + o_frho;
   P.rhor = ctx->eam_d.p + o_rhor;
   P.z2r = ctx->eam_d.p + o_z2r;
+  ctx->eam_one_ok = false;
+  {
+    const char *e = getenv("B200_EAM_ONE");
+    if (ntypes == 1 && !(e && atoi(e) == 0)) {
+      // single element: pack {rhor value cubic} and {rhor cubic | z2r cubic} per knot
+      const int tr = type2rhor[n1 + 1], tz = type2z2r[n1 + 1];
+      const size_t K = (size_t)nr + 1;
+      std::vector<double> pk(K * 12, 0.0);
+      for (size_t m = 0; m < K; m++) {
+        const double *a = rhor_spline + ((size_t)tr * K + m) * 7, *z = z2r_spline + ((size_t)tz * K + m) * 7;
+        for (int c = 0; c < 4; c++) pk[m * 4 + c] = a[3 + c];
+        double *f8 = &pk[K * 4 + m * 8];
+        f8[0] = a[3]; f8[1] = a[4]; f8[2] = a[5]; f8[3] = 0.0;
+        f8[4] = z[3]; f8[5] = z[4]; f8[6] = z[5]; f8[7] = z[6];
+      }
+      TRY(reserve(ctx, ctx->eam_one_d, pk.size()));
+      CK(cudaMemcpy(ctx->eam_one_d.p, pk.data(), sizeof(double) * pk.size(), cudaMemcpyHostToDevice));
+      ctx->eam_one.rho4 = reinterpret_cast<const double2 *>(ctx->eam_one_d.p);
+      ctx->eam_one.frc8 = reinterpret_cast<const double2 *>(ctx->eam_one_d.p + K * 4);
+      ctx->eam_one.scale = scale[n1 + 1];
+      ctx->eam_one_ok = true;
+    }
+  }
   {  // mixed mode: float copies of the r-space splines, one 32-byte sector per knot
     std::vector<float> tf((kh + kz) * 8, 0.0f);
     for (size_t q = 0; q < kh; q++)

@@ -297,3 +297,119 @@ __global__ void __launch_bounds__(128) k_eam_force(int nlocal, int nstride,
     if (threadIdx.x == 0) atomicAdd(&ev[0], v[0]);
   }
 }
+
+// ------------------------------------------------------------------- EAM, one atom type
+// The flat eam kernels are bound by the L1 data pipe, and most of its load is the spline
+// coefficients: 10 scattered 8-byte reads per in-cutoff pair (profiles/r01d_ncu_full_k_eam_force.txt:
+// 484 M load sectors for 45 M in-cutoff pairs).  For a single-element potential (funcfl, the
+// bench input) the two r-space tables are indexed by the same knot, so the host packs them:
+//   rho4[m] = {c3,c4,c5,c6} of rhor                     (32 B, two 16-byte loads)
+//   frc8[m] = {c3,c4,c5 of rhor, -, c3,c4,c5,c6 of z2r} (64 B, four 16-byte loads)
+// The derivative quadratic is not stored: PairEAM::array2spline builds it from the same cubic
+// (c0 = 3 c3/dr, c1 = 2 c4/dr, c2 = c5/dr, pair_eam.cpp:1517-1545), so
+// f'(p) = rdr * ((3 c3 p + 2 c4) p + c5) to rounding (<= 2 ulp, far inside the 1e-12 bound).
+struct EAMFast {
+  const double2 *rho4;  // [(nr+1)][2]
+  const double2 *frc8;  // [(nr+1)][4]
+  double scale;
+};
+
+template <int T>
+__global__ void __launch_bounds__(128) k_eam_rho_one(int nlocal, int nstride,
+                                                     const double4 *__restrict__ xt,
+                                                     const int *__restrict__ numneigh,
+                                                     const int *__restrict__ neigh, EAMParams P,
+                                                     EAMFast F, double *__restrict__ rho) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / T, t = tid % T;
+  double rhoi = 0.0;
+  if (i < nlocal) {
+    const double4 pi = xt[i];
+    const int jnum = numneigh[i];
+    const int *jl = neigh + (size_t)i * T + t;
+#pragma unroll 4
+    for (int n = t, kk = 0; n < jnum; n += T, kk++) {
+      const int j = jl[(size_t)kk * nstride * T] & NEIGHMASK;
+      const double4 pj = ld_xt(xt + j);
+      const double rsq = rsq_ref(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+      if (rsq < P.cutforcesq) {
+        double p = sqrt(rsq) * P.rdr + 1.0;
+        int m = (int)p;
+        m = min(m, P.nr - 1);
+        p -= m;
+        p = fmin(p, 1.0);
+        const double2 a = __ldg(F.rho4 + 2 * m), b = __ldg(F.rho4 + 2 * m + 1);
+        const double rj = ((a.x * p + a.y) * p + b.x) * p + b.y;
+        rhoi += rj;
+        atomicAdd(&rho[j], rj);
+      }
+    }
+  }
+  if (T > 1) rhoi = group_sum<T>(rhoi);
+  if (i < nlocal && t == 0) atomicAdd(&rho[i], rhoi);
+}
+
+template <bool EV, int T>
+__global__ void __launch_bounds__(128) k_eam_force_one(
+    int nlocal, int nstride, const double4 *__restrict__ xt, const int *__restrict__ numneigh,
+    const int *__restrict__ neigh, EAMParams P, EAMFast F, const double *__restrict__ fp,
+    double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
+    double *__restrict__ ev) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / T, t = tid % T;
+  double evdwl = 0.0, fxi = 0.0, fyi = 0.0, fzi = 0.0;
+  if (i < nlocal) {
+    const double4 pi = xt[i];
+    const int jnum = numneigh[i];
+    const int *jl = neigh + (size_t)i * T + t;
+    const double fpi = fp[i];
+#pragma unroll 2
+    for (int n = t, kk = 0; n < jnum; n += T, kk++) {
+      const int j = jl[(size_t)kk * nstride * T] & NEIGHMASK;
+      const double4 pj = ld_xt(xt + j);
+      const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
+      const double rsq = rsq_ref(delx, dely, delz);
+      if (rsq < P.cutforcesq) {
+        const double r = sqrt(rsq);
+        double p = r * P.rdr + 1.0;
+        int m = (int)p;
+        m = min(m, P.nr - 1);
+        p -= m;
+        p = fmin(p, 1.0);
+        const double2 *c = F.frc8 + 4 * m;
+        const double2 q0 = __ldg(c), q1 = __ldg(c + 1), q2 = __ldg(c + 2), q3 = __ldg(c + 3);
+        const double rhop = P.rdr * ((3.0 * q0.x * p + 2.0 * q0.y) * p + q1.x);   // rhoip == rhojp
+        const double z2p = P.rdr * ((3.0 * q2.x * p + 2.0 * q2.y) * p + q3.x);
+        const double z2 = ((q2.x * p + q2.y) * p + q3.x) * p + q3.y;
+        const double recip = 1.0 / r;
+        const double phi = z2 * recip;
+        const double phip = z2p * recip - phi * recip;
+        const double psip = fpi * rhop + fp[j] * rhop + phip;
+        const double fpair = -F.scale * psip * recip;
+        fxi += delx * fpair;
+        fyi += dely * fpair;
+        fzi += delz * fpair;
+        atomicAdd(&fx[j], -(delx * fpair));
+        atomicAdd(&fy[j], -(dely * fpair));
+        atomicAdd(&fz[j], -(delz * fpair));
+        if (EV) evdwl += F.scale * phi;
+      }
+    }
+  }
+  if (T > 1) {
+    fxi = group_sum<T>(fxi);
+    fyi = group_sum<T>(fyi);
+    fzi = group_sum<T>(fzi);
+  }
+  if (i < nlocal && t == 0) {
+    atomicAdd(&fx[i], fxi);
+    atomicAdd(&fy[i], fyi);
+    atomicAdd(&fz[i], fzi);
+  }
+  if (EV) {
+    __shared__ double red[32];
+    double v[1] = {evdwl};
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) atomicAdd(&ev[0], v[0]);
+  }
+}
