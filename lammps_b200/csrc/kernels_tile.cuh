@@ -457,20 +457,35 @@ __global__ void __launch_bounds__(512) k_tile_build(
       const int b = atombin[gi];
       const int bx = b % G.mbin[0], by = (b / G.mbin[0]) % G.mbin[1], bz = b / (G.mbin[0] * G.mbin[1]);
       unsigned long long qlo = 0, qhi = 0;
-      auto test = [&](int s, unsigned flags) {
+      auto push = [&](int s, unsigned flags) {
+        const unsigned long long e = (unsigned)s | flags;
+        qlo = (qlo >> 16) | (qhi << 48);
+        qhi = (qhi >> 16) | (e << 48);
+        n++;
+        nf += flags >> 15;
+        if ((n & 7) == 0 && n <= maxslots)
+          list[(size_t)((n >> 3) - 1) * NI + g] = make_uint4((unsigned)qlo, (unsigned)(qlo >> 32),
+                                                           (unsigned)qhi, (unsigned)(qhi >> 32));
+      };
+      auto near = [&](int s) -> bool {  // the reference's test: rsq <= cutneighsq[itype][jtype]
         const double3 pj = tile_pos3(T, s);
         const double rsq = rsq_ref(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-        const double c = ONETYPE ? cut1 : __ldg(cut_i + T.type[s]);
-        if (rsq <= c) {
-          const unsigned long long e = (unsigned)s | flags;
-          qlo = (qlo >> 16) | (qhi << 48);
-          qhi = (qhi >> 16) | (e << 48);
-          n++;
-          nf += flags >> 15;
-          if ((n & 7) == 0 && n <= maxslots)
-            list[(size_t)((n >> 3) - 1) * NI + g] = make_uint4((unsigned)qlo, (unsigned)(qlo >> 32),
-                                                             (unsigned)qhi, (unsigned)(qhi >> 32));
+        return rsq <= (ONETYPE ? cut1 : __ldg(cut_i + T.type[s]));
+      };
+      auto test = [&](int s, unsigned flags) {
+        if (near(s)) push(s, flags);
+      };
+      // a run of consecutive staged atoms with the same flags: two distance tests in flight
+      // (four were measured slower: 2.71 vs 2.57 ms per build at 4 M atoms)
+      // (they are independent; the stores of `push` are not on their path)
+      auto run = [&](int lo, int hi, unsigned flags) {
+        int s = lo;
+        for (; s + 1 < hi; s += 2) {
+          const bool a = near(s), b = near(s + 1);
+          if (a) push(s, flags);
+          if (b) push(s + 1, flags);
         }
+        if (s < hi) test(s, flags);
       };
       for (int r = 0; r < F.nrows; r++) {
         const int dy = F.dy[r], dz = F.dz[r];
@@ -478,10 +493,10 @@ __global__ void __launch_bounds__(512) k_tile_build(
         const unsigned short *bo = sbo + srow * ncol, *bg = sbg + srow * ncol;
         const int ca = bx + F.dxlo[r] - xs, cb = bx + F.dxhi[r] + 1 - xs;
         if (dz > 0 || (dz == 0 && dy > 0)) {  // upper half stencil: members of i's half list
-          for (int s = bo[ca]; s < bo[cb]; s++) test(s, TILE_FWD);
-          for (int s = bg[ca]; s < bg[cb]; s++) test(s, TILE_FWD | TILE_GHOST);
+          run(bo[ca], bo[cb], TILE_FWD);
+          run(bg[ca], bg[cb], TILE_FWD | TILE_GHOST);
         } else if (dz < 0 || dy < 0) {        // lower half: owned j holds (j,i) in ITS half list
-          for (int s = bo[ca]; s < bo[cb]; s++) test(s, 0u);
+          run(bo[ca], bo[cb], 0u);
         } else {
           // row (0,0): bins left of own bin -> transposed; own bin -> by list position;
           // right -> members.  Owned atoms of a row are staged in index order, so that is s > li.
@@ -497,7 +512,7 @@ __global__ void __launch_bounds__(512) k_tile_build(
             }
             test(s, TILE_FWD | TILE_GHOST);
           }
-          for (int s = bg[c0 + 1]; s < bg[cb]; s++) test(s, TILE_FWD | TILE_GHOST);
+          run(bg[c0 + 1], bg[cb], TILE_FWD | TILE_GHOST);
         }
       }
       if ((n & 7) && (n >> 3) < (maxslots >> 3)) {
