@@ -138,6 +138,7 @@ struct b200_ctx {
   bool overlap = true;  // B200_OVERLAP=0 disables
   // CUDA graph of one plain timestep (no rebuild, no tallies, one sub-domain): small systems
   // are launch-bound (bench/in.lj: 32 k atoms, ~9 launches of a few microseconds each)
+  bool ghost_f_clean = false;  // ghost forces are zero (forward halo / rebuild did it; tile path)
   bool use_graph = true;  // B200_GRAPH=0 disables
   cudaGraphExec_t step_graph = nullptr;
   int graph_launches = 0;
@@ -1266,6 +1267,7 @@ static int reneighbor(b200_ctx *ctx) {
   TRY(build_list(ctx));
   // a rebuild invalidates ghost forces of the old ghost set
   for (int d = 0; d < 3; d++) CK(cudaMemsetAsync(ctx->f[d] + nl, 0, sizeof(double) * ng, s));
+  ctx->ghost_f_clean = true;
   ctx->ago = 0;
   ctx->nbuilds++;
   ph_end(ctx, ph2);
@@ -1279,8 +1281,9 @@ static int force_clear(b200_ctx *ctx) {
   // mixed mode: the pair kernel stores f_i and k_merge_ff writes the ghosts; only the float4
   // scatter array is cleared (inside pair_compute)
   if (ctx->tiles_active) {
-    // tile kernels store f of every owned atom; only the ghosts (Newton scatter targets) are cleared
-    if (ctx->nghost > 0)
+    // tile kernels store f of every owned atom; only the ghosts (Newton scatter targets) are
+    // cleared -- unless the forward halo or the rebuild of this step already did
+    if (ctx->nghost > 0 && !ctx->ghost_f_clean)
       for (int d = 0; d < 3; d++)
         CK(cudaMemsetAsync(ctx->f[d] + ctx->nlocal, 0, sizeof(double) * ctx->nghost, ctx->stream));
   } else if (ctx->prec != B200_PREC_MIXED)
@@ -1293,6 +1296,12 @@ static int forward_comm(b200_ctx *ctx) {
   const int ph4 = ph_begin(ctx, B200_PH_FORWARD);
   const int c = ctx->cur;
   cudaStream_t s = ctx->stream;
+  // tile path: the unpack kernel also zeroes the ghost forces (force_clear then has nothing to do)
+  Vec3Ptr fclear{{nullptr, nullptr, nullptr}};
+  if (ctx->tiles_active && ctx->nghost > 0) {
+    fclear = Vec3Ptr{{ctx->f[0], ctx->f[1], ctx->f[2]}};
+    ctx->ghost_f_clean = true;
+  }
   if (ctx->p2p && ctx->remote_mask) {
     // pack + transfer in one kernel: records are stored straight into the neighbours' rbuf
     const long long seq = ++ctx->seqF;
@@ -1301,7 +1310,7 @@ static int forward_comm(b200_ctx *ctx) {
         ctx->fwdP, seq, ctx->p2p_counter + 0, (int *)ctx->p2p_counter + 4);
     k_p2p_unpack_forward<0><<<cdiv(std::max(ctx->nghost, 1), 256), 256, 0, s>>>(
         ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->geom, ctx->rbuf.p, ctx->xt[c], nullptr,
-        ctx->fwdP, seq, ctx->p2p_counter + 1, (int *)ctx->p2p_counter + 4);
+        ctx->fwdP, seq, ctx->p2p_counter + 1, (int *)ctx->p2p_counter + 4, fclear);
     ctx->launches += 2;
   } else {
     if (ctx->remote_mask && ctx->nsend > 0) {
@@ -1314,7 +1323,7 @@ static int forward_comm(b200_ctx *ctx) {
     if (ctx->nghost > 0) {
       k_unpack_forward<<<cdiv(ctx->nghost, 256), 256, 0, s>>>(ctx->nghost, ctx->nlocal, ctx->gsrc.p,
                                                              ctx->gdir.p, ctx->geom, ctx->rbuf.p,
-                                                             ctx->xt[c]);
+                                                             ctx->xt[c], fclear);
       ctx->launches++;
     }
   }
@@ -1373,7 +1382,7 @@ static int forward_scalar(b200_ctx *ctx, double *a) {
         seq, ctx->p2p_counter + 0, (int *)ctx->p2p_counter + 4);
     k_p2p_unpack_forward<1><<<cdiv(std::max(ctx->nghost, 1), 256), 256, 0, s>>>(
         ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->geom, ctx->rbuf.p, nullptr, a,
-        ctx->fwdP, seq, ctx->p2p_counter + 1, (int *)ctx->p2p_counter + 4);
+        ctx->fwdP, seq, ctx->p2p_counter + 1, (int *)ctx->p2p_counter + 4, Vec3Ptr{{nullptr, nullptr, nullptr}});
     ctx->launches += 2;
     LAUNCH_CHECK();
     return B200_OK;
@@ -1450,6 +1459,7 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag, int part = 0, bool 
   const bool ev = eflag || vflag;
   const bool mixed = ctx->prec == B200_PREC_MIXED;
   if (joined) *joined = true;
+  ctx->ghost_f_clean = false;  // (force_clear has run; the pair kernels write ghost forces now)
   if (part == 1) {
     const int ph6 = ph_begin(ctx, B200_PH_PAIR);
     TRY(launch_tile_lj(ctx, s, eflag, ctx->tile_ids.p + ctx->tile_nint, ctx->tile_nbnd));

@@ -213,14 +213,25 @@ __global__ void __launch_bounds__(256) k_pack_forward(int nsend, const int *__re
   o[2] = q.z + g.shift[dir][2];
 }
 
+struct Vec3Ptr {
+  double *a[3];
+};
+
 // ghost g <- local owner + periodic shift, or <- received record
+// fclear (may be null): ghost forces are zeroed in the same pass -- Verlet::force_clear for the
+// tile path, whose pair kernels accumulate into ghost slots only (owned f_i is stored)
 __global__ void __launch_bounds__(256) k_unpack_forward(int nghost, int nlocal,
                                                         const int *__restrict__ gsrc,
                                                         const unsigned char *__restrict__ gdir,
                                                         Geom g, const double *__restrict__ rbuf,
-                                                        double4 *__restrict__ xt) {
+                                                        double4 *__restrict__ xt, Vec3Ptr fclear) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nghost) return;
+  if (fclear.a[0]) {
+    fclear.a[0][nlocal + k] = 0.0;
+    fclear.a[1][nlocal + k] = 0.0;
+    fclear.a[2][nlocal + k] = 0.0;
+  }
   const int src = gsrc[k];
   double *o = reinterpret_cast<double *>(xt + nlocal + k);
   if (src >= 0) {
@@ -236,10 +247,6 @@ __global__ void __launch_bounds__(256) k_unpack_forward(int nghost, int nlocal,
     o[2] = r[2];
   }
 }
-
-struct Vec3Ptr {
-  double *a[3];
-};
 
 // ghost contributions: local images are added to their owner at once (an owner has up to 7
 // images -> RED.ADD.F64), ghosts owned elsewhere are packed for the way back.
@@ -398,11 +405,16 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_p2p_unpack_forward(
     int nghost, int nlocal, const int *__restrict__ gsrc, const unsigned char *__restrict__ gdir,
     Geom g, const double *__restrict__ rbuf, double4 *__restrict__ xt, double *__restrict__ a,
-    P2PMap pm, long long seq, unsigned *counter, int *err) {
+    P2PMap pm, long long seq, unsigned *counter, int *err, Vec3Ptr fclear) {
   p2p_wait(pm.flag_in, pm.in_mask, seq, err);
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < nghost) {
     const int src = gsrc[k];
+    if (MODE == 0 && fclear.a[0]) {
+      fclear.a[0][nlocal + k] = 0.0;
+      fclear.a[1][nlocal + k] = 0.0;
+      fclear.a[2][nlocal + k] = 0.0;
+    }
     if (MODE == 0) {
       double *o = reinterpret_cast<double *>(xt + nlocal + k);
       if (src >= 0) {
