@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(128) k_eam_rho(int nlocal, int nstride,
       const double rsq = rsq_ref(delx, dely, delz);
       if (rsq < P.cutforcesq) {
         const int jtype = d2type(pj.w);
-        double p = sqrt(rsq) * P.rdr + 1.0;
+        double rinv;
+        double p = sqrt_nr(rsq, rinv) * P.rdr + 1.0;
         int m = (int)p;
         m = min(m, P.nr - 1);
         p -= m;
@@ -247,7 +248,9 @@ __global__ void __launch_bounds__(128) k_eam_force(int nlocal, int nstride,
       const double rsq = rsq_ref(delx, dely, delz);
       if (rsq < P.cutforcesq) {
         const int jtype = d2type(pj.w);
-        const double r = sqrt(rsq);
+        double recip;  // sqrt and 1/r without the IEEE slow paths (<= 1 ulp; rsq > 0 here)
+        const double r = sqrt_nr(rsq, recip);
+        recip = fma(recip, fma(-r, recip, 1.0), recip);
         double p = r * P.rdr + 1.0;
         int m = (int)p;
         m = min(m, P.nr - 1);
@@ -264,7 +267,6 @@ __global__ void __launch_bounds__(128) k_eam_force(int nlocal, int nstride,
         c = P.z2r + ((size_t)P.type2z2r[itype * n1 + jtype] * (P.nr + 1) + m) * 7;
         const double z2p = (__ldg(c) * p + __ldg(c + 1)) * p + __ldg(c + 2);
         const double z2 = ((__ldg(c + 3) * p + __ldg(c + 4)) * p + __ldg(c + 5)) * p + __ldg(c + 6);
-        const double recip = 1.0 / r;
         const double phi = z2 * recip;
         const double phip = z2p * recip - phi * recip;
         const double psip = fpi * rhojp + fp[j] * rhoip + phip;
@@ -333,7 +335,8 @@ __global__ void __launch_bounds__(128) k_eam_rho_one(int nlocal, int nstride,
       const double4 pj = ld_xt(xt + j);
       const double rsq = rsq_ref(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
       if (rsq < P.cutforcesq) {
-        double p = sqrt(rsq) * P.rdr + 1.0;
+        double rinv;
+        double p = sqrt_nr(rsq, rinv) * P.rdr + 1.0;
         int m = (int)p;
         m = min(m, P.nr - 1);
         p -= m;
@@ -370,7 +373,9 @@ __global__ void __launch_bounds__(128) k_eam_force_one(
       const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
       const double rsq = rsq_ref(delx, dely, delz);
       if (rsq < P.cutforcesq) {
-        const double r = sqrt(rsq);
+        double recip;  // sqrt and 1/r without the IEEE slow paths (<= 1 ulp; rsq > 0 here)
+        const double r = sqrt_nr(rsq, recip);
+        recip = fma(recip, fma(-r, recip, 1.0), recip);
         double p = r * P.rdr + 1.0;
         int m = (int)p;
         m = min(m, P.nr - 1);
@@ -381,7 +386,6 @@ __global__ void __launch_bounds__(128) k_eam_force_one(
         const double rhop = P.rdr * ((3.0 * q0.x * p + 2.0 * q0.y) * p + q1.x);   // rhoip == rhojp
         const double z2p = P.rdr * ((3.0 * q2.x * p + 2.0 * q2.y) * p + q3.x);
         const double z2 = ((q2.x * p + q2.y) * p + q3.x) * p + q3.y;
-        const double recip = 1.0 / r;
         const double phi = z2 * recip;
         const double phip = z2p * recip - phi * recip;
         const double psip = fpi * rhop + fp[j] * rhop + phip;

@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(128) k_eam_rho_mixed(int nlocal, int nstride,
     const double rsq = rsq_ref(delx, dely, delz);
     if (rsq < P.cutforcesq) {
       const int jtype = d2type(pj.w);
-      float p = sqrtf((float)rsq) * F.rdr + 1.0f;
+      const float rsqf = (float)rsq;
+      float p = rsqf * rsqrtf(rsqf) * F.rdr + 1.0f;  // MUFU.RSQ, no IEEE slow path
       int m = (int)p;
       m = min(m, P.nr - 1);
       p -= (float)m;
@@ -199,7 +200,9 @@ __global__ void __launch_bounds__(128) k_eam_force_mixed(
       const double rsq = rsq_ref(delx, dely, delz);
       if (rsq < P.cutforcesq) {
         const int jtype = d2type(pj.w);
-        const float r = sqrtf((float)rsq);
+        const float rsqf = (float)rsq;
+        const float recip = rsqrtf(rsqf);  // MUFU.RSQ, no IEEE slow paths
+        const float r = rsqf * recip;
         float p = r * F.rdr + 1.0f;
         int m = (int)p;
         m = min(m, P.nr - 1);
@@ -218,7 +221,6 @@ __global__ void __launch_bounds__(128) k_eam_force_mixed(
         const float4 z0 = __ldg(zc), z1 = __ldg(zc + 1);
         const float z2p = (z0.x * p + z0.y) * p + z0.z;
         const float z2 = ((z0.w * p + z1.x) * p + z1.y) * p + z1.z;
-        const float recip = 1.0f / r;
         const float phi = z2 * recip;
         const float phip = z2p * recip - phi * recip;
         const float psip = fpi * rhojp + (float)fp[j] * rhoip + phip;

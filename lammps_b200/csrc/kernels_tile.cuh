@@ -263,39 +263,6 @@ __device__ __forceinline__ int tile_own_atom(const TileGeom &G, const TileHdr *H
 }
 
 
-// Reciprocal and square root without the IEEE special-case paths the compiler emits for `1.0/x`
-// and `sqrt(x)` (a slow-path call per use that also stops it interleaving neighbouring pairs):
-// MUFU seed + Newton steps, <= 1 ulp for the normal, positive arguments a pair distance can be.
-__device__ __forceinline__ double rcp_nr(double a) {
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-  double e = fma(-a, x, 1.0);
-  e = fma(e, e, e);
-  x = fma(x, e, x);
-  e = fma(-a, x, 1.0);
-  return fma(x, e, x);
-}
-__device__ __forceinline__ double sqrt_nr(double a, double &rinv) {  // returns sqrt(a), rinv ~ 1/sqrt(a)
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double g = a * y, h = 0.5 * y;
-  double r = fma(-h, g, 0.5);
-  g = fma(g, r, g);
-  h = fma(h, r, h);
-  r = fma(-h, g, 0.5);
-  g = fma(g, r, g);
-  h = fma(h, r, h);
-  const double d = fma(-g, g, a);
-  g = fma(d, h, g);
-  rinv = h + h;
-  return g;
-}
-__device__ __forceinline__ float rcp_f(float a) {
-  float x;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(a));
-  return x;
-}
-
 // Walk the n entries of list row g: 8 entries per 16-byte word, next word prefetched.
 // body(e, valid) must be branch-free (entries past n are zero padding -> valid = false): the
 // eight bodies of a word then interleave in the instruction stream.  ghost(e) runs only for
