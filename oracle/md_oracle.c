@@ -25,7 +25,7 @@
 #define IMGMASK 1023       /* lmptype.h:122-125 (LAMMPS_SMALLBIG) */
 #define IMGBITS 10
 #define IMG2BITS 20
-#define MAXSWAP 6
+#define MAXSWAP 24 /* 2 * maxneed swaps per dimension, maxneed <= 4 */
 
 #define MIN(a, b) ((a) < (b) ? (a) : (b))
 #define MAX(a, b) ((a) > (b) ? (a) : (b))
@@ -310,27 +310,30 @@ void orc_pbc(Orc *o) {
 /* ------------------------------------------------------------------ comm */
 
 /* comm_brick.cpp:172-430 CommBrick::setup, 1x1x1 processor grid, mode SINGLE.
-   maxneed[d] = int(cutghost*1/prd)+1 must be 1 (box edge > cutghost); non-periodic dims
-   get maxneed = min(maxneed, procgrid-1) = 0 swaps. */
+   maxneed[d] = int(cutghost*1/prd)+1 (comm_brick.cpp:267-269): more than one layer of periodic
+   images when the box edge is shorter than the ghost cutoff (the 7 A box of the reference's
+   atomic-pair-eam.yaml); non-periodic dims get maxneed = min(maxneed, procgrid-1) = 0 swaps.
+   Swaps beyond the first pair of a dimension forward only ghosts received by the previous
+   pair, restricted to one half of the sub-box (slab bound at its middle, :385-411). */
 static void comm_setup(Orc *o) {
   o->cutghost = o->cutneighmax; /* comm.cpp:683 with no user cutoff */
   int iswap = 0;
   for (int dim = 0; dim < 3; dim++) {
     int maxneed = (int)(o->cutghost * 1 / o->prd[dim]) + 1;
     if (!o->periodic[dim]) maxneed = MIN(maxneed, 0);
-    if (maxneed > 1) die("box edge shorter than ghost cutoff is not supported by the oracle");
+    if (iswap + 2 * maxneed > MAXSWAP) die("box edge much shorter than the ghost cutoff: too many swaps");
     double sublo = o->boxlo[dim], subhi = o->boxhi[dim];
     for (int ineed = 0; ineed < 2 * maxneed; ineed++) {
       o->pbc_flag[iswap] = 0;
       o->pbc[iswap][0] = o->pbc[iswap][1] = o->pbc[iswap][2] = 0;
       if (ineed % 2 == 0) {
-        o->slablo[iswap] = -BIG;
+        o->slablo[iswap] = ineed < 2 ? -BIG : 0.5 * (sublo + subhi);
         o->slabhi[iswap] = sublo + o->cutghost;
         o->pbc_flag[iswap] = 1; /* myloc == 0 */
         o->pbc[iswap][dim] = 1;
       } else {
         o->slablo[iswap] = subhi - o->cutghost;
-        o->slabhi[iswap] = BIG;
+        o->slabhi[iswap] = ineed < 2 ? BIG : 0.5 * (sublo + subhi);
         o->pbc_flag[iswap] = 1; /* myloc == procgrid-1 */
         o->pbc[iswap][dim] = -1;
       }

@@ -1,0 +1,52 @@
+"""The oracle against the reference's own known-answer fixture for this path:
+unittest/force-styles/tests/atomic-pair-eam.yaml (test_pair_style.cpp:354-425): 32 atoms of two
+elements in a 7 A box (shorter than the ghost cutoff: two layers of periodic images), funcfl
+potentials Al_jnp.eam + Cu_u3.eam mixed by PairEAM::file2array, energy / virial / forces at
+setup and after `fix nve` + `run 4` with `neigh_modify delay 2 every 2 check no`.
+Same comparison as the reference's test: |a - b| <= epsilon * max(|a|, |b|), epsilon = 6e-12
+(5x for the forces after the run, test_pair_style.cpp:411).  CPU only: pins oracle/md_oracle.c
+and the host-side table construction lammps_b200/eam.py (file2array_funcfl + array2spline)."""
+from pathlib import Path
+
+import numpy as np
+
+from common import by_tag, make_oracle
+from lammps_b200 import eam as eam_mod
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def _system():
+    d = np.load(GOLDEN / "ref_yaml_pair_eam.npz")
+    files = [eam_mod.Funcfl(float(d[f"{k}_mass"]), int(d[f"{k}_nrho"]), float(d[f"{k}_drho"]),
+                            int(d[f"{k}_nr"]), float(d[f"{k}_dr"]), float(d[f"{k}_cut"]),
+                            d[f"{k}_frho"], d[f"{k}_zr"], d[f"{k}_rhor"]) for k in ("al", "cu")]
+    T = eam_mod.funcfl_tables(files, [0, 1])      # pair_coeff 1 1 Al_jnp.eam / 2 2 Cu_u3.eam
+    # in.metal: units metal (skin 2.0), neigh_modify delay 2 every 2 check no, timestep 0.0001;
+    # PairEAM::coeff sets the masses from the funcfl files
+    s = dict(kind="eam", units="metal", x=d["x"], v=d["v"], type=d["type"], tag=d["tag"],
+             image=d["image"], mass=T.mass, lo=d["lo"], hi=d["hi"], skin=2.0, every=2, delay=2,
+             check=False, dt=0.0001, tables=T.as_dict())
+    return s, d
+
+
+def _close(a, b, eps):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.all(np.abs(a - b) <= eps * np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-300))
+
+
+def test_pair_eam_yaml_init_and_run():
+    s, d = _system()
+    eps = float(d["epsilon"])
+    o = make_oracle(s)
+    o.setup(1, 1)
+    assert o.nlocal == 32 and o.nghost > 32 * 7      # more than one layer of images
+    (f,) = by_tag(o.tag(), o.f())
+    assert _close(f, d["init_forces"], eps), np.abs(f - d["init_forces"]).max()
+    assert _close(o.eng_vdwl, d["init_vdwl"], eps)
+    assert _close(o.virial, d["init_stress"], eps)
+    o.run(4, 0, 4)                                   # tallies on the last step, like the test
+    (f,) = by_tag(o.tag(), o.f())
+    assert _close(f, d["run_forces"], 5 * eps), np.abs(f - d["run_forces"]).max()
+    assert _close(o.eng_vdwl, d["run_vdwl"], eps)
+    assert _close(o.virial, d["run_stress"], eps)
