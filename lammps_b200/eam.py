@@ -187,3 +187,126 @@ def funcfl_tables(files: list[Funcfl], type_map: list[int]) -> EAMTables:
                      frho_spline=np.ascontiguousarray(frho_s),
                      rhor_spline=np.ascontiguousarray(rhor_s),
                      z2r_spline=np.ascontiguousarray(z2r_s), mass=mass)
+
+
+# ----------------------------------------------------------------------------- setfl (eam/alloy)
+@dataclass
+class Setfl:
+    """Numeric content of a DYNAMO setfl file (pair_eam.cpp:738-805 PairEAM::read_setfl).
+    Arrays are 0-based here: frho[e][k], rhor[e][k], z2r[i][j][k] for i >= j."""
+    elements: list
+    mass: np.ndarray
+    nrho: int
+    drho: float
+    nr: int
+    dr: float
+    cut: float
+    frho: np.ndarray   # [nelements, nrho]
+    rhor: np.ndarray   # [nelements, nr]
+    z2r: dict          # (i, j) with i >= j -> [nr]
+
+
+def read_setfl(path: str, fs: bool = False) -> Setfl:
+    """3 comment lines; `nelements names...`; `nrho drho nr dr cut`; per element a header
+    (Z mass ...) + nrho F values + nr rho values; then r*phi for every pair i >= j.
+    fs=True: the Finnis-Sinclair variant (PairEAM::read_fs, pair_eam.cpp:856-960): every element
+    carries one density function per partner element, rhor[i][j] (nelements x nr values)."""
+    with open(path) as fh:
+        lines = fh.read().splitlines()
+    t = lines[3].split()
+    nel = int(t[0])
+    names = t[1:1 + nel]
+    if len(names) != nel:
+        raise ValueError("Incorrect element names in EAM potential file")
+    t = lines[4].split()
+    nrho, drho, nr, dr, cut = int(t[0]), float(t[1]), int(t[2]), float(t[3]), float(t[4])
+    if nrho <= 0 or nr <= 0 or dr <= 0.0:
+        raise ValueError("Invalid EAM potential file")
+    pos = 5
+    toks: list = []
+
+    def header():
+        # a header line holds 4 tokens, the last one a word: it cannot be taken for data
+        nonlocal pos
+        h = lines[pos].split()
+        pos += 1
+        return h
+
+    def take(n):
+        nonlocal pos, toks
+        while len(toks) < n:
+            toks.extend(lines[pos].replace("D", "E").replace("d", "e").split())
+            pos += 1
+        out, toks = toks[:n], toks[n:]
+        return np.array([float(v) for v in out])
+
+    mass = np.zeros(nel)
+    frho = np.zeros((nel, nrho))
+    rhor = np.zeros((nel, nel, nr)) if fs else np.zeros((nel, nr))
+    for e in range(nel):
+        assert not toks, "setfl data blocks must end at a line break"
+        mass[e] = float(header()[1])
+        frho[e] = take(nrho)
+        if fs:
+            for j in range(nel):
+                rhor[e, j] = take(nr)
+        else:
+            rhor[e] = take(nr)
+    z2r = {}
+    for i in range(nel):
+        for j in range(i + 1):
+            z2r[(i, j)] = take(nr)
+    return Setfl(names, mass, nrho, drho, nr, dr, cut, frho, rhor, z2r)
+
+
+def setfl_tables(f: Setfl, type_elements: list) -> EAMTables:
+    """`pair_coeff * * file E1 E2 ...`: type_elements[t-1] = element name of atom type t.
+    PairEAM::coeff (map), file2array_setfl (pair_eam.cpp:1211-1325), array2spline."""
+    ntypes = len(type_elements)
+    map_ = [-1] + [f.elements.index(e) if e != "NULL" else -1 for e in type_elements]
+    nel = len(f.elements)
+    nr, nrho, dr, drho = f.nr, f.nrho, f.dr, f.drho
+    nfrho = nel + 1                                     # + one array of zeros
+    frho = np.zeros((nfrho, nrho + 1))
+    frho[:nel, 1:] = f.frho
+    type2frho = np.array([0] + [map_[i] if map_[i] >= 0 else nfrho - 1
+                                for i in range(1, ntypes + 1)], dtype=np.int32)
+    type2rhor = np.zeros((ntypes + 1, ntypes + 1), dtype=np.int32)
+    if f.rhor.ndim == 3:                                # eam/fs: file2array_fs, pair_eam.cpp:1331-1456
+        rhor = np.zeros((nel * nel, nr + 1))
+        rhor[:, 1:] = f.rhor.reshape(nel * nel, nr)
+        for i in range(1, ntypes + 1):
+            for j in range(1, ntypes + 1):
+                type2rhor[i, j] = map_[i] * nel + map_[j]
+    else:
+        rhor = np.zeros((nel, nr + 1))
+        rhor[:, 1:] = f.rhor
+        for i in range(1, ntypes + 1):
+            type2rhor[i, 1:] = map_[i]                  # the density depends on the source element
+    nz2r = nel * (nel + 1) // 2
+    z2r = np.zeros((nz2r, nr + 1))
+    n = 0
+    for i in range(nel):
+        for j in range(i + 1):
+            z2r[n, 1:] = f.z2r[(i, j)]
+            n += 1
+    type2z2r = np.zeros((ntypes + 1, ntypes + 1), dtype=np.int32)
+    for i in range(1, ntypes + 1):
+        for j in range(1, ntypes + 1):
+            irow, icol = map_[i], map_[j]
+            if irow == -1 or icol == -1:
+                continue
+            if irow < icol:
+                irow, icol = icol, irow
+            type2z2r[i, j] = sum(m + 1 for m in range(irow)) + icol
+    frho_s = np.stack([_interpolate(nrho, drho, frho[i]) for i in range(nfrho)])
+    rhor_s = np.stack([_interpolate(nr, dr, rhor[i]) for i in range(rhor.shape[0])])
+    z2r_s = np.stack([_interpolate(nr, dr, z2r[i]) for i in range(nz2r)])
+    mass = np.array([0.0] + [f.mass[map_[i]] if map_[i] >= 0 else 0.0 for i in range(1, ntypes + 1)])
+    return EAMTables(ntypes=ntypes, nr=nr, nrho=nrho, dr=dr, drho=drho, rdr=1.0 / dr,
+                     rdrho=1.0 / drho, rhomax=(nrho - 1) * drho, cutmax=f.cut,
+                     cutforcesq=f.cut * f.cut, type2frho=type2frho, type2rhor=type2rhor,
+                     type2z2r=type2z2r, scale=np.ones((ntypes + 1, ntypes + 1)),
+                     frho_spline=np.ascontiguousarray(frho_s),
+                     rhor_spline=np.ascontiguousarray(rhor_s),
+                     z2r_spline=np.ascontiguousarray(z2r_s), mass=mass)

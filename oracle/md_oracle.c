@@ -5,11 +5,16 @@
  * leg may load it; the product path never does.
  *
  * Scope: one process, orthogonal box, atom_style atomic, newton on, half/bin/atomonly/newton
- * list, pair lj/cut or eam (funcfl tables), fix nve.  Each function cites the reference
+ * list, pair lj/cut or eam (funcfl / setfl / fs tables built by lammps_b200/eam.py), fix nve.  Each function cites the reference
  * file:line (relative to /root/reference/src) whose arithmetic it restates.  The code keeps
  * the reference's operation ORDER (atom order, swap order, neighbour order) so that results
- * can be compared bit-for-bit with oracle/_ref (the compiled reference); see
- * tests/test_oracle_vs_ref.py which pins it.
+ * can be compared bit-for-bit with oracle/_ref (the compiled reference).
+ *
+ * PINNED (tests/test_oracle_golden.py, tests/test_oracle_reference_yaml.py): against fixtures
+ * generated from the compiled reference (pair sets, forces, thermo), against the reference's
+ * published bench logs (bench/log.15Jul25.{lj,eam}.fixed.g++.1), against
+ * unittest/cplusplus/test_neighbor_class.cpp:235-269, and against the reference's known-answer
+ * vectors unittest/force-styles/tests/atomic-pair-eam{,_alloy,_fs}.yaml at their own epsilon.
  *
  * Build: gcc -O2 -fPIC -shared -ffp-contract=off -o oracle/libmd_oracle.so oracle/md_oracle.c -lm
  * (-ffp-contract=off: the reference is built for baseline x86-64, i.e. without FMA contraction)

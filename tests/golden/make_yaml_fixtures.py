@@ -8,6 +8,11 @@
                           types, positions, velocities), the numeric content of the two funcfl
                           potential files, and the reference answers init_/run_ vdwl, stress,
                           forces (run_ = after `fix nve` + `run 4`, test_pair_style.cpp:158-160)
+  ref_yaml_pair_eam_alloy.npz  atomic-pair-eam_alloy.yaml (`pair_coeff * * CuNi.eam.alloy Cu Ni`,
+                          epsilon 5e-12): same input state, the numeric content of the setfl file,
+                          and the reference answers
+  ref_yaml_pair_eam_fs.npz     atomic-pair-eam_fs.yaml (`pair_coeff * * AlFe_mm.eam.fs Al Fe`,
+                          Finnis-Sinclair file with per-element-pair densities)
 """
 import sys
 from pathlib import Path
@@ -80,6 +85,33 @@ def pair_eam_fixture():
     np.savez_compressed(OUT / "ref_yaml_pair_eam.npz", **out)
 
 
+def pair_eam_alloy_fixture(yaml_name="atomic-pair-eam_alloy.yaml", style="eam/alloy",
+                           potential="CuNi.eam.alloy", types=("Cu", "Ni"),
+                           out_name="ref_yaml_pair_eam_alloy.npz"):
+    y = yaml.safe_load((TESTS / yaml_name).read_text())
+    assert y["pair_style"] == style and y["natoms"] == 32
+    assert y["pair_coeff"].split() == ["*", "*", potential, *types]
+    d = read_data_file(TESTS / "data.metal")
+    order = np.argsort(d["tag"])
+    out = {k: (v[order] if k in ("tag", "type", "x", "v", "image") else v) for k, v in d.items()}
+    f = eam.read_setfl(str(REF / "potentials" / potential), fs=style == "eam/fs")
+    out.update(elements=np.array(f.elements), type_elements=np.array(types), mass=f.mass,
+               nrho=f.nrho, drho=f.drho, nr=f.nr, dr=f.dr, cut=f.cut, frho=f.frho, rhor=f.rhor)
+    for (i, j), z in f.z2r.items():
+        out[f"z2r_{i}_{j}"] = z
+    for pre in ("init", "run"):
+        out[f"{pre}_vdwl"] = float(y[f"{pre}_vdwl"])
+        out[f"{pre}_stress"] = block(y[f"{pre}_stress"], 6)[0]
+        fr = block(y[f"{pre}_forces"], 4)
+        assert np.array_equal(fr[:, 0].astype(int), np.arange(1, 33))
+        out[f"{pre}_forces"] = fr[:, 1:]
+    out["epsilon"] = float(y["epsilon"])
+    np.savez_compressed(OUT / out_name, **out)
+
+
 if __name__ == "__main__":
+    pair_eam_alloy_fixture()
+    pair_eam_alloy_fixture("atomic-pair-eam_fs.yaml", "eam/fs", "AlFe_mm.eam.fs", ("Al", "Fe"),
+                           "ref_yaml_pair_eam_fs.npz")
     pair_eam_fixture()
     print("written", OUT / "ref_yaml_pair_eam.npz")

@@ -224,3 +224,32 @@ def test_step_granular_equals_run():
     (x2,) = by_tag(a2["tag"], a2["x"])
     assert np.abs(x1 - x2).max() < 1e-10
     assert e1.stats()["nbuilds"] == e2.stats()["nbuilds"]
+
+
+@pytest.mark.parametrize("fixture", ["ref_yaml_pair_eam.npz", "ref_yaml_pair_eam_alloy.npz",
+                                     "ref_yaml_pair_eam_fs.npz"])
+def test_two_element_eam_tables_from_reference_fixtures(fixture):
+    """eam (two funcfl files), eam/alloy (setfl) and eam/fs tables of the reference's own
+    known-answer tests, on the CUDA path: the 32-atom cell of data.metal replicated 3x3x3 (the
+    engine keeps one layer of periodic images) against the oracle, which reproduces the yaml
+    answers themselves on the original cell (tests/test_oracle_reference_yaml.py)."""
+    from test_oracle_reference_yaml import _alloy_system, _system
+    s, _ = _system() if fixture == "ref_yaml_pair_eam.npz" else _alloy_system(fixture)
+    prd = np.asarray(s["hi"]) - np.asarray(s["lo"])
+    x0 = s["lo"] + np.mod(s["x"] - s["lo"], prd)
+    reps = [(i, j, k) for i in range(3) for j in range(3) for k in range(3)]
+    s = dict(s)
+    s["x"] = np.concatenate([x0 + prd * np.array(r) for r in reps])
+    s["v"] = np.tile(s["v"], (27, 1))
+    s["type"] = np.tile(s["type"], 27)
+    s["tag"] = np.arange(1, len(s["x"]) + 1, dtype=np.int32)
+    s["hi"] = s["lo"] + 3 * prd
+    s.pop("image", None)
+    e, o = _check_static(s, fixture)
+    to = o.run(20, 0, 0)
+    te = e.run(20, 0)
+    a = e.get_atoms(fields=("x", "tag"))
+    (xe,) = by_tag(a["tag"], a["x"])
+    (xo,) = by_tag(o.tag(), o.x())
+    assert np.abs(xe - xo).max() < 1e-10
+    assert abs(te[-1][2] - to[-1][2]) <= 1e-10 * abs(to[-1][2])

@@ -50,3 +50,40 @@ def test_pair_eam_yaml_init_and_run():
     assert _close(f, d["run_forces"], 5 * eps), np.abs(f - d["run_forces"]).max()
     assert _close(o.eng_vdwl, d["run_vdwl"], eps)
     assert _close(o.virial, d["run_stress"], eps)
+
+
+def _alloy_system(name="ref_yaml_pair_eam_alloy.npz"):
+    d = np.load(GOLDEN / name)
+    nel = len(d["elements"])
+    f = eam_mod.Setfl([str(e) for e in d["elements"]], d["mass"], int(d["nrho"]), float(d["drho"]),
+                      int(d["nr"]), float(d["dr"]), float(d["cut"]), d["frho"], d["rhor"],
+                      {(i, j): d[f"z2r_{i}_{j}"] for i in range(nel) for j in range(i + 1)})
+    T = eam_mod.setfl_tables(f, [str(e) for e in d["type_elements"]])   # pair_coeff * * file Cu Ni
+    s = dict(kind="eam", units="metal", x=d["x"], v=d["v"], type=d["type"], tag=d["tag"],
+             image=d["image"], mass=T.mass, lo=d["lo"], hi=d["hi"], skin=2.0, every=2, delay=2,
+             check=False, dt=0.0001, tables=T.as_dict())
+    return s, d
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("fixture", ["ref_yaml_pair_eam_alloy.npz", "ref_yaml_pair_eam_fs.npz"])
+def test_pair_eam_alloy_and_fs_yaml_init_and_run(fixture):
+    """atomic-pair-eam_alloy.yaml: setfl file (file2array_setfl, pair_eam.cpp:1211-1325) with the
+    element order of the file (Ni, Cu) different from the type order (Cu, Ni), epsilon 5e-12;
+    atomic-pair-eam_fs.yaml: Finnis-Sinclair file (file2array_fs, :1331-1456), densities per
+    element pair, so rho_i and rho_j of a pair come from different tables"""
+    s, d = _alloy_system(fixture)
+    eps = float(d["epsilon"])
+    o = make_oracle(s)
+    o.setup(1, 1)
+    (f,) = by_tag(o.tag(), o.f())
+    assert _close(f, d["init_forces"], eps), np.abs(f - d["init_forces"]).max()
+    assert _close(o.eng_vdwl, d["init_vdwl"], eps)
+    assert _close(o.virial, d["init_stress"], eps)
+    o.run(4, 0, 4)
+    (f,) = by_tag(o.tag(), o.f())
+    assert _close(f, d["run_forces"], 5 * eps), np.abs(f - d["run_forces"]).max()
+    assert _close(o.eng_vdwl, d["run_vdwl"], eps)
+    assert _close(o.virial, d["run_stress"], eps)
