@@ -120,11 +120,15 @@ class EAMTables:
         return d
 
 
-def funcfl_tables(files: list[Funcfl], type_map: list[int]) -> EAMTables:
+def funcfl_tables(files: list[Funcfl], type_map: list[int], energy_scale: float = 1.0) -> EAMTables:
     """`pair_coeff i i file` for each type: type_map[t] (t = 1..ntypes) = index into files.
 
-    file2array_funcfl + array2spline + init_one.
+    file2array_funcfl + array2spline + init_one.  energy_scale != 1: the reader's transparent
+    unit conversion (read_funcfl, pair_eam.cpp:701-706): F(rho) * c, Z(r) * sqrt(c).
     """
+    if energy_scale != 1.0:
+        files = [Funcfl(f.mass, f.nrho, f.drho, f.nr, f.dr, f.cut, f.frho * energy_scale,
+                        f.zr * np.sqrt(energy_scale), f.rhor) for f in files]
     ntypes = len(type_map)
     map_ = [-1] + list(type_map)
     nfuncfl = len(files)
@@ -259,9 +263,13 @@ def read_setfl(path: str, fs: bool = False) -> Setfl:
     return Setfl(names, mass, nrho, drho, nr, dr, cut, frho, rhor, z2r)
 
 
-def setfl_tables(f: Setfl, type_elements: list) -> EAMTables:
+def setfl_tables(f: Setfl, type_elements: list, energy_scale: float = 1.0) -> EAMTables:
     """`pair_coeff * * file E1 E2 ...`: type_elements[t-1] = element name of atom type t.
-    PairEAM::coeff (map), file2array_setfl (pair_eam.cpp:1211-1325), array2spline."""
+    PairEAM::coeff (map), file2array_setfl (pair_eam.cpp:1211-1325), array2spline.
+    energy_scale != 1: the reader's unit conversion (read_setfl/read_fs: F(rho) * c, r*phi * c)."""
+    if energy_scale != 1.0:
+        f = Setfl(f.elements, f.mass, f.nrho, f.drho, f.nr, f.dr, f.cut, f.frho * energy_scale,
+                  f.rhor, {k: v * energy_scale for k, v in f.z2r.items()})
     ntypes = len(type_elements)
     map_ = [-1] + [f.elements.index(e) if e != "NULL" else -1 for e in type_elements]
     nel = len(f.elements)

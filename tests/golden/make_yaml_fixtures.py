@@ -65,6 +65,18 @@ def block(text, ncol):
     return a
 
 
+def answers(out, yaml_name, prefix=""):
+    y = yaml.safe_load((TESTS / yaml_name).read_text())
+    for pre in ("init", "run"):
+        out[f"{prefix}{pre}_vdwl"] = float(y[f"{pre}_vdwl"])
+        out[f"{prefix}{pre}_stress"] = block(y[f"{pre}_stress"], 6)[0]
+        f = block(y[f"{pre}_forces"], 4)
+        assert np.array_equal(f[:, 0].astype(int), np.arange(1, 33))
+        out[f"{prefix}{pre}_forces"] = f[:, 1:]
+    out[f"{prefix}epsilon"] = float(y["epsilon"])
+    return y
+
+
 def pair_eam_fixture():
     y = yaml.safe_load((TESTS / "atomic-pair-eam.yaml").read_text())
     assert y["pair_style"] == "eam" and y["natoms"] == 32
@@ -82,6 +94,9 @@ def pair_eam_fixture():
         assert np.array_equal(f[:, 0].astype(int), np.arange(1, 33))
         out[f"{pre}_forces"] = f[:, 1:]
     out["epsilon"] = float(y["epsilon"])
+    # the same system under `units real` (the readers convert the metal-units files): answers only
+    yr = answers(out, "atomic-pair-eam_real.yaml", "real_")
+    assert yr["pair_coeff"] == y["pair_coeff"] and "units index real" in yr["pre_commands"]
     np.savez_compressed(OUT / "ref_yaml_pair_eam.npz", **out)
 
 
@@ -106,6 +121,8 @@ def pair_eam_alloy_fixture(yaml_name="atomic-pair-eam_alloy.yaml", style="eam/al
         assert np.array_equal(fr[:, 0].astype(int), np.arange(1, 33))
         out[f"{pre}_forces"] = fr[:, 1:]
     out["epsilon"] = float(y["epsilon"])
+    yr = answers(out, yaml_name.replace(".yaml", "_real.yaml"), "real_")
+    assert yr["pair_coeff"] == y["pair_coeff"] and "units index real" in yr["pre_commands"]
     np.savez_compressed(OUT / out_name, **out)
 
 

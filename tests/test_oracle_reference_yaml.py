@@ -12,19 +12,21 @@ import numpy as np
 
 from common import by_tag, make_oracle
 from lammps_b200 import eam as eam_mod
+from lammps_b200 import units as units_mod
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
 
-def _system():
+def _system(units="metal"):
     d = np.load(GOLDEN / "ref_yaml_pair_eam.npz")
+    c = units_mod.METAL2REAL_ENERGY if units == "real" else 1.0
     files = [eam_mod.Funcfl(float(d[f"{k}_mass"]), int(d[f"{k}_nrho"]), float(d[f"{k}_drho"]),
                             int(d[f"{k}_nr"]), float(d[f"{k}_dr"]), float(d[f"{k}_cut"]),
                             d[f"{k}_frho"], d[f"{k}_zr"], d[f"{k}_rhor"]) for k in ("al", "cu")]
-    T = eam_mod.funcfl_tables(files, [0, 1])      # pair_coeff 1 1 Al_jnp.eam / 2 2 Cu_u3.eam
+    T = eam_mod.funcfl_tables(files, [0, 1], c)   # pair_coeff 1 1 Al_jnp.eam / 2 2 Cu_u3.eam
     # in.metal: units metal (skin 2.0), neigh_modify delay 2 every 2 check no, timestep 0.0001;
     # PairEAM::coeff sets the masses from the funcfl files
-    s = dict(kind="eam", units="metal", x=d["x"], v=d["v"], type=d["type"], tag=d["tag"],
+    s = dict(kind="eam", units=units, x=d["x"], v=d["v"], type=d["type"], tag=d["tag"],
              image=d["image"], mass=T.mass, lo=d["lo"], hi=d["hi"], skin=2.0, every=2, delay=2,
              check=False, dt=0.0001, tables=T.as_dict())
     return s, d
@@ -33,6 +35,29 @@ def _system():
 def _close(a, b, eps):
     a, b = np.asarray(a, float), np.asarray(b, float)
     return np.all(np.abs(a - b) <= eps * np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-300))
+
+
+def _check(s, d, pre):
+    eps = float(d[pre + "epsilon"])
+    o = make_oracle(s)
+    o.setup(1, 1)
+    (f,) = by_tag(o.tag(), o.f())
+    assert _close(f, d[pre + "init_forces"], eps), np.abs(f - d[pre + "init_forces"]).max()
+    assert _close(o.eng_vdwl, d[pre + "init_vdwl"], eps)
+    assert _close(o.virial, d[pre + "init_stress"], eps)
+    o.run(4, 0, 4)                                   # tallies on the last step, like the test
+    (f,) = by_tag(o.tag(), o.f())
+    assert _close(f, d[pre + "run_forces"], 5 * eps), np.abs(f - d[pre + "run_forces"]).max()
+    assert _close(o.eng_vdwl, d[pre + "run_vdwl"], eps)
+    assert _close(o.virial, d[pre + "run_stress"], eps)
+    return o
+
+
+def test_pair_eam_real_units_yaml():
+    """atomic-pair-eam_real.yaml: the same files under `units real`; the reader converts F(rho)
+    and Z(r) (pair_eam.cpp:701-706) and fix nve integrates with the real-units ftm2v"""
+    s, d = _system("real")
+    _check(s, d, "real_")
 
 
 def test_pair_eam_yaml_init_and_run():
@@ -52,14 +77,15 @@ def test_pair_eam_yaml_init_and_run():
     assert _close(o.virial, d["run_stress"], eps)
 
 
-def _alloy_system(name="ref_yaml_pair_eam_alloy.npz"):
+def _alloy_system(name="ref_yaml_pair_eam_alloy.npz", units="metal"):
     d = np.load(GOLDEN / name)
+    c = units_mod.METAL2REAL_ENERGY if units == "real" else 1.0
     nel = len(d["elements"])
     f = eam_mod.Setfl([str(e) for e in d["elements"]], d["mass"], int(d["nrho"]), float(d["drho"]),
                       int(d["nr"]), float(d["dr"]), float(d["cut"]), d["frho"], d["rhor"],
                       {(i, j): d[f"z2r_{i}_{j}"] for i in range(nel) for j in range(i + 1)})
-    T = eam_mod.setfl_tables(f, [str(e) for e in d["type_elements"]])   # pair_coeff * * file Cu Ni
-    s = dict(kind="eam", units="metal", x=d["x"], v=d["v"], type=d["type"], tag=d["tag"],
+    T = eam_mod.setfl_tables(f, [str(e) for e in d["type_elements"]], c)   # pair_coeff * * file Cu Ni
+    s = dict(kind="eam", units=units, x=d["x"], v=d["v"], type=d["type"], tag=d["tag"],
              image=d["image"], mass=T.mass, lo=d["lo"], hi=d["hi"], skin=2.0, every=2, delay=2,
              check=False, dt=0.0001, tables=T.as_dict())
     return s, d
@@ -87,3 +113,10 @@ def test_pair_eam_alloy_and_fs_yaml_init_and_run(fixture):
     assert _close(f, d["run_forces"], 5 * eps), np.abs(f - d["run_forces"]).max()
     assert _close(o.eng_vdwl, d["run_vdwl"], eps)
     assert _close(o.virial, d["run_stress"], eps)
+
+
+@pytest.mark.parametrize("fixture", ["ref_yaml_pair_eam_alloy.npz", "ref_yaml_pair_eam_fs.npz"])
+def test_pair_eam_alloy_and_fs_real_units_yaml(fixture):
+    """atomic-pair-eam_alloy_real.yaml / atomic-pair-eam_fs_real.yaml (units real)"""
+    s, d = _alloy_system(fixture, "real")
+    _check(s, d, "real_")
