@@ -7,9 +7,13 @@
 //   v      3 x double[nmax] SoA,  f 3 x double[nmax] SoA (owned + ghost, Newton on)
 //   tag/mask/image int32[nmax], xhold 3 x double[nmax]
 //   ostart/gstart  int32[mbins+1]  bin -> first owned / first ghost index (counting sort)
-//   tile list (default): uint16 entries into the shared-memory staging of a bin tile, 8 per
+//   tile list (lj/cut): uint16 entries into the shared-memory staging of a bin tile, 8 per
 //          16-byte word, [slot/8][list row]; see kernels_tile.cuh
-//   neigh  (B200_LIST=flat) int32[maxneigh][nstride] transposed half list, numneigh int32[nlocal]
+//   neigh  (eam, B200_LIST=flat) int32[maxneigh][nstride] transposed half list; numneigh
+//          int32[nlocal] holds the half-list count in both layouts
+// Streams: `stream` (high priority) carries the timestep and the halo; `stream2` only runs the
+// interior tiles beside the halo on multi-GPU runs; the plain timestep of a single sub-domain is
+// replayed from a CUDA graph (graph_step).
 //   gsrc   int32[nghost], gdir uint8[nghost]: owner index and direction of every ghost
 #include "common.cuh"
 #include "kernels_halo.cuh"

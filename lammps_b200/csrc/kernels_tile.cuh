@@ -28,9 +28,13 @@
 // the ghost, which the reverse halo returns to its owner exactly as the reference does with
 // Newton on.  Energy is tallied on FWD entries only, so every pair counts once; the virial
 // uses the f.x form over owned+ghost atoms as before (pair.cpp:1809-1825).
-// rsq uses the reference's operation order (rsq_ref) in the build and in the pair kernels, in
-// both precisions, so list membership and cutoff decisions are those of the CPU path.
-// No tensor cores: nothing here is a dense contraction.
+// rsq uses the reference's operation order (rsq_ref) in the build and in the FP64-staged pair
+// kernels, so list membership and cutoff decisions are those of the CPU path; the fixed-point
+// mixed kernel decides in FP32 and re-takes every decision within 2e-6 of the cutoff in FP64.
+// Kernels: k_tile_count / k_tile_split (per-tile sizes, interior|boundary order for the
+// halo/compute overlap), k_tile_build (list), k_tile_export (test hook), k_tile_lj (FP64 and
+// FP64-staged mixed), k_tile_lj_fx (fixed-point staged mixed), k_tile_eam_rho / k_tile_eam_force
+// (behind B200_LIST=tile).  No tensor cores: nothing here is a dense contraction.
 #pragma once
 #include "common.cuh"
 #include "kernels_pair.cuh"
