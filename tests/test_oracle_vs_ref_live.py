@@ -1,0 +1,84 @@
+"""The oracle against the UNMODIFIED reference compiled here (oracle/_ref/liblammps_ref.so,
+driven through its C library API), on cases the committed fixtures do not cover: two atom
+types with mixed and explicit lj/cut coefficients, pair_modify shift, a non-cubic box, and
+`check yes` rebuilds.  Skipped where oracle/_ref is not built.  CPU only."""
+import numpy as np
+import pytest
+
+from common import by_tag, make_oracle
+from lammps_b200 import pair_lj
+from oracle import ref_harness as R
+from oracle.oracle import canonical_pairs_box
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+
+SETUP = """
+units lj
+atom_style atomic
+lattice fcc 0.8442
+region box block 0 {nx} 0 {ny} 0 {nz}
+create_box 2 box
+create_atoms 1 box
+set type 1 type/ratio 2 0.4 4711
+mass 1 1.0
+mass 2 1.7
+velocity all create 1.44 87287 loop geom
+pair_style lj/cut 2.5
+pair_coeff 1 1 1.0 1.0 2.5
+pair_coeff 2 2 0.8 1.1 2.2
+{cross}
+pair_modify shift {shift}
+neighbor 0.3 bin
+neigh_modify {neigh}
+fix 1 all nve
+timestep 0.005
+thermo 10
+run 0
+"""
+
+
+@pytest.mark.parametrize("cross,shift,neigh,every,delay,check", [
+    ("pair_coeff 1 2 0.9 1.05 2.4", "no", "delay 0 every 20 check no", 20, 0, False),
+    ("", "yes", "delay 0 every 1 check yes", 1, 0, True),     # geometric mixing, shifted energy
+])
+def test_two_type_lj_matches_the_compiled_reference(cross, shift, neigh, every, delay, check):
+    nsteps = 40
+    with R.RefLammps() as ref:
+        ref.commands(SETUP.format(nx=6, ny=5, nz=7, cross=cross, shift=shift, neigh=neigh))
+        n = ref.natoms()
+        lo, hi = ref.box()
+        x0, v0 = ref.atom_vec3("x", n), ref.atom_vec3("v", n)
+        typ, tag = ref.atom_int("type", n), ref.atom_int("id", n)
+        f0 = ref.atom_vec3("f", n)
+        pe0 = ref.thermo("pe") * n
+        nall = n + ref.setting("nghost")
+        pi, pj = ref.neighbor_pairs("lj/cut")
+        kref = canonical_pairs_box(pi, pj, ref.atom_int("id", nall), ref.atom_vec3("x", nall), lo, hi,
+                                   nlocal=n)
+        ref.command(f"run {nsteps}")
+        x1, f1, tag1 = ref.atom_vec3("x", n), ref.atom_vec3("f", n), ref.atom_int("id", n)
+        pe1, press1 = ref.thermo("pe") * n, ref.thermo("press")
+    coeffs = {(1, 1): (1.0, 1.0, 2.5), (2, 2): (0.8, 1.1, 2.2)}
+    if cross:
+        coeffs[(1, 2)] = (0.9, 1.05, 2.4)
+    s = dict(kind="lj", units="lj", x=x0, v=v0, type=typ, tag=tag, mass=np.array([0.0, 1.0, 1.7]),
+             lo=lo, hi=hi, skin=0.3, every=every, delay=delay, check=check, dt=0.005,
+             tables=pair_lj.lj_cut_tables(2, coeffs, 2.5, offset_flag=shift == "yes"))
+    o = make_oracle(s)
+    o.setup(1, 1)
+    pi, pj = o.pairs()
+    kor = canonical_pairs_box(pi, pj, o.tag(True), o.x(True), lo, hi, nlocal=o.nlocal)
+    assert np.array_equal(kor, kref), "half-list pair sets differ"
+    (fo,) = by_tag(o.tag(), o.f())
+    (fr,) = by_tag(tag, f0)
+    assert np.abs(fo - fr).max() <= 1e-13 * np.abs(fr).max()
+    assert abs(o.eng_vdwl - pe0) <= 1e-13 * abs(pe0)
+    o.run(nsteps, 0, nsteps)
+    xo, fo = by_tag(o.tag(), o.x(), o.f())
+    xr, fr = by_tag(tag1, x1, f1)
+    prd = hi - lo
+    d = xo - xr
+    d -= prd * np.rint(d / prd)
+    assert np.abs(d).max() <= 1e-11
+    assert np.abs(fo - fr).max() <= 1e-9 * np.abs(fr).max()
+    assert abs(o.eng_vdwl - pe1) <= 1e-11 * abs(pe1)
