@@ -82,3 +82,41 @@ def test_two_type_lj_matches_the_compiled_reference(cross, shift, neigh, every, 
     assert np.abs(d).max() <= 1e-11
     assert np.abs(fo - fr).max() <= 1e-9 * np.abs(fr).max()
     assert abs(o.eng_vdwl - pe1) <= 1e-11 * abs(pe1)
+
+
+def test_nve_on_a_sub_group_matches_the_compiled_reference():
+    """`fix nve` applied to a group (FixNVE's `mask[i] & groupbit`, fix_nve.cpp:68-145): atoms
+    outside the group feel forces but do not move -- the sub-group aspect of the reference's
+    fix-timestep-nve.yaml, on an atomic system"""
+    nsteps = 30
+    text = SETUP.format(nx=5, ny=5, nz=5, cross="", shift="no", neigh="delay 0 every 5 check no")
+    text = text.replace("fix 1 all nve", "group movers id <= 300\nfix 1 movers nve")
+    with R.RefLammps() as ref:
+        ref.commands(text)
+        n = ref.natoms()
+        lo, hi = ref.box()
+        x0, v0 = ref.atom_vec3("x", n), ref.atom_vec3("v", n)
+        typ, tag, mask = ref.atom_int("type", n), ref.atom_int("id", n), ref.atom_int("mask", n)
+        ref.command(f"run {nsteps}")
+        x1, v1, tag1 = ref.atom_vec3("x", n), ref.atom_vec3("v", n), ref.atom_int("id", n)
+    groupbit = 2                       # group `all` is bit 0, the first user group bit 1
+    assert set(np.unique(mask)) == {1, 3}
+    from oracle.oracle import Oracle
+    from lammps_b200 import units
+    o = Oracle()
+    o.set_box(lo, hi)
+    o.set_atoms(x0, v0, typ, tag, np.array([0.0, 1.0, 1.7]), mask=mask)
+    o.set_neighbor(0.3, every=5, delay=0, check=False)
+    o.fix_nve(0.005, units.get("lj").ftm2v, groupbit)
+    o.pair_lj_cut(pair_lj.lj_cut_tables(2, {(1, 1): (1.0, 1.0, 2.5), (2, 2): (0.8, 1.1, 2.2)}, 2.5))
+    o.setup(1, 1)
+    o.run(nsteps, 0, 0)
+    xo, vo = by_tag(o.tag(), o.x(), o.v())
+    xr, vr = by_tag(tag1, x1, v1)
+    prd = hi - lo
+    d = xo - xr
+    d -= prd * np.rint(d / prd)
+    assert np.abs(d).max() <= 1e-12 and np.abs(vo - vr).max() <= 1e-11
+    frozen = np.sort(tag)[300:] - 1                   # ids > 300 are outside the group
+    (xs,) = by_tag(tag, x0)
+    assert np.array_equal(xr[frozen], xs[frozen])     # they never moved
