@@ -22,6 +22,7 @@
 #include "kernels_pair_mixed.cuh"
 #include "kernels_step.cuh"
 #include "kernels_tile.cuh"
+#include "kernels_tile2.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -125,6 +126,10 @@ struct b200_ctx {
   bool use_tiles = true;
   int list_mode = 0;            // B200_LIST: 0 auto (tiles for lj/cut, flat for eam), 1 tile, 2 flat
   bool tiles_active = false;    // the current list is the tile list
+  // the tile list holds every ghost partner of an owned atom (k_tile_build<.,FULLGHOST>): the
+  // pair kernel stores complete owned forces, nothing is scattered onto ghosts, and the step has
+  // no force clear and no reverse halo; energy and virial are tallied inside the pair kernel
+  bool full_ghost = false;
   int tile_req[3] = {0, 0, 0};  // B200_TILE=tx,ty,tz override of the tile size
   int tile_level = -1;
   TileGeom tg;
@@ -132,9 +137,14 @@ struct b200_ctx {
   int ibin_lo[3] = {0, 0, 0}, ibin_n[3] = {0, 0, 0};  // local bins that can hold owned atoms
   DBuf<int> tile_ibase;
   DBuf<unsigned short> tl_iloc, tl_num;
+  DBuf<int> tl_gi;              // global index of the owned atom of every list row
+  // FP64 lj/cut on tiles: k_tile_lj2 launch shape {threads, CTAs/SM, pair bodies in flight}
+  // (B200_LJ2=threads,minb,ilp; B200_LJ2=0 selects the first-generation k_tile_lj)
+  int lj2[3] = {352, 2, 2};
+  bool use_lj2 = true;
   DBuf<uint4> tl_list;
   int *tflags = nullptr;  // [8] device: max staged, max owned/tile, max entries, max FWD, owned total, overflow
-  int tile_NI = 0, tile_scap = 0, tile_slots = 0, tile_threads = 256, tile_maxfull = 0;
+  int tile_NI = 0, tile_scap = 0, tile_slots = 0, tile_threads = 256, tile_maxfull = 0, tile_maxown = 0;
   // halo/compute overlap (multi-GPU, tile list): tiles that stage no ghost ("interior") run on
   // stream2 while the forward halo, the boundary tiles and the reverse halo run on `stream`
   DBuf<int> tile_bflag, tile_bpos, tile_ids;
@@ -916,9 +926,12 @@ static int tile_attr(b200_ctx *ctx, K kernel) {
   return B200_OK;
 }
 
+static int lj2_attrs(b200_ctx *ctx);
 static int tile_kernel_attrs(b200_ctx *ctx) {
-  TRY(tile_attr(ctx, k_tile_build<true>));
-  TRY(tile_attr(ctx, k_tile_build<false>));
+  TRY(tile_attr(ctx, (k_tile_build<true, true>)));
+  TRY(tile_attr(ctx, (k_tile_build<false, true>)));
+  TRY(tile_attr(ctx, (k_tile_build<true, false>)));
+  TRY(tile_attr(ctx, (k_tile_build<false, false>)));
   TRY(tile_attr(ctx, k_tile_export));
 #define A3(K) \
   TRY(tile_attr(ctx, K<false, false, false>)); TRY(tile_attr(ctx, K<false, false, true>)); \
@@ -927,6 +940,7 @@ static int tile_kernel_attrs(b200_ctx *ctx) {
   TRY(tile_attr(ctx, K<true, true, false>));   TRY(tile_attr(ctx, K<true, true, true>));
   A3(k_tile_lj)
 #undef A3
+  TRY(lj2_attrs(ctx));
   TRY(tile_attr(ctx, k_tile_lj_fx<false, false>));
   TRY(tile_attr(ctx, k_tile_lj_fx<false, true>));
   TRY(tile_attr(ctx, k_tile_lj_fx<true, false>));
@@ -969,7 +983,7 @@ static int build_tiles(b200_ctx *ctx) {
       TRY(reserve(ctx, ctx->tile_bpos, (size_t)G.ntiles + 2));
       TRY(reserve(ctx, ctx->tile_ids, (size_t)G.ntiles + 2));
       k_tile_count<<<G.ntiles, 128, 0, s>>>(G, ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p,
-                                            ctx->tile_bflag.p, ctx->tflags);
+                                            ctx->tile_bflag.p, ctx->tflags, eam ? 1 : 0);
       ctx->launches++;
       LAUNCH_CHECK();
       TRY(scan_inplace(ctx, ctx->tile_ibase.p, G.ntiles));
@@ -990,7 +1004,7 @@ static int build_tiles(b200_ctx *ctx) {
       if (h[4] != nl)
         return ctx->fail(B200_ELOST, "bin tiles cover %d of %d owned atoms", h[4], nl);
       ctx->tile_NI = ctx->h_flags[16];
-      ctx->tile_scap = cdiv(std::max(h[0], 1), 64) * 64;
+      ctx->tile_scap = cdiv(std::max(h[0], 1) + 1, 64) * 64;  // + the dummy atom of padding entries
       const size_t need = std::max(tile_smem_bytes(ctx->tile_scap, G.srow_y * G.srow_z, G.sbx, true, false),
                                    tile_smem_bytes(ctx->tile_scap, G.srow_y * G.srow_z, G.sbx, false, eam));
       const bool last = ctx->tile_req[0] > 0 || ctx->tile_level == TILE_NMENU - 1;
@@ -1003,6 +1017,7 @@ static int build_tiles(b200_ctx *ctx) {
   const TileGeom &G = ctx->tg;
   const int rows = G.srow_y * G.srow_z;
   // one thread per owned atom of the fullest tile; very full tiles take two passes
+  ctx->tile_maxown = h[1];
   int thr = cdiv(std::max(h[1], 1), 32) * 32;
   if (thr > 352) thr = cdiv(cdiv(h[1], cdiv(h[1], 352)), 32) * 32;
   ctx->tile_threads = std::min(std::max(thr, 64), 352);
@@ -1015,20 +1030,22 @@ static int build_tiles(b200_ctx *ctx) {
     TRY(reserve(ctx, ctx->tl_list, NI * (ctx->tile_slots / 8)));
     TRY(reserve(ctx, ctx->tl_iloc, NI));
     TRY(reserve(ctx, ctx->tl_num, NI));
+    TRY(reserve(ctx, ctx->tl_gi, NI));
     TRY(reserve(ctx, ctx->numneigh, (size_t)std::max(nl, 1)));
     CK(cudaMemsetAsync(ctx->tflags + 2, 0, 2 * sizeof(int), s));
     CK(cudaMemsetAsync(ctx->tflags + 5, 0, sizeof(int), s));
     const int ph1 = ph_begin(ctx, B200_PH_BUILD);
-    if (ctx->ntypes == 1)
-      k_tile_build<true><<<G.ntiles, ctx->tile_threads, smem, s>>>(
-          G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,
-          ctx->tile_NI, ctx->tile_slots, ctx->cutneighsq_h[n1 + 1], ctx->cutneighsq_d.p, ctx->ntypes,
-          ctx->tl_iloc.p, ctx->tl_num.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags);
-    else
-      k_tile_build<false><<<G.ntiles, ctx->tile_threads, smem, s>>>(
-          G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,
-          ctx->tile_NI, ctx->tile_slots, 0.0, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,
-          ctx->tl_num.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags);
+    const bool one = ctx->ntypes == 1;
+    const double cut1 = one ? ctx->cutneighsq_h[n1 + 1] : 0.0;
+#define TB(ONE, FULL)                                                                                  \
+  k_tile_build<ONE, FULL><<<G.ntiles, ctx->tile_threads, smem, s>>>(                                  \
+      G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,   \
+      ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,           \
+      ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags)
+    // lj/cut: every ghost partner is stored (no scatter, no reverse halo); eam: FWD ghosts only
+    if (!eam) { if (one) TB(true, true); else TB(false, true); }
+    else      { if (one) TB(true, false); else TB(false, false); }
+#undef TB
     ctx->launches++;
     LAUNCH_CHECK();
     ph_end(ctx, ph1);
@@ -1045,6 +1062,7 @@ static int build_tiles(b200_ctx *ctx) {
                        ctx->max_numneigh, ctx->one);
     if (ctx->tile_maxfull <= ctx->tile_slots) {
       ctx->tiles_active = true;
+      ctx->full_ghost = !eam;
       ctx->maxneigh = ctx->tile_slots;
       return B200_OK;
     }
@@ -1065,6 +1083,7 @@ static int build_list(b200_ctx *ctx) {
     if (ctx->tiles_active) return B200_OK;
   }
   ctx->tiles_active = false;
+  ctx->full_ghost = false;
   if (ctx->maxneigh == 0) ctx->maxneigh = 96;
   for (int attempt = 0; attempt < 4; attempt++) {
     ctx->nstride = cdiv(std::max(nl, 1), 32) * 32;
@@ -1284,7 +1303,9 @@ static int force_clear(b200_ctx *ctx) {
   const int nall = ctx->nlocal + ctx->nghost;
   // mixed mode: the pair kernel stores f_i and k_merge_ff writes the ghosts; only the float4
   // scatter array is cleared (inside pair_compute)
-  if (ctx->tiles_active) {
+  if (ctx->tiles_active && ctx->full_ghost) {
+    // nothing to clear: owned forces are stored, ghost forces do not exist
+  } else if (ctx->tiles_active) {
     // tile kernels store f of every owned atom; only the ghosts (Newton scatter targets) are
     // cleared -- unless the forward halo or the rebuild of this step already did
     if (ctx->nghost > 0 && !ctx->ghost_f_clean)
@@ -1302,7 +1323,7 @@ static int forward_comm(b200_ctx *ctx) {
   cudaStream_t s = ctx->stream;
   // tile path: the unpack kernel also zeroes the ghost forces (force_clear then has nothing to do)
   Vec3Ptr fclear{{nullptr, nullptr, nullptr}};
-  if (ctx->tiles_active && ctx->nghost > 0) {
+  if (ctx->tiles_active && !ctx->full_ghost && ctx->nghost > 0) {
     fclear = Vec3Ptr{{ctx->f[0], ctx->f[1], ctx->f[2]}};
     ctx->ghost_f_clean = true;
   }
@@ -1369,6 +1390,8 @@ static int reverse_halo(b200_ctx *ctx, Vec3Ptr a) {
 }
 
 static int reverse_comm(b200_ctx *ctx) {
+  // lj/cut on tiles evaluates boundary pairs on both sides: no ghost forces to return
+  if (ctx->tiles_active && ctx->full_ghost) return B200_OK;
   const int ph5 = ph_begin(ctx, B200_PH_REVERSE);
   Vec3Ptr f{{ctx->f[0], ctx->f[1], ctx->f[2]}};
   TRY(reverse_halo<3>(ctx, f));
@@ -1407,13 +1430,58 @@ static int forward_scalar(b200_ctx *ctx, double *a) {
   return B200_OK;
 }
 
+// FP64 lj/cut, second-generation kernel (kernels_tile2.cuh).  The launch shapes instantiated:
+// {threads per CTA, CTAs per SM} in {352x2, 448x2, 320x2, 256x2, 320x3, 256x4}, 2 or 4 pair bodies in flight.
+#define LJ2_SHAPES(X) X(352, 2) X(448, 2) X(320, 2) X(256, 2) X(320, 3) X(256, 4)
+static int lj2_attrs(b200_ctx *ctx) {
+#define X(T, B)                                                    \
+  TRY(tile_attr(ctx, k_tile_lj2<false, true, 2, T, B>));           \
+  TRY(tile_attr(ctx, k_tile_lj2<false, true, 4, T, B>));           \
+  TRY(tile_attr(ctx, k_tile_lj2<true, true, 2, T, B>));            \
+  TRY(tile_attr(ctx, k_tile_lj2<false, false, 2, T, B>));          \
+  TRY(tile_attr(ctx, k_tile_lj2<true, false, 2, T, B>));
+  LJ2_SHAPES(X)
+#undef X
+  return B200_OK;
+}
+
+static int launch_tile_lj2(b200_ctx *ctx, cudaStream_t s, int eflag, const int *ids, int ntiles) {
+  const TileGeom &G = ctx->tg;
+  const int nl = ctx->nlocal, c = ctx->cur, scap = ctx->tile_scap;
+  const bool one = ctx->ntypes == 1;
+  const size_t sm = tile2_smem_bytes(scap, !one);
+  const int T = ctx->lj2[0], B = ctx->lj2[1], ilp = (one && !eflag) ? ctx->lj2[2] : 2;
+  // no more threads than the fullest tile has atoms (whole warps)
+  const int thr = std::max(32, std::min(T, cdiv(std::max(ctx->tile_maxown, 1), 32) * 32));
+#define L2(EV, ONE, ILP, TT, BB)                                                                    \
+  k_tile_lj2<EV, ONE, ILP, TT, BB><<<ntiles, thr, sm, s>>>(                                        \
+      G, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tile_NI,             \
+      ctx->tile_slots, ctx->tl_iloc.p, ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->f[0],      \
+      ctx->f[1], ctx->f[2], ctx->lj_one, ctx->lj_tab.p, ctx->ntypes, ctx->ev, scap, ctx->tflags, ids)
+#define X(TT, BB)                                                      \
+  if (T == TT && B == BB) {                                            \
+    if (one && !eflag) { if (ilp == 4) L2(false, true, 4, TT, BB); else L2(false, true, 2, TT, BB); } \
+    else if (one) L2(true, true, 2, TT, BB);                           \
+    else if (!eflag) L2(false, false, 2, TT, BB);                      \
+    else L2(true, false, 2, TT, BB);                                   \
+  } else
+  LJ2_SHAPES(X)
+  return ctx->fail(B200_EARG, "no k_tile_lj2 instance for %d threads x %d CTAs/SM", T, B);
+#undef X
+#undef L2
+  ctx->launches++;
+  LAUNCH_CHECK();
+  return B200_OK;
+}
+
 // lj/cut over `ntiles` tiles of the tile list (ids == nullptr: all tiles in order) on stream s
 static int launch_tile_lj(b200_ctx *ctx, cudaStream_t s, int eflag, const int *ids, int ntiles) {
   if (ntiles <= 0) return B200_OK;
   const TileGeom &G = ctx->tg;
   const int nl = ctx->nlocal, c = ctx->cur, thr = ctx->tile_threads, scap = ctx->tile_scap;
   const size_t sm = tile_smem_bytes(scap, G.srow_y * G.srow_z, G.sbx, false, false);
-  const bool one = ctx->ntypes == 1, mixed = ctx->prec == B200_PREC_MIXED;
+ const bool one = ctx->ntypes == 1, mixed = ctx->prec == B200_PREC_MIXED;
+  if (!mixed && ctx->use_lj2) return launch_tile_lj2(ctx, s, eflag, ids, ntiles);
 #define TLJ(EV, ONE, MX)                                                                            \
   k_tile_lj<EV, ONE, MX><<<ntiles, thr, sm, s>>>(                                                   \
       G, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tile_NI,             \
@@ -1468,14 +1536,14 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag, int part = 0, bool 
     const int ph6 = ph_begin(ctx, B200_PH_PAIR);
     TRY(launch_tile_lj(ctx, s, eflag, ctx->tile_ids.p + ctx->tile_nint, ctx->tile_nbnd));
     ph_end(ctx, ph6);
-    if (vflag && nl + ng > 0) {
+    if (vflag && nl + ng > 0 && !ctx->full_ghost) {
       CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
       const int gv = std::min(cdiv(nl + ng, 256), 148 * 8);
       k_virial_fdotr<<<gv, 256, 0, s>>>(nl + ng, ctx->xt[c], ctx->f[0], ctx->f[1], ctx->f[2], ctx->ev);
       ctx->launches++;
       LAUNCH_CHECK();
     } else if (joined)
-      *joined = false;
+      *joined = false;  // (FULLGHOST: the virial was tallied pairwise inside the tile kernels)
     return B200_OK;
   }
   if (ev) CK(cudaMemsetAsync(ctx->ev, 0, 7 * sizeof(double), s));
@@ -1526,7 +1594,7 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag, int part = 0, bool 
       return ctx->fail(B200_EARG, "no pair style set");
     LAUNCH_CHECK();
     ph_end(ctx, ph6);
-    if (vflag && nl + ng > 0) {
+    if (vflag && nl + ng > 0 && !ctx->full_ghost) {
       const int ph7 = ph_begin(ctx, B200_PH_THERMO);
       const int gv = std::min(cdiv(nl + ng, 256), 148 * 8);
       k_virial_fdotr<<<gv, 256, 0, s>>>(nl + ng, xt, fx, fy, fz, ctx->ev);
@@ -1768,6 +1836,13 @@ int b200_create(b200_ctx **out, int device, int precision) {
     if (const char *e = getenv("B200_OVERLAP")) ctx->overlap = atoi(e) != 0;
     if (const char *e = getenv("B200_GRAPH")) ctx->use_graph = atoi(e) != 0;
     if (const char *e = getenv("B200_MIXED_FX")) ctx->mixed_fx = atoi(e) != 0;
+    if (const char *e = getenv("B200_LJ2")) {
+      int a[3];
+      const int k = sscanf(e, "%d,%d,%d", &a[0], &a[1], &a[2]);
+      if (k == 1 && a[0] == 0) ctx->use_lj2 = false;
+      else if (k == 3 && (a[2] == 2 || a[2] == 4))
+        for (int d = 0; d < 3; d++) ctx->lj2[d] = a[d];
+    }
   }
   TRY(dalloc(ctx, &ctx->ev, 8));
   TRY(dalloc(ctx, &ctx->flags, 4));
@@ -1813,7 +1888,7 @@ void b200_destroy(b200_ctx *ctx) {
   F(ctx->neigh.p);
   F(ctx->numneigh.p); F(ctx->lj_tab.p); F(ctx->eam_i.p); F(ctx->eam_d.p); F(ctx->eam_one_d.p); F(ctx->ev); F(ctx->flags);
   F(ctx->cnt64);
-  F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p);
+  F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p); F(ctx->tl_gi.p);
   if (ctx->h_ev) cudaFreeHost(ctx->h_ev);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   for (auto &r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -249,6 +249,15 @@ __device__ __forceinline__ void tile_stage(int nlocal, const double4 *__restrict
       T.gmap[s] = src;
     }
   }
+  if (threadIdx.x == 0) {
+    // slot S: the dummy atom that the padding entries of a list row name (k_tile_build); its
+    // record must be readable (the branch-free bodies evaluate it before discarding it)
+    const int S = H->S;
+    T.x[S] = T.y[S] = T.z[S] = 1.0e10;
+    if (WITH_FP) T.fp[S] = 0.0;
+    T.type[S] = 1;
+    T.gmap[S] = 0;
+  }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 }
@@ -271,7 +280,7 @@ __device__ __forceinline__ int tile_own_atom(const TileGeom &G, const TileHdr *H
 // body(e, valid) must be branch-free (entries past n are zero padding -> valid = false): the
 // eight bodies of a word then interleave in the instruction stream.  ghost(e) runs only for
 // FWD|GHOST entries, behind one test per word.
-template <int ILP, class Body, class Ghost>
+template <int ILP, bool SCATTER, class Body, class Ghost>
 __device__ __forceinline__ void tile_walk(const uint4 *__restrict__ list, int g, int n, int NI,
                                           Body &&body, Ghost &&ghost) {
   const uint4 *lp = list + g;
@@ -285,7 +294,7 @@ __device__ __forceinline__ void tile_walk(const uint4 *__restrict__ list, int g,
     auto step2 = [&](unsigned w, int kb) {
       body(w & 0xffffu, kb < n);
       body(w >> 16, kb + 1 < n);
-      if (w & (TILE_GHOST | (TILE_GHOST << 16))) {
+      if (SCATTER && (w & (TILE_GHOST | (TILE_GHOST << 16)))) {
         if ((w & TILE_GHOST) && kb < n) ghost(w & 0xffffu);
         if ((w & (TILE_GHOST << 16)) && kb + 1 < n) ghost(w >> 16);
       }
@@ -295,7 +304,7 @@ __device__ __forceinline__ void tile_walk(const uint4 *__restrict__ list, int g,
       body(w0 >> 16, kb + 1 < n);
       body(w1 & 0xffffu, kb + 2 < n);
       body(w1 >> 16, kb + 3 < n);
-      if ((w0 | w1) & (TILE_GHOST | (TILE_GHOST << 16))) {
+      if (SCATTER && ((w0 | w1) & (TILE_GHOST | (TILE_GHOST << 16)))) {
         if ((w0 & TILE_GHOST) && kb < n) ghost(w0 & 0xffffu);
         if ((w0 & (TILE_GHOST << 16)) && kb + 1 < n) ghost(w0 >> 16);
         if ((w1 & TILE_GHOST) && kb + 2 < n) ghost(w1 & 0xffffu);
@@ -327,12 +336,13 @@ __global__ void __launch_bounds__(128) k_tile_count(TileGeom G, const int *__res
                                                     const int *__restrict__ gstart,
                                                     int *__restrict__ tile_ibase,
                                                     int *__restrict__ tile_bflag,
-                                                    int *__restrict__ tflags) {
+                                                    int *__restrict__ tflags, int reverse_halo) {
   __shared__ TileHdr H;
   const TilePos P = tile_pos(G, blockIdx.x);
   const int S = tile_rows(G, P, ostart, gstart, &H);
-  // "boundary" tile: it stages a ghost (must wait for the forward halo) or its staged bins reach
-  // the first/last owned bin of a dimension -- then it may own atoms within the ghost cutoff of a
+  // "boundary" tile: it stages a ghost (must wait for the forward halo) or -- only when the pair
+  // style scatters onto ghosts and a reverse halo follows (eam on tiles) -- its staged bins reach
+  // the first/last owned bin of a dimension: then it may own atoms within the ghost cutoff of a
   // face, whose forces the reverse halo adds to (2 bins >= cutghost, nbin_standard.cpp:82-214).
   // Every other tile touches owned atoms only and can run beside the halo.
   int ghosts = 0;
@@ -340,7 +350,8 @@ __global__ void __launch_bounds__(128) k_tile_count(TileGeom G, const int *__res
   const int t0[3] = {P.tx0, P.ty0, P.tz0};
 #pragma unroll
   for (int d = 0; d < 3; d++)
-    ghosts |= (t0[d] - G.s[d] <= G.ilo[d]) || (t0[d] + G.t[d] - 1 + G.s[d] >= G.ilo[d] + G.nib[d] - 1);
+    if (reverse_halo)
+      ghosts |= (t0[d] - G.s[d] <= G.ilo[d]) || (t0[d] + G.t[d] - 1 + G.s[d] >= G.ilo[d] + G.nib[d] - 1);
   ghosts = __syncthreads_or(ghosts);
   if (threadIdx.x == 0) {
     tile_bflag[blockIdx.x] = ghosts ? 1 : 0;
@@ -370,14 +381,23 @@ __global__ void __launch_bounds__(256) k_tile_split(int ntiles, const int *__res
 // entry n of list row g lives in word (n/8)*NI + g (uint4), lane-contiguous for a warp.
 // tflags: [2] max entries per atom, [3] max FWD entries per atom, [5] tile overflow.
 // ---------------------------------------------------------------------------------------
-template <bool ONETYPE>
+// FULLGHOST: a row also holds the ghost partners that are NOT members of atom i's half list
+// (ghosts of the lower half stencil, of the bins left of the own bin, own-bin ghosts below i in
+// the (z,y,x) order), flagged GHOST without FWD.  Every pair that crosses the sub-domain
+// boundary is then evaluated from both sides -- on this rank for the owned atom, on the ghost's
+// owner for its own atom -- exactly like owned-owned pairs are inside a sub-domain: the pair
+// kernel stores complete forces for its owned atoms and there is neither a Newton scatter onto
+// ghosts nor a reverse halo (lj/cut on tiles).  The FWD entries are unchanged: still exactly the
+// reference's half/Newton-on list.  Without FULLGHOST (eam on tiles) only FWD ghosts are stored
+// and the pair kernels scatter onto them.
+template <bool ONETYPE, bool FULLGHOST>
 __global__ void __launch_bounds__(512) k_tile_build(
     TileGeom G, FullStencil F, int nlocal, const double4 *__restrict__ xt,
     const int *__restrict__ ostart, const int *__restrict__ gstart,
     const int *__restrict__ atombin, const int *__restrict__ tile_ibase, int NI, int maxslots,
     double cut1, const double *__restrict__ cutneighsq, int ntypes,
-    unsigned short *__restrict__ iloc, unsigned short *__restrict__ tnum, uint4 *__restrict__ list,
-    int *__restrict__ numneigh_half, int scap, int *__restrict__ tflags) {
+    unsigned short *__restrict__ iloc, unsigned short *__restrict__ tnum, int *__restrict__ tgi,
+    uint4 *__restrict__ list, int *__restrict__ numneigh_half, int scap, int *__restrict__ tflags) {
   extern __shared__ __align__(128) unsigned char tsm[];
   TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
   const TileS T = tile_carve(tsm, scap, false);
@@ -388,8 +408,8 @@ __global__ void __launch_bounds__(512) k_tile_build(
   const int tile = blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
   const TilePos P = tile_pos(G, tile);
   const int S = tile_rows(G, P, ostart, gstart, H);
-  if (S > scap || S > TILE_MAXSTAGE) {
-    if (tid == 0) atomicMax(&tflags[5], S);
+  if (S + 1 > scap || S + 1 > TILE_MAXSTAGE) {  // + 1: the dummy atom that padding entries name
+    if (tid == 0) atomicMax(&tflags[5], S + 1);
     return;
   }
   // staged index of the first owned / first ghost atom of every staged bin (+ end sentinel)
@@ -468,33 +488,40 @@ __global__ void __launch_bounds__(512) k_tile_build(
           run(bg[ca], bg[cb], TILE_FWD | TILE_GHOST);
         } else if (dz < 0 || dy < 0) {        // lower half: owned j holds (j,i) in ITS half list
           run(bo[ca], bo[cb], 0u);
+          if (FULLGHOST) run(bg[ca], bg[cb], TILE_GHOST);
         } else {
           // row (0,0): bins left of own bin -> transposed; own bin -> by list position;
           // right -> members.  Owned atoms of a row are staged in index order, so that is s > li.
           for (int s = bo[ca]; s < bo[cb]; s++)
             if (s != li) test(s, s > li ? TILE_FWD : 0u);
           const int c0 = bx - xs;
+          if (FULLGHOST) run(bg[ca], bg[c0], TILE_GHOST);
           for (int s = bg[c0]; s < bg[c0 + 1]; s++) {  // own-bin ghosts: npair_bin.cpp:156-171
             const double3 pj = tile_pos3(T, s);
-            if (pj.z < pi.z) continue;
-            if (pj.z == pi.z) {
-              if (pj.y < pi.y) continue;
-              if (pj.y == pi.y && pj.x < pi.x) continue;
+            bool member = true;
+            if (pj.z < pi.z) member = false;
+            else if (pj.z == pi.z) {
+              if (pj.y < pi.y) member = false;
+              else if (pj.y == pi.y && pj.x < pi.x) member = false;
             }
-            test(s, TILE_FWD | TILE_GHOST);
+            if (member) test(s, TILE_FWD | TILE_GHOST);
+            else if (FULLGHOST) test(s, TILE_GHOST);
           }
           run(bg[c0 + 1], bg[cb], TILE_FWD | TILE_GHOST);
         }
       }
       if ((n & 7) && (n >> 3) < (maxslots >> 3)) {
+        // the rest of the last word names staged slot S: a dummy atom the pair kernels park far
+        // away, so they need no per-entry bounds test (kernels_tile2.cuh)
         for (int k = n & 7; k < 8; k++) {
           qlo = (qlo >> 16) | (qhi << 48);
-          qhi >>= 16;
+          qhi = (qhi >> 16) | ((unsigned long long)S << 48);
         }
         list[(size_t)(n >> 3) * NI + g] = make_uint4((unsigned)qlo, (unsigned)(qlo >> 32),
                                                    (unsigned)qhi, (unsigned)(qhi >> 32));
       }
       iloc[g] = (unsigned short)li;
+      tgi[g] = gi;
       numneigh_half[gi] = nf;
     } else {
       iloc[g] = (unsigned short)TILE_NOATOM;
@@ -569,14 +596,14 @@ __global__ void __launch_bounds__(352, TILE_MINB) k_tile_lj(
   const int tile = tile_ids ? tile_ids[blockIdx.x] : blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
   const TilePos P = tile_pos(G, tile);
   const int S = tile_rows(G, P, ostart, gstart, H);
-  if (S > scap) {  // cannot happen between rebuilds (the rows are those the build staged)
-    if (tid == 0) atomicMax(&tflags[5], S);
+  if (S + 1 > scap) {  // cannot happen between rebuilds (the rows are those the build staged)
+    if (tid == 0) atomicMax(&tflags[5], S + 1);
     return;
   }
   tile_stage<false>(nlocal, xt, nullptr, H, T);
   const int ni = H->ni, ibase = tile_ibase[tile];
   const int n1 = ntypes + 1, n2 = n1 * n1;
-  double evdwl = 0.0;
+  double evdwl = 0.0, vir[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int ti = tid; ti < ni; ti += bd) {
     const int g = ibase + ti;
     const int li = iloc[g];
@@ -585,7 +612,6 @@ __global__ void __launch_bounds__(352, TILE_MINB) k_tile_lj(
     const int gi = T.gmap[li];
     const int itype = T.type[li];
     double fxi = 0.0, fyi = 0.0, fzi = 0.0;
-    float gxi = 0.0f, gyi = 0.0f, gzi = 0.0f;
     // pair force of one entry (times del gives the force on i); 0 outside the cutoff
     auto pair = [&](unsigned e, bool valid, double &delx, double &dely, double &delz, double &fp64,
                     float &fp32, double &epair) {
@@ -626,46 +652,39 @@ __global__ void __launch_bounds__(352, TILE_MINB) k_tile_lj(
         }
       }
     };
-    tile_walk<MIXED ? 4 : 2>(
+    // (the list is FULLGHOST: ghost partners are ordinary entries, nothing is scattered)
+    tile_walk<MIXED ? 4 : 2, false>(
         list, g, n, NI,
         [&](unsigned e, bool valid) {
           double delx, dely, delz, f64 = 0.0, ep = 0.0;
           float f32 = 0.0f;
           pair(e, valid, delx, dely, delz, f64, f32, ep);
-          if (MIXED) {
-            gxi += (float)delx * f32; gyi += (float)dely * f32; gzi += (float)delz * f32;
+          if (MIXED) {  // FP32 pair math, FP64 accumulation
+            fxi += (double)((float)delx * f32); fyi += (double)((float)dely * f32);
+            fzi += (double)((float)delz * f32);
           } else {
             fxi += delx * f64; fyi += dely * f64; fzi += delz * f64;
           }
-          if (EV) evdwl += ep;
-        },
-        [&](unsigned e) {  // Newton scatter onto a ghost; the reverse halo returns it to the owner
-          double delx, dely, delz, f64 = 0.0, ep = 0.0;
-          float f32 = 0.0f;
-          pair(e, true, delx, dely, delz, f64, f32, ep);
-          const int gj = T.gmap[e & TILE_IDX];
-          if (MIXED) {
-            atomicAdd(&fx[gj], -(double)((float)delx * f32));
-            atomicAdd(&fy[gj], -(double)((float)dely * f32));
-            atomicAdd(&fz[gj], -(double)((float)delz * f32));
-          } else {
-            atomicAdd(&fx[gj], -(delx * f64));
-            atomicAdd(&fy[gj], -(dely * f64));
-            atomicAdd(&fz[gj], -(delz * f64));
+          if (EV) {
+            // energy and virial are tallied once per pair, on the half-list (FWD) copy
+            // (Pair::ev_tally, pair.cpp:1087-1182: v = del (x) del * fpair)
+            evdwl += ep;
+            const double w = (e & TILE_FWD) ? (MIXED ? (double)f32 : f64) : 0.0;
+            vir[0] += delx * delx * w; vir[1] += dely * dely * w; vir[2] += delz * delz * w;
+            vir[3] += delx * dely * w; vir[4] += delx * delz * w; vir[5] += dely * delz * w;
           }
-        });
-    if (MIXED) {
-      fxi = (double)gxi; fyi = (double)gyi; fzi = (double)gzi;
-    }
+        },
+        [&](unsigned) {});
     fx[gi] = fxi;
     fy[gi] = fyi;
     fz[gi] = fzi;
   }
   if (EV) {
-    double v[1] = {evdwl};
+    double v[7] = {evdwl, vir[0], vir[1], vir[2], vir[3], vir[4], vir[5]};
     __syncthreads();
-    block_sum<1>(v, T.x);
-    if (tid == 0) atomicAdd(&ev[0], v[0]);
+    block_sum<7>(v, T.x);
+    if (tid == 0)
+      for (int k = 0; k < 7; k++) atomicAdd(&ev[k], v[k]);
   }
 }
 
@@ -688,8 +707,8 @@ __global__ void __launch_bounds__(352, TILE_MINB) k_tile_eam_rho(
   const int tile = tile_ids ? tile_ids[blockIdx.x] : blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
   const TilePos Tp = tile_pos(G, tile);
   const int S = tile_rows(G, Tp, ostart, gstart, H);
-  if (S > scap) {
-    if (tid == 0) atomicMax(&tflags[5], S);
+  if (S + 1 > scap) {
+    if (tid == 0) atomicMax(&tflags[5], S + 1);
     return;
   }
   tile_stage<false>(nlocal, xt, nullptr, H, T);
@@ -727,7 +746,7 @@ __global__ void __launch_bounds__(352, TILE_MINB) k_tile_eam_rho(
         return in ? ((__ldg(c + 3) * p + __ldg(c + 4)) * p + __ldg(c + 5)) * p + __ldg(c + 6) : 0.0;
       }
     };
-    tile_walk<MIXED ? 4 : 2>(
+    tile_walk<MIXED ? 4 : 2, true>(
         list, g, n, NI,
         [&](unsigned e, bool valid) {
           const int j = e & TILE_IDX;
@@ -762,8 +781,8 @@ __global__ void __launch_bounds__(352, TILE_MINB) k_tile_eam_force(
   const int tile = tile_ids ? tile_ids[blockIdx.x] : blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
   const TilePos Tp = tile_pos(G, tile);
   const int S = tile_rows(G, Tp, ostart, gstart, H);
-  if (S > scap) {
-    if (tid == 0) atomicMax(&tflags[5], S);
+  if (S + 1 > scap) {
+    if (tid == 0) atomicMax(&tflags[5], S + 1);
     return;
   }
   tile_stage<true>(nlocal, xt, fp, H, T);
@@ -846,7 +865,7 @@ __global__ void __launch_bounds__(352, TILE_MINB) k_tile_eam_force(
         if (EV) epair = (in && (e & TILE_FWD)) ? sc * phi : 0.0;
       }
     };
-    tile_walk<MIXED ? 4 : 2>(
+    tile_walk<MIXED ? 4 : 2, true>(
         list, g, n, NI,
         [&](unsigned e, bool valid) {
           double delx, dely, delz, f64 = 0.0, ep = 0.0;
@@ -891,10 +910,10 @@ __global__ void __launch_bounds__(352, TILE_MINB) k_tile_eam_force(
 
 // tile_walk for the fixed-point kernel: four branch-free bodies per step; a body returns true
 // when its cutoff decision must be re-taken in FP64 (then `exact(e)` adds that entry's
-// contribution), FWD|GHOST entries additionally call `ghost(e)`.  Both are rare.
-template <class Body, class Exact, class Ghost>
+// contribution; rare).  `fold()` runs once per list word (FP32 partial sums -> FP64).
+template <class Body, class Exact, class Fold>
 __device__ __forceinline__ void tile_walk_fx(const uint4 *__restrict__ list, int g, int n, int NI,
-                                             Body &&body, Exact &&exact, Ghost &&ghost) {
+                                             Body &&body, Exact &&exact, Fold &&fold) {
   const uint4 *lp = list + g;
   uint4 q = n > 0 ? __ldg(lp) : make_uint4(0, 0, 0, 0);
   for (int k0 = 0; k0 < n; k0 += 8) {
@@ -909,16 +928,11 @@ __device__ __forceinline__ void tile_walk_fx(const uint4 *__restrict__ list, int
         if (a2) exact(w1 & 0xffffu);
         if (a3) exact(w1 >> 16);
       }
-      if ((w0 | w1) & (TILE_GHOST | (TILE_GHOST << 16))) {
-        if ((w0 & TILE_GHOST) && kb < n) ghost(w0 & 0xffffu);
-        if ((w0 & (TILE_GHOST << 16)) && kb + 1 < n) ghost(w0 >> 16);
-        if ((w1 & TILE_GHOST) && kb + 2 < n) ghost(w1 & 0xffffu);
-        if ((w1 & (TILE_GHOST << 16)) && kb + 3 < n) ghost(w1 >> 16);
-      }
     };
     step4(c.x, c.y, k0);
     asm volatile("" ::: "memory");
     step4(c.z, c.w, k0 + 4);
+    fold();
     asm volatile("" ::: "memory");
   }
 }
@@ -957,8 +971,8 @@ __global__ void __launch_bounds__(352, TILE_FX_MINB) k_tile_lj_fx(
   const int tile = tile_ids ? tile_ids[blockIdx.x] : blockIdx.x, tid = threadIdx.x, bd = blockDim.x;
   const TilePos P = tile_pos(G, tile);
   const int S = tile_rows(G, P, ostart, gstart, H);
-  if (S > scap) {
-    if (tid == 0) atomicMax(&tflags[5], S);
+  if (S + 1 > scap) {
+    if (tid == 0) atomicMax(&tflags[5], S + 1);
     return;
   }
   {  // stage: one warp per run, LDG.256 of the record, fixed-point conversion, STS.32
@@ -979,12 +993,17 @@ __global__ void __launch_bounds__(352, TILE_FX_MINB) k_tile_lj_fx(
         gmap[s] = src;
       }
     }
+    if (tid == 0) {  // the dummy atom of padding entries (never `valid`, but its type is read)
+      qx[S] = qy[S] = qz[S] = 0;
+      stype[S] = 1;
+      gmap[S] = 0;
+    }
     __syncthreads();
   }
   const int ni = H->ni, ibase = tile_ibase[tile];
   const int n1 = ntypes + 1, n2 = n1 * n1;
   const float inv = (float)(1.0 / G.fxscale);
-  double evdwl = 0.0;
+  double evdwl = 0.0, vir[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int ti = tid; ti < ni; ti += bd) {
     const int g = ibase + ti;
     const int li = iloc[g];
@@ -992,7 +1011,11 @@ __global__ void __launch_bounds__(352, TILE_FX_MINB) k_tile_lj_fx(
     const int xi = qx[li], yi = qy[li], zi = qz[li];
     const int gi = gmap[li];
     const int itype = stype[li];
+    // FP32 pair math, FP64 accumulation: the FP32 partial sums of one list word (8 entries) are
+    // added to FP64 accumulators, so the rounding of the sum does not grow with the list length
+    double fxi = 0.0, fyi = 0.0, fzi = 0.0;
     float gxi = 0.0f, gyi = 0.0f, gzi = 0.0f, ei = 0.0f;
+    float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f, w4 = 0.0f, w5 = 0.0f;
     // FP32 pair function of entry e; `in` decided by the caller
     auto lj = [&](float rsq, int tij, bool in, bool fwd, float &fpair, float &epair) {
       const float lj1 = ONETYPE ? onef.lj1 : __ldg(tabf + tij);
@@ -1024,6 +1047,13 @@ __global__ void __launch_bounds__(352, TILE_FX_MINB) k_tile_lj_fx(
       const double4 a = ld_xt(xt + gi), b = ld_xt(xt + gmap[j]);
       return rsq_ref(a.x - b.x, a.y - b.y, a.z - b.z) < (ONETYPE ? one.cutsq : __ldg(tab + tij));
     };
+    // energy and virial: once per pair, on the half-list (FWD) copy (Pair::ev_tally)
+    auto tally = [&](unsigned e, float delx, float dely, float delz, float f32, float ep) {
+      ei += ep;
+      const float w = (e & TILE_FWD) ? f32 : 0.0f;
+      w0 += delx * delx * w; w1 += dely * dely * w; w2 += delz * delz * w;
+      w3 += delx * dely * w; w4 += delx * delz * w; w5 += dely * delz * w;
+    };
     tile_walk_fx(
         list, g, n, NI,
         [&](unsigned e, bool valid) -> bool {  // fast path; returns "too close to call"
@@ -1033,7 +1063,7 @@ __global__ void __launch_bounds__(352, TILE_FX_MINB) k_tile_lj_fx(
           const bool amb = valid && fabsf(rsq - cutsq) < 2.0e-6f * cutsq;
           lj(rsq, tij, valid && !amb && rsq < cutsq, e & TILE_FWD, f32, ep);
           gxi += delx * f32; gyi += dely * f32; gzi += delz * f32;
-          if (EV) ei += ep;
+          if (EV) tally(e, delx, dely, delz, f32, ep);
           return amb;
         },
         [&](unsigned e) {  // an ambiguous entry: decide in FP64, then the same FP32 pair function
@@ -1042,30 +1072,26 @@ __global__ void __launch_bounds__(352, TILE_FX_MINB) k_tile_lj_fx(
           geom(e & TILE_IDX, delx, dely, delz, rsq, tij, cutsq);
           lj(rsq, tij, exact_in(e & TILE_IDX, tij), e & TILE_FWD, f32, ep);
           gxi += delx * f32; gyi += dely * f32; gzi += delz * f32;
-          if (EV) ei += ep;
+          if (EV) tally(e, delx, dely, delz, f32, ep);
         },
-        [&](unsigned e) {  // Newton scatter onto a ghost; the reverse halo returns it to the owner
-          float delx, dely, delz, rsq, cutsq, f32, ep = 0.0f;
-          int tij;
-          const int j = e & TILE_IDX;
-          geom(j, delx, dely, delz, rsq, tij, cutsq);
-          bool in = rsq < cutsq;
-          if (fabsf(rsq - cutsq) < 2.0e-6f * cutsq) in = exact_in(j, tij);
-          lj(rsq, tij, in, false, f32, ep);
-          const int gj = gmap[j];
-          atomicAdd(&fx[gj], -(double)(delx * f32));
-          atomicAdd(&fy[gj], -(double)(dely * f32));
-          atomicAdd(&fz[gj], -(double)(delz * f32));
+        [&]() {  // end of a list word: fold the FP32 partial sums into the FP64 accumulators
+          fxi += (double)gxi; fyi += (double)gyi; fzi += (double)gzi;
+          gxi = gyi = gzi = 0.0f;
         });
-    fx[gi] = (double)gxi;
-    fy[gi] = (double)gyi;
-    fz[gi] = (double)gzi;
-    if (EV) evdwl += (double)ei;  // <= ~110 terms per atom in FP32, FP64 across atoms
+    fx[gi] = fxi;
+    fy[gi] = fyi;
+    fz[gi] = fzi;
+    if (EV) {
+      evdwl += (double)ei;  // <= ~60 terms per atom in FP32, FP64 across atoms
+      vir[0] += (double)w0; vir[1] += (double)w1; vir[2] += (double)w2;
+      vir[3] += (double)w3; vir[4] += (double)w4; vir[5] += (double)w5;
+    }
   }
   if (EV) {
-    double v[1] = {evdwl};
+    double v[7] = {evdwl, vir[0], vir[1], vir[2], vir[3], vir[4], vir[5]};
     __syncthreads();
-    block_sum<1>(v, reinterpret_cast<double *>(tsm + TILE_HDR_BYTES));
-    if (tid == 0) atomicAdd(&ev[0], v[0]);
+    block_sum<7>(v, reinterpret_cast<double *>(tsm + TILE_HDR_BYTES));
+    if (tid == 0)
+      for (int k = 0; k < 7; k++) atomicAdd(&ev[k], v[k]);
   }
 }
