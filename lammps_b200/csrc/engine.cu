@@ -118,6 +118,13 @@ struct b200_ctx {
   DBuf<double> mig_send, mig_recv;
   int *allcounts = nullptr;  // [nranks*32] device (all-gathered counters)
   int *h_counts = nullptr;   // pinned [nranks*32]
+  char *ag_dev = nullptr;    // persistent staging of allgather_host: [(nranks+1) * AG_BYTES] device
+  char *ag_host = nullptr;   // ... and pinned host
+  // every rank tracks every rank's halo-arena capacity (doubles): the growth rule is
+  // deterministic in the all-gathered counts, so all ranks know without talking when some arena
+  // is about to move and the IPC handles must be exchanged again
+  std::vector<size_t> peer_cap_s, peer_cap_r;
+  std::vector<int> rank_nbr;  // [nranks][27] neighbour ranks of every rank
   // list
   DBuf<int> neigh, numneigh;
   int maxneigh = 0, nstride = 0, max_numneigh = 0;
@@ -430,14 +437,18 @@ size_t alloc_delta(const void *p) {
 }  // namespace
 
 // all-gather `bytes` per rank from a host record (through device staging) back to the host
+// (staging buffers are allocated once in b200_comm_init: a cudaMalloc/cudaFree pair per call
+// used to put a device-wide synchronisation into every rebuild)
+#define AG_BYTES 512
 static int allgather_host(b200_ctx *ctx, const void *mine, void *all, size_t bytes) {
-  char *stage = nullptr;
-  CK(cudaMalloc((void **)&stage, bytes * (ctx->nranks + 1)));
-  CK(cudaMemcpyAsync(stage, mine, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  NK(g_nccl.AllGather(stage, stage + bytes, bytes, ncclChar, ctx->nccl, ctx->stream));
-  CK(cudaMemcpyAsync(all, stage + bytes, bytes * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  if (bytes > AG_BYTES || !ctx->ag_dev) return ctx->fail(B200_EARG, "allgather_host: record of %zu bytes", bytes);
+  char *stage = ctx->ag_dev, *hst = ctx->ag_host;
+  memcpy(hst, mine, bytes);
+  CK(cudaMemcpyAsync(stage, hst, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  NK(g_nccl.AllGather(stage, stage + AG_BYTES, bytes, ncclChar, ctx->nccl, ctx->stream));
+  CK(cudaMemcpyAsync(hst + AG_BYTES, stage + AG_BYTES, bytes * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(stage);
+  memcpy(all, hst + AG_BYTES, bytes * ctx->nranks);
   return B200_OK;
 }
 
@@ -467,6 +478,8 @@ static int p2p_init(b200_ctx *ctx) {
   ctx->peer_roff.assign(ctx->nranks, 0);
   ctx->peer_gen.assign(ctx->nranks, 0);
   ctx->peer_off.assign((size_t)ctx->nranks * 2 * (NDIR + 1), 0);
+  ctx->peer_cap_s.assign(ctx->nranks, 0);
+  ctx->peer_cap_r.assign(ctx->nranks, 0);
   int ok = 1;
   for (int r = 0; r < ctx->nranks; r++) ok &= all[r].ok;
   if (ok)
@@ -494,11 +507,21 @@ static int p2p_init(b200_ctx *ctx) {
 }
 
 // sbuf/rbuf capacity (doubles) inside the arena; (re)allocates when too small
-static int ensure_arena(b200_ctx *ctx, size_t ns, size_t nr) {
+// the growth rule, shared by the owner of an arena and by everybody tracking it: capacities in
+// doubles for ns / nr doubles of send / recv staging; returns true when the arena must move
+static bool arena_rule(size_t ns, size_t nr, size_t &cap_s, size_t &cap_r) {
+  if (cap_s >= ns && cap_r >= nr && cap_s > 0) return false;
   const size_t need_s = (ns * sizeof(double) + 4095) / 4096 * 4096;
   const size_t need_r = (nr * sizeof(double) + 4095) / 4096 * 4096;
-  if (ctx->arena && ctx->sbuf.cap >= ns && ctx->rbuf.cap >= nr) return B200_OK;
-  const size_t cap_s = need_s + need_s / 4 + (1u << 20), cap_r = need_r + need_r / 4 + (1u << 20);
+  cap_s = (need_s + need_s / 2 + (1u << 20)) / sizeof(double);
+  cap_r = (need_r + need_r / 2 + (1u << 20)) / sizeof(double);
+  return true;
+}
+
+static int ensure_arena(b200_ctx *ctx, size_t ns, size_t nr) {
+  size_t cs = ctx->arena ? ctx->sbuf.cap : 0, cr = ctx->arena ? ctx->rbuf.cap : 0;
+  if (!arena_rule(ns, nr, cs, cr)) return B200_OK;
+  const size_t cap_s = cs * sizeof(double), cap_r = cr * sizeof(double);
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->arena) {
     cudaFree(ctx->arena);
@@ -516,28 +539,47 @@ static int ensure_arena(b200_ctx *ctx, size_t ns, size_t nr) {
   return B200_OK;
 }
 
-// at every border build: publish offsets + arena, (re)map neighbours whose arena moved, and
-// lay out the per-direction tables the pack/unpack kernels take by value
+// At every border build.  The per-direction offsets of EVERY rank follow from the all-gathered
+// border counts (h_counts), so nothing but the counts crosses the wire on an ordinary rebuild;
+// only when some rank's arena moved (all ranks know: arena_rule is deterministic in the counts)
+// are the CUDA IPC handles exchanged again and the moved arenas re-mapped.  Then the per-direction
+// tables the pack/unpack kernels take by value are laid out.
 static int p2p_publish_borders(b200_ctx *ctx) {
   if (!ctx->p2p) return B200_OK;
-  PeerInfo mine;
-  memset(&mine, 0, sizeof mine);
-  memcpy(mine.sendoff, ctx->sendoff, sizeof mine.sendoff);
-  memcpy(mine.recvoff, ctx->recvoff, sizeof mine.recvoff);
-  mine.gen = ctx->arena_gen;
-  mine.roff = ctx->arena_roff;
-  mine.arena_delta = alloc_delta(ctx->arena);
-  mine.ok = cudaIpcGetMemHandle(&mine.arena, ctx->arena) == cudaSuccess;
-  std::vector<PeerInfo> all(ctx->nranks);
-  TRY(allgather_host(ctx, &mine, all.data(), sizeof(PeerInfo)));
-  const int W2 = 2 * (NDIR + 1);
-  for (int r = 0; r < ctx->nranks; r++) {
-    memcpy(&ctx->peer_off[(size_t)r * W2], all[r].sendoff, sizeof(int) * (NDIR + 1));
-    memcpy(&ctx->peer_off[(size_t)r * W2 + NDIR + 1], all[r].recvoff, sizeof(int) * (NDIR + 1));
-    if (!all[r].ok) return ctx->fail(B200_ECUDA, "rank %d cannot export its halo arena through CUDA IPC", r);
+  const int W2 = 2 * (NDIR + 1), nr = ctx->nranks;
+  bool any_moved = false;
+  for (int r = 0; r < nr; r++) {
+    const int *nb = &ctx->rank_nbr[(size_t)r * NDIR];
+    int *so = &ctx->peer_off[(size_t)r * W2], *ro = so + NDIR + 1;
+    so[0] = ro[0] = 0;
+    for (int dir = 0; dir < NDIR; dir++) {
+      const bool rem = dir != 13 && nb[dir] >= 0 && nb[dir] != r;
+      const int from = nb[NDIR - 1 - dir];
+      const int mine = ctx->h_counts[r * 32 + dir];
+      const int theirs = rem ? (from >= 0 ? ctx->h_counts[from * 32 + dir] : 0) : mine;
+      so[dir + 1] = so[dir] + mine;
+      ro[dir + 1] = ro[dir] + theirs;
+    }
+    any_moved |= arena_rule((size_t)so[NDIR] * 4, (size_t)ro[NDIR] * 4, ctx->peer_cap_s[r], ctx->peer_cap_r[r]);
+  }
+  if (ctx->peer_cap_s[ctx->rank] != ctx->sbuf.cap || ctx->peer_cap_r[ctx->rank] != ctx->rbuf.cap)
+    return ctx->fail(B200_ECUDA, "halo arena bookkeeping out of step (%zu/%zu tracked, %zu/%zu allocated)",
+                     ctx->peer_cap_s[ctx->rank], ctx->peer_cap_r[ctx->rank], ctx->sbuf.cap, ctx->rbuf.cap);
+  std::vector<PeerInfo> all;
+  if (any_moved) {
+    PeerInfo mine;
+    memset(&mine, 0, sizeof mine);
+    mine.gen = ctx->arena_gen;
+    mine.roff = ctx->arena_roff;
+    mine.arena_delta = alloc_delta(ctx->arena);
+    mine.ok = cudaIpcGetMemHandle(&mine.arena, ctx->arena) == cudaSuccess;
+    all.resize(nr);
+    TRY(allgather_host(ctx, &mine, all.data(), sizeof(PeerInfo)));
+    for (int r = 0; r < nr; r++)
+      if (!all[r].ok) return ctx->fail(B200_ECUDA, "rank %d cannot export its halo arena through CUDA IPC", r);
   }
   // map (or re-map) the arenas of the ranks I talk to
-  for (int dir = 0; dir < NDIR; dir++) {
+  for (int dir = 0; dir < NDIR && any_moved; dir++) {
     if (!((ctx->remote_mask >> dir) & 1u)) continue;
     const int r = ctx->nbr[dir];
     if (r < 0 || r == ctx->rank) continue;
@@ -714,6 +756,18 @@ static int setup_geometry(b200_ctx *ctx) {
     ctx->remote_mask = 0;
     for (int dir = 0; dir < NDIR; dir++)
       if (dir != 13 && ctx->nbr[dir] >= 0 && ctx->nbr[dir] != ctx->rank) ctx->remote_mask |= 1u << dir;
+    // the neighbour table of every rank (p2p_publish_borders derives all ranks' offsets from it)
+    ctx->rank_nbr.assign((size_t)np * NDIR, -1);
+    for (int gidx = 0; gidx < np; gidx++) {
+      const int loc[3] = {gidx / (P[1] * P[2]), (gidx / P[2]) % P[1], gidx % P[2]};
+      const int r = ctx->rankmap.empty() ? gidx : ctx->rankmap[gidx];
+      if (r < 0 || r >= np) return ctx->fail(B200_EARG, "rank grid entry %d out of range", r);
+      int nb[NDIR];
+      b200_neighbor_ranks(P, loc, ctx->periodic, nb);
+      for (int dir = 0; dir < NDIR; dir++)
+        ctx->rank_nbr[(size_t)r * NDIR + dir] =
+            nb[dir] < 0 ? -1 : (ctx->rankmap.empty() ? nb[dir] : ctx->rankmap[nb[dir]]);
+    }
     Owner &o = ctx->owner;
     memset(&o, 0, sizeof o);
     auto bounds = [&](int d, int l, double &lo, double &hi) {
@@ -1180,8 +1234,11 @@ static int reneighbor(b200_ctx *ctx) {
       ctx->nlocal = nl0;
       TRY(alloc_atoms(ctx, (int)((nl0 + narrive) * 1.2) + 1024));
     }
-    TRY(reserve(ctx, ctx->mig_send, (size_t)nleave * MIG_W));
-    TRY(reserve(ctx, ctx->mig_recv, (size_t)narrive * MIG_W));
+    // (sized with a floor at the first rebuild: the first rebuild that really migrates atoms
+    // must not be the one that allocates)
+    const size_t mig_floor = std::max<size_t>(8192, (size_t)nl0 / 32);
+    TRY(reserve(ctx, ctx->mig_send, std::max((size_t)nleave, mig_floor) * MIG_W));
+    TRY(reserve(ctx, ctx->mig_recv, std::max((size_t)narrive, mig_floor) * MIG_W));
     CK(cudaMemcpyAsync(ctx->diroffset, moff, (NDIR + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     if (nleave > 0) {
       k_pack_migrate<<<cdiv(nl0, 256), 256, 0, s>>>(nl0, ctx->atombin[c], ctx->slot, ctx->diroffset,
@@ -1791,6 +1848,23 @@ static int fetch_ev(b200_ctx *ctx) {
   return B200_OK;
 }
 
+// CUDA loads kernels lazily, on first launch.  The kernels that only run when atoms migrate
+// between sub-domains are first needed inside the first rebuild of a RUN (setup has no leavers):
+// load them when the communicator is created instead.
+static int preload_rebuild_kernels(b200_ctx *ctx) {
+  cudaFuncAttributes a;
+  CK(cudaFuncGetAttributes(&a, k_pack_migrate));
+  CK(cudaFuncGetAttributes(&a, k_unpack_migrate));
+  CK(cudaFuncGetAttributes(&a, k_pbc_bin<true>));
+  CK(cudaFuncGetAttributes(&a, k_pack_border));
+  CK(cudaFuncGetAttributes(&a, k_ghost_make));
+  CK(cudaFuncGetAttributes(&a, k_ghost_place));
+  CK(cudaFuncGetAttributes(&a, k_permute_owned));
+  CK(cudaFuncGetAttributes(&a, k_tile_split));
+  CK(cudaFuncGetAttributes(&a, k_tile_count));
+  return B200_OK;
+}
+
 // =====================================================================================
 //                                        C ABI
 // =====================================================================================
@@ -1882,7 +1956,8 @@ void b200_destroy(b200_ctx *ctx) {
   F(ctx->sendlist.p); F(ctx->gsrc.p); F(ctx->gbin.p); F(ctx->gslot.p); F(ctx->gdir.p);
   F(ctx->gdir_tmp.p); F(ctx->gtmp.p); F(ctx->counts); F(ctx->diroffset); F(ctx->recvoffset); F(ctx->allcounts);
   F(ctx->senddir.p); F(ctx->gtag_tmp.p); F(ctx->gsrc_tmp.p); F(ctx->arena); F(ctx->pflags); F(ctx->p2p_counter);
-  F(ctx->mig_send.p); F(ctx->mig_recv.p);
+  F(ctx->mig_send.p); F(ctx->mig_recv.p); F(ctx->ag_dev);
+  if (ctx->ag_host) cudaFreeHost(ctx->ag_host);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   if (ctx->nccl && g_nccl.ok) g_nccl.CommDestroy(ctx->nccl);
   F(ctx->neigh.p);
@@ -2539,7 +2614,10 @@ int b200_comm_init(b200_ctx *ctx, int nranks, int rank, const void *id128) {
   ctx->h_counts = nullptr;
   TRY(dalloc(ctx, &ctx->allcounts, (size_t)32 * nranks));
   CK(cudaMallocHost((void **)&ctx->h_counts, sizeof(int) * 32 * nranks));
+  CK(cudaMalloc((void **)&ctx->ag_dev, (size_t)AG_BYTES * (nranks + 1)));
+  CK(cudaMallocHost((void **)&ctx->ag_host, (size_t)AG_BYTES * (nranks + 1)));
   TRY(p2p_init(ctx));
+  TRY(preload_rebuild_kernels(ctx));
   return B200_OK;
 }
 

@@ -263,3 +263,4 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_lj2(
       for (int k = 0; k < 7; k++) atomicAdd(&ev[k], v[k]);
   }
 }
+
