@@ -199,6 +199,42 @@ int b200_neighbor_ranks(const int procgrid[3], const int myloc[3], const int per
                         int nbr[27]);
 int b200_comm_init(b200_ctx *ctx, int nranks, int rank, const void *id128);
 
+/* ---- several sub-domains in ONE process: `package b200 gpus N` (precedent for one process
+ *      owning several devices: GPU/fix_gpu.cpp:123-247, lib/gpu/lal_device.cpp; there is no MPI
+ *      in this image).  A group is N contexts -- one brick sub-domain each, on N
+ *      devices or sharing devices -- with one host thread per context; what CommBrick does with
+ *      MPI (comm_brick.cpp:172-430, 599-899) happens between them through peer memory: counts
+ *      through shared host memory, migration/border records with cudaMemcpyAsync between the
+ *      contexts' buffers, the per-step halo with the same peer-store kernels as between
+ *      processes.  Per-context settings (b200_set_box, b200_set_neighbor, b200_pair_*,
+ *      b200_fix_nve) are made on every b200_group_context(); everything that communicates goes
+ *      through the b200_group_* calls below.  Atoms are handed over for the whole box and come
+ *      back concatenated in sub-domain order. */
+typedef struct b200_group b200_group;
+int b200_group_create(b200_group **out, int nsub, const int *devices /*[nsub]*/, int precision);
+void b200_group_destroy(b200_group *g);
+const char *b200_group_last_error(const b200_group *g);
+int b200_group_size(const b200_group *g);
+b200_ctx *b200_group_context(b200_group *g, int i);
+/*      sub-domain grid: the factorisation of n with the smallest surface (ProcMap::onelevel_grid,
+ *      procmap.cpp:48); sub-domain i sits at grid location (i/(py*pz), (i/pz)%py, i%pz) */
+int b200_group_auto_grid(int n, const double prd[3], int grid[3]);
+int b200_group_set_grid(b200_group *g, const int grid[3]);
+int b200_group_set_atoms(b200_group *g, int n, int ntypes, const double *mass, const double *x,
+                         const double *v, const int *type, const int *tag, const int *mask,
+                         const int *image);
+int b200_group_count(b200_group *g, int *nlocal_total, int *nghost_total);
+int b200_group_get_atoms(b200_group *g, double *x, double *v, double *f, int *type, int *tag,
+                         int *mask, int *image);
+int b200_group_setup(b200_group *g, int eflag, int vflag);
+int b200_group_step(b200_group *g, int eflag, int vflag, int *rebuilt);
+int b200_group_run(b200_group *g, int nsteps, int64_t first_step, int thermo_every,
+                   double *thermo_out, int max_thermo, int *n_thermo);
+int b200_group_get_tallies(b200_group *g, double *eng_vdwl, double virial[6]);
+int b200_group_ke_sum(b200_group *g, double *mv2);
+int b200_group_last_run_ms(b200_group *g, double *ms);
+int b200_group_get_stats(b200_group *g, b200_stats *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <type_traits>
 
 namespace {
@@ -46,8 +50,61 @@ struct PhaseRec {
 
 }  // namespace
 
+// ------------------------------------------------------------------ in-process group
+// Several sub-domains driven by ONE host process (the LAMMPS package's `package b200 gpus N`,
+// no MPI in the image; precedent for one process owning several devices:
+// GPU/fix_gpu.cpp:123-247).  Every sub-domain is an ordinary context with its own host thread;
+// the few collectives of a rebuild are rendezvous through shared host memory, bulk rebuild
+// traffic is cudaMemcpyAsync between the contexts' buffers, and the per-step halo is the same
+// peer-memory kernels as between processes (plain pointers instead of CUDA IPC mappings).
+// Sub-domains may share a device (how the 1-GPU test box exercises migration and borders).
+struct b200_group {
+  int n = 0;
+  std::vector<b200_ctx *> ctx;
+  int grid[3] = {1, 1, 1};
+  std::string err;
+  bool shared_dev = false;  // two or more sub-domains on one device
+  // sense-reversing barrier of the n context threads
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  unsigned long long phase = 0;
+  void barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    const unsigned long long my = phase;
+    if (++arrived == n) {
+      arrived = 0;
+      phase++;
+      cv.notify_all();
+    } else
+      cv.wait(lk, [&] { return phase != my; });
+  }
+  // exchange tables (written between two barriers, read after the first)
+  std::vector<int> counts;      // [n][32]
+  std::vector<double> red;      // [n][8]
+  std::vector<int> redi;        // [n]
+  struct Pub {
+    const double *src = nullptr;
+    int off[NDIR + 1] = {0};
+    cudaEvent_t ready = nullptr;
+  };
+  std::vector<Pub> pub;
+  // one worker thread per context: run(fn) executes fn(i) on all of them and joins
+  std::vector<std::thread> workers;
+  std::function<int(int)> job;
+  std::vector<int> rc;
+  unsigned long long job_seq = 0, job_done = 0;
+  int job_finished = 0;
+  bool quit = false;
+  std::mutex jmu;
+  std::condition_variable jcv, dcv;
+  // atoms handed to b200_group_set_atoms, split by owning sub-domain (kept for re-upload)
+  std::vector<int> owner_of;
+};
+
 struct b200_ctx {
   int device = 0, prec = 0;
+  b200_group *grp = nullptr;  // in-process group this context belongs to (rank = its index)
   cudaStream_t stream = nullptr;
   std::string err;
   size_t dev_bytes = 0;
@@ -196,6 +253,8 @@ struct b200_ctx {
   int *h_flags = nullptr; // pinned [32]
   double eng_vdwl = 0, virial[6] = {0, 0, 0, 0, 0, 0};
   bool setup_done = false;
+  // tallies stay per sub-domain (a host that reduces them itself: LAMMPS + MPI)
+  bool local_tallies = false;
   cudaEvent_t run_a = nullptr, run_b = nullptr;
   double last_run_ms = 0;
   // profiling
@@ -367,7 +426,30 @@ bool load_nccl(std::string &why) {
 // (2 ranks along a dimension) match up in issue order.
 static int halo_exchange(b200_ctx *ctx, const double *src, const int *srcoff, double *dst,
                          const int *dstoff, int width, bool reverse) {
-  if (ctx->nranks == 1 || !ctx->remote_mask) return B200_OK;
+  if (ctx->nranks == 1) return B200_OK;
+  if (ctx->grp) {
+    // in-process: publish where my segments are, then pull mine from the neighbours' buffers
+    b200_group *g = ctx->grp;
+    b200_group::Pub &me = g->pub[ctx->rank];
+    me.src = src;
+    memcpy(me.off, srcoff, sizeof me.off);
+    CK(cudaEventRecord(me.ready, ctx->stream));
+    g->barrier();
+    for (int dir = 0; dir < NDIR; dir++) {
+      if (!((ctx->remote_mask >> dir) & 1u)) continue;
+      const int from = reverse ? ctx->nbr[dir] : ctx->nbr[NDIR - 1 - dir];
+      const size_t nr = (size_t)(dstoff[dir + 1] - dstoff[dir]) * width;
+      if (!nr || from < 0) continue;
+      const b200_group::Pub &p = g->pub[from];
+      CK(cudaStreamWaitEvent(ctx->stream, p.ready, 0));
+      CK(cudaMemcpyAsync(dst + (size_t)dstoff[dir] * width, p.src + (size_t)p.off[dir] * width,
+                         nr * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    g->barrier();  // every pull is done: the source buffers may be reused
+    return B200_OK;
+  }
+  if (!ctx->remote_mask) return B200_OK;
   NK(g_nccl.GroupStart());
   for (int dir = 0; dir < NDIR; dir++) {
     if (!((ctx->remote_mask >> dir) & 1u)) continue;
@@ -387,6 +469,19 @@ static int halo_exchange(b200_ctx *ctx, const double *src, const int *srcoff, do
 // The 32 device counters of every rank, on the host: [r*32 + dir] and the error word [r*32+27].
 // One all-gather + one D2H copy + one stream sync (rebuild steps only).
 static int sync_counts(b200_ctx *ctx) {
+  if (ctx->grp) {
+    b200_group *g = ctx->grp;
+    CK(cudaMemcpyAsync(ctx->h_counts + 32 * (size_t)ctx->nranks, ctx->counts, sizeof(int) * 32,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_flags + 40, ctx->p2p_counter + 4, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(&g->counts[(size_t)ctx->rank * 32], ctx->h_counts + 32 * (size_t)ctx->nranks, sizeof(int) * 32);
+    g->barrier();
+    memcpy(ctx->h_counts, g->counts.data(), sizeof(int) * 32 * ctx->nranks);
+    g->barrier();
+    if (ctx->h_flags[40]) return ctx->fail(B200_ECUDA, "peer-memory halo timed out waiting for a neighbour");
+    return B200_OK;
+  }
   if (ctx->nranks > 1) {
     NK(g_nccl.AllGather(ctx->counts, ctx->allcounts, 32, ncclInt, ctx->nccl, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counts, ctx->allcounts, sizeof(int) * 32 * ctx->nranks,
@@ -566,6 +661,16 @@ static int p2p_publish_borders(b200_ctx *ctx) {
     return ctx->fail(B200_ECUDA, "halo arena bookkeeping out of step (%zu/%zu tracked, %zu/%zu allocated)",
                      ctx->peer_cap_s[ctx->rank], ctx->peer_cap_r[ctx->rank], ctx->sbuf.cap, ctx->rbuf.cap);
   std::vector<PeerInfo> all;
+  if (ctx->grp) {
+    // in-process: the neighbours' arenas are plain pointers; re-read them when anything moved
+    b200_group *g = ctx->grp;
+    g->barrier();  // every context has (re)allocated its arena for this build
+    for (int r = 0; r < nr; r++) {
+      ctx->peer_arena[r] = g->ctx[r]->arena;
+      ctx->peer_roff[r] = g->ctx[r]->arena_roff;
+    }
+    any_moved = false;
+  }
   if (any_moved) {
     PeerInfo mine;
     memset(&mine, 0, sizeof mine);
@@ -1355,6 +1460,16 @@ static int reneighbor(b200_ctx *ctx) {
 }
 
 // ------------------------------------------------------------------ step pieces
+// Sub-domains that SHARE a device: the peer-memory halo kernels spin on flags another context's
+// kernel raises, and streams of one device share a few hardware queues -- a spinning unpack
+// kernel queued ahead of the pack kernel it waits for would never see it run.  So the contexts
+// meet on the host after the pack launches and again after the unpack launches: every queue
+// then holds this halo's pack kernels before its unpack kernels, and the previous halo's unpack
+// kernels before this one's pack kernels.  (One device per sub-domain needs none of this.)
+static inline void shared_device_rendezvous(b200_ctx *ctx) {
+  if (ctx->grp && ctx->grp->shared_dev) ctx->grp->barrier();
+}
+
 static int force_clear(b200_ctx *ctx) {
   const int ph3 = ph_begin(ctx, B200_PH_CLEAR);
   const int nall = ctx->nlocal + ctx->nghost;
@@ -1390,9 +1505,11 @@ static int forward_comm(b200_ctx *ctx) {
     k_p2p_pack_forward<0><<<cdiv(std::max(ctx->nsend, 1), 256), 256, 0, s>>>(
         ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->diroffset, ctx->geom, ctx->xt[c], nullptr,
         ctx->fwdP, seq, ctx->p2p_counter + 0, (int *)ctx->p2p_counter + 4);
+    shared_device_rendezvous(ctx);
     k_p2p_unpack_forward<0><<<cdiv(std::max(ctx->nghost, 1), 256), 256, 0, s>>>(
         ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->geom, ctx->rbuf.p, ctx->xt[c], nullptr,
         ctx->fwdP, seq, ctx->p2p_counter + 1, (int *)ctx->p2p_counter + 4, fclear);
+    shared_device_rendezvous(ctx);
     ctx->launches += 2;
   } else {
     if (ctx->remote_mask && ctx->nsend > 0) {
@@ -1423,9 +1540,11 @@ static int reverse_halo(b200_ctx *ctx, Vec3Ptr a) {
     k_p2p_pack_reverse<W><<<cdiv(std::max(ctx->nghost, 1), 256), 256, 0, s>>>(
         ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->recvoffset, a, ctx->revP, seq,
         ctx->p2p_counter + 2, (int *)ctx->p2p_counter + 4);
+    shared_device_rendezvous(ctx);
     k_p2p_unpack_reverse<W><<<cdiv(std::max(ctx->nsend, 1), 256), 256, 0, s>>>(
         ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->sbuf.p, a, ctx->revP, seq,
         ctx->p2p_counter + 3, (int *)ctx->p2p_counter + 4);
+    shared_device_rendezvous(ctx);
     ctx->launches += 2;
     LAUNCH_CHECK();
     return B200_OK;
@@ -1464,9 +1583,11 @@ static int forward_scalar(b200_ctx *ctx, double *a) {
     k_p2p_pack_forward<1><<<cdiv(std::max(ctx->nsend, 1), 256), 256, 0, s>>>(
         ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->diroffset, ctx->geom, nullptr, a, ctx->fwdP,
         seq, ctx->p2p_counter + 0, (int *)ctx->p2p_counter + 4);
+    shared_device_rendezvous(ctx);
     k_p2p_unpack_forward<1><<<cdiv(std::max(ctx->nghost, 1), 256), 256, 0, s>>>(
         ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->geom, ctx->rbuf.p, nullptr, a,
         ctx->fwdP, seq, ctx->p2p_counter + 1, (int *)ctx->p2p_counter + 4, Vec3Ptr{{nullptr, nullptr, nullptr}});
+    shared_device_rendezvous(ctx);
     ctx->launches += 2;
     LAUNCH_CHECK();
     return B200_OK;
@@ -1807,10 +1928,19 @@ static int decide(b200_ctx *ctx, int *rebuild) {
       return B200_OK;
     }
     // Neighbor::check_distance: MPI_Allreduce(MAX) of the moved flag (neighbor.cpp:2487)
-    if (ctx->nranks > 1)
+    if (ctx->nranks > 1 && !ctx->grp)
       NK(g_nccl.AllReduce(ctx->flags, ctx->flags, 1, ncclInt, ncclMax, ctx->nccl, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->grp) {  // the vote of the whole group
+      b200_group *g = ctx->grp;
+      g->redi[ctx->rank] = ctx->h_flags[0];
+      g->barrier();
+      int m = 0;
+      for (int r = 0; r < g->n; r++) m = std::max(m, g->redi[r]);
+      g->barrier();
+      ctx->h_flags[0] = m;
+    }
     if (ctx->h_flags[0]) {
       if (ctx->ago == std::max(ctx->every, ctx->delay)) ctx->ndanger++;
       *rebuild = 1;
@@ -1837,12 +1967,27 @@ static int ke_reduce(b200_ctx *ctx) {
   return B200_OK;
 }
 
+// sum of n <= 8 host doubles over the contexts of an in-process group (result on every context)
+static int group_sum(b200_ctx *ctx, double *v, int n) {
+  b200_group *g = ctx->grp;
+  memcpy(&g->red[(size_t)ctx->rank * 8], v, sizeof(double) * n);
+  g->barrier();
+  for (int k = 0; k < n; k++) {
+    double t = 0.0;
+    for (int r = 0; r < g->n; r++) t += g->red[(size_t)r * 8 + k];
+    v[k] = t;
+  }
+  g->barrier();
+  return B200_OK;
+}
+
 static int fetch_ev(b200_ctx *ctx) {
   // MPI_Allreduce(SUM) of compute_pe / compute_pressure virial / compute_temp
-  if (ctx->nranks > 1)
+  if (ctx->nranks > 1 && !ctx->grp && !ctx->local_tallies)
     NK(g_nccl.AllReduce(ctx->ev, ctx->ev, 8, ncclDouble, ncclSum, ctx->nccl, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_ev, ctx->ev, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->grp && !ctx->local_tallies) TRY(group_sum(ctx, ctx->h_ev, 8));
   ctx->eng_vdwl = ctx->h_ev[0];
   for (int k = 0; k < 6; k++) ctx->virial[k] = ctx->h_ev[1 + k];
   return B200_OK;
@@ -2447,10 +2592,11 @@ int b200_ke_sum(b200_ctx *ctx, double *mv2) {
   if (!ctx || !mv2) return B200_EARG;
   TRY(flush_final(ctx));
   TRY(ke_reduce(ctx));
-  if (ctx->nranks > 1)
+  if (ctx->nranks > 1 && !ctx->grp && !ctx->local_tallies)
     NK(g_nccl.AllReduce(ctx->ev + 7, ctx->ev + 7, 1, ncclDouble, ncclSum, ctx->nccl, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_ev + 7, ctx->ev + 7, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->grp && !ctx->local_tallies) TRY(group_sum(ctx, ctx->h_ev + 7, 1));
   *mv2 = ctx->h_ev[7];
   return B200_OK;
 }
@@ -2618,6 +2764,316 @@ int b200_comm_init(b200_ctx *ctx, int nranks, int rank, const void *id128) {
   CK(cudaMallocHost((void **)&ctx->ag_host, (size_t)AG_BYTES * (nranks + 1)));
   TRY(p2p_init(ctx));
   TRY(preload_rebuild_kernels(ctx));
+  return B200_OK;
+}
+
+
+// =====================================================================================
+//                 in-process group: N sub-domains driven by one host process
+// =====================================================================================
+static int group_fail(b200_group *g, int code, const std::string &msg) {
+  g->err = msg;
+  return code;
+}
+
+// run fn(i) on the worker thread of every context and wait; returns the first failure
+static int group_run(b200_group *g, std::function<int(int)> fn) {
+  {
+    std::unique_lock<std::mutex> lk(g->jmu);
+    g->job = std::move(fn);
+    g->job_finished = 0;
+    g->job_seq++;
+  }
+  g->jcv.notify_all();
+  std::unique_lock<std::mutex> lk(g->jmu);
+  g->dcv.wait(lk, [&] { return g->job_finished == g->n; });
+  for (int i = 0; i < g->n; i++)
+    if (g->rc[i] != B200_OK) {
+      g->err = "sub-domain " + std::to_string(i) + ": " + g->ctx[i]->err;
+      return g->rc[i];
+    }
+  return B200_OK;
+}
+
+static void group_worker(b200_group *g, int i) {
+  cudaSetDevice(g->ctx[i]->device);
+  unsigned long long seen = 0;
+  for (;;) {
+    std::function<int(int)> fn;
+    {
+      std::unique_lock<std::mutex> lk(g->jmu);
+      g->jcv.wait(lk, [&] { return g->quit || g->job_seq != seen; });
+      if (g->quit) return;
+      seen = g->job_seq;
+      fn = g->job;
+    }
+    const int rc = fn(i);
+    {
+      std::unique_lock<std::mutex> lk(g->jmu);
+      g->rc[i] = rc;
+      g->job_finished++;
+    }
+    g->dcv.notify_all();
+  }
+}
+
+// what b200_comm_init does for processes, for the contexts of a group
+static int group_comm_init(b200_ctx *ctx, b200_group *g, int rank) {
+  ctx->grp = g;
+  ctx->nranks = g->n;
+  ctx->rank = rank;
+  ctx->geom_ready = false;
+  CK(cudaSetDevice(ctx->device));
+  cudaFreeHost(ctx->h_counts);
+  ctx->h_counts = nullptr;
+  CK(cudaMallocHost((void **)&ctx->h_counts, sizeof(int) * 32 * (g->n + 1)));
+  const size_t fbytes = 2u << 20;
+  CK(cudaMalloc((void **)&ctx->pflags, fbytes));
+  CK(cudaMemset(ctx->pflags, 0, fbytes));
+  CK(cudaMalloc((void **)&ctx->p2p_counter, 8 * sizeof(unsigned)));
+  CK(cudaMemset(ctx->p2p_counter, 0, 8 * sizeof(unsigned)));
+  CK(cudaEventCreateWithFlags(&g->pub[rank].ready, cudaEventDisableTiming));
+  ctx->peer_flags.assign(g->n, nullptr);
+  ctx->peer_arena.assign(g->n, nullptr);
+  ctx->peer_base.assign(g->n, nullptr);
+  ctx->peer_roff.assign(g->n, 0);
+  ctx->peer_gen.assign(g->n, 0);
+  ctx->peer_off.assign((size_t)g->n * 2 * (NDIR + 1), 0);
+  ctx->peer_cap_s.assign(g->n, 0);
+  ctx->peer_cap_r.assign(g->n, 0);
+  ctx->p2p = true;
+  TRY(preload_rebuild_kernels(ctx));
+  return B200_OK;
+}
+
+int b200_group_create(b200_group **out, int nsub, const int *devices, int precision) {
+  if (!out || nsub < 1 || nsub > 64) return B200_EARG;
+  *out = nullptr;
+  b200_group *g = new b200_group();
+  g->n = nsub;
+  g->ctx.assign(nsub, nullptr);
+  g->rc.assign(nsub, B200_OK);
+  g->counts.assign((size_t)nsub * 32, 0);
+  g->red.assign((size_t)nsub * 8, 0.0);
+  g->redi.assign(nsub, 0);
+  g->pub.resize(nsub);
+  *out = g;
+  for (int i = 0; i < nsub; i++) {
+    const int rc = b200_create(&g->ctx[i], devices ? devices[i] : 0, precision);
+    if (rc != B200_OK) return group_fail(g, rc, g->ctx[i] ? g->ctx[i]->err : "cannot create a device context");
+  }
+  // peer access between the distinct devices of the group (the per-step halo stores straight
+  // into the neighbour's staging buffer)
+  for (int i = 0; i < nsub; i++)
+    for (int j = 0; j < nsub; j++) {
+      const int a = g->ctx[i]->device, b = g->ctx[j]->device;
+      if (a == b) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, a, b);
+      if (!can) return group_fail(g, B200_ECUDA, "devices of the group cannot access each other's memory");
+      cudaSetDevice(a);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return group_fail(g, B200_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+  for (int i = 0; i < nsub; i++)
+    for (int j = 0; j < i; j++) g->shared_dev |= g->ctx[i]->device == g->ctx[j]->device;
+  for (int i = 0; i < nsub; i++) {
+    const int rc = group_comm_init(g->ctx[i], g, i);
+    if (rc != B200_OK) return group_fail(g, rc, g->ctx[i]->err);
+  }
+  for (int i = 0; i < nsub; i++)
+    for (int r = 0; r < nsub; r++) g->ctx[i]->peer_flags[r] = g->ctx[r]->pflags;
+  for (int i = 0; i < nsub; i++) g->workers.emplace_back(group_worker, g, i);
+  return B200_OK;
+}
+
+void b200_group_destroy(b200_group *g) {
+  if (!g) return;
+  {
+    std::unique_lock<std::mutex> lk(g->jmu);
+    g->quit = true;
+  }
+  g->jcv.notify_all();
+  for (auto &t : g->workers) t.join();
+  for (int i = 0; i < g->n; i++) {
+    if (g->pub[i].ready) cudaEventDestroy(g->pub[i].ready);
+    if (g->ctx[i]) {
+      g->ctx[i]->grp = nullptr;
+      b200_destroy(g->ctx[i]);
+    }
+  }
+  delete g;
+}
+
+const char *b200_group_last_error(const b200_group *g) { return g ? g->err.c_str() : "null group"; }
+int b200_group_size(const b200_group *g) { return g ? g->n : 0; }
+b200_ctx *b200_group_context(b200_group *g, int i) { return (g && i >= 0 && i < g->n) ? g->ctx[i] : nullptr; }
+
+// brick grid for n sub-domains of a box with edge lengths prd: the factorisation with the
+// smallest sub-domain surface (ProcMap::onelevel_grid / best_factors, procmap.cpp:48,690-750)
+int b200_group_auto_grid(int n, const double prd[3], int grid[3]) {
+  if (n < 1 || !prd || !grid) return B200_EARG;
+  double best = 1.0e300;
+  for (int px = 1; px <= n; px++) {
+    if (n % px) continue;
+    for (int py = 1; py <= n / px; py++) {
+      if ((n / px) % py) continue;
+      const int pz = n / px / py;
+      const double lx = prd[0] / px, ly = prd[1] / py, lz = prd[2] / pz;
+      const double surf = lx * ly + ly * lz + lx * lz;
+      if (surf < best) {
+        best = surf;
+        grid[0] = px; grid[1] = py; grid[2] = pz;
+      }
+    }
+  }
+  return B200_OK;
+}
+
+int b200_group_set_grid(b200_group *g, const int grid[3]) {
+  if (!g || !grid || grid[0] * grid[1] * grid[2] != g->n)
+    return g ? group_fail(g, B200_EARG, "sub-domain grid does not match the number of sub-domains") : B200_EARG;
+  for (int d = 0; d < 3; d++) g->grid[d] = grid[d];
+  for (int i = 0; i < g->n; i++) {
+    const int loc[3] = {i / (grid[1] * grid[2]), (i / grid[2]) % grid[1], i % grid[2]};
+    const int rc = b200_set_decomposition(g->ctx[i], grid, loc);
+    if (rc != B200_OK) return group_fail(g, rc, g->ctx[i]->err);
+  }
+  return B200_OK;
+}
+
+// all owned atoms of the whole box (already wrapped into it, Domain::pbc): split by owning
+// sub-domain [sublo, subhi) with the bounds b200_set_decomposition gives every context
+int b200_group_set_atoms(b200_group *g, int n, int ntypes, const double *mass, const double *x,
+                         const double *v, const int *type, const int *tag, const int *mask,
+                         const int *image) {
+  if (!g || n < 0 || !mass || (n && (!x || !v || !type || !tag))) return B200_EARG;
+  b200_ctx *c0 = g->ctx[0];
+  if (!c0->have_box) return group_fail(g, B200_EARG, "b200_set_box before b200_group_set_atoms");
+  std::vector<std::vector<int>> idx(g->n);
+  const int *P = g->grid;
+  for (int i = 0; i < n; i++) {
+    int loc[3];
+    for (int d = 0; d < 3; d++) {
+      const double c = x[3 * (size_t)i + d];
+      int l = (int)((c - c0->boxlo[d]) / c0->prd[d] * P[d]);
+      l = std::min(std::max(l, 0), P[d] - 1);
+      // the exact bounds of setup_geometry (boxlo + prd * l / P, last one closed at boxhi)
+      auto lo = [&](int q) { return c0->boxlo[d] + c0->prd[d] * (q * 1.0 / P[d]); };
+      while (l > 0 && c < lo(l)) l--;
+      while (l < P[d] - 1 && c >= lo(l + 1)) l++;
+      loc[d] = l;
+    }
+    idx[(loc[0] * P[1] + loc[1]) * P[2] + loc[2]].push_back(i);
+  }
+  for (int r = 0; r < g->n; r++) {
+    const std::vector<int> &id = idx[r];
+    const size_t m = id.size();
+    std::vector<double> xs(3 * m), vs(3 * m);
+    std::vector<int> ts(m), gs(m), ms(mask ? m : 0), is(image ? m : 0);
+    for (size_t k = 0; k < m; k++) {
+      const size_t i = id[k];
+      for (int d = 0; d < 3; d++) { xs[3 * k + d] = x[3 * i + d]; vs[3 * k + d] = v[3 * i + d]; }
+      ts[k] = type[i]; gs[k] = tag[i];
+      if (mask) ms[k] = mask[i];
+      if (image) is[k] = image[i];
+    }
+    const int rc = b200_set_atoms(g->ctx[r], (int)m, ntypes, mass, xs.data(), vs.data(), ts.data(), gs.data(),
+                                  mask ? ms.data() : nullptr, image ? is.data() : nullptr);
+    if (rc != B200_OK) return group_fail(g, rc, g->ctx[r]->err);
+  }
+  return B200_OK;
+}
+
+int b200_group_count(b200_group *g, int *nlocal_total, int *nghost_total) {
+  if (!g) return B200_EARG;
+  int a = 0, b = 0;
+  for (int i = 0; i < g->n; i++) { a += g->ctx[i]->nlocal; b += g->ctx[i]->nghost; }
+  if (nlocal_total) *nlocal_total = a;
+  if (nghost_total) *nghost_total = b;
+  return B200_OK;
+}
+
+// owned atoms of all sub-domains, concatenated in sub-domain order
+int b200_group_get_atoms(b200_group *g, double *x, double *v, double *f, int *type, int *tag, int *mask,
+                         int *image) {
+  if (!g) return B200_EARG;
+  std::vector<size_t> off(g->n + 1, 0);
+  for (int i = 0; i < g->n; i++) off[i + 1] = off[i] + g->ctx[i]->nlocal;
+  return group_run(g, [&](int i) {
+    const size_t o = off[i];
+    return b200_get_atoms(g->ctx[i], 0, x ? x + 3 * o : nullptr, v ? v + 3 * o : nullptr, f ? f + 3 * o : nullptr,
+                          type ? type + o : nullptr, tag ? tag + o : nullptr, mask ? mask + o : nullptr,
+                          image ? image + o : nullptr);
+  });
+}
+
+int b200_group_setup(b200_group *g, int eflag, int vflag) {
+  if (!g) return B200_EARG;
+  return group_run(g, [&](int i) { return b200_setup(g->ctx[i], eflag, vflag); });
+}
+
+int b200_group_step(b200_group *g, int eflag, int vflag, int *rebuilt) {
+  if (!g) return B200_EARG;
+  std::vector<int> rb(g->n, 0);
+  const int rc = group_run(g, [&](int i) { return b200_step(g->ctx[i], eflag, vflag, &rb[i]); });
+  if (rebuilt) *rebuilt = rb[0];
+  return rc;
+}
+
+int b200_group_run(b200_group *g, int nsteps, int64_t first_step, int thermo_every, double *thermo_out,
+                   int max_thermo, int *n_thermo) {
+  if (!g) return B200_EARG;
+  std::vector<int> nt(g->n, 0);
+  std::vector<std::vector<double>> scratch(g->n);
+  for (int i = 1; i < g->n; i++) scratch[i].assign((size_t)10 * std::max(max_thermo, 1), 0.0);
+  const int rc = group_run(g, [&](int i) {
+    return b200_run(g->ctx[i], nsteps, first_step, thermo_every, i == 0 ? thermo_out : scratch[i].data(),
+                    max_thermo, &nt[i]);
+  });
+  if (n_thermo) *n_thermo = nt[0];
+  return rc;
+}
+
+int b200_group_get_tallies(b200_group *g, double *eng_vdwl, double virial[6]) {
+  return g ? b200_get_tallies(g->ctx[0], eng_vdwl, virial) : B200_EARG;  // group sums on every context
+}
+
+int b200_group_ke_sum(b200_group *g, double *mv2) {
+  if (!g || !mv2) return B200_EARG;
+  std::vector<double> r(g->n, 0.0);
+  const int rc = group_run(g, [&](int i) { return b200_ke_sum(g->ctx[i], &r[i]); });
+  *mv2 = r[0];
+  return rc;
+}
+
+int b200_group_last_run_ms(b200_group *g, double *ms) {
+  if (!g || !ms) return B200_EARG;
+  double m = 0.0;
+  for (int i = 0; i < g->n; i++) m = std::max(m, g->ctx[i]->last_run_ms);
+  *ms = m;
+  return B200_OK;
+}
+
+// counters summed over the sub-domains (builds, ago, bins, ... are those of sub-domain 0)
+int b200_group_get_stats(b200_group *g, b200_stats *out) {
+  if (!g || !out) return B200_EARG;
+  b200_stats t;
+  for (int i = 0; i < g->n; i++) {
+    const int rc = b200_get_stats(g->ctx[i], i == 0 ? out : &t);
+    if (rc != B200_OK) return group_fail(g, rc, g->ctx[i]->err);
+    if (i > 0) {
+      out->npairs += t.npairs;
+      out->list_entries += t.list_entries;
+      out->launches += t.launches;
+      out->device_bytes += t.device_bytes;
+      out->max_numneigh = std::max(out->max_numneigh, t.max_numneigh);
+      out->tiles_interior += t.tiles_interior;
+      out->tiles_boundary += t.tiles_boundary;
+    }
+  }
   return B200_OK;
 }
 

@@ -31,6 +31,11 @@ EXPORTS = [
     "b200_pair_compute", "b200_get_tallies", "b200_ke_sum", "b200_get_stats",
     "b200_get_neighbor_list", "b200_get_eam_rho_fp", "b200_set_profiling",
     "b200_get_phase_times", "b200_comm_unique_id", "b200_comm_init", "b200_neighbor_ranks",
+    "b200_group_create", "b200_group_destroy", "b200_group_last_error", "b200_group_size",
+    "b200_group_context", "b200_group_auto_grid", "b200_group_set_grid", "b200_group_set_atoms",
+    "b200_group_count", "b200_group_get_atoms", "b200_group_setup", "b200_group_step",
+    "b200_group_run", "b200_group_get_tallies", "b200_group_ke_sum", "b200_group_last_run_ms",
+    "b200_group_get_stats",
 ]
 
 
@@ -67,6 +72,12 @@ def load_library():
         L.b200_last_error.argtypes = [C.c_void_p]
         L.b200_destroy.restype = None
         L.b200_destroy.argtypes = [C.c_void_p]
+        L.b200_group_last_error.restype = C.c_char_p
+        L.b200_group_last_error.argtypes = [C.c_void_p]
+        L.b200_group_destroy.restype = None
+        L.b200_group_destroy.argtypes = [C.c_void_p]
+        L.b200_group_context.restype = C.c_void_p
+        L.b200_group_context.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -306,3 +317,153 @@ class Engine:
         norm = n if u.normalize else 1
         return {"step": int(raw[0]), "temp": temp, "e_pair": pe / norm,
                 "toteng": (pe + ke) / norm, "press": press}
+
+
+class EngineGroup:
+    """Several brick sub-domains driven by this one process (`package b200 gpus N`): the mirror of
+    the b200_group_* entry points.  `devices` lists the CUDA device of every sub-domain; devices
+    may repeat (several sub-domains sharing one GPU: how a 1-GPU box exercises migration, borders
+    and the peer-memory halo).  Same vocabulary as `Engine`; per-context settings are applied to
+    every sub-domain."""
+
+    def __init__(self, devices, precision="double", units="lj", grid=None):
+        self.L = load_library()
+        if self.L.b200_device_count() <= 0:
+            raise B200Error("no CUDA device visible (the B200 engine has no CPU fallback)")
+        dev = _i(devices)
+        self.n = len(dev)
+        self.g = C.c_void_p()
+        prec = {"double": 0, "mixed": 1}[precision]
+        self._chk(self.L.b200_group_create(C.byref(self.g), C.c_int(self.n), _p(dev), C.c_int(prec)))
+        # sub-domain views: Engine objects around the group's contexts (not owning them)
+        self.sub = []
+        for i in range(self.n):
+            e = Engine.__new__(Engine)
+            e.L = self.L
+            e.h = C.c_void_p(self.L.b200_group_context(self.g, C.c_int(i)))
+            e.precision, e.units = precision, _units.get(units)
+            e.boxlo = e.boxhi = None
+            e.natoms_total, e.step, e.thermo_every, e.dt = 0, 0, 0, e.units.dt
+            e.close = lambda: None
+            self.sub.append(e)
+        self.units = _units.get(units)
+        self.grid = grid
+        self.step = 0
+        self.natoms_total = 0
+        self.boxlo = self.boxhi = None
+        self.dt = self.units.dt
+
+    def close(self):
+        if getattr(self, "g", None) and self.g:
+            for e in self.sub:
+                e.h = C.c_void_p()
+            self.L.b200_group_destroy(self.g)
+            self.g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            msg = self.L.b200_group_last_error(self.g) if self.g else b""
+            raise B200Error(f"b200 group error {rc}: {(msg or b'').decode()}")
+
+    def set_box(self, lo, hi, periodic=(1, 1, 1)):
+        self.boxlo, self.boxhi = _d(lo).copy(), _d(hi).copy()
+        for e in self.sub:
+            e.set_box(lo, hi, periodic)
+        grid = self.grid
+        if grid is None:
+            g3 = np.zeros(3, np.int32)
+            prd = _d(hi) - _d(lo)
+            self._chk(self.L.b200_group_auto_grid(C.c_int(self.n), _p(prd), _p(g3)))
+            grid = tuple(int(v) for v in g3)
+        self.grid = tuple(grid)
+        self._chk(self.L.b200_group_set_grid(self.g, _p(_i(self.grid))))
+
+    def neighbor(self, *a, **k):
+        for e in self.sub:
+            e.neighbor(*a, **k)
+
+    def fix_nve(self, dt=None, groupbit=1):
+        for e in self.sub:
+            e.fix_nve(dt, groupbit)
+        self.dt = self.sub[0].dt
+
+    def pair_lj_cut(self, tables):
+        for e in self.sub:
+            e.pair_lj_cut(tables)
+
+    def pair_eam(self, tables):
+        for e in self.sub:
+            e.pair_eam(tables)
+
+    def set_atoms(self, x, v, type, tag, mass, mask=None, image=None, natoms_total=None):
+        x, v, type, tag, mass = _d(x), _d(v), _i(type), _i(tag), _d(mass)
+        n = x.shape[0]
+        mk = _i(mask) if mask is not None else None
+        im = _i(image) if image is not None else None
+        self.natoms_total = natoms_total if natoms_total is not None else n
+        for e in self.sub:
+            e.natoms_total, e.mass, e.boxlo, e.boxhi = self.natoms_total, mass, self.boxlo, self.boxhi
+        self._chk(self.L.b200_group_set_atoms(self.g, C.c_int(n), C.c_int(mass.shape[0] - 1), _p(mass),
+                                              _p(x), _p(v), _p(type), _p(tag), _p(mk), _p(im)))
+
+    def setup(self, eflag=1, vflag=1):
+        self._chk(self.L.b200_group_setup(self.g, C.c_int(eflag), C.c_int(vflag)))
+
+    def run(self, nsteps, thermo_every=0):
+        cap = (nsteps // thermo_every + 2) if thermo_every > 0 else 2
+        out = np.zeros((cap, 10))
+        n = C.c_int(0)
+        self._chk(self.L.b200_group_run(self.g, C.c_int(nsteps), C.c_int64(self.step),
+                                        C.c_int(thermo_every), _p(out), C.c_int(cap), C.byref(n)))
+        self.step += nsteps
+        return out[:n.value]
+
+    def last_run_ms(self):
+        ms = C.c_double(0)
+        self._chk(self.L.b200_group_last_run_ms(self.g, C.byref(ms)))
+        return ms.value
+
+    def counts(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self._chk(self.L.b200_group_count(self.g, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def get_atoms(self, fields=("x", "v", "f", "type", "tag", "image")):
+        n, _ = self.counts()
+        shapes = {"x": ((n, 3), np.float64), "v": ((n, 3), np.float64), "f": ((n, 3), np.float64),
+                  "type": ((n,), np.int32), "tag": ((n,), np.int32), "mask": ((n,), np.int32),
+                  "image": ((n,), np.int32)}
+        out = {k: np.zeros(*shapes[k]) for k in fields}
+        g = lambda k: _p(out[k]) if k in out else None  # noqa: E731
+        self._chk(self.L.b200_group_get_atoms(self.g, g("x"), g("v"), g("f"), g("type"), g("tag"),
+                                              g("mask"), g("image")))
+        return out
+
+    def tallies(self):
+        e = C.c_double(0)
+        v = np.zeros(6)
+        self._chk(self.L.b200_group_get_tallies(self.g, C.byref(e), _p(v)))
+        return e.value, v
+
+    def ke_sum(self):
+        e = C.c_double(0)
+        self._chk(self.L.b200_group_ke_sum(self.g, C.byref(e)))
+        return e.value
+
+    def stats(self):
+        s = Stats()
+        self._chk(self.L.b200_group_get_stats(self.g, C.byref(s)))
+        d = {k: getattr(s, k) for k, _ in Stats._fields_ if k not in ("nbins", "tile")}
+        d["nbins"], d["tile"] = list(s.nbins), list(s.tile)
+        return d
+
+    def thermo_row(self, raw):
+        e = self.sub[0]
+        e.natoms_total, e.boxlo, e.boxhi = self.natoms_total, self.boxlo, self.boxhi
+        return e.thermo_row(raw)
