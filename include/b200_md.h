@@ -121,6 +121,17 @@ int b200_pair_compute(b200_ctx *ctx, int eflag, int vflag); /* Pair::compute pai
  *      sum_i m_i v_i^2 (ComputeTemp::compute_scalar, compute_temp.cpp:73-97) */
 int b200_get_tallies(b200_ctx *ctx, double *eng_vdwl, double virial[6]);
 int b200_ke_sum(b200_ctx *ctx, double *mv2);
+/*      the same for any group bit, with the kinetic tensor sums m*(vx vx, vy vy, vz vz, vx vy,
+ *      vx vz, vy vz) of ComputeTemp::compute_vector (compute_temp.cpp:100-140): what
+ *      compute temp/b200 needs, so that a thermo step moves 56 bytes instead of the atoms */
+int b200_ke_group(b200_ctx *ctx, int groupbit, double *mv2, double tensor[6]);
+/*      wait for everything enqueued on the context (timer sync, Timer::stamp with _sync) */
+int b200_sync(b200_ctx *ctx);
+/* ---- run-time knobs by name = the keywords of `package b200` (input.cpp Input::package):
+ *      list tile|flat|auto, tile "tx,ty,tz", overlap yes|no, graph yes|no, tpa 1|2|4|8,
+ *      mixed_fx yes|no, tallies local|global (local: eng_vdwl / virial / ke stay per sub-domain
+ *      for a host that reduces them itself, e.g. LAMMPS over MPI) */
+int b200_set_option(b200_ctx *ctx, const char *key, const char *value);
 
 /* ---- statistics: neighbor->ncalls / ndanger / ago, pair counts, phase timings */
 typedef struct {
@@ -232,6 +243,7 @@ int b200_group_run(b200_group *g, int nsteps, int64_t first_step, int thermo_eve
                    double *thermo_out, int max_thermo, int *n_thermo);
 int b200_group_get_tallies(b200_group *g, double *eng_vdwl, double virial[6]);
 int b200_group_ke_sum(b200_group *g, double *mv2);
+int b200_group_ke_group(b200_group *g, int groupbit, double *mv2, double tensor[6]);
 int b200_group_last_run_ms(b200_group *g, double *ms);
 int b200_group_get_stats(b200_group *g, b200_stats *out);
 

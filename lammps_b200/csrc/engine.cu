@@ -247,6 +247,7 @@ struct b200_ctx {
   bool pending_final = false;  // final_integrate of the last step is deferred (fused into the next initial)
   // tallies / flags
   double *ev = nullptr;   // [8] device: eng, virial[6], ke
+  double *ke7 = nullptr;  // [7] device: b200_ke_group accumulators
   int *flags = nullptr;   // [4] device: moved, err, maxcount, grand_total
   unsigned long long *cnt64 = nullptr;
   double *h_ev = nullptr; // pinned [8]
@@ -2064,6 +2065,7 @@ int b200_create(b200_ctx **out, int device, int precision) {
     }
   }
   TRY(dalloc(ctx, &ctx->ev, 8));
+  TRY(dalloc(ctx, &ctx->ke7, 8));
   TRY(dalloc(ctx, &ctx->flags, 4));
   TRY(dalloc(ctx, &ctx->tflags, 8));
   TRY(tile_kernel_attrs(ctx));
@@ -2075,7 +2077,7 @@ int b200_create(b200_ctx **out, int device, int precision) {
   memset(&ctx->owner, 0, sizeof ctx->owner);
   TRY(dalloc(ctx, &ctx->diroffset, NDIR + 1));
   TRY(dalloc(ctx, &ctx->cnt64, 1));
-  CK(cudaMallocHost((void **)&ctx->h_ev, 8 * sizeof(double)));
+  CK(cudaMallocHost((void **)&ctx->h_ev, 16 * sizeof(double)));
   CK(cudaMallocHost((void **)&ctx->h_flags, 64 * sizeof(int)));
   CK(cudaMemsetAsync(ctx->ev, 0, 8 * sizeof(double), ctx->stream));
   CK(cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), ctx->stream));
@@ -2106,7 +2108,7 @@ void b200_destroy(b200_ctx *ctx) {
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   if (ctx->nccl && g_nccl.ok) g_nccl.CommDestroy(ctx->nccl);
   F(ctx->neigh.p);
-  F(ctx->numneigh.p); F(ctx->lj_tab.p); F(ctx->eam_i.p); F(ctx->eam_d.p); F(ctx->eam_one_d.p); F(ctx->ev); F(ctx->flags);
+  F(ctx->numneigh.p); F(ctx->lj_tab.p); F(ctx->eam_i.p); F(ctx->eam_d.p); F(ctx->eam_one_d.p); F(ctx->ev); F(ctx->ke7); F(ctx->flags);
   F(ctx->cnt64);
   F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p); F(ctx->tl_gi.p);
   if (ctx->h_ev) cudaFreeHost(ctx->h_ev);
@@ -2251,7 +2253,7 @@ int b200_get_atoms(b200_ctx *ctx, int with_ghosts, double *x, double *v, double 
     if (type) CK(cudaMemcpyAsync(type, itmp, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
   }
-  if (v) {  // velocities exist for owned atoms only
+  if (v && nl > 0) {  // velocities exist for owned atoms only
     k_soa_to_aos<<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], stage);
     ctx->launches++;
     LAUNCH_CHECK();
@@ -2598,6 +2600,77 @@ int b200_ke_sum(b200_ctx *ctx, double *mv2) {
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->grp && !ctx->local_tallies) TRY(group_sum(ctx, ctx->h_ev + 7, 1));
   *mv2 = ctx->h_ev[7];
+  return B200_OK;
+}
+
+// sum m v^2 and the kinetic tensor sums of the atoms in `groupbit` (ComputeTemp,
+// compute_temp.cpp:73-140); summed over all sub-domains unless tallies are local
+int b200_ke_group(b200_ctx *ctx, int groupbit, double *mv2, double tensor[6]) {
+  if (!ctx) return B200_EARG;
+  TRY(flush_final(ctx));
+  CK(cudaSetDevice(ctx->device));
+  const int nl = ctx->nlocal, c = ctx->cur;
+  double *acc = ctx->ke7;
+  CK(cudaMemsetAsync(acc, 0, 7 * sizeof(double), ctx->stream));
+  if (nl > 0) {
+    k_ke_group<<<std::min(cdiv(nl, 256), 148 * 8), 256, 0, ctx->stream>>>(
+        nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->mask[c], ctx->mass_d.p, groupbit, acc);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  if (ctx->nranks > 1 && !ctx->grp && !ctx->local_tallies)
+    NK(g_nccl.AllReduce(acc, acc, 7, ncclDouble, ncclSum, ctx->nccl, ctx->stream));
+  double h[8];
+  CK(cudaMemcpyAsync(ctx->h_ev + 8, acc, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(h, ctx->h_ev + 8, 7 * sizeof(double));
+  if (ctx->grp && !ctx->local_tallies) TRY(group_sum(ctx, h, 7));
+  if (mv2) *mv2 = h[0];
+  if (tensor) memcpy(tensor, h + 1, 6 * sizeof(double));
+  return B200_OK;
+}
+
+int b200_sync(b200_ctx *ctx) {
+  if (!ctx) return B200_EARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->stream2) CK(cudaStreamSynchronize(ctx->stream2));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+// run-time knobs by name (the `package b200` keywords; the B200_* environment variables set the
+// same fields at b200_create).  Takes effect at the next rebuild / setup.
+int b200_set_option(b200_ctx *ctx, const char *key, const char *value) {
+  if (!ctx || !key || !value) return B200_EARG;
+  drop_step_graph(ctx);
+  const std::string k = key, v = value;
+  auto yes = [&]() { return v == "yes" || v == "on" || v == "1" || v == "true"; };
+  if (k == "list") {
+    if (v == "tile") ctx->list_mode = 1;
+    else if (v == "flat") ctx->list_mode = 2;
+    else if (v == "auto") ctx->list_mode = 0;
+    else return ctx->fail(B200_EARG, "package b200 list: tile, flat or auto (got %s)", value);
+    ctx->geom_ready = false;
+  } else if (k == "tile") {
+    int t[3];
+    if (sscanf(value, "%d,%d,%d", &t[0], &t[1], &t[2]) != 3 || t[0] < 1 || t[1] < 1 || t[2] < 1)
+      return ctx->fail(B200_EARG, "package b200 tile: three positive bin counts (got %s)", value);
+    for (int d = 0; d < 3; d++) ctx->tile_req[d] = t[d];
+    ctx->geom_ready = false;
+  } else if (k == "overlap") ctx->overlap = yes();
+  else if (k == "graph") ctx->use_graph = yes();
+  else if (k == "mixed_fx") ctx->mixed_fx = yes();
+  else if (k == "tpa") {
+    const int t = atoi(value);
+    if (t != 1 && t != 2 && t != 4 && t != 8) return ctx->fail(B200_EARG, "package b200 tpa: 1, 2, 4 or 8");
+    ctx->tpa = t;
+    ctx->geom_ready = false;
+  } else if (k == "tallies") {
+    if (v == "local") ctx->local_tallies = true;
+    else if (v == "global") ctx->local_tallies = false;
+    else return ctx->fail(B200_EARG, "tallies: local or global");
+  } else
+    return ctx->fail(B200_EARG, "unknown option %s", key);
   return B200_OK;
 }
 
@@ -3046,6 +3119,15 @@ int b200_group_ke_sum(b200_group *g, double *mv2) {
   std::vector<double> r(g->n, 0.0);
   const int rc = group_run(g, [&](int i) { return b200_ke_sum(g->ctx[i], &r[i]); });
   *mv2 = r[0];
+  return rc;
+}
+
+int b200_group_ke_group(b200_group *g, int groupbit, double *mv2, double tensor[6]) {
+  if (!g) return B200_EARG;
+  std::vector<double> r((size_t)g->n * 7, 0.0);
+  const int rc = group_run(g, [&](int i) { return b200_ke_group(g->ctx[i], groupbit, &r[7 * (size_t)i], &r[7 * (size_t)i + 1]); });
+  if (mv2) *mv2 = r[0];
+  if (tensor) memcpy(tensor, &r[1], 6 * sizeof(double));
   return rc;
 }
 

@@ -115,6 +115,31 @@ __global__ void __launch_bounds__(256) k_ke(int nlocal, const double4 *__restric
   if (threadIdx.x == 0) atomicAdd(&ev[7], v[0]);
 }
 
+// ComputeTemp::compute_scalar + compute_vector (compute_temp.cpp:73-140) for any group bit:
+// out[0] += sum m v^2, out[1..6] += sum m (vx vx, vy vy, vz vz, vx vy, vx vz, vy vz)
+__global__ void __launch_bounds__(256) k_ke_group(int nlocal, const double4 *__restrict__ xt,
+                                                  const double *__restrict__ vx,
+                                                  const double *__restrict__ vy,
+                                                  const double *__restrict__ vz,
+                                                  const int *__restrict__ mask,
+                                                  const double *__restrict__ mass, int groupbit,
+                                                  double *__restrict__ out) {
+  double v[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
+    if (mask[i] & groupbit) {
+      const double w = reinterpret_cast<const double *>(xt)[4 * (size_t)i + 3];
+      const double m = mass[d2type(w)], a = vx[i], b = vy[i], c = vz[i];
+      v[0] += (a * a + b * b + c * c) * m;
+      v[1] += m * a * a; v[2] += m * b * b; v[3] += m * c * c;
+      v[4] += m * a * b; v[5] += m * a * c; v[6] += m * b * c;
+    }
+  }
+  __shared__ double red[7 * 32];
+  block_sum<7>(v, red);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 7; k++) atomicAdd(&out[k], v[k]);
+}
+
 // host array <-> device layout converters (b200_set_atoms / b200_get_atoms)
 __global__ void __launch_bounds__(256) k_pack_xt(int n, const double *__restrict__ x3,
                                                  const int *__restrict__ type,

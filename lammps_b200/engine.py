@@ -35,7 +35,7 @@ EXPORTS = [
     "b200_group_context", "b200_group_auto_grid", "b200_group_set_grid", "b200_group_set_atoms",
     "b200_group_count", "b200_group_get_atoms", "b200_group_setup", "b200_group_step",
     "b200_group_run", "b200_group_get_tallies", "b200_group_ke_sum", "b200_group_last_run_ms",
-    "b200_group_get_stats",
+    "b200_group_get_stats", "b200_group_ke_group", "b200_ke_group", "b200_sync", "b200_set_option",
 ]
 
 
@@ -263,6 +263,20 @@ class Engine:
         e = C.c_double(0)
         self._chk(self.L.b200_ke_sum(self.h, C.byref(e)))
         return e.value
+
+    def ke_group(self, groupbit=1):
+        """(sum m v^2, kinetic tensor sums[6]) of the atoms in a group bit (compute temp/b200)"""
+        e = C.c_double(0)
+        t = np.zeros(6)
+        self._chk(self.L.b200_ke_group(self.h, C.c_int(groupbit), C.byref(e), _p(t)))
+        return e.value, t
+
+    def set_option(self, key, value):
+        """a `package b200` keyword (list, tile, overlap, graph, tpa, mixed_fx, tallies)"""
+        self._chk(self.L.b200_set_option(self.h, str(key).encode(), str(value).encode()))
+
+    def sync(self):
+        self._chk(self.L.b200_sync(self.h))
 
     def stats(self) -> dict:
         s = Stats()

@@ -1,10 +1,19 @@
 /* ----------------------------------------------------------------------
    fix B200: "package b200 [ngpu] keyword value ..."
-     device D            CUDA device of this process (default: $LOCAL_RANK or 0)
+     gpus N              N GPUs driven by this process, one brick sub-domain each
+                         (devices D, D+1, ...; default 1)
+     subdomains M        M >= N sub-domains, dealt round-robin onto the N GPUs
+                         (several per GPU: a test/debug configuration)
+     device D            first CUDA device of this process (default: $LOCAL_RANK or 0)
      prec double|mixed   arithmetic of the pair kernels (default double)
-     profile yes|no      per-phase device timing printed after each run (default no)
-   The context is created here and destroyed with the fix, like the GPU
-   package ties its device to fix GPU (precedent: src/GPU/fix_gpu.cpp).
+     profile yes|no      step stage by stage with a device sync after each, so that
+                         the Timer breakdown (Pair/Neigh/Comm/Modify) is filled, and
+                         print per-phase device times after each run (default no)
+     list tile|flat|auto neighbour list layout      tile tx ty tz   bins per tile
+     overlap yes|no      interior tiles beside the halo          graph yes|no  CUDA graph
+     tpa 1|2|4|8         lanes per atom of the flat kernels      mixed_fx yes|no
+   The device contexts are created here and destroyed with the fix, like the
+   GPU package ties its devices to fix GPU (precedent: src/GPU/fix_gpu.cpp).
 ------------------------------------------------------------------------- */
 
 #include "fix_b200.h"
@@ -22,49 +31,89 @@
 using namespace LAMMPS_NS;
 
 FixB200::FixB200(LAMMPS *lmp, int narg, char **arg) :
-    Fix(lmp, narg, arg), ctx(nullptr), device(0), prec(B200_PREC_DOUBLE), profile_flag(0)
+    Fix(lmp, narg, arg), host_stale(0), ctx(nullptr), grp(nullptr), nsub(1), device(0),
+    prec(B200_PREC_DOUBLE), profile_flag(0)
 {
   if (const char *lr = getenv("LOCAL_RANK")) device = atoi(lr);
 
+  int ngpu = 1, nsubdom = 0;
+  std::vector<std::pair<std::string, std::string>> options;
   int iarg = 3;
-  // optional leading GPU count, accepted for symmetry with "package gpu N"; one GPU per process
+  // optional leading GPU count, like "package gpu N"
   if (iarg < narg && utils::is_integer(arg[iarg])) {
-    int ngpu = utils::inumeric(FLERR, arg[iarg], false, lmp);
-    if (ngpu > 1)
-      error->all(FLERR, "package b200: one GPU per process; run one process per GPU instead");
+    ngpu = utils::inumeric(FLERR, arg[iarg], false, lmp);
     iarg++;
   }
   while (iarg < narg) {
     if (iarg + 2 > narg) error->all(FLERR, "Illegal package b200 command: missing value");
-    if (strcmp(arg[iarg], "device") == 0) {
+    const std::string key = arg[iarg];
+    if (key == "device") {
       device = utils::inumeric(FLERR, arg[iarg + 1], false, lmp);
-    } else if (strcmp(arg[iarg], "prec") == 0) {
+    } else if (key == "gpus") {
+      ngpu = utils::inumeric(FLERR, arg[iarg + 1], false, lmp);
+    } else if (key == "subdomains") {
+      nsubdom = utils::inumeric(FLERR, arg[iarg + 1], false, lmp);
+    } else if (key == "prec") {
       if (strcmp(arg[iarg + 1], "double") == 0) prec = B200_PREC_DOUBLE;
       else if (strcmp(arg[iarg + 1], "mixed") == 0) prec = B200_PREC_MIXED;
       else error->all(FLERR, "Illegal package b200 prec value: {}", arg[iarg + 1]);
-    } else if (strcmp(arg[iarg], "profile") == 0) {
+    } else if (key == "profile") {
       profile_flag = utils::logical(FLERR, arg[iarg + 1], false, lmp);
+    } else if (key == "tile") {
+      if (iarg + 4 > narg) error->all(FLERR, "Illegal package b200 command: tile needs three values");
+      options.emplace_back("tile", std::string(arg[iarg + 1]) + "," + arg[iarg + 2] + "," + arg[iarg + 3]);
+      iarg += 2;
+    } else if (key == "list" || key == "overlap" || key == "graph" || key == "tpa" || key == "mixed_fx") {
+      options.emplace_back(key, arg[iarg + 1]);
     } else
       error->all(FLERR, "Unknown package b200 keyword: {}", arg[iarg]);
     iarg += 2;
   }
+  if (ngpu < 1) error->all(FLERR, "Illegal package b200 command: gpus must be >= 1");
+  if (nsubdom == 0) nsubdom = ngpu;
+  if (nsubdom < ngpu) error->all(FLERR, "Illegal package b200 command: fewer sub-domains than GPUs");
 
-  if (b200_device_count() <= 0)
+  const int have = b200_device_count();
+  if (have <= 0)
     error->all(FLERR, "package b200: no CUDA device visible (the B200 package has no CPU fallback)");
-  int rc = b200_create(&ctx, device, prec);
-  if (rc != B200_OK) {
-    std::string msg = ctx ? b200_last_error(ctx) : "cannot create device context";
-    if (ctx) b200_destroy(ctx);
-    ctx = nullptr;
-    error->one(FLERR, "package b200: {}", msg);
+  if (device + ngpu > have)
+    error->all(FLERR, "package b200: devices {}..{} requested but {} visible", device, device + ngpu - 1, have);
+
+  if (nsubdom > 1) {
+    // one process, several sub-domains: LAMMPS sees one rank owning the whole box
+    if (comm->nprocs > 1)
+      error->all(FLERR, "package b200 gpus/subdomains > 1 is the single-process mode; with MPI run one "
+                        "rank per GPU instead");
+    nsub = nsubdom;
+    std::vector<int> devs(nsub);
+    for (int i = 0; i < nsub; i++) devs[i] = device + i % ngpu;
+    int rc = b200_group_create(&grp, nsub, devs.data(), prec);
+    if (rc != B200_OK) {
+      std::string msg = grp ? b200_group_last_error(grp) : "cannot create the device group";
+      if (grp) b200_group_destroy(grp);
+      grp = nullptr;
+      error->one(FLERR, "package b200: {}", msg);
+    }
+  } else {
+    int rc = b200_create(&ctx, device, prec);
+    if (rc != B200_OK) {
+      std::string msg = ctx ? b200_last_error(ctx) : "cannot create device context";
+      if (ctx) b200_destroy(ctx);
+      ctx = nullptr;
+      error->one(FLERR, "package b200: {}", msg);
+    }
   }
+  for (int i = 0; i < nctx(); i++)
+    for (auto &kv : options) check(b200_set_option(context(i), kv.first.c_str(), kv.second.c_str()), FLERR);
   if (comm->me == 0)
-    utils::logmesg(lmp, "B200 package: device {} precision {}\n", device,
-                   prec == B200_PREC_DOUBLE ? "double" : "mixed");
+    utils::logmesg(lmp, "B200 package: device {} precision {}{}\n", device,
+                   prec == B200_PREC_DOUBLE ? "double" : "mixed",
+                   nsub > 1 ? fmt::format(", {} sub-domains on {} GPU(s) in this process", nsub, ngpu) : "");
 }
 
 FixB200::~FixB200()
 {
+  if (grp) b200_group_destroy(grp);
   if (ctx) b200_destroy(ctx);
 }
 
@@ -87,7 +136,47 @@ double FixB200::memory_usage()
 void FixB200::check(int rc, const char *file, int line)
 {
   if (rc == B200_OK) return;
-  error->one(file, line, "B200 package: {} (code {})", ctx ? b200_last_error(ctx) : "no context", rc);
+  std::string msg = "no context";
+  if (grp) {
+    msg = b200_group_last_error(grp);
+    if (msg.empty())
+      for (int i = 0; i < nsub && msg.empty(); i++) msg = b200_last_error(b200_group_context(grp, i));
+  } else if (ctx)
+    msg = b200_last_error(ctx);
+  error->one(file, line, "B200 package: {} (code {})", msg, rc);
+}
+
+/* ---------------------------------------------------------------------- */
+
+void FixB200::dev_setup(int eflag, int vflag)
+{
+  check(grp ? b200_group_setup(grp, eflag, vflag) : b200_setup(ctx, eflag, vflag), FLERR);
+}
+
+void FixB200::dev_step(int eflag, int vflag, int *rebuilt)
+{
+  check(grp ? b200_group_step(grp, eflag, vflag, rebuilt) : b200_step(ctx, eflag, vflag, rebuilt), FLERR);
+}
+
+void FixB200::dev_tallies(double *eng_vdwl, double *virial)
+{
+  check(grp ? b200_group_get_tallies(grp, eng_vdwl, virial) : b200_get_tallies(ctx, eng_vdwl, virial), FLERR);
+}
+
+void FixB200::dev_ke(int groupbit, double *mv2, double *tensor)
+{
+  check(grp ? b200_group_ke_group(grp, groupbit, mv2, tensor) : b200_ke_group(ctx, groupbit, mv2, tensor),
+        FLERR);
+}
+
+void FixB200::dev_counts(int *nlocal, int *nghost)
+{
+  check(grp ? b200_group_count(grp, nlocal, nghost) : b200_get_counts(ctx, nlocal, nghost), FLERR);
+}
+
+void FixB200::dev_stats(b200_stats *st)
+{
+  check(grp ? b200_group_get_stats(grp, st) : b200_get_stats(ctx, st), FLERR);
 }
 
 FixB200 *FixB200::instance(LAMMPS *lmp)

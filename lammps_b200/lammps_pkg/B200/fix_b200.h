@@ -1,6 +1,7 @@
 /* -*- c++ -*- ----------------------------------------------------------
    fix B200 -- created by "package b200 ..." (or on demand by -sf b200);
-   owns the device context of the B200 package.
+   owns the device side of the B200 package: one context (one GPU per
+   process) or an in-process group of sub-domains on several GPUs.
 ------------------------------------------------------------------------- */
 
 #ifdef FIX_CLASS
@@ -15,6 +16,10 @@ FixStyle(B200,FixB200);
 #include "b200_lmp.h"
 #include "fix.h"
 
+#include <string>
+#include <utility>
+#include <vector>
+
 namespace LAMMPS_NS {
 
 class FixB200 : public Fix {
@@ -25,18 +30,33 @@ class FixB200 : public Fix {
   void init() override;
   double memory_usage() override;
 
-  b200_ctx *context() { return ctx; }
+  // sub-domain contexts: 1 without a group
+  int nctx() const { return grp ? nsub : 1; }
+  b200_ctx *context(int i = 0) { return grp ? b200_group_context(grp, i) : ctx; }
+  b200_group *group() { return grp; }
   int precision() const { return prec; }
   int profile() const { return profile_flag; }
+  // 1 while the device copy of the atoms is newer than atom->x/v/f (set by verlet/b200)
+  int host_stale;
+
   // turn a negative b200_* status into error->one() with the library's message
   void check(int rc, const char *file, int line);
+
+  // the calls that communicate between sub-domains, for one context or a group alike
+  void dev_setup(int eflag, int vflag);
+  void dev_step(int eflag, int vflag, int *rebuilt);
+  void dev_tallies(double *eng_vdwl, double *virial);
+  void dev_ke(int groupbit, double *mv2, double *tensor);
+  void dev_counts(int *nlocal, int *nghost);
+  void dev_stats(b200_stats *st);
 
   // the package fix of this LAMMPS instance; issues "package b200" defaults if absent
   static FixB200 *instance(class LAMMPS *);
 
  private:
   b200_ctx *ctx;
-  int device, prec, profile_flag;
+  b200_group *grp;
+  int nsub, device, prec, profile_flag;
 };
 
 }    // namespace LAMMPS_NS

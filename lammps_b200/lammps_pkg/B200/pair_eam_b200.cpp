@@ -40,10 +40,11 @@ void PairEAMB200::init_style()
   if (he_flag) error->all(FLERR, "Pair style eam/b200 does not support eam/he tables");
 }
 
+// see PairLJCutB200::compute: a silent no-op would hand stale forces to host-side callers
 void PairEAMB200::compute(int, int)
 {
-  if (strcmp(update->integrate_style, "verlet/b200") != 0)
-    error->all(FLERR, "Pair style eam/b200 requires run_style verlet/b200");
+  error->all(FLERR, "Pair style eam/b200 computes forces only inside run_style verlet/b200 "
+                    "(minimize, rerun and other host-side callers of Pair::compute are not supported)");
 }
 
 int PairEAMB200::b200_upload(b200_ctx *ctx)

@@ -29,12 +29,14 @@ void PairLJCutB200::init_style()
     error->all(FLERR, "Pair style lj/cut/b200 requires an atomic system (no special bonds)");
 }
 
-// forces live on the device and are computed inside run_style verlet/b200; a host-side
-// evaluation would be a CPU fallback, which this package does not have
+// Forces live on the device and are computed inside run_style verlet/b200 (b200_step), which
+// never calls Pair::compute.  Whoever does call it -- minimize, rerun, compute group/group, a
+// foreign run_style -- would get stale forces and energies from a silent no-op, and a host-side
+// evaluation would be the CPU fallback this package does not have: refuse.
 void PairLJCutB200::compute(int, int)
 {
-  if (strcmp(update->integrate_style, "verlet/b200") != 0)
-    error->all(FLERR, "Pair style lj/cut/b200 requires run_style verlet/b200");
+  error->all(FLERR, "Pair style lj/cut/b200 computes forces only inside run_style verlet/b200 "
+                    "(minimize, rerun and other host-side callers of Pair::compute are not supported)");
 }
 
 int PairLJCutB200::b200_upload(b200_ctx *ctx)

@@ -3,11 +3,12 @@
 
    Same sequence of stages as Verlet::setup()/run() (src/verlet.cpp), but
    every stage of a timestep -- fix nve half-kicks and drift, the rebuild
-   decision, ghost halo or pbc/exchange/borders/list build, force clear,
-   pair forces with energy/virial tallies, reverse halo -- executes on the
-   device through the C ABI of libb200md.  Host arrays (atom->x/v/f,
-   pair->eng_vdwl/virial, neighbor statistics) are refreshed only when host
-   code needs them: on output steps and at the end of a run.
+   decision, ghost halo or pbc/exchange/borders/list build, pair forces
+   with energy/virial tallies -- executes on the device through the C ABI
+   of libb200md.  Host arrays (atom->x/v/f) are refreshed only when host
+   code needs them: when a dump, a restart or a compute without a /b200
+   version is due, and at the end of a run; a thermo step whose computes
+   are temp/b200, pe and pressure moves a few scalars.
 ------------------------------------------------------------------------- */
 
 #include "verlet_b200.h"
@@ -15,6 +16,7 @@
 #include "atom.h"
 #include "atom_vec.h"
 #include "comm.h"
+#include "compute.h"
 #include "domain.h"
 #include "error.h"
 #include "fix.h"
@@ -30,12 +32,14 @@
 #include "update.h"
 
 #include <cstring>
+#include <vector>
 
 using namespace LAMMPS_NS;
 using namespace FixConst;
 
 VerletB200::VerletB200(LAMMPS *lmp, int narg, char **arg) :
-    Verlet(lmp, narg, arg), pkg(nullptr), ctx(nullptr), bpair(nullptr), bnve(nullptr), resident(0), joined(0)
+    Verlet(lmp, narg, arg), pkg(nullptr), ctx(nullptr), bpair(nullptr), bnve(nullptr), resident(0),
+    joined(0), thermo_on_device(0)
 {
 }
 
@@ -46,7 +50,7 @@ void VerletB200::init()
   Verlet::init();
 
   pkg = FixB200::instance(lmp);
-  ctx = pkg->context();
+  ctx = pkg->group() ? nullptr : pkg->context();
 
   if (domain->triclinic) error->all(FLERR, "run_style verlet/b200 requires an orthogonal box");
   if (domain->dimension != 3) error->all(FLERR, "run_style verlet/b200 requires a 3d system");
@@ -78,15 +82,30 @@ void VerletB200::init()
   }
   if (!bnve) error->all(FLERR, "run_style verlet/b200 requires fix nve/b200");
   resident = 0;
+  pkg->host_stale = 0;
+
+  // a thermo step needs no atoms on the host if every compute is one that reads device sums
+  // (temp/b200) or the pair style's scalars (pe, pressure on a temp/b200)
+  thermo_on_device = 1;
+  for (auto &c : modify->get_compute_list()) {
+    const std::string style = c->style;
+    if (style == "temp/b200" || style == "pe" || style == "pressure") continue;
+    thermo_on_device = 0;
+  }
+  for (auto &c : modify->get_compute_list())
+    if (strcmp(c->style, "temp") == 0) thermo_on_device = 0;
 
   // one MPI rank = one GPU = one brick sub-domain: join the NCCL communicator once.  The
-  // ncclUniqueId travels over MPI; afterwards all halo traffic is device-to-device NCCL.
+  // ncclUniqueId travels over MPI; afterwards all halo traffic is device-to-device.  The host
+  // reduces energy, virial and kinetic energy over the ranks itself (compute pe / pressure /
+  // temp call MPI_Allreduce), so the device tallies stay per rank.
   if (comm->nprocs > 1 && !joined) {
     char id[128];
     memset(id, 0, sizeof id);
     if (comm->me == 0) B200_CHECK(pkg, b200_comm_unique_id(id));
     MPI_Bcast(id, 128, MPI_CHAR, 0, world);
     B200_CHECK(pkg, b200_comm_init(ctx, comm->nprocs, comm->me, id));
+    B200_CHECK(pkg, b200_set_option(ctx, "tallies", "local"));
     joined = 1;
   }
 }
@@ -98,25 +117,42 @@ void VerletB200::init()
 
 void VerletB200::upload()
 {
-  B200_CHECK(pkg, b200_set_box(ctx, domain->boxlo, domain->boxhi, domain->periodicity));
-  B200_CHECK(pkg, b200_set_decomposition(ctx, comm->procgrid, comm->myloc));
-  if (comm->nprocs > 1)
-    B200_CHECK(pkg,
-               b200_set_rank_grid(ctx, &comm->grid2proc[0][0][0],
-                                  comm->procgrid[0] * comm->procgrid[1] * comm->procgrid[2]));
-  B200_CHECK(pkg,
-             b200_set_neighbor(ctx, neighbor->skin, neighbor->every, neighbor->delay,
-                               neighbor->dist_check, neighbor->oneatom));
-  const int nlocal = atom->nlocal;
-  B200_CHECK(pkg,
-             b200_set_atoms(ctx, nlocal, atom->ntypes, atom->mass, nlocal ? &atom->x[0][0] : nullptr,
-                            nlocal ? &atom->v[0][0] : nullptr, atom->type, atom->tag, atom->mask,
-                            atom->image));
-  B200_CHECK(pkg, bpair->b200_upload(ctx));
   double dtv, dtf;
   int groupbit;
   bnve->b200_params(dtv, dtf, groupbit);
-  B200_CHECK(pkg, b200_fix_nve(ctx, dtv, dtf, groupbit));
+  for (int i = 0; i < pkg->nctx(); i++) {
+    b200_ctx *c = pkg->context(i);
+    B200_CHECK(pkg, b200_set_box(c, domain->boxlo, domain->boxhi, domain->periodicity));
+    B200_CHECK(pkg,
+               b200_set_neighbor(c, neighbor->skin, neighbor->every, neighbor->delay,
+                                 neighbor->dist_check, neighbor->oneatom));
+  }
+  const int nlocal = atom->nlocal;
+  if (pkg->group()) {
+    // single process, several sub-domains: this rank owns the whole box and hands all of it over
+    int grid[3];
+    B200_CHECK(pkg, b200_group_auto_grid(pkg->nctx(), domain->prd, grid));
+    B200_CHECK(pkg, b200_group_set_grid(pkg->group(), grid));
+    B200_CHECK(pkg,
+               b200_group_set_atoms(pkg->group(), nlocal, atom->ntypes, atom->mass,
+                                    nlocal ? &atom->x[0][0] : nullptr, nlocal ? &atom->v[0][0] : nullptr,
+                                    atom->type, atom->tag, atom->mask, atom->image));
+  } else {
+    B200_CHECK(pkg, b200_set_decomposition(ctx, comm->procgrid, comm->myloc));
+    if (comm->nprocs > 1)
+      B200_CHECK(pkg,
+                 b200_set_rank_grid(ctx, &comm->grid2proc[0][0][0],
+                                    comm->procgrid[0] * comm->procgrid[1] * comm->procgrid[2]));
+    B200_CHECK(pkg,
+               b200_set_atoms(ctx, nlocal, atom->ntypes, atom->mass, nlocal ? &atom->x[0][0] : nullptr,
+                              nlocal ? &atom->v[0][0] : nullptr, atom->type, atom->tag, atom->mask,
+                              atom->image));
+  }
+  for (int i = 0; i < pkg->nctx(); i++) {
+    b200_ctx *c = pkg->context(i);
+    B200_CHECK(pkg, bpair->b200_upload(c));
+    B200_CHECK(pkg, b200_fix_nve(c, dtv, dtf, groupbit));
+  }
 }
 
 /* ----------------------------------------------------------------------
@@ -127,22 +163,39 @@ void VerletB200::upload()
 void VerletB200::download(int with_ghosts)
 {
   int nlocal, nghost;
-  B200_CHECK(pkg, b200_get_counts(ctx, &nlocal, &nghost));
+  pkg->dev_counts(&nlocal, &nghost);
+  if (pkg->group()) with_ghosts = 0;    // ghosts live between the sub-domains, not on this host
   const int nall = nlocal + (with_ghosts ? nghost : 0);
   while (nall > atom->nmax) atom->avec->grow(0);
   atom->nlocal = nlocal;
   atom->nghost = with_ghosts ? nghost : 0;
+  pkg->host_stale = 0;
   if (nall == 0) return;
-  B200_CHECK(pkg,
-             b200_get_atoms(ctx, with_ghosts, &atom->x[0][0], &atom->v[0][0], &atom->f[0][0], atom->type,
-                            atom->tag, atom->mask, atom->image));
+  if (pkg->group())
+    B200_CHECK(pkg,
+               b200_group_get_atoms(pkg->group(), &atom->x[0][0], &atom->v[0][0], &atom->f[0][0],
+                                    atom->type, atom->tag, atom->mask, atom->image));
+  else
+    B200_CHECK(pkg,
+               b200_get_atoms(ctx, with_ghosts, &atom->x[0][0], &atom->v[0][0], &atom->f[0][0], atom->type,
+                              atom->tag, atom->mask, atom->image));
 }
 
 void VerletB200::fetch_tallies()
 {
   Pair *pair = force->pair;
-  B200_CHECK(pkg, b200_get_tallies(ctx, &pair->eng_vdwl, pair->virial));
+  pkg->dev_tallies(&pair->eng_vdwl, pair->virial);
   pair->eng_coul = 0.0;
+}
+
+// compute pe/atom, stress/atom, centroid/stress/atom ask the pair style for per-atom tallies
+// (Pair::ev_tally eatom/vatom, pair.cpp:1087-1182): the device kernels do not keep them, and
+// handing back zeros would be silently wrong
+void VerletB200::refuse_per_atom_tallies()
+{
+  if ((eflag & ENERGY_ATOM) || (vflag & (VIRIAL_ATOM | VIRIAL_CENTROID)))
+    error->all(FLERR, "run_style verlet/b200 does not provide per-atom energy or virial "
+                      "(compute pe/atom, stress/atom and friends need the CPU pair styles)");
 }
 
 /* ---------------------------------------------------------------------- */
@@ -164,11 +217,20 @@ void VerletB200::device_setup(int flag, int output_flag)
   }
   force->setup();
   ev_set(update->ntimestep);
+  refuse_per_atom_tallies();
+  // list options of neigh_modify the device build does not implement (neighbor.cpp:2727-2940);
+  // checked here because Neighbor::init() runs after Integrate::init()
+  if (neighbor->exclude) error->all(FLERR, "run_style verlet/b200 does not support neigh_modify exclude");
+  if (neighbor->includegroup)
+    error->all(FLERR, "run_style verlet/b200 does not support neigh_modify include");
+  if (neighbor->style != Neighbor::BIN)
+    error->all(FLERR, "run_style verlet/b200 requires neighbor style bin");
 
   // device side: ghosts, bins, half list, forces (+ tallies)
   upload();
-  B200_CHECK(pkg, b200_set_profiling(ctx, pkg->profile()));
-  B200_CHECK(pkg, b200_setup(ctx, eflag ? 1 : 0, vflag ? 1 : 0));
+  for (int i = 0; i < pkg->nctx(); i++)
+    B200_CHECK(pkg, b200_set_profiling(pkg->context(i), pkg->profile()));
+  pkg->dev_setup(eflag ? 1 : 0, vflag ? 1 : 0);
   resident = 1;
   download(0);
   if (eflag || vflag) fetch_tallies();
@@ -204,12 +266,47 @@ void VerletB200::reset_dt()
 }
 
 /* ----------------------------------------------------------------------
+   `package b200 profile yes`: one timestep stage by stage, each followed by
+   a device sync and the Timer stamp Verlet::run gives it (verlet.cpp:257-355),
+   so that Finish prints the usual Pair / Neigh / Comm / Modify breakdown
+------------------------------------------------------------------------- */
+
+void VerletB200::step_by_stage(int ef, int vf)
+{
+  int nflag = 0;
+  B200_CHECK(pkg, b200_initial_integrate(ctx));
+  B200_CHECK(pkg, b200_sync(ctx));
+  timer->stamp(Timer::MODIFY);
+  B200_CHECK(pkg, b200_decide(ctx, &nflag));
+  if (nflag) {
+    B200_CHECK(pkg, b200_reneighbor(ctx));
+    B200_CHECK(pkg, b200_sync(ctx));
+    timer->stamp(Timer::NEIGH);
+  } else {
+    B200_CHECK(pkg, b200_forward_comm(ctx));
+    B200_CHECK(pkg, b200_sync(ctx));
+    timer->stamp(Timer::COMM);
+  }
+  B200_CHECK(pkg, b200_force_clear(ctx));
+  B200_CHECK(pkg, b200_pair_compute(ctx, ef, vf));
+  B200_CHECK(pkg, b200_sync(ctx));
+  timer->stamp(Timer::PAIR);
+  B200_CHECK(pkg, b200_reverse_comm(ctx));
+  B200_CHECK(pkg, b200_sync(ctx));
+  timer->stamp(Timer::COMM);
+  B200_CHECK(pkg, b200_final_integrate(ctx));
+  B200_CHECK(pkg, b200_sync(ctx));
+  timer->stamp(Timer::MODIFY);
+}
+
+/* ----------------------------------------------------------------------
    run for N steps
 ------------------------------------------------------------------------- */
 
 void VerletB200::run(int n)
 {
   bigint ntimestep;
+  const int by_stage = pkg->profile() && !pkg->group();
 
   for (int i = 0; i < n; i++) {
     if (timer->check_timeout(i)) {
@@ -219,18 +316,27 @@ void VerletB200::run(int n)
 
     ntimestep = ++update->ntimestep;
     ev_set(ntimestep);
+    refuse_per_atom_tallies();
 
     // one whole timestep on the device; asynchronous unless the rebuild vote or a tally
     // needs a word back (verlet.cpp:229-360 is the sequence it implements)
     timer->stamp();
     int rebuilt = 0;
-    B200_CHECK(pkg, b200_step(ctx, eflag ? 1 : 0, vflag ? 1 : 0, &rebuilt));
+    if (by_stage)
+      step_by_stage(eflag ? 1 : 0, vflag ? 1 : 0);
+    else
+      pkg->dev_step(eflag ? 1 : 0, vflag ? 1 : 0, &rebuilt);
     resident = 1;
+    pkg->host_stale = 1;
 
     if (ntimestep == output->next) {
-      download(0);
+      // atoms come to the host only for consumers that read them: a dump, a restart, a
+      // compute without a /b200 version.  A thermo step of device-aware computes does not.
+      const bool need_atoms = !thermo_on_device || ntimestep == output->next_dump_any ||
+          ntimestep == output->next_restart;
+      if (need_atoms) download(0);
       if (eflag || vflag) fetch_tallies();
-      timer->stamp(Timer::PAIR);
+      if (!by_stage) timer->stamp(Timer::PAIR);
       output->write(ntimestep);
       timer->stamp(Timer::OUTPUT);
     }
@@ -245,7 +351,7 @@ void VerletB200::run(int n)
 void VerletB200::publish_neighbor_stats()
 {
   b200_stats st;
-  B200_CHECK(pkg, b200_get_stats(ctx, &st));
+  pkg->dev_stats(&st);
   neighbor->ncalls = st.nbuilds;
   neighbor->ndanger = st.ndanger;
   neighbor->ago = (int) st.ago;
@@ -253,8 +359,15 @@ void VerletB200::publish_neighbor_stats()
   if (list) {
     const int nlocal = atom->nlocal;
     list->grow(nlocal, nlocal + atom->nghost);
-    int64_t npairs = 0;
-    B200_CHECK(pkg, b200_get_neighbor_list(ctx, list->numneigh, nullptr, 0, &npairs));
+    // numneigh in the order the atoms were downloaded in (sub-domain after sub-domain)
+    int off = 0;
+    for (int i = 0; i < pkg->nctx(); i++) {
+      int nl = 0, ng = 0;
+      int64_t npairs = 0;
+      B200_CHECK(pkg, b200_get_counts(pkg->context(i), &nl, &ng));
+      B200_CHECK(pkg, b200_get_neighbor_list(pkg->context(i), list->numneigh + off, nullptr, 0, &npairs));
+      off += nl;
+    }
     for (int i = 0; i < nlocal; i++) list->ilist[i] = i;
     list->inum = nlocal;
     list->gnum = 0;
@@ -270,7 +383,7 @@ void VerletB200::cleanup()
     if (pkg->profile() && comm->me == 0) {
       double ms[B200_NPHASE];
       int64_t calls[B200_NPHASE];
-      B200_CHECK(pkg, b200_get_phase_times(ctx, ms, calls));
+      B200_CHECK(pkg, b200_get_phase_times(pkg->context(0), ms, calls));
       static const char *names[B200_NPHASE] = {"nve initial", "nve final", "halo forward",
                                                "halo reverse", "pair", "neigh (all)",
                                                "neigh list build", "force clear", "tallies"};

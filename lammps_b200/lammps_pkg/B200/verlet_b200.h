@@ -30,17 +30,20 @@ class VerletB200 : public Verlet {
 
  protected:
   class FixB200 *pkg;
-  b200_ctx *ctx;
+  b200_ctx *ctx;    // the context of this process (nullptr when the package drives a group)
   B200PairStyle *bpair;
   B200NVEFix *bnve;
-  int resident;    // 1 while the device copy of the atoms is newer than the host copy
+  int resident;    // 1 once atoms have been handed to the device in this run
   int joined;      // 1 once this rank joined the NCCL communicator of the package
+  int thermo_on_device;    // every compute a thermo step evaluates reads device sums or scalars
 
   void upload();                  // host atom arrays + all parameters -> device
   void download(int with_ghosts); // device -> host atom arrays (x, v, f, type, tag, mask, image)
   void fetch_tallies();           // eng_vdwl / virial -> force->pair
   void device_setup(int flag, int output_flag);
   void publish_neighbor_stats();
+  void refuse_per_atom_tallies();
+  void step_by_stage(int eflag, int vflag);    // `package b200 profile yes`: Timer breakdown
 };
 
 }    // namespace LAMMPS_NS

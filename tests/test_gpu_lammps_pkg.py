@@ -130,7 +130,7 @@ run 1
 """)
     r = subprocess.run([str(EXE), "-in", str(script)], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode != 0
-    assert "requires run_style verlet/b200" in (r.stdout + r.stderr)
+    assert "run_style verlet/b200" in (r.stdout + r.stderr)
 
 
 def _both(tmp_path, body, nsteps_dump):
@@ -226,3 +226,129 @@ dump_modify 1 sort id format float %.10g
 run 50
 """
     _compare(_both(tmp_path, body, 50), ftol=1e-8, ttol=1e-9)
+
+
+LJ_BODY = """
+units lj
+lattice fcc 0.8442
+region box block 0 10 0 10 0 10
+create_box 1 box
+create_atoms 1 box
+mass 1 1.0
+velocity all create 1.44 87287 loop geom
+pair_style lj/cut 2.5
+pair_coeff 1 1 1.0 1.0 2.5
+neighbor 0.3 bin
+neigh_modify every 20 delay 0 check no
+fix 1 all nve
+"""
+
+
+def _run_b200(tmp_path, body, extra=(), expect_fail=False):
+    (tmp_path / "in.t").write_text(body)
+    r = subprocess.run([str(EXE), "-sf", "b200", *extra, "-in", "in.t"], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=600)
+    if expect_fail:
+        assert r.returncode != 0, "expected an error:\n" + r.stdout[-1500:]
+    else:
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout + r.stderr
+
+
+def test_eight_subdomains_in_one_process_reproduce_the_golden_log():
+    """`-pk b200 subdomains 8`: one LAMMPS process, the box split into 2x2x2 brick sub-domains
+    with migration, borders and the peer-memory halo between them (here all on one GPU; with
+    `gpus 8` one per GPU).  Thermo output and neighbour statistics must still be the reference's."""
+    out = run_lmp(["-sf", "b200", "-pk", "b200", "subdomains", "8", "-in", "in.lj"])
+    g = json.loads((GOLDEN / "ref_lj_32k.json").read_text())["published_log"]
+    assert "8 sub-domains on 1 GPU(s) in this process" in out
+    rows = thermo_rows(out)
+    assert [int(r[0]) for r in rows] == [int(r[0]) for r in g["thermo"]]
+    for got, ref in zip(rows, g["thermo"]):
+        for a, b in zip(got[1:], ref[1:]):
+            assert close_to_printed(a, b), f"step {int(ref[0])}: {got} vs golden {ref}"
+    m = re.search(r"Neighbor list builds = (\d+)", out)
+    assert m and int(m.group(1)) == g["builds"]
+    m = re.search(r"Total # of neighbors = (\d+)", out)
+    assert m and int(m.group(1)) == g["neighbors"]
+
+
+def test_thermo_every_step_uses_device_sums_and_matches_reference(tmp_path):
+    """thermo 1: temp/b200 (device sum of m v^2), pe and pressure from the device tallies -- no atom
+    download on thermo steps -- against lmp_ref, every step; then a dump and a restart written
+    from device-resident atoms are read back by the reference."""
+    body = LJ_BODY + """
+thermo 1
+thermo_modify format float %.12g
+dump 1 all custom 30 f.dump id x y z fx
+dump_modify 1 sort id format float %.10g
+run 30
+write_restart r.restart
+"""
+    outs = _both(tmp_path, body, 30)
+    _compare(outs, ftol=1e-8, ttol=1e-9)
+    assert len(outs["b200"][0]) == 31
+    # the restart file written by lmp_b200 continues in the reference exactly like its own
+    cont = """
+read_restart RESTART
+pair_style lj/cut 2.5
+pair_coeff 1 1 1.0 1.0 2.5
+neighbor 0.3 bin
+neigh_modify every 20 delay 0 check no
+fix 1 all nve
+thermo 10
+thermo_modify format float %.12g
+run 10
+"""
+    refexe = ROOT / "oracle" / "_ref" / "lmp_ref"
+    rows = {}
+    for tag in ("ref", "b200"):
+        d = tmp_path / ("cont_" + tag)
+        d.mkdir()
+        (d / "in.c").write_text(cont.replace("RESTART", str(tmp_path / tag / "r.restart")))
+        r = subprocess.run([str(refexe), "-in", "in.c"], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:]
+        rows[tag] = thermo_rows(r.stdout)
+    assert len(rows["ref"]) == len(rows["b200"]) == 2
+    for x, y in zip(rows["ref"], rows["b200"]):
+        for u, v in zip(x, y):
+            assert abs(u - v) <= 1e-9 * max(1.0, abs(u)), (x, y)
+
+
+def test_per_atom_tallies_are_refused_not_zero(tmp_path):
+    out = _run_b200(tmp_path, LJ_BODY + """
+compute pea all pe/atom
+dump 1 all custom 10 f.dump id c_pea
+run 10
+""", expect_fail=True)
+    assert "does not provide per-atom energy or virial" in out
+
+
+def test_minimize_is_refused_not_silently_wrong(tmp_path):
+    out = _run_b200(tmp_path, LJ_BODY + "minimize 1.0e-4 1.0e-6 10 100\n", expect_fail=True)
+    assert "computes forces only inside run_style verlet/b200" in out
+
+
+def test_neigh_modify_exclude_is_refused(tmp_path):
+    out = _run_b200(tmp_path, LJ_BODY + "neigh_modify exclude type 1 1\nrun 5\n", expect_fail=True)
+    assert "does not support neigh_modify exclude" in out
+
+
+def test_neighbor_list_overflow_is_reported(tmp_path):
+    """B200_ECAPACITY through the package: `neigh_modify one 20` cannot hold a 40-neighbour list"""
+    out = _run_b200(tmp_path, LJ_BODY + "neigh_modify one 20 page 2000\nrun 5\n", expect_fail=True)
+    assert "Neighbor list overflow, boost neigh_modify one" in out
+
+
+def test_profile_fills_the_timer_breakdown(tmp_path):
+    """`package b200 profile yes` steps stage by stage and stamps Timer::PAIR/NEIGH/COMM/MODIFY
+    (verlet.cpp:257-355), so Finish's breakdown -- the reference's profiling surface -- is filled"""
+    out = _run_b200(tmp_path, LJ_BODY + "thermo 50\nrun 100\n", extra=("-pk", "b200", "profile", "yes"))
+    t = {}
+    for sec in ("Pair", "Neigh", "Comm", "Modify"):
+        m = re.search(rf"^{sec}\s*\|\s*([0-9.eE+-]+)\s*\|\s*([0-9.eE+-]+)", out, re.M)
+        assert m, f"no {sec} line in the timing breakdown:\n" + out[-1500:]
+        t[sec] = float(m.group(2))
+    assert t["Pair"] > 0 and t["Neigh"] > 0 and t["Modify"] > 0
+    assert t["Pair"] > t["Comm"], t
+    assert "B200 device time by phase" in out
