@@ -152,6 +152,95 @@ def pair_algorithmic(kind, ps, pc):
     return 2 * 4.0 * ps + 2 * 32 + 8 * 3 + 24 + 24, 2 * 8.0 * ps + 24.0 * pc + 45.0 * pc
 
 
+def measure_pc_ratio(kind):
+    """In-cutoff fraction of the stored half-list pairs, measured on the list itself: a 32k-atom
+    melt of the same state point (an intensive property), after 40 steps, through the engine's
+    list export.  Returns Pc/Ps."""
+    from lammps_b200.engine import Engine
+    s = build_system(kind, (20, 20, 20))
+    e = Engine(int(os.environ.get("LOCAL_RANK", "0")), "double", s["units"])
+    n = len(s["x"])
+    configure(e, s, s["x"], s["v"], s["type"], np.arange(1, n + 1, dtype=np.int32), n)
+    e.setup(0, 0)
+    e.run(40, 0)
+    # the list in force after those steps and the positions it is evaluated on
+    a = e.get_atoms(ghosts=True, fields=("x",))
+    _, pi, pj = e.neighbor_list()
+    d = a["x"][pi] - a["x"][pj]
+    rsq = (d * d).sum(axis=1)
+    cutsq = float(np.max(s["tables"]["cutsq"])) if kind == "lj" else float(s["tables"]["cutforcesq"])
+    ratio = float((rsq < cutsq).mean())
+    e.close()
+    return ratio
+
+
+def fp_peaks():
+    """FP64 / FP32 FMA peaks of this GPU from the repo's microbenchmark (tools/microbench/fp_peak,
+    built by __graft_entry__.build); None when the binary is missing."""
+    exe = ROOT / "tools" / "microbench" / "fp_peak"
+    if not exe.exists():
+        return None
+    try:
+        out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60).stdout
+    except Exception:
+        return None
+    pk = {}
+    for ln in out.splitlines():
+        m = re.match(r"(DFMA|FFMA)\s+ILP=8 grid=296x1024 .* ([0-9.]+) TFLOP/s", ln)
+        if m:
+            pk["fp64" if m.group(1) == "DFMA" else "fp32"] = float(m.group(2))
+    return pk or None
+
+
+def also_block(args, local_rank):
+    """Other configurations of BASELINE.json, measured after the timed region of the headline
+    (one GPU): device-resident atom-steps/s over 100 steps after preconditioning."""
+    from lammps_b200.engine import Engine
+    res = {}
+
+    def quick(workload, precision, steps=100):
+        kind, cells1, _ = WORKLOADS[workload]
+        s = build_system(kind, (cells1,) * 3)
+        n = len(s["x"])
+        e = Engine(local_rank, precision, s["units"])
+        configure(e, s, s["x"], s["v"], s["type"], np.arange(1, n + 1, dtype=np.int32), n)
+        e.setup(1, 1)
+        e.run(20, 0)
+        e.run(steps, 0)
+        ms = e.last_run_ms()
+        e.profiling(True)
+        e.run(steps, 0)
+        ph = e.phase_times()
+        e.close()
+        pair_ms, pair_calls = ph["pair"]
+        return {"value": n * steps / (ms * 1e-3), "unit": "atom-steps/s", "natoms": n, "steps": steps,
+                "ms_per_step": ms / steps, "pair_us_per_step": pair_ms * 1e3 / max(pair_calls, 1),
+                "precision": precision}
+
+    for name, wl, prec in (("lj4m_double", "lj4m", "double"), ("lj4m_mixed", "lj4m", "mixed"),
+                           ("eam2m_double", "eam2m", "double"), ("eam2m_mixed", "eam2m", "mixed")):
+        try:
+            res[name] = quick(wl, prec)
+        except Exception as ex:  # a side measurement must not take the headline down
+            res[name] = {"error": str(ex)[:200]}
+    # the reference's own small inputs, unmodified, through the LAMMPS package
+    exe = ROOT / "lammps_b200" / "lammps_pkg" / "lmp_b200"
+    inputs = ROOT / "lammps_b200" / "lammps_pkg" / "bench_inputs"
+    for name, inp in (("in.lj_32k_lmp_b200", "in.lj"), ("in.eam_32k_lmp_b200", "in.eam")):
+        if not exe.exists() or not (inputs / inp).exists():
+            continue
+        try:
+            out = subprocess.run([str(exe), "-sf", "b200", "-in", inp], cwd=inputs, capture_output=True,
+                                 text=True, timeout=300).stdout
+            m = re.search(r"Loop time of ([0-9.eE+-]+) on \d+ procs for (\d+) steps with (\d+) atoms", out)
+            t, nst, nat = float(m.group(1)), int(m.group(2)), int(m.group(3))
+            res[name] = {"value": nat * nst / t, "unit": "atom-steps/s", "natoms": nat, "steps": nst,
+                         "note": "unmodified bench input, lmp_b200 -sf b200, LAMMPS loop time"}
+        except Exception as ex:
+            res[name] = {"error": str(ex)[:200]}
+    return res
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -267,7 +356,8 @@ def run_b200(args):
     hbm_peak, peak_src = peaks()
     pair_ms, pair_calls = ph["pair"]
     ps = st["npairs"] / max(nown, 1)
-    pc = ps * (27.54 / 37.59 if kind == "lj" else 21.99 / 37.74)   # in-cutoff fraction, SURVEY 8(a)
+    pc_ratio = measure_pc_ratio(kind) if rank == 0 else 0.0     # measured on the list
+    pc = ps * pc_ratio
     bytes_atom, flops_atom = pair_algorithmic(kind, ps, pc)
     pair_s = pair_ms * 1e-3 / max(pair_calls, 1)
     achieved = bytes_atom * nown / pair_s / 1e9
@@ -302,6 +392,7 @@ def run_b200(args):
                 "us_per_launch": pair_s * 1e6, "flop_per_atom": flops_atom,
                 "tflops": flops_atom * nown / pair_s / 1e12,
                 "share_of_step": min(1.0, pair_s * args.steps / max(dev_ms * 1e-3, 1e-12)),
+                "pairs_in_cutoff_per_atom": pc, "in_cutoff_fraction_measured": pc_ratio,
                 "note": note}
     phases = {k: {"ms": round(t, 3), "calls": c} for k, (t, c) in ph.items() if c}
     # the limiting phases in one flat record (microseconds per timestep of the profiling pass)
@@ -350,8 +441,25 @@ def run_b200(args):
         "wall_s_timed_region": wall,
         "host_setup_s": host_setup_s,
     }
+    # the same kernel against the FP pipe it computes on (north_star: pipe utilisation of the pair
+    # kernels): measured FMA peaks from the microbenchmark; `executed` counts what the kernel
+    # really issues (18 FP64 instructions = 2 x 18 flop per list entry, both sides of every pair)
+    pk = fp_peaks()
+    if pk and kind == "lj":
+        pipe = "fp64" if args.precision == "double" else "fp32"
+        if pipe in pk:
+            entries = st["list_entries"] / max(nown, 1)
+            executed = entries * 36.0 * nown / pair_s / 1e12
+            roofline["pipe"] = {"bound": pipe, "peak_tflops": pk[pipe], "peak_source":
+                                "tools/microbench/fp_peak (FMA, 296 x 1024 threads, ILP 8) on this GPU",
+                                "algorithmic_tflops": flops_atom * nown / pair_s / 1e12,
+                                "algorithmic_frac": flops_atom * nown / pair_s / 1e12 / pk[pipe],
+                                "executed_tflops": executed, "executed_frac": executed / pk[pipe]}
     if world == 1 and not args.no_cpu_baseline:
         res["cpu_baseline"] = cpu_baseline(kind, budget_s=20.0)
+    if world == 1 and args.workload == "lj32m" and not args.no_also:
+        e.close()
+        res["also"] = also_block(args, local_rank)
     sys.stdout.flush()
     os.dup2(stdout_fd, 1)
     print(json.dumps(res), flush=True)
@@ -433,6 +541,7 @@ def main():
     ap.add_argument("--workload", default="lj32m", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="double", choices=["double", "mixed"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the side measurements (eam2m, lj4m, lmp_b200)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

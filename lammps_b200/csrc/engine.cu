@@ -245,6 +245,14 @@ struct b200_ctx {
   int groupbit = 1;
   bool have_nve = false;
   bool pending_final = false;  // final_integrate of the last step is deferred (fused into the next initial)
+  // fix nve fused into the pair kernel (k_tile_lj2<..., NVE>): on such a step the kernel applies
+  // final_integrate(n) and initial_integrate(n+1) itself and writes the new positions to the
+  // other xt buffer; `ahead` = the atoms already carry step n+1's initial_integrate.  Only inside
+  // b200_run on steps nobody looks at (no tallies, not the last).  B200_FUSE=0 disables.
+  bool fuse_nve = true, ahead = false;
+  bool fuse_now = false;   // the pair launches of the step being enqueued carry the integrator
+  int fuse_check = 0;      // ... and the displacement check for the next step's decide()
+  int fuse_min_atoms = 65536;
   // tallies / flags
   double *ev = nullptr;   // [8] device: eng, virial[6], ke
   double *ke7 = nullptr;  // [7] device: b200_ke_group accumulators
@@ -1446,7 +1454,7 @@ static int reneighbor(b200_ctx *ctx) {
     k_ghost_place<<<cdiv(ng, 256), 256, 0, s>>>(ng, nl, ctx->gtmp.p, ctx->gtag_tmp.p, ctx->gsrc_tmp.p,
                                                 ctx->gbin.p, ctx->gslot.p, ctx->gdir_tmp.p,
                                                 ctx->gstart.p, ctx->xt[c], ctx->tag[c], ctx->mask[c],
-                                                ctx->gsrc.p, ctx->gdir.p);
+                                                ctx->gsrc.p, ctx->gdir.p, ctx->xt[c ^ 1]);
     ctx->launches++;
   }
   LAUNCH_CHECK();
@@ -1618,28 +1626,43 @@ static int lj2_attrs(b200_ctx *ctx) {
   TRY(tile_attr(ctx, k_tile_lj2<false, true, 4, T, B>));           \
   TRY(tile_attr(ctx, k_tile_lj2<true, true, 2, T, B>));            \
   TRY(tile_attr(ctx, k_tile_lj2<false, false, 2, T, B>));          \
+  TRY(tile_attr(ctx, (k_tile_lj2<false, true, 2, T, B, true>)));   \
+  TRY(tile_attr(ctx, (k_tile_lj2<false, false, 2, T, B, true>)));  \
   TRY(tile_attr(ctx, k_tile_lj2<true, false, 2, T, B>));
   LJ2_SHAPES(X)
 #undef X
   return B200_OK;
 }
 
-static int launch_tile_lj2(b200_ctx *ctx, cudaStream_t s, int eflag, const int *ids, int ntiles) {
+static int launch_tile_lj2(b200_ctx *ctx, cudaStream_t s, int eflag, const int *ids, int ntiles,
+                           bool fuse = false, int do_check = 0) {
   const TileGeom &G = ctx->tg;
   const int nl = ctx->nlocal, c = ctx->cur, scap = ctx->tile_scap;
   const bool one = ctx->ntypes == 1;
   const size_t sm = tile2_smem_bytes(scap, !one);
-  const int T = ctx->lj2[0], B = ctx->lj2[1], ilp = (one && !eflag) ? ctx->lj2[2] : 2;
+  const int T = ctx->lj2[0], B = ctx->lj2[1], ilp = (one && !eflag && !fuse) ? ctx->lj2[2] : 2;
+  NveFuse nv;
+  memset(&nv, 0, sizeof nv);
+  if (fuse)
+    nv = NveFuse{ctx->xt[c ^ 1], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->mask[c], ctx->mass_d.p,
+                 ctx->dtv, ctx->dtf, ctx->groupbit, do_check, ctx->xh[0], ctx->xh[1], ctx->xh[2],
+                 ctx->triggersq, ctx->flags};
   // no more threads than the fullest tile has atoms (whole warps)
   const int thr = std::max(32, std::min(T, cdiv(std::max(ctx->tile_maxown, 1), 32) * 32));
 #define L2(EV, ONE, ILP, TT, BB)                                                                    \
   k_tile_lj2<EV, ONE, ILP, TT, BB><<<ntiles, thr, sm, s>>>(                                        \
       G, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tile_NI,             \
       ctx->tile_slots, ctx->tl_iloc.p, ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->f[0],      \
-      ctx->f[1], ctx->f[2], ctx->lj_one, ctx->lj_tab.p, ctx->ntypes, ctx->ev, scap, ctx->tflags, ids)
+      ctx->f[1], ctx->f[2], ctx->lj_one, ctx->lj_tab.p, ctx->ntypes, ctx->ev, scap, ctx->tflags, ids, nv)
+#define L2N(ONE, TT, BB)                                                                            \
+  k_tile_lj2<false, ONE, 2, TT, BB, true><<<ntiles, thr, sm, s>>>(                                  \
+      G, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tile_NI,             \
+      ctx->tile_slots, ctx->tl_iloc.p, ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->f[0],      \
+      ctx->f[1], ctx->f[2], ctx->lj_one, ctx->lj_tab.p, ctx->ntypes, ctx->ev, scap, ctx->tflags, ids, nv)
 #define X(TT, BB)                                                      \
   if (T == TT && B == BB) {                                            \
-    if (one && !eflag) { if (ilp == 4) L2(false, true, 4, TT, BB); else L2(false, true, 2, TT, BB); } \
+    if (fuse) { if (one) L2N(true, TT, BB); else L2N(false, TT, BB); } \
+    else if (one && !eflag) { if (ilp == 4) L2(false, true, 4, TT, BB); else L2(false, true, 2, TT, BB); } \
     else if (one) L2(true, true, 2, TT, BB);                           \
     else if (!eflag) L2(false, false, 2, TT, BB);                      \
     else L2(true, false, 2, TT, BB);                                   \
@@ -1647,6 +1670,7 @@ static int launch_tile_lj2(b200_ctx *ctx, cudaStream_t s, int eflag, const int *
   LJ2_SHAPES(X)
   return ctx->fail(B200_EARG, "no k_tile_lj2 instance for %d threads x %d CTAs/SM", T, B);
 #undef X
+#undef L2N
 #undef L2
   ctx->launches++;
   LAUNCH_CHECK();
@@ -1660,7 +1684,7 @@ static int launch_tile_lj(b200_ctx *ctx, cudaStream_t s, int eflag, const int *i
   const int nl = ctx->nlocal, c = ctx->cur, thr = ctx->tile_threads, scap = ctx->tile_scap;
   const size_t sm = tile_smem_bytes(scap, G.srow_y * G.srow_z, G.sbx, false, false);
  const bool one = ctx->ntypes == 1, mixed = ctx->prec == B200_PREC_MIXED;
-  if (!mixed && ctx->use_lj2) return launch_tile_lj2(ctx, s, eflag, ids, ntiles);
+  if (!mixed && ctx->use_lj2) return launch_tile_lj2(ctx, s, eflag, ids, ntiles, ctx->fuse_now, ctx->fuse_check);
 #define TLJ(EV, ONE, MX)                                                                            \
   k_tile_lj<EV, ONE, MX><<<ntiles, thr, sm, s>>>(                                                   \
       G, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tile_NI,             \
@@ -1914,6 +1938,8 @@ static int final_integrate(b200_ctx *ctx) {
 
 // A deferred final_integrate must be applied before anything reads or replaces v.
 static int flush_final(b200_ctx *ctx) {
+  if (ctx->ahead)
+    return ctx->fail(B200_EARG, "atoms are one half-step ahead (fused integrator): a run did not end on a tallied step");
   if (!ctx->pending_final) return B200_OK;
   ctx->pending_final = false;
   return final_integrate(ctx);
@@ -2056,6 +2082,8 @@ int b200_create(b200_ctx **out, int device, int precision) {
     if (const char *e = getenv("B200_OVERLAP")) ctx->overlap = atoi(e) != 0;
     if (const char *e = getenv("B200_GRAPH")) ctx->use_graph = atoi(e) != 0;
     if (const char *e = getenv("B200_MIXED_FX")) ctx->mixed_fx = atoi(e) != 0;
+    if (const char *e = getenv("B200_FUSE")) ctx->fuse_nve = atoi(e) != 0;
+    if (const char *e = getenv("B200_FUSE_MIN")) ctx->fuse_min_atoms = atoi(e);
     if (const char *e = getenv("B200_LJ2")) {
       int a[3];
       const int k = sscanf(e, "%d,%d,%d", &a[0], &a[1], &a[2]);
@@ -2450,14 +2478,22 @@ static bool plain_step(const b200_ctx *ctx, int eflag, int vflag) {
   // (`check yes` schedules rebuild irregularly and often; re-instantiating the graph after every
   // rebuild then costs more than it saves -- measured on bench/in.eam)
   if (!ctx->use_graph || eflag || vflag || ctx->profiling || ctx->nranks > 1 || ctx->remote_mask ||
-      !ctx->pending_final || ctx->nlocal <= 0 || ctx->dist_check)
+      !ctx->pending_final || ctx->nlocal <= 0 || ctx->dist_check || ctx->ahead)
     return false;
   const int64_t a = ctx->ago + 1;
   const bool due = a >= ctx->delay && a % ctx->every == 0;  // Neighbor::decide
   return !due;  // with `check yes` a due step needs the device vote; with `check no` it rebuilds
 }
 
-static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt);
+static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt, bool allow_fuse = false);
+
+// may this step's pair kernel carry fix nve (k_tile_lj2<..., NVE>)?  Static part of the answer;
+// the list kind is known only after the step's rebuild decision
+static bool fuse_candidate(const b200_ctx *ctx, int eflag, int vflag, bool allow_fuse) {
+  return allow_fuse && !eflag && !vflag && ctx->fuse_nve && ctx->have_nve && ctx->pair_style == 1 &&
+         ctx->prec == B200_PREC_DOUBLE && ctx->use_lj2 && ctx->nlocal > 0 &&
+         (ctx->nranks > 1 || ctx->nlocal >= ctx->fuse_min_atoms);
+}
 
 static int graph_step(b200_ctx *ctx) {
   if (!ctx->step_graph) {
@@ -2489,17 +2525,30 @@ static int graph_step(b200_ctx *ctx) {
   return B200_OK;
 }
 
-static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt) {
-  if (plain_step(ctx, eflag, vflag)) {
+static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt, bool allow_fuse) {
+  const bool fcand = fuse_candidate(ctx, eflag, vflag, allow_fuse);
+  if (!fcand && plain_step(ctx, eflag, vflag)) {
     if (rebuilt) *rebuilt = 0;
     return graph_step(ctx);
   }
-  const int chk = check_due_next(ctx) ? 1 : 0;
-  if (chk) CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
-  TRY(initial_integrate(ctx, chk));
+  if (ctx->ahead) {
+    // the previous step's pair kernel already applied this step's initial_integrate (and its
+    // displacement check)
+    ctx->ahead = false;
+  } else {
+    const int chk = check_due_next(ctx) ? 1 : 0;
+    if (chk) CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
+    TRY(initial_integrate(ctx, chk));
+  }
   int nflag = 0;
   TRY(decide(ctx, &nflag));
   if (nflag) TRY(reneighbor(ctx));
+  const bool fuse = fcand && ctx->tiles_active && ctx->full_ghost;
+  if (fuse) {
+    ctx->fuse_check = check_due_next(ctx) ? 1 : 0;  // for the NEXT step's decide()
+    if (ctx->fuse_check) CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
+    ctx->fuse_now = true;
+  }
   if (overlap_active(ctx)) {
     // interior tiles start now; halo, boundary tiles and the reverse halo overlap with them
     bool joined = false;
@@ -2514,6 +2563,16 @@ static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt) {
     TRY(force_clear(ctx));
     TRY(pair_compute(ctx, eflag, vflag));
     TRY(reverse_comm(ctx));
+  }
+  if (fuse) {
+    // the pair kernels wrote x(n+1) into the other position buffer: it is the live one now
+    ctx->fuse_now = false;
+    std::swap(ctx->xt[ctx->cur], ctx->xt[ctx->cur ^ 1]);
+    ctx->ahead = true;
+    ctx->pending_final = false;
+    ctx->ghost_f_clean = true;
+    if (rebuilt) *rebuilt = nflag;
+    return B200_OK;
   }
   // FixNVE::final_integrate: on steps whose velocities nobody reads (no tallies) it is deferred
   // and fused with the next step's initial_integrate (k_nve_final_initial)
@@ -2548,7 +2607,7 @@ int b200_run(b200_ctx *ctx, int nsteps, int64_t first_step, int thermo_every, do
     const int64_t step = first_step + sidx;
     const int ev = (thermo_every > 0 && step % thermo_every == 0) || sidx == nsteps;
     int nflag = 0;
-    TRY(one_step(ctx, ev, ev, &nflag));
+    TRY(one_step(ctx, ev, ev, &nflag, /*allow_fuse=*/sidx < nsteps));
     if (ev) {
       const int ph10 = ph_begin(ctx, B200_PH_THERMO);
       TRY(ke_reduce(ctx));
@@ -2660,6 +2719,7 @@ int b200_set_option(b200_ctx *ctx, const char *key, const char *value) {
   } else if (k == "overlap") ctx->overlap = yes();
   else if (k == "graph") ctx->use_graph = yes();
   else if (k == "mixed_fx") ctx->mixed_fx = yes();
+  else if (k == "fuse") ctx->fuse_nve = yes();
   else if (k == "tpa") {
     const int t = atoi(value);
     if (t != 1 && t != 2 && t != 4 && t != 8) return ctx->fail(B200_EARG, "package b200 tpa: 1, 2, 4 or 8");

@@ -180,12 +180,15 @@ __global__ void __launch_bounds__(256) k_ghost_place(
     const int *__restrict__ gsrc_tmp, const int *__restrict__ gbin, const int *__restrict__ gslot,
     const unsigned char *__restrict__ gdir_tmp, const int *__restrict__ gstart,
     double4 *__restrict__ xt, int *__restrict__ tag, int *__restrict__ mask,
-    int *__restrict__ gsrc, unsigned char *__restrict__ gdir) {
+    int *__restrict__ gsrc, unsigned char *__restrict__ gdir, double4 *__restrict__ xt_alt) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nghost) return;
   const int gi = gstart[gbin[q]] + gslot[q];
   const int src = gsrc_tmp[q];
   xt[nlocal + gi] = gtmp[q];
+  // the other position buffer takes the record too: a pair kernel with the fused integrator
+  // writes owned positions there and the halo then refreshes x,y,z only -- the type must be in place
+  xt_alt[nlocal + gi] = gtmp[q];
   tag[nlocal + gi] = gtag_tmp[q];
   mask[nlocal + gi] = src >= 0 ? mask[src] : 1;
   gsrc[gi] = src;
