@@ -132,6 +132,12 @@ struct b200_ctx {
   std::vector<double> mass_h;
   DBuf<double> mass_d;
   double4 *xt[2] = {nullptr, nullptr};
+  // mixed precision: sub-domain-wide fixed-point records {qx,qy,qz,type} of all atoms (k_tile_lj2f
+  // stages them with one cp.async each); [cur] is live like xt[cur]; kept current by the fused
+  // integrator's epilogue (owned) and k_xt_to_q (ghosts after a halo, everything after a rebuild)
+  int4 *qrec[2] = {nullptr, nullptr};
+  QGeom qgeom;
+  bool gq_ok = false, q_owned_valid = false, q_ghost_valid = false;
   double *v[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
   double *f[3] = {nullptr, nullptr, nullptr};
   double *xh[3] = {nullptr, nullptr, nullptr};
@@ -200,12 +206,14 @@ struct b200_ctx {
   FullStencil fst;
   int ibin_lo[3] = {0, 0, 0}, ibin_n[3] = {0, 0, 0};  // local bins that can hold owned atoms
   DBuf<int> tile_ibase;
+  DBuf<unsigned char> tile_hdrs;  // every tile's row tables, written at each rebuild (tile_rows_cached)
   DBuf<unsigned short> tl_iloc, tl_num;
   DBuf<int> tl_gi;              // global index of the owned atom of every list row
   // FP64 lj/cut on tiles: k_tile_lj2 launch shape {threads, CTAs/SM, pair bodies in flight}
   // (B200_LJ2=threads,minb,ilp; B200_LJ2=0 selects the first-generation k_tile_lj)
   int lj2[3] = {352, 2, 2};
   bool use_lj2 = true;
+  int lj2f[2] = {256, 4};       // k_tile_lj2f (mixed): threads, CTAs per SM (B200_LJ2F=threads,minb)
   DBuf<uint4> tl_list;
   int *tflags = nullptr;  // [8] device: max staged, max owned/tile, max entries, max FWD, owned total, overflow
   int tile_NI = 0, tile_scap = 0, tile_slots = 0, tile_threads = 256, tile_maxfull = 0, tile_maxown = 0;
@@ -770,6 +778,10 @@ static int alloc_atoms(b200_ctx *ctx, int nmax) {
   for (int b = 0; b < 2; b++) {
     const int k = (b == c) ? keep : 0;
     TRY(regrow(ctx->xt[b], nmax, k, sizeof(double4)));
+    if (ctx->prec == B200_PREC_MIXED) {
+      TRY(regrow(ctx->qrec[b], nmax, 0, sizeof(int4)));
+      ctx->q_owned_valid = ctx->q_ghost_valid = false;
+    }
     for (int d = 0; d < 3; d++) TRY(regrow(ctx->v[b][d], nmax, k, sizeof(double)));
     TRY(regrow(ctx->tag[b], nmax, k, sizeof(int)));
     TRY(regrow(ctx->mask[b], nmax, k, sizeof(int)));
@@ -1028,6 +1040,26 @@ static int setup_geometry(b200_ctx *ctx) {
     }
     ctx->tile_level = -1;
   }
+  {
+    // sub-domain-wide fixed point of the mixed lj/cut kernel: origin a safe margin outside the
+    // ghost shell, 30 bits over the largest extent, power-of-two scale
+    double ext = 0.0;
+    const double margin = ctx->cutghost + 2.0 * ctx->skin;
+    for (int d = 0; d < 3; d++) ext = std::max(ext, ctx->subhi[d] - ctx->sublo[d] + 2.0 * margin);
+    ctx->qgeom.ox = ctx->sublo[0] - margin;
+    ctx->qgeom.oy = ctx->sublo[1] - margin;
+    ctx->qgeom.oz = ctx->sublo[2] - margin;
+    ctx->qgeom.scale = std::ldexp(1.0, (int)std::floor(std::log2(1073741824.0 / ext)));
+    double cmin = 1.0e300;
+    for (int i = 1; i <= n; i++)
+      for (int j = 1; j <= n; j++)
+        if (ctx->cutsq_h[i * n1 + j] > 0.0) cmin = std::min(cmin, ctx->cutsq_h[i * n1 + j]);
+    // grid spacing against the 2e-6 decision band of the kernel (see k_tile_lj2f)
+    ctx->gq_ok = ctx->prec == B200_PREC_MIXED && ctx->pair_style == 1 && cmin < 1.0e300 &&
+                 1.0 / ctx->qgeom.scale <= 1.4e-7 * std::sqrt(cmin);
+    if (const char *e = getenv("B200_GQ")) ctx->gq_ok = ctx->gq_ok && atoi(e) != 0;
+    ctx->q_owned_valid = ctx->q_ghost_valid = false;
+  }
   TRY(reserve(ctx, ctx->ostart, (size_t)g.mbins + 2));
   TRY(reserve(ctx, ctx->gstart, (size_t)g.mbins + 2));
   TRY(reserve(ctx, ctx->tilesum, (size_t)cdiv(g.mbins + 1, SCAN_TILE) + 2));
@@ -1095,6 +1127,7 @@ static int tile_attr(b200_ctx *ctx, K kernel) {
 }
 
 static int lj2_attrs(b200_ctx *ctx);
+static int lj2f_attrs(b200_ctx *ctx);
 static int tile_kernel_attrs(b200_ctx *ctx) {
   TRY(tile_attr(ctx, (k_tile_build<true, true>)));
   TRY(tile_attr(ctx, (k_tile_build<false, true>)));
@@ -1109,6 +1142,7 @@ static int tile_kernel_attrs(b200_ctx *ctx) {
   A3(k_tile_lj)
 #undef A3
   TRY(lj2_attrs(ctx));
+  TRY(lj2f_attrs(ctx));
   TRY(tile_attr(ctx, k_tile_lj_fx<false, false>));
   TRY(tile_attr(ctx, k_tile_lj_fx<false, true>));
   TRY(tile_attr(ctx, k_tile_lj_fx<true, false>));
@@ -1150,8 +1184,9 @@ static int build_tiles(b200_ctx *ctx) {
       TRY(reserve(ctx, ctx->tile_bflag, (size_t)G.ntiles + 2));
       TRY(reserve(ctx, ctx->tile_bpos, (size_t)G.ntiles + 2));
       TRY(reserve(ctx, ctx->tile_ids, (size_t)G.ntiles + 2));
+      TRY(reserve(ctx, ctx->tile_hdrs, (size_t)G.ntiles * TILE_HDR_BYTES));
       k_tile_count<<<G.ntiles, 128, 0, s>>>(G, ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p,
-                                            ctx->tile_bflag.p, ctx->tflags, eam ? 1 : 0);
+                                            ctx->tile_bflag.p, ctx->tflags, eam ? 1 : 0, ctx->tile_hdrs.p);
       ctx->launches++;
       LAUNCH_CHECK();
       TRY(scan_inplace(ctx, ctx->tile_ibase.p, G.ntiles));
@@ -1462,6 +1497,7 @@ static int reneighbor(b200_ctx *ctx) {
   // a rebuild invalidates ghost forces of the old ghost set
   for (int d = 0; d < 3; d++) CK(cudaMemsetAsync(ctx->f[d] + nl, 0, sizeof(double) * ng, s));
   ctx->ghost_f_clean = true;
+  ctx->q_owned_valid = ctx->q_ghost_valid = false;
   ctx->ago = 0;
   ctx->nbuilds++;
   ph_end(ctx, ph2);
@@ -1499,6 +1535,7 @@ static int force_clear(b200_ctx *ctx) {
 }
 
 static int forward_comm(b200_ctx *ctx) {
+  ctx->q_ghost_valid = false;  // ghost positions change: their fixed-point records follow in q_refresh
   const int ph4 = ph_begin(ctx, B200_PH_FORWARD);
   const int c = ctx->cur;
   cudaStream_t s = ctx->stream;
@@ -1653,12 +1690,14 @@ static int launch_tile_lj2(b200_ctx *ctx, cudaStream_t s, int eflag, const int *
   k_tile_lj2<EV, ONE, ILP, TT, BB><<<ntiles, thr, sm, s>>>(                                        \
       G, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tile_NI,             \
       ctx->tile_slots, ctx->tl_iloc.p, ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->f[0],      \
-      ctx->f[1], ctx->f[2], ctx->lj_one, ctx->lj_tab.p, ctx->ntypes, ctx->ev, scap, ctx->tflags, ids, nv)
+      ctx->f[1], ctx->f[2], ctx->lj_one, ctx->lj_tab.p, ctx->ntypes, ctx->ev, scap, ctx->tflags, ids, nv, \
+      ctx->tile_hdrs.p)
 #define L2N(ONE, TT, BB)                                                                            \
   k_tile_lj2<false, ONE, 2, TT, BB, true><<<ntiles, thr, sm, s>>>(                                  \
       G, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tile_NI,             \
       ctx->tile_slots, ctx->tl_iloc.p, ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->f[0],      \
-      ctx->f[1], ctx->f[2], ctx->lj_one, ctx->lj_tab.p, ctx->ntypes, ctx->ev, scap, ctx->tflags, ids, nv)
+      ctx->f[1], ctx->f[2], ctx->lj_one, ctx->lj_tab.p, ctx->ntypes, ctx->ev, scap, ctx->tflags, ids, nv, \
+      ctx->tile_hdrs.p)
 #define X(TT, BB)                                                      \
   if (T == TT && B == BB) {                                            \
     if (fuse) { if (one) L2N(true, TT, BB); else L2N(false, TT, BB); } \
@@ -1677,6 +1716,93 @@ static int launch_tile_lj2(b200_ctx *ctx, cudaStream_t s, int eflag, const int *
   return B200_OK;
 }
 
+// mixed-precision lj/cut, second-generation kernel (k_tile_lj2f); B200_LJ2F=threads,minb
+#define LJ2F_SHAPES(X) X(352, 2) X(352, 3) X(320, 3) X(256, 4) X(448, 2)
+static int lj2f_attrs(b200_ctx *ctx) {
+#define X(T, B)                                                    \
+  TRY(tile_attr(ctx, k_tile_lj2f<false, true, T, B>));             \
+  TRY(tile_attr(ctx, k_tile_lj2f<true, true, T, B>));              \
+  TRY(tile_attr(ctx, k_tile_lj2f<false, false, T, B>));            \
+  TRY(tile_attr(ctx, k_tile_lj2f<true, false, T, B>));             \
+  TRY(tile_attr(ctx, (k_tile_lj2f<false, true, T, B, true>)));     \
+  TRY(tile_attr(ctx, (k_tile_lj2f<false, false, T, B, true>)));    \
+  TRY(tile_attr(ctx, (k_tile_lj2f<false, true, T, B, true, true>)));   \
+  TRY(tile_attr(ctx, (k_tile_lj2f<false, false, T, B, true, true>)));  \
+  TRY(tile_attr(ctx, (k_tile_lj2f<false, true, T, B, false, true>)));  \
+  TRY(tile_attr(ctx, (k_tile_lj2f<false, false, T, B, false, true>)));
+  LJ2F_SHAPES(X)
+#undef X
+  return B200_OK;
+}
+
+// bring the fixed-point records up to date with xt[cur] (no-op unless the mixed kernel uses them)
+static int q_refresh(b200_ctx *ctx, bool ghosts) {
+  if (!(ctx->gq_ok && ctx->tiles_active && ctx->prec == B200_PREC_MIXED && ctx->mixed_fx && ctx->use_lj2))
+    return B200_OK;
+  const int c = ctx->cur, nl = ctx->nlocal, ng = ctx->nghost;
+  if (!ctx->q_owned_valid && nl > 0) {
+    k_xt_to_q<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(0, nl, ctx->xt[c], ctx->qrec[c], ctx->qgeom);
+    ctx->launches++;
+  }
+  ctx->q_owned_valid = true;
+  if (ghosts) {
+    if (!ctx->q_ghost_valid && ng > 0) {
+      k_xt_to_q<<<cdiv(ng, 256), 256, 0, ctx->stream>>>(nl, ng, ctx->xt[c], ctx->qrec[c], ctx->qgeom);
+      ctx->launches++;
+    }
+    ctx->q_ghost_valid = true;
+  }
+  LAUNCH_CHECK();
+  return B200_OK;
+}
+
+static int launch_tile_lj2f(b200_ctx *ctx, cudaStream_t s, int eflag, const int *ids, int ntiles, bool fuse,
+                            int do_check) {
+  const TileGeom &G = ctx->tg;
+  const int nl = ctx->nlocal, c = ctx->cur, scap = ctx->tile_scap;
+  const bool one = ctx->ntypes == 1;
+  const size_t sm = tile2f_smem_bytes(scap);
+  const int T = ctx->lj2f[0], B = ctx->lj2f[1];
+  const int thr = std::max(32, std::min(T, cdiv(std::max(ctx->tile_maxown, 1), 32) * 32));
+  NveFuse nv;
+  memset(&nv, 0, sizeof nv);
+  if (fuse)
+    nv = NveFuse{ctx->xt[c ^ 1], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->mask[c], ctx->mass_d.p,
+                 ctx->dtv, ctx->dtf, ctx->groupbit, do_check, ctx->xh[0], ctx->xh[1], ctx->xh[2],
+                 ctx->triggersq, ctx->flags};
+#define ARGS                                                                                        \
+  G, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tile_NI, ctx->tile_slots, \
+      ctx->tl_iloc.p, ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->f[0], ctx->f[1], ctx->f[2],  \
+      ctx->lj_one, ctx->lj_onef, ctx->lj_tab.p, ctx->lj_tabf.p, ctx->ntypes, ctx->ev, scap,         \
+      ctx->tflags, ids, nv, ctx->tile_hdrs.p, ctx->qrec[c], ctx->qrec[c ^ 1], ctx->qgeom
+#define X(TT, BB)                                                                        \
+  if (T == TT && B == BB) {                                                              \
+    if (fuse && ctx->gq_ok) {                                                            \
+      if (one) k_tile_lj2f<false, true, TT, BB, true, true><<<ntiles, thr, sm, s>>>(ARGS);   \
+      else k_tile_lj2f<false, false, TT, BB, true, true><<<ntiles, thr, sm, s>>>(ARGS);  \
+    } else if (ctx->gq_ok && !eflag) {                                                   \
+      if (one) k_tile_lj2f<false, true, TT, BB, false, true><<<ntiles, thr, sm, s>>>(ARGS);  \
+      else k_tile_lj2f<false, false, TT, BB, false, true><<<ntiles, thr, sm, s>>>(ARGS); \
+    } else if (fuse) {                                                                   \
+      if (one) k_tile_lj2f<false, true, TT, BB, true><<<ntiles, thr, sm, s>>>(ARGS);     \
+      else k_tile_lj2f<false, false, TT, BB, true><<<ntiles, thr, sm, s>>>(ARGS);        \
+    } else if (one) {                                                                    \
+      if (eflag) k_tile_lj2f<true, true, TT, BB><<<ntiles, thr, sm, s>>>(ARGS);          \
+      else k_tile_lj2f<false, true, TT, BB><<<ntiles, thr, sm, s>>>(ARGS);               \
+    } else {                                                                             \
+      if (eflag) k_tile_lj2f<true, false, TT, BB><<<ntiles, thr, sm, s>>>(ARGS);         \
+      else k_tile_lj2f<false, false, TT, BB><<<ntiles, thr, sm, s>>>(ARGS);              \
+    }                                                                                    \
+  } else
+  LJ2F_SHAPES(X)
+  return ctx->fail(B200_EARG, "no k_tile_lj2f instance for %d threads x %d CTAs/SM", T, B);
+#undef X
+#undef ARGS
+  ctx->launches++;
+  LAUNCH_CHECK();
+  return B200_OK;
+}
+
 // lj/cut over `ntiles` tiles of the tile list (ids == nullptr: all tiles in order) on stream s
 static int launch_tile_lj(b200_ctx *ctx, cudaStream_t s, int eflag, const int *ids, int ntiles) {
   if (ntiles <= 0) return B200_OK;
@@ -1685,6 +1811,8 @@ static int launch_tile_lj(b200_ctx *ctx, cudaStream_t s, int eflag, const int *i
   const size_t sm = tile_smem_bytes(scap, G.srow_y * G.srow_z, G.sbx, false, false);
  const bool one = ctx->ntypes == 1, mixed = ctx->prec == B200_PREC_MIXED;
   if (!mixed && ctx->use_lj2) return launch_tile_lj2(ctx, s, eflag, ids, ntiles, ctx->fuse_now, ctx->fuse_check);
+  if (mixed && ctx->mixed_fx && ctx->use_lj2)
+    return launch_tile_lj2f(ctx, s, eflag, ids, ntiles, ctx->fuse_now, ctx->fuse_check);
 #define TLJ(EV, ONE, MX)                                                                            \
   k_tile_lj<EV, ONE, MX><<<ntiles, thr, sm, s>>>(                                                   \
       G, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tile_NI,             \
@@ -1717,6 +1845,7 @@ static bool overlap_active(const b200_ctx *ctx) {
 
 // fork: interior tiles on stream2, after everything enqueued on `stream` so far
 static int pair_interior_async(b200_ctx *ctx, int eflag, int vflag) {
+  TRY(q_refresh(ctx, false));
   if (eflag || vflag) CK(cudaMemsetAsync(ctx->ev, 0, 7 * sizeof(double), ctx->stream));
   CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
   CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
@@ -1734,6 +1863,7 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag, int part = 0, bool 
   const bool ev = eflag || vflag;
   const bool mixed = ctx->prec == B200_PREC_MIXED;
   if (joined) *joined = true;
+  TRY(q_refresh(ctx, true));
   ctx->ghost_f_clean = false;  // (force_clear has run; the pair kernels write ghost forces now)
   if (part == 1) {
     const int ph6 = ph_begin(ctx, B200_PH_PAIR);
@@ -1917,6 +2047,7 @@ static int initial_integrate(b200_ctx *ctx, int do_check) {
     LAUNCH_CHECK();
   }
   ctx->pending_final = false;
+  ctx->q_owned_valid = false;  // owned positions moved
   ph_end(ctx, ph8);
   return B200_OK;
 }
@@ -2084,6 +2215,10 @@ int b200_create(b200_ctx **out, int device, int precision) {
     if (const char *e = getenv("B200_MIXED_FX")) ctx->mixed_fx = atoi(e) != 0;
     if (const char *e = getenv("B200_FUSE")) ctx->fuse_nve = atoi(e) != 0;
     if (const char *e = getenv("B200_FUSE_MIN")) ctx->fuse_min_atoms = atoi(e);
+    if (const char *e = getenv("B200_LJ2F")) {
+      int a[2];
+      if (sscanf(e, "%d,%d", &a[0], &a[1]) == 2) { ctx->lj2f[0] = a[0]; ctx->lj2f[1] = a[1]; }
+    }
     if (const char *e = getenv("B200_LJ2")) {
       int a[3];
       const int k = sscanf(e, "%d,%d,%d", &a[0], &a[1], &a[2]);
@@ -2121,7 +2256,7 @@ void b200_destroy(b200_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   auto F = [](auto *p) { if (p) cudaFree((void *)p); };
   for (int b = 0; b < 2; b++) {
-    F(ctx->xt[b]);
+    F(ctx->xt[b]); F(ctx->qrec[b]);
     for (int d = 0; d < 3; d++) F(ctx->v[b][d]);
     F(ctx->tag[b]); F(ctx->mask[b]); F(ctx->image[b]); F(ctx->atombin[b]);
   }
@@ -2138,7 +2273,7 @@ void b200_destroy(b200_ctx *ctx) {
   F(ctx->neigh.p);
   F(ctx->numneigh.p); F(ctx->lj_tab.p); F(ctx->eam_i.p); F(ctx->eam_d.p); F(ctx->eam_one_d.p); F(ctx->ev); F(ctx->ke7); F(ctx->flags);
   F(ctx->cnt64);
-  F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p); F(ctx->tl_gi.p);
+  F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p); F(ctx->tl_gi.p); F(ctx->tile_hdrs.p);
   if (ctx->h_ev) cudaFreeHost(ctx->h_ev);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   for (auto &r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -2491,7 +2626,7 @@ static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt, bool allo
 // the list kind is known only after the step's rebuild decision
 static bool fuse_candidate(const b200_ctx *ctx, int eflag, int vflag, bool allow_fuse) {
   return allow_fuse && !eflag && !vflag && ctx->fuse_nve && ctx->have_nve && ctx->pair_style == 1 &&
-         ctx->prec == B200_PREC_DOUBLE && ctx->use_lj2 && ctx->nlocal > 0 &&
+         (ctx->prec == B200_PREC_DOUBLE || ctx->mixed_fx) && ctx->use_lj2 && ctx->nlocal > 0 &&
          (ctx->nranks > 1 || ctx->nlocal >= ctx->fuse_min_atoms);
 }
 
@@ -2568,6 +2703,10 @@ static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt, bool allo
     // the pair kernels wrote x(n+1) into the other position buffer: it is the live one now
     ctx->fuse_now = false;
     std::swap(ctx->xt[ctx->cur], ctx->xt[ctx->cur ^ 1]);
+    // the fused epilogue of the mixed kernel wrote the owned atoms' fixed-point records as well
+    std::swap(ctx->qrec[ctx->cur], ctx->qrec[ctx->cur ^ 1]);
+    ctx->q_owned_valid = ctx->gq_ok && ctx->prec == B200_PREC_MIXED;
+    ctx->q_ghost_valid = false;
     ctx->ahead = true;
     ctx->pending_final = false;
     ctx->ghost_f_clean = true;

@@ -209,6 +209,23 @@ __device__ __forceinline__ int tile_rows(const TileGeom &G, const TilePos &P,
   return H->S;
 }
 
+// The row tables of a tile depend only on the bin starts, i.e. they change at a rebuild and not
+// in between: k_tile_count stores every tile's finished header (TILE_HDR_BYTES each) and the
+// per-step kernels fetch it with cp.async instead of recomputing it (two dependent rounds of
+// global loads, two scans and ~1000 instructions per CTA and launch).  Ends with a __syncthreads.
+__device__ __forceinline__ int tile_rows_cached(const unsigned char *__restrict__ hdrs, int tile,
+                                                TileHdr *H) {
+  const uint4 *src = reinterpret_cast<const uint4 *>(hdrs + (size_t)tile * TILE_HDR_BYTES);
+  uint4 *dst = reinterpret_cast<uint4 *>(H);
+  for (int k = threadIdx.x; k < (int)(TILE_HDR_BYTES / 16); k += blockDim.x)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + k)),
+                 "l"(src + k)
+                 : "memory");
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  return H->S;
+}
+
 __device__ __forceinline__ double3 tile_pos3(const TileS &T, int s) {
   return make_double3(T.x[s], T.y[s], T.z[s]);
 }
@@ -336,8 +353,10 @@ __global__ void __launch_bounds__(128) k_tile_count(TileGeom G, const int *__res
                                                     const int *__restrict__ gstart,
                                                     int *__restrict__ tile_ibase,
                                                     int *__restrict__ tile_bflag,
-                                                    int *__restrict__ tflags, int reverse_halo) {
-  __shared__ TileHdr H;
+                                                    int *__restrict__ tflags, int reverse_halo,
+                                                    unsigned char *__restrict__ hdrs) {
+  __shared__ __align__(16) unsigned char hraw[TILE_HDR_BYTES];
+  TileHdr &H = *reinterpret_cast<TileHdr *>(hraw);
   const TilePos P = tile_pos(G, blockIdx.x);
   const int S = tile_rows(G, P, ostart, gstart, &H);
   // "boundary" tile: it stages a ghost (must wait for the forward halo) or -- only when the pair
@@ -353,6 +372,13 @@ __global__ void __launch_bounds__(128) k_tile_count(TileGeom G, const int *__res
     if (reverse_halo)
       ghosts |= (t0[d] - G.s[d] <= G.ilo[d]) || (t0[d] + G.t[d] - 1 + G.s[d] >= G.ilo[d] + G.nib[d] - 1);
   ghosts = __syncthreads_or(ghosts);
+  {  // the finished header, for the per-step kernels (tile_rows_cached)
+    if (threadIdx.x == 0) H.pad0 = 0;
+    __syncthreads();
+    uint4 *dst = reinterpret_cast<uint4 *>(hdrs + (size_t)blockIdx.x * TILE_HDR_BYTES);
+    const uint4 *src = reinterpret_cast<const uint4 *>(hraw);
+    for (int k = threadIdx.x; k < (int)(TILE_HDR_BYTES / 16); k += blockDim.x) dst[k] = src[k];
+  }
   if (threadIdx.x == 0) {
     tile_bflag[blockIdx.x] = ghosts ? 1 : 0;
     const int ni = H.ni;

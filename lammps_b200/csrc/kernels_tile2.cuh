@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_lj2(
     const int *__restrict__ tgi, const uint4 *__restrict__ list, double *__restrict__ fx,
     double *__restrict__ fy, double *__restrict__ fz, LJOne one, const double *__restrict__ tab,
     int ntypes, double *__restrict__ ev, int scap, int *__restrict__ tflags,
-    const int *__restrict__ tile_ids, NveFuse nv) {
+    const int *__restrict__ tile_ids, NveFuse nv, const unsigned char *__restrict__ hdrs) {
   extern __shared__ __align__(128) unsigned char tsm[];
   TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
   double *pos = reinterpret_cast<double *>(tsm + TILE_HDR_BYTES);
@@ -96,8 +96,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_lj2(
   const int tile = tile_ids ? tile_ids[blockIdx.x] : blockIdx.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const TilePos P = tile_pos(G, tile);
-  if (tid == 0) *chunk_ctr = 0;
-  const int S = tile_rows(G, P, ostart, gstart, H);
+  const int S = tile_rows_cached(hdrs, tile, H);  // (the stored header carries a zero chunk counter)
   if (S + 1 > scap) {  // cannot happen between rebuilds (the rows are those the build staged)
     if (tid == 0) atomicMax(&tflags[5], S + 1);
     return;
@@ -315,3 +314,300 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_lj2(
   }
 }
 
+
+// global index of staged atom s (row tables; used on rare paths only)
+__device__ __forceinline__ int tile_global_index(const TileHdr *H, int nlocal, int s) {
+  int lo = 0, hi = H->nrows;  // rowbase[lo] <= s < rowbase[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (H->rowbase[mid] <= s) lo = mid; else hi = mid;
+  }
+  const int k = s - H->rowbase[lo], no = H->row_no[lo];
+  return k < no ? H->row_o0[lo] + k : nlocal + H->row_g0[lo] + (k - no);
+}
+
+// ---------------------------------------------------------------------------------------
+// lj/cut over a tile, mixed precision, second generation (replaces k_tile_lj_fx as the default
+// of `prec mixed`).  FP32 pair math on fixed-point staged positions, FP64 accumulation:
+//   * a staged atom is ONE 16-byte record {qx, qy, qz, type}: q = rn((x - origin) * fxscale) as
+//     int32 (resolution ~1.5e-8 sigma, differences of two staged coordinates are exact): one
+//     LDS.128 and one address per list entry (k_tile_lj_fx: four LDS.32 from four arrays), and
+//     16 instead of 20 bytes of shared memory per staged atom;
+//   * differences, rsq and the running force sums stay in fixed-point units (the scale is folded
+//     into the reciprocal and applied to the sums once per list word);
+//   * a cutoff decision within 2e-6 (relative) of the cutoff is re-taken in FP64 from the global
+//     positions with the reference's operation order, so the set of interacting pairs is the CPU
+//     path's; everything else of k_tile_lj2: no ghost scatter (FULLGHOST list), dummy-padded rows,
+//     software-pipelined shared-memory and list loads, chunk scheduling, fused fix nve;
+//   * FP32 partial sums of one list word (8 entries) are added to FP64 accumulators.
+// Tolerances (BASELINE.json): forces <= 1e-5 relative, energy/pressure <= 1e-6.
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ size_t tile2f_smem_bytes(int scap) {
+  return (TILE_HDR_BYTES + (size_t)scap * sizeof(int4) + 127) / 128 * 128;
+}
+
+// Sub-domain-wide fixed point (GQ = true): every atom's record {qx,qy,qz,type} relative to ONE
+// origin (the corner of the local bin grid) lives in a global int4 array that the integrators
+// keep current, so staging a tile is one 16-byte cp.async per atom -- no conversion, half the
+// staging bytes of the double4 records.  30 bits per coordinate (the dummy atom of padding
+// entries sits at -2^30, so differences cannot overflow); engine.cu uses it when the grid
+// spacing extent / 2^30 is fine enough for the 2e-6 decision band (up to ~370 sigma per
+// sub-domain edge), else the tile-relative conversion below (GQ = false).
+struct QGeom {
+  double ox, oy, oz, scale;
+};
+__device__ __forceinline__ int4 q_record(const double4 &p, const QGeom &Q) {
+  return make_int4(__double2int_rn((p.x - Q.ox) * Q.scale), __double2int_rn((p.y - Q.oy) * Q.scale),
+                   __double2int_rn((p.z - Q.oz) * Q.scale), d2type(p.w));
+}
+__global__ void __launch_bounds__(256) k_xt_to_q(int first, int n, const double4 *__restrict__ xt,
+                                                 int4 *__restrict__ q, QGeom Q) {
+  const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < first + n) q[i] = q_record(xt[i], Q);
+}
+
+template <bool EV, bool ONETYPE, int MAXT, int MINB, bool NVE = false, bool GQ = false>
+__global__ void __launch_bounds__(MAXT, MINB) k_tile_lj2f(
+    TileGeom G, int nlocal, const double4 *__restrict__ xt, const int *__restrict__ ostart,
+    const int *__restrict__ gstart, const int *__restrict__ tile_ibase, int NI, int maxslots,
+    const unsigned short *__restrict__ iloc, const unsigned short *__restrict__ tnum,
+    const int *__restrict__ tgi, const uint4 *__restrict__ list, double *__restrict__ fx,
+    double *__restrict__ fy, double *__restrict__ fz, LJOne one, LJOneF onef,
+    const double *__restrict__ tab, const float *__restrict__ tabf, int ntypes,
+    double *__restrict__ ev, int scap, int *__restrict__ tflags, const int *__restrict__ tile_ids,
+    NveFuse nv, const unsigned char *__restrict__ hdrs, const int4 *__restrict__ qin,
+    int4 *__restrict__ qout, QGeom Q) {
+  extern __shared__ __align__(128) unsigned char tsm[];
+  TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
+  int4 *rec = reinterpret_cast<int4 *>(tsm + TILE_HDR_BYTES);
+  int *chunk_ctr = reinterpret_cast<int *>(&H->pad0);
+  const unsigned rec_s = (unsigned)__cvta_generic_to_shared(rec);
+  const int tile = tile_ids ? tile_ids[blockIdx.x] : blockIdx.x, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const TilePos P = tile_pos(G, tile);
+  const int S = tile_rows_cached(hdrs, tile, H);  // (the stored header carries a zero chunk counter)
+  if (S + 1 > scap) {
+    if (tid == 0) atomicMax(&tflags[5], S + 1);
+    return;
+  }
+  if (GQ) {  // stage: one warp per run, one 16-byte cp.async per atom from the global fixed-point records
+    const int nrows = H->nrows;
+    for (int r = warp; r < nrows; r += nwarp) {
+      const int base = H->rowbase[r], no = H->row_no[r], n = no + H->row_ng[r];
+      const int o0 = H->row_o0[r], g0 = nlocal + H->row_g0[r] - no;
+      for (int k = lane; k < n; k += 32) {
+        const int src = k < no ? o0 + k : g0 + k;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rec_s + (unsigned)(base + k) * 16u),
+                     "l"(qin + src)
+                     : "memory");
+      }
+    }
+    if (tid == 0) rec[S] = make_int4(-(1 << 30), -(1 << 30), -(1 << 30), 1);  // the dummy atom
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+  } else {  // stage: one warp per run of records, LDG.256 of the record, fixed-point conversion, STS.128
+    const double ox = G.bin0[0] + (P.tx0 - G.s[0]) * G.bsize[0] - G.fxpad,
+                 oy = G.bin0[1] + (P.ty0 - G.s[1]) * G.bsize[1] - G.fxpad,
+                 oz = G.bin0[2] + (P.tz0 - G.s[2]) * G.bsize[2] - G.fxpad;
+    const int nrows = H->nrows;
+    for (int r = warp; r < nrows; r += nwarp) {
+      const int base = H->rowbase[r], no = H->row_no[r], n = no + H->row_ng[r];
+      const int o0 = H->row_o0[r], g0 = nlocal + H->row_g0[r] - no;
+      for (int k = lane; k < n; k += 32) {
+        const int src = k < no ? o0 + k : g0 + k;
+        const double4 p = ld_xt(xt + src);
+        rec[base + k] = make_int4(__double2int_rn((p.x - ox) * G.fxscale), __double2int_rn((p.y - oy) * G.fxscale),
+                                  __double2int_rn((p.z - oz) * G.fxscale), d2type(p.w));
+      }
+    }
+    // the dummy atom of padding entries: a corner of the fixed-point range, > one cutoff (the
+    // pad) away from every staged atom in each coordinate
+    if (tid == 0) rec[S] = make_int4(0, 0, 0, 1);
+    __syncthreads();
+  }
+  const int ni = H->ni, ibase = tile_ibase[tile];
+  const int n1 = ntypes + 1, n2 = n1 * n1;
+  const double dscale = GQ ? Q.scale : G.fxscale;
+  const float scale = (float)dscale, s2 = scale * scale, inv = (float)(1.0 / dscale);
+  // the single-type constants in fixed-point units: rsq_q = rsq * scale^2
+  const float cutq1 = (float)(one.cutsq * dscale * dscale);
+  double evdwl = 0.0, vir[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (;;) {
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(chunk_ctr, 1);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (chunk * 32 >= ni) break;
+    const int ti = chunk * 32 + lane;
+    if (ti >= ni) continue;
+    const int g = ibase + ti;
+    const uint4 *lp = list + g;
+    uint4 q0 = __ldg(lp), q1 = __ldg(lp + NI);
+    const int li = iloc[g];
+    const int n = min((int)tnum[g], maxslots);
+    if (n == 0) q0 = make_uint4(S, S, S, S);
+    const int gi = tgi[g];
+    const int4 me = rec[li];
+    const int itype = ONETYPE ? 1 : me.w;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    int imask = 0;
+    if (NVE) {
+      asm volatile("ld.global.f64 %0, [%1];" : "=d"(v0) : "l"(nv.vx + gi));
+      asm volatile("ld.global.f64 %0, [%1];" : "=d"(v1) : "l"(nv.vy + gi));
+      asm volatile("ld.global.f64 %0, [%1];" : "=d"(v2) : "l"(nv.vz + gi));
+      asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(imask) : "l"(nv.mask + gi));
+    }
+    double fxi = 0.0, fyi = 0.0, fzi = 0.0;          // FP64 accumulators (real units)
+    float gx = 0.0f, gy = 0.0f, gz = 0.0f;           // FP32 partial sums of one list word (q units)
+    float ei = 0.0f, w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f, w4 = 0.0f, w5 = 0.0f;
+
+    auto ldrec = [&](unsigned e) -> int4 {
+      int4 r;
+      const unsigned a = rec_s + (e & TILE_IDX) * 16u;
+      asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+      return r;
+    };
+    // FP32 pair function in fixed-point units: rsq_q -> fpair (force on i = dq * inv * fpair)
+    auto ljf = [&](float rsq_q, int tij, float &fpair, float &epair) {
+      const float lj1 = ONETYPE ? onef.lj1 : __ldg(tabf + tij);
+      const float lj2 = ONETYPE ? onef.lj2 : __ldg(tabf + n2 + tij);
+      const float r2inv = rcp_f(rsq_q) * s2;
+      const float u = r2inv * r2inv;
+      const float r6inv = u * r2inv;
+      fpair = (u * u) * fmaf(lj1, r6inv, -lj2);
+      if (EV) {
+        const float lj3 = ONETYPE ? onef.lj3 : __ldg(tabf + 2 * n2 + tij);
+        const float lj4 = ONETYPE ? onef.lj4 : __ldg(tabf + 3 * n2 + tij);
+        const float off = ONETYPE ? onef.offset : __ldg(tabf + 4 * n2 + tij);
+        epair = r6inv * fmaf(lj3, r6inv, -lj4) - off;
+      }
+    };
+    auto geom = [&](const int4 &pj, float &dx, float &dy, float &dz, float &rsq, int &tij, float &cutq) {
+      dx = (float)(me.x - pj.x);
+      dy = (float)(me.y - pj.y);
+      dz = (float)(me.z - pj.z);
+      rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      tij = 0;
+      cutq = cutq1;
+      if (!ONETYPE) {
+        tij = itype * n1 + pj.w;
+        cutq = (float)__ldg(tab + tij) * s2;
+      }
+    };
+    auto tally = [&](unsigned e, float dx, float dy, float dz, float f, float ep) {
+      const bool fwd = (e & TILE_FWD) != 0;
+      ei += fwd ? ep : 0.0f;
+      const float w = fwd ? f : 0.0f;
+      w0 = fmaf(dx * dx, w, w0); w1 = fmaf(dy * dy, w, w1); w2 = fmaf(dz * dz, w, w2);
+      w3 = fmaf(dx * dy, w, w3); w4 = fmaf(dx * dz, w, w4); w5 = fmaf(dy * dz, w, w5);
+    };
+    // fast path, branch-free; returns true when the decision is too close to call in FP32
+    auto body = [&](unsigned e, const int4 &pj) -> bool {
+      float dx, dy, dz, rsq, cutq, fp, ep = 0.0f;
+      int tij;
+      geom(pj, dx, dy, dz, rsq, tij, cutq);
+      const bool amb = fabsf(rsq - cutq) < 2.0e-6f * cutq;
+      const bool in = rsq < cutq && !amb;
+      ljf(rsq, tij, fp, ep);
+      const float f = in ? fp : 0.0f;
+      gx = fmaf(dx, f, gx);
+      gy = fmaf(dy, f, gy);
+      gz = fmaf(dz, f, gz);
+      if (EV) tally(e, dx, dy, dz, f, in ? ep : 0.0f);
+      return amb;
+    };
+    // an ambiguous entry: the reference's FP64 test on the global positions decides
+    auto exact = [&](unsigned e) {
+      const int4 pj = ldrec(e);
+      float dx, dy, dz, rsq, cutq, fp, ep = 0.0f;
+      int tij;
+      geom(pj, dx, dy, dz, rsq, tij, cutq);
+      if (!(fabsf(rsq - cutq) < 2.0e-6f * cutq)) return;
+      const double4 a = ld_xt(xt + gi), b = ld_xt(xt + tile_global_index(H, nlocal, e & TILE_IDX));
+      if (rsq_ref(a.x - b.x, a.y - b.y, a.z - b.z) < (ONETYPE ? one.cutsq : __ldg(tab + tij))) {
+        ljf(rsq, tij, fp, ep);
+        gx = fmaf(dx, fp, gx);
+        gy = fmaf(dy, fp, gy);
+        gz = fmaf(dz, fp, gz);
+        if (EV) tally(e, dx, dy, dz, fp, ep);
+      }
+    };
+    auto entry = [&](const uint4 &w, int k) -> unsigned {
+      const unsigned v = k < 2 ? w.x : (k < 4 ? w.y : (k < 6 ? w.z : w.w));
+      return (k & 1) ? (v >> 16) : (v & 0xffffu);
+    };
+
+    // four entries per step; their records are loaded one step ahead
+    int4 cur[4], nxt[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) cur[k] = ldrec(entry(q0, k));
+    for (int k0 = 0; k0 < n; k0 += 8) {
+      const uint4 c = q0;
+      q0 = q1;
+      if (k0 + 16 < n) q1 = __ldg(lp + (size_t)((k0 >> 3) + 2) * NI);
+      const uint4 cn = (k0 + 8 < n) ? q0 : c;
+      bool again = false;
+#pragma unroll
+      for (int st = 0; st < 2; st++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) nxt[k] = st == 0 ? ldrec(entry(c, 4 + k)) : ldrec(entry(cn, k));
+#pragma unroll
+        for (int k = 0; k < 4; k++) again |= body(entry(c, st * 4 + k), cur[k]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) cur[k] = nxt[k];
+      }
+      if (again) {
+#pragma unroll 1
+        for (int k = 0; k < 8; k++) {
+          const unsigned v = k < 2 ? c.x : (k < 4 ? c.y : (k < 6 ? c.z : c.w));
+          exact((k & 1) ? (v >> 16) : (v & 0xffffu));
+        }
+      }
+      // end of a list word: fold the FP32 partial sums into the FP64 accumulators
+      fxi += (double)gx; fyi += (double)gy; fzi += (double)gz;
+      gx = gy = gz = 0.0f;
+    }
+    // fixed-point units -> real units: del = dq / scale
+    const double dinv = 1.0 / dscale;
+    fxi *= dinv; fyi *= dinv; fzi *= dinv;
+    if (EV) {
+      evdwl += (double)ei;
+      const double d2 = dinv * dinv;
+      vir[0] += (double)w0 * d2; vir[1] += (double)w1 * d2; vir[2] += (double)w2 * d2;
+      vir[3] += (double)w3 * d2; vir[4] += (double)w4 * d2; vir[5] += (double)w5 * d2;
+    }
+    if (NVE) {
+      const double4 p0 = ld_xt(xt + gi);
+      double px = p0.x, py = p0.y, pz = p0.z;
+      if (imask & nv.groupbit) {
+        const double dtfm = nv.dtf / nv.mass[itype];
+        const double ka = __dmul_rn(dtfm, fxi), kb = __dmul_rn(dtfm, fyi), kc = __dmul_rn(dtfm, fzi);
+        double a = v0, b = v1, cc = v2;
+        a = __dadd_rn(__dadd_rn(a, ka), ka);
+        b = __dadd_rn(__dadd_rn(b, kb), kb);
+        cc = __dadd_rn(__dadd_rn(cc, kc), kc);
+        nv.vx[gi] = a; nv.vy[gi] = b; nv.vz[gi] = cc;
+        px = __dadd_rn(px, __dmul_rn(nv.dtv, a));
+        py = __dadd_rn(py, __dmul_rn(nv.dtv, b));
+        pz = __dadd_rn(pz, __dmul_rn(nv.dtv, cc));
+      }
+      nv.xt_out[gi] = make_double4(px, py, pz, p0.w);
+      if (GQ) qout[gi] = q_record(make_double4(px, py, pz, p0.w), Q);  // next step's staged record
+      if (nv.do_check) {
+        const double dx = px - nv.xhx[gi], dy = py - nv.xhy[gi], dz = pz - nv.xhz[gi];
+        if (rsq_ref(dx, dy, dz) > nv.triggersq) *nv.moved = 1;
+      }
+    } else {
+      fx[gi] = fxi;
+      fy[gi] = fyi;
+      fz[gi] = fzi;
+    }
+  }
+  (void)inv;
+  if (EV) {
+    double v[7] = {evdwl, vir[0], vir[1], vir[2], vir[3], vir[4], vir[5]};
+    __syncthreads();
+    block_sum<7>(v, reinterpret_cast<double *>(rec));
+    if (tid == 0)
+      for (int k = 0; k < 7; k++) atomicAdd(&ev[k], v[k]);
+  }
+}

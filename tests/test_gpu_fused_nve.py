@@ -83,3 +83,27 @@ def test_fused_nve_between_subdomains(fused):
     positions the next step's halo packs"""
     from test_gpu_subdomains import _check
     _check(melted(lj_system((12, 12, 12)), 40), 8, 100)
+
+
+def test_fused_nve_mixed_precision_drift(fused):
+    """the mixed kernel with the sub-domain-wide fixed-point records AND the fused integrator (its
+    epilogue writes the next step's staged record): 100-step thermo drift within the mixed-mode
+    tolerances of test_gpu_mixed.py"""
+    from test_gpu_mixed import DRIFT
+    s = lj_system((12, 12, 12))
+    o = make_oracle(s)
+    o.setup(1, 1)
+    e = make_engine(s, "mixed")
+    e.setup(1, 1)
+    to = o.run(100, 0, 50)
+    te = e.run(100, 50)
+    assert len(to) == len(te) == 2
+    assert e.stats()["nbuilds"] == o.ncalls
+    for ro, re_ in zip(to, te):
+        a, b = e.thermo_row(ro), e.thermo_row(re_)
+        for k, tol in DRIFT.items():
+            assert abs(a[k] - b[k]) <= tol * max(abs(a[k]), 1e-3), (k, a[k], b[k])
+    a = e.get_atoms(fields=("x", "tag"))
+    (xe,) = by_tag(a["tag"], a["x"])
+    (xo,) = by_tag(o.tag(), o.x())
+    assert np.abs(xe - xo).max() < 5e-3   # chaotic divergence of an FP32-force trajectory, bounded
