@@ -89,10 +89,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_lj2(
     const int *__restrict__ tile_ids, NveFuse nv, const unsigned char *__restrict__ hdrs) {
   extern __shared__ __align__(128) unsigned char tsm[];
   TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
+  // staged positions: {x,y} as one 16-byte pair per atom, z in its own array -- an entry costs one
+  // LDS.128 and one LDS.64 (16 wavefronts per warp on scattered partners; three LDS.64 cost 18.5)
   double *pos = reinterpret_cast<double *>(tsm + TILE_HDR_BYTES);
+  double *posz = pos + (size_t)2 * scap;
   int *stype = reinterpret_cast<int *>(pos + (size_t)3 * scap);
   int *chunk_ctr = reinterpret_cast<int *>(&H->pad0);
   const unsigned pos_s = (unsigned)__cvta_generic_to_shared(pos);
+  const unsigned posz_s = (unsigned)__cvta_generic_to_shared(posz);
   const int tile = tile_ids ? tile_ids[blockIdx.x] : blockIdx.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const TilePos P = tile_pos(G, tile);
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_lj2(
     if (tid == 0) atomicMax(&tflags[5], S + 1);
     return;
   }
-  {  // stage: one warp per run of records, cp.async of x,y,z (and type) of each record
+  {  // stage: one warp per run of records, cp.async of {x,y}, z (and type) of each record
     const int nrows = H->nrows;
     for (int r = warp; r < nrows; r += nwarp) {
       const int base = H->rowbase[r], no = H->row_no[r], n = no + H->row_ng[r];
@@ -109,14 +113,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_lj2(
       for (int k = lane; k < n; k += 32) {
         const int src = k < no ? o0 + k : g0 + k, s = base + k;
         const double *p = reinterpret_cast<const double *>(xt + src);
-        double *d = pos + 3 * s;
-        cp_async8(d, p);
-        cp_async8(d + 1, p + 1);
-        cp_async8(d + 2, p + 2);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(pos_s + (unsigned)s * 16u), "l"(p)
+                     : "memory");
+        cp_async8(posz + s, p + 2);
         if (!ONETYPE) cp_async4(stype + s, p + 3);
       }
     }
-    if (tid < 3) pos[3 * S + tid] = TILE2_FAR;  // the dummy atom padding entries point at
+    if (tid < 2) pos[2 * S + tid] = TILE2_FAR;  // the dummy atom padding entries point at
+    if (tid == 2) posz[S] = TILE2_FAR;
     if (!ONETYPE && tid == 3) stype[S] = 1;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_lj2(
     const int n = min((int)tnum[g], maxslots);
     if (n == 0) q0 = make_uint4(S, S, S, S);  // nothing was written: name the dummy atom
     const int gi = tgi[g];
-    const double pix = pos[3 * li], piy = pos[3 * li + 1], piz = pos[3 * li + 2];
+    const double pix = pos[2 * li], piy = pos[2 * li + 1], piz = posz[li];
     const int itype = ONETYPE ? 1 : stype[li];
     double fxi = 0.0, fyi = 0.0, fzi = 0.0;
     // fused integrator: the atom's velocity and group mask are requested now (volatile asm keeps
@@ -160,14 +164,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_tile_lj2(
     struct P3 { double x, y, z; };
     auto ldpos = [&](unsigned e) -> P3 {
       P3 p;
-#ifdef TILE2_X_NOCONFLICT  // timing experiment only (wrong physics)
-      const unsigned a = pos_s + (((e & TILE_IDX) & ~15u) | (threadIdx.x & 15u)) * 24u;
-#else
-      const unsigned a = pos_s + (e & TILE_IDX) * 24u;
-#endif
-      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(p.x) : "r"(a));
-      asm volatile("ld.shared.f64 %0, [%1+8];" : "=d"(p.y) : "r"(a));
-      asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(p.z) : "r"(a));
+      const unsigned j = e & TILE_IDX;
+      asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(p.x), "=d"(p.y) : "r"(pos_s + j * 16u));
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(p.z) : "r"(posz_s + j * 8u));
       return p;
     };
     // geometry of entry e: del, rsq (FMA form), pair-type index, cutoff
