@@ -23,6 +23,8 @@
 #include "kernels_step.cuh"
 #include "kernels_tile.cuh"
 #include "kernels_tile2.cuh"
+#include "kernels_eam2.cuh"
+#include "kernels_build2.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -213,6 +215,16 @@ struct b200_ctx {
   // (B200_LJ2=threads,minb,ilp; B200_LJ2=0 selects the first-generation k_tile_lj)
   int lj2[3] = {352, 2, 2};
   bool use_lj2 = true;
+  // eam on tiles, second generation (kernels_eam2.cuh): FULLGHOST + NEAR/FAR split rows, density
+  // and embedding in one kernel, fix nve fused into the force kernel.  Single-element potentials
+  // in FP64 (B200_EAM2=0 / `package b200 eam2 no` selects the flat half list kernels).
+  int eam2 = 2;                 // 0 never, 1 whenever usable, 2 auto: small sub-domains (see eam2_usable)
+  long long eam2_max_bins = 60000;
+  bool build2 = false;          // warp-per-bin list build (kernels_build2.cuh; B200_BUILD2=1): measured slower
+                                // than k_tile_build (4.5 vs 2.7 ms per build at 4 M atoms), kept as a cross-check
+  bool eam2_active = false;     // the current list was built for those kernels
+  double eam2_margin = 0.35;    // NEAR = stored within force cutoff + eam2_margin * skin (B200_EAM2_MARGIN)
+  DBuf<unsigned short> tl_far;  // FAR entries per row (SPLIT rows)
   int lj2f[2] = {256, 4};       // k_tile_lj2f (mixed): threads, CTAs per SM (B200_LJ2F=threads,minb)
   DBuf<uint4> tl_list;
   int *tflags = nullptr;  // [8] device: max staged, max owned/tile, max entries, max FWD, owned total, overflow
@@ -1024,6 +1036,32 @@ static int setup_geometry(b200_ctx *ctx) {
         fs.nrows++;
       }
     if (!ok) ctx->use_tiles = false;  // unusual stencil: the flat list handles it
+    {
+      // Order in which the build walks the stencil rows = order of the entries in a list row.  Any
+      // order that does not put the rows of neighbouring z-planes next to each other makes the
+      // lj/cut tile kernels ~8 % faster (687 -> 632 us at 4 M atoms, profiles/r02ad_probe_fst_order.txt):
+      // the two entries a thread has in flight then come from different staged rows.  Default 9:
+      // mirrored pairs (-dy,-dz),(dy,dz) from the centre row outwards; B200_FST_ORDER=0 keeps the
+      // sorted order, 1..8 are the other permutations that were measured.
+      const char *e = getenv("B200_FST_ORDER");
+      const int mode = e ? atoi(e) : 9;
+      FullStencil t = fs;
+      std::vector<int> ord;
+      const int n = fs.nrows, h = (n + 1) / 2;
+      if (mode == 1) { for (int i = 0; i < h; i++) { ord.push_back(i); if (i + h < n) ord.push_back(i + h); } }
+      else if (mode == 2) { for (int i = 0; i < n; i++) ord.push_back(n - 1 - i); }
+      else if (mode == 3) { for (int st = 0; st < 5; st++) for (int i = st; i < n; i += 5) ord.push_back(i); }
+      else if (mode == 4) { const int q = (n + 2) / 3; for (int i = 0; i < q; i++) for (int k = 0; k < 3; k++) if (i + k * q < n) ord.push_back(i + k * q); }
+      else if (mode == 5) { for (int i = 0; i < n; i++) ord.push_back(i); unsigned x = 12345; for (int i = n - 1; i > 0; i--) { x = x * 1664525u + 1013904223u; std::swap(ord[i], ord[(x >> 8) % (i + 1)]); } }
+      else if (mode == 6) { for (int i = 0; i < h; i++) { ord.push_back(i); if (n - 1 - i > i) ord.push_back(n - 1 - i); } }
+      else if (mode == 7) { const int q = (n + 3) / 4; for (int i = 0; i < q; i++) for (int k = 0; k < 4; k++) if (i + k * q < n) ord.push_back(i + k * q); }
+      else if (mode == 8) { for (int i = 0; i < h; i++) { if (i + h < n) ord.push_back(i + h); ord.push_back(i); } }
+      else if (mode == 9) { for (int i = h - 1; i >= 0; i--) { ord.push_back(i); if (n - 1 - i > i) ord.push_back(n - 1 - i); } }
+      if ((int)ord.size() == n)
+        for (int i = 0; i < n; i++) {
+          fs.dy[i] = t.dy[ord[i]]; fs.dz[i] = t.dz[ord[i]]; fs.dxlo[i] = t.dxlo[ord[i]]; fs.dxhi[i] = t.dxhi[ord[i]];
+        }
+    }
     auto host_bin = [&](double x, int d) {  // NBin::coord2bin, nbin.cpp:141-173
       int ix;
       if (x >= g.boxhi[d]) ix = (int)((x - g.boxhi[d]) * g.bininv[d]) + g.nbin[d];
@@ -1092,6 +1130,7 @@ static const int TILE_MENU[][3] = {{8, 8, 4}, {8, 4, 4}, {4, 4, 4}, {4, 4, 2}, {
 static const int TILE_NMENU = sizeof(TILE_MENU) / sizeof(TILE_MENU[0]);
 static const size_t TILE_SMEM_MAX = 227 * 1024;      // opt-in limit per CTA on sm_100
 static const size_t TILE_SMEM_TWO = 113 * 1024;      // two CTAs per SM fit below this
+static const size_t BUILD2_SMEM_MAX = 226 * 1024;    // k_tile_build2: dynamic part next to its static arrays
 
 static void set_tile_geom(b200_ctx *ctx, const int t[3]) {
   TileGeom &G = ctx->tg;
@@ -1133,7 +1172,21 @@ static int tile_kernel_attrs(b200_ctx *ctx) {
   TRY(tile_attr(ctx, (k_tile_build<false, true>)));
   TRY(tile_attr(ctx, (k_tile_build<true, false>)));
   TRY(tile_attr(ctx, (k_tile_build<false, false>)));
+  TRY(tile_attr(ctx, (k_tile_build<true, true, true>)));
   TRY(tile_attr(ctx, k_tile_export));
+  // (k_tile_build2 also has 256 bytes of static shared memory: the opt-in limit covers both)
+#define B2A(K) CK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUILD2_SMEM_MAX))
+  B2A((k_tile_build2<true, true, false>));
+  B2A((k_tile_build2<false, true, false>));
+  B2A((k_tile_build2<true, false, false>));
+  B2A((k_tile_build2<false, false, false>));
+  B2A((k_tile_build2<true, true, true>));
+#undef B2A
+  TRY(tile_attr(ctx, (k_tile_eam2_rho<false, 352, 2>)));
+  TRY(tile_attr(ctx, (k_tile_eam2_rho<true, 352, 2>)));
+  TRY(tile_attr(ctx, (k_tile_eam2_force<false, 352, 2, false>)));
+  TRY(tile_attr(ctx, (k_tile_eam2_force<true, 352, 2, false>)));
+  TRY(tile_attr(ctx, (k_tile_eam2_force<false, 352, 2, true>)));
 #define A3(K) \
   TRY(tile_attr(ctx, K<false, false, false>)); TRY(tile_attr(ctx, K<false, false, true>)); \
   TRY(tile_attr(ctx, K<false, true, false>));  TRY(tile_attr(ctx, K<false, true, true>));  \
@@ -1156,12 +1209,30 @@ static int tile_kernel_attrs(b200_ctx *ctx) {
   return B200_OK;
 }
 
+// may eam run on the second-generation tile kernels?  (single element, one atom type, FP64)
+// Auto: measured on one B200 (profiles/r02ab_probe_build2_eam_sizes.txt) the tile kernels win on
+// small systems (32 k atoms: 249 vs 215 M atom-steps/s -- half the launches, no reverse halos) and
+// lose on large ones (2 M atoms: pair 1.70 vs 1.33 ms, list build 2.0 vs 0.7 ms: the spline
+// tables, not the scatter, are what loads the L1 data pipe, and every owned-owned pair looks them
+// up twice).  The switch is the number of global bins per sub-domain, identical on every rank (all
+// ranks must walk the same sequence of halos).
+static bool eam2_usable(const b200_ctx *ctx) {
+  if (!(ctx->eam2 && ctx->pair_style == 2 && ctx->eam_one_ok && ctx->ntypes == 1 &&
+        ctx->prec == B200_PREC_DOUBLE))
+    return false;
+  if (ctx->eam2 == 1) return true;
+  const long long bins = (long long)ctx->geom.nbin[0] * ctx->geom.nbin[1] * ctx->geom.nbin[2];
+  return bins / std::max(ctx->nranks, 1) <= ctx->eam2_max_bins;
+}
+
 // rc: B200_OK with ctx->tiles_active set, or tiles_active == false when no tile size fits
 static int build_tiles(b200_ctx *ctx) {
   const int nl = ctx->nlocal, c = ctx->cur;
   cudaStream_t s = ctx->stream;
   ctx->tiles_active = false;
   const bool eam = ctx->pair_style == 2;
+  const bool eam2 = eam && eam2_usable(ctx);
+  ctx->eam2_active = false;
   if (ctx->tile_level < 0) {
     // first build for this geometry: the largest tile that still gives every SM several CTAs
     int lvl = 0;
@@ -1186,7 +1257,7 @@ static int build_tiles(b200_ctx *ctx) {
       TRY(reserve(ctx, ctx->tile_ids, (size_t)G.ntiles + 2));
       TRY(reserve(ctx, ctx->tile_hdrs, (size_t)G.ntiles * TILE_HDR_BYTES));
       k_tile_count<<<G.ntiles, 128, 0, s>>>(G, ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p,
-                                            ctx->tile_bflag.p, ctx->tflags, eam ? 1 : 0, ctx->tile_hdrs.p);
+                                            ctx->tile_bflag.p, ctx->tflags, (eam && !eam2) ? 1 : 0, ctx->tile_hdrs.p);
       ctx->launches++;
       LAUNCH_CHECK();
       TRY(scan_inplace(ctx, ctx->tile_ibase.p, G.ntiles));
@@ -1208,8 +1279,12 @@ static int build_tiles(b200_ctx *ctx) {
         return ctx->fail(B200_ELOST, "bin tiles cover %d of %d owned atoms", h[4], nl);
       ctx->tile_NI = ctx->h_flags[16];
       ctx->tile_scap = cdiv(std::max(h[0], 1) + 1, 64) * 64;  // + the dummy atom of padding entries
-      const size_t need = std::max(tile_smem_bytes(ctx->tile_scap, G.srow_y * G.srow_z, G.sbx, true, false),
-                                   tile_smem_bytes(ctx->tile_scap, G.srow_y * G.srow_z, G.sbx, false, eam));
+      const size_t bneed = ctx->build2 ? build2_smem_bytes(ctx->tile_scap, G.srow_y * G.srow_z, G.sbx, ctx->ntypes != 1,
+                                                           std::max(ctx->tile_slots, 112))
+                                       : tile_smem_bytes(ctx->tile_scap, G.srow_y * G.srow_z, G.sbx, true, false);
+      const size_t need = std::max(bneed,
+                                   eam2 ? eam2_smem_bytes(ctx->tile_scap, true)
+                                        : tile_smem_bytes(ctx->tile_scap, G.srow_y * G.srow_z, G.sbx, false, eam));
       const bool last = ctx->tile_req[0] > 0 || ctx->tile_level == TILE_NMENU - 1;
       fits = h[0] <= TILE_MAXSTAGE && need <= (last ? TILE_SMEM_MAX : TILE_SMEM_TWO);
     }
@@ -1234,6 +1309,7 @@ static int build_tiles(b200_ctx *ctx) {
     TRY(reserve(ctx, ctx->tl_iloc, NI));
     TRY(reserve(ctx, ctx->tl_num, NI));
     TRY(reserve(ctx, ctx->tl_gi, NI));
+    if (eam2) TRY(reserve(ctx, ctx->tl_far, NI));
     TRY(reserve(ctx, ctx->numneigh, (size_t)std::max(nl, 1)));
     CK(cudaMemsetAsync(ctx->tflags + 2, 0, 2 * sizeof(int), s));
     CK(cudaMemsetAsync(ctx->tflags + 5, 0, sizeof(int), s));
@@ -1246,9 +1322,29 @@ static int build_tiles(b200_ctx *ctx) {
       ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,           \
       ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags)
     // lj/cut: every ghost partner is stored (no scatter, no reverse halo); eam: FWD ghosts only
-    if (!eam) { if (one) TB(true, true); else TB(false, true); }
+    const size_t smem2 = build2_smem_bytes(ctx->tile_scap, rows, G.sbx, !one, ctx->tile_slots);
+    const double rs = eam2 ? std::max(0.0, std::sqrt(ctx->eam.cutforcesq) + ctx->eam2_margin * ctx->skin) : 0.0;
+#define TB2(ONE, FULL, SPL)                                                                            \
+  k_tile_build2<ONE, FULL, SPL><<<G.ntiles, B2_WARPS * 32, smem2, s>>>(                               \
+      G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p, ctx->tile_NI,      \
+      ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p, ctx->tl_num.p,          \
+      ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags, rs * rs,             \
+      eam2 ? ctx->tl_far.p : nullptr)
+    if (ctx->build2 && smem2 <= BUILD2_SMEM_MAX) {
+      if (eam2) TB2(true, true, true);
+      else if (!eam) { if (one) TB2(true, true, false); else TB2(false, true, false); }
+      else           { if (one) TB2(true, false, false); else TB2(false, false, false); }
+    } else if (eam2) {
+      // NEAR = partners stored within the force cutoff + a margin of the skin (kernels_eam2.cuh)
+      k_tile_build<true, true, true><<<G.ntiles, ctx->tile_threads, smem, s>>>(
+          G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,
+          ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,
+          ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags,
+          rs * rs, ctx->tl_far.p);
+    } else if (!eam) { if (one) TB(true, true); else TB(false, true); }
     else      { if (one) TB(true, false); else TB(false, false); }
 #undef TB
+#undef TB2
     ctx->launches++;
     LAUNCH_CHECK();
     ph_end(ctx, ph1);
@@ -1265,7 +1361,8 @@ static int build_tiles(b200_ctx *ctx) {
                        ctx->max_numneigh, ctx->one);
     if (ctx->tile_maxfull <= ctx->tile_slots) {
       ctx->tiles_active = true;
-      ctx->full_ghost = !eam;
+      ctx->full_ghost = !eam || eam2;
+      ctx->eam2_active = eam2;
       ctx->maxneigh = ctx->tile_slots;
       return B200_OK;
     }
@@ -1280,13 +1377,15 @@ static int build_list(b200_ctx *ctx) {
   // eam evaluates an expensive pair function: computing every owned-owned pair from both sides
   // costs more there than the Newton scatter it removes (profiles/r01g_probe_eam_*), so the
   // flat half list stays the default for it
-  const bool want_tiles = ctx->list_mode == 1 || (ctx->list_mode == 0 && ctx->pair_style == 1);
+  const bool want_tiles = ctx->list_mode == 1 ||
+                          (ctx->list_mode == 0 && (ctx->pair_style == 1 || (ctx->pair_style == 2 && eam2_usable(ctx))));
   if (ctx->use_tiles && want_tiles && nl > 0) {
     TRY(build_tiles(ctx));
     if (ctx->tiles_active) return B200_OK;
   }
   ctx->tiles_active = false;
   ctx->full_ghost = false;
+  ctx->eam2_active = false;
   if (ctx->maxneigh == 0) ctx->maxneigh = 96;
   for (int attempt = 0; attempt < 4; attempt++) {
     ctx->nstride = cdiv(std::max(nl, 1), 32) * 32;
@@ -1895,6 +1994,37 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag, int part = 0, bool 
     const int NI = ctx->tile_NI, slots = ctx->tile_slots, scap = ctx->tile_scap;
     if (ctx->pair_style == 1) {
       TRY(launch_tile_lj(ctx, s, eflag, nullptr, G.ntiles));
+    } else if (ctx->pair_style == 2 && ctx->eam2_active) {
+      // kernels_eam2.cuh: density + embedding, fp forward halo, force (+ fix nve when fused)
+      const int thr2 = std::max(32, std::min(352, cdiv(std::max(ctx->tile_maxown, 1), 32) * 32));
+      const size_t smr = eam2_smem_bytes(scap, false), smf = eam2_smem_bytes(scap, true);
+      const unsigned short *tf = ctx->tl_far.p;
+      const int *tg2 = ctx->tl_gi.p;
+#define ER(EV)                                                                                         \
+  k_tile_eam2_rho<EV, 352, 2><<<G.ntiles, thr2, smr, s>>>(nl, xt, ib, NI, slots, il, tn, tf, tg2, tl,  \
+                                                           ctx->eam, ctx->eam_one, ctx->rho, ctx->fp,   \
+                                                           ctx->ev, ctx->flags + 1, scap, ctx->tflags,  \
+                                                           nullptr, ctx->tile_hdrs.p)
+      if (eflag) ER(true); else ER(false);
+#undef ER
+      TRY(forward_scalar(ctx, ctx->fp));
+      NveFuse nv;
+      memset(&nv, 0, sizeof nv);
+      const bool fuse = ctx->fuse_now && !ev;
+      if (fuse)
+        nv = NveFuse{ctx->xt[c ^ 1], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->mask[c], ctx->mass_d.p,
+                     ctx->dtv, ctx->dtf, ctx->groupbit, ctx->fuse_check, ctx->xh[0], ctx->xh[1], ctx->xh[2],
+                     ctx->triggersq, ctx->flags};
+#define EF(EV, NVE)                                                                                      \
+  k_tile_eam2_force<EV, 352, 2, NVE><<<G.ntiles, thr2, smf, s>>>(nl, xt, ib, NI, slots, il, tn, tf, tg2, \
+                                                                  tl, ctx->eam, ctx->eam_one, ctx->fp, fx, \
+                                                                  fy, fz, ctx->ev, scap, ctx->tflags,      \
+                                                                  nullptr, nv, ctx->tile_hdrs.p)
+      if (fuse) EF(false, true);
+      else if (ev) EF(true, false);
+      else EF(false, false);
+#undef EF
+      ctx->launches += 2;
     } else if (ctx->pair_style == 2) {
       const size_t sm1 = tile_smem_bytes(scap, rows, G.sbx, false, false);
       const size_t sm3 = tile_smem_bytes(scap, rows, G.sbx, false, true);
@@ -2215,6 +2345,9 @@ int b200_create(b200_ctx **out, int device, int precision) {
     if (const char *e = getenv("B200_MIXED_FX")) ctx->mixed_fx = atoi(e) != 0;
     if (const char *e = getenv("B200_FUSE")) ctx->fuse_nve = atoi(e) != 0;
     if (const char *e = getenv("B200_FUSE_MIN")) ctx->fuse_min_atoms = atoi(e);
+    if (const char *e = getenv("B200_EAM2")) ctx->eam2 = strcmp(e, "auto") == 0 ? 2 : (atoi(e) != 0 ? 1 : 0);
+    if (const char *e = getenv("B200_BUILD2")) ctx->build2 = atoi(e) != 0;
+    if (const char *e = getenv("B200_EAM2_MARGIN")) ctx->eam2_margin = atof(e);
     if (const char *e = getenv("B200_LJ2F")) {
       int a[2];
       if (sscanf(e, "%d,%d", &a[0], &a[1]) == 2) { ctx->lj2f[0] = a[0]; ctx->lj2f[1] = a[1]; }
@@ -2273,7 +2406,7 @@ void b200_destroy(b200_ctx *ctx) {
   F(ctx->neigh.p);
   F(ctx->numneigh.p); F(ctx->lj_tab.p); F(ctx->eam_i.p); F(ctx->eam_d.p); F(ctx->eam_one_d.p); F(ctx->ev); F(ctx->ke7); F(ctx->flags);
   F(ctx->cnt64);
-  F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p); F(ctx->tl_gi.p); F(ctx->tile_hdrs.p);
+  F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p); F(ctx->tl_gi.p); F(ctx->tile_hdrs.p); F(ctx->tl_far.p);
   if (ctx->h_ev) cudaFreeHost(ctx->h_ev);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   for (auto &r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -2625,9 +2758,9 @@ static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt, bool allo
 // may this step's pair kernel carry fix nve (k_tile_lj2<..., NVE>)?  Static part of the answer;
 // the list kind is known only after the step's rebuild decision
 static bool fuse_candidate(const b200_ctx *ctx, int eflag, int vflag, bool allow_fuse) {
-  return allow_fuse && !eflag && !vflag && ctx->fuse_nve && ctx->have_nve && ctx->pair_style == 1 &&
-         (ctx->prec == B200_PREC_DOUBLE || ctx->mixed_fx) && ctx->use_lj2 && ctx->nlocal > 0 &&
-         (ctx->nranks > 1 || ctx->nlocal >= ctx->fuse_min_atoms);
+  const bool lj = ctx->pair_style == 1 && (ctx->prec == B200_PREC_DOUBLE || ctx->mixed_fx) && ctx->use_lj2;
+  return allow_fuse && !eflag && !vflag && ctx->fuse_nve && ctx->have_nve && (lj || eam2_usable(ctx)) &&
+         ctx->nlocal > 0 && (ctx->nranks > 1 || ctx->nlocal >= ctx->fuse_min_atoms);
 }
 
 static int graph_step(b200_ctx *ctx) {
@@ -2678,7 +2811,7 @@ static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt, bool allo
   int nflag = 0;
   TRY(decide(ctx, &nflag));
   if (nflag) TRY(reneighbor(ctx));
-  const bool fuse = fcand && ctx->tiles_active && ctx->full_ghost;
+  const bool fuse = fcand && ctx->tiles_active && ctx->full_ghost && (ctx->pair_style == 1 || ctx->eam2_active);
   if (fuse) {
     ctx->fuse_check = check_due_next(ctx) ? 1 : 0;  // for the NEXT step's decide()
     if (ctx->fuse_check) CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
@@ -2859,6 +2992,8 @@ int b200_set_option(b200_ctx *ctx, const char *key, const char *value) {
   else if (k == "graph") ctx->use_graph = yes();
   else if (k == "mixed_fx") ctx->mixed_fx = yes();
   else if (k == "fuse") ctx->fuse_nve = yes();
+  else if (k == "eam2") { ctx->eam2 = v == "auto" ? 2 : (yes() ? 1 : 0); ctx->geom_ready = false; }
+  else if (k == "build2") ctx->build2 = yes();
   else if (k == "tpa") {
     const int t = atoi(value);
     if (t != 1 && t != 2 && t != 4 && t != 8) return ctx->fail(B200_EARG, "package b200 tpa: 1, 2, 4 or 8");
@@ -2941,7 +3076,8 @@ int b200_get_neighbor_list(b200_ctx *ctx, int *numneigh, int *neigh, int64_t cap
     const size_t sm = TILE_HDR_BYTES + (size_t)ctx->tile_scap * sizeof(int);
     k_tile_export<<<G.ntiles, 256, sm, ctx->stream>>>(G, nl, ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p,
                                                      ctx->tile_NI, ctx->tile_slots, ctx->tl_num.p,
-                                                     ctx->tl_list.p, dfirst, dflat, ctx->tile_scap);
+                                                     ctx->tl_list.p, dfirst, dflat, ctx->tile_scap,
+                                                     ctx->eam2_active ? ctx->tl_far.p : nullptr);
   } else
     k_export_csr<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->nstride, ctx->tpa, ctx->numneigh.p,
                                                          ctx->neigh.p, dfirst, dflat);

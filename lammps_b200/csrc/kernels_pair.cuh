@@ -341,8 +341,10 @@ __global__ void __launch_bounds__(128) k_eam_rho_one(int nlocal, int nstride,
         m = min(m, P.nr - 1);
         p -= m;
         p = fmin(p, 1.0);
-        const double2 a = __ldg(F.rho4 + 2 * m), b = __ldg(F.rho4 + 2 * m + 1);
-        const double rj = ((a.x * p + a.y) * p + b.x) * p + b.y;
+        // one 32-byte record per knot, one LDG.256: a scattered load costs the L1 data pipe a
+        // wavefront per lane whatever its width (profiles/r02z_ncu_eam.txt)
+        const double4 a = ld_xt(reinterpret_cast<const double4 *>(F.rho4 + 2 * m));
+        const double rj = ((a.x * p + a.y) * p + a.z) * p + a.w;
         rhoi += rj;
         atomicAdd(&rho[j], rj);
       }
@@ -381,11 +383,11 @@ __global__ void __launch_bounds__(128) k_eam_force_one(
         m = min(m, P.nr - 1);
         p -= m;
         p = fmin(p, 1.0);
-        const double2 *c = F.frc8 + 4 * m;
-        const double2 q0 = __ldg(c), q1 = __ldg(c + 1), q2 = __ldg(c + 2), q3 = __ldg(c + 3);
-        const double rhop = P.rdr * ((3.0 * q0.x * p + 2.0 * q0.y) * p + q1.x);   // rhoip == rhojp
-        const double z2p = P.rdr * ((3.0 * q2.x * p + 2.0 * q2.y) * p + q3.x);
-        const double z2 = ((q2.x * p + q2.y) * p + q3.x) * p + q3.y;
+        const double4 *c = reinterpret_cast<const double4 *>(F.frc8 + 4 * m);  // two LDG.256
+        const double4 qa = ld_xt(c), qb = ld_xt(c + 1);
+        const double rhop = P.rdr * ((3.0 * qa.x * p + 2.0 * qa.y) * p + qa.z);   // rhoip == rhojp
+        const double z2p = P.rdr * ((3.0 * qb.x * p + 2.0 * qb.y) * p + qb.z);
+        const double z2 = ((qb.x * p + qb.y) * p + qb.z) * p + qb.w;
         const double phi = z2 * recip;
         const double phip = z2p * recip - phi * recip;
         const double psip = fpi * rhop + fp[j] * rhop + phip;

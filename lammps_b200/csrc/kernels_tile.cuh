@@ -416,14 +416,22 @@ __global__ void __launch_bounds__(256) k_tile_split(int ntiles, const int *__res
 // ghosts nor a reverse halo (lj/cut on tiles).  The FWD entries are unchanged: still exactly the
 // reference's half/Newton-on list.  Without FULLGHOST (eam on tiles) only FWD ghosts are stored
 // and the pair kernels scatter onto them.
-template <bool ONETYPE, bool FULLGHOST>
+// SPLIT (eam on tiles, kernels_eam2.cuh): a row is filled from both ends.  Partners whose distance
+// at build time is <= sqrt(splitsq) (force cutoff + a margin) are the NEAR entries, words 0, 1, ...
+// as before; the others are the FAR entries, stored from the last word of the row downwards
+// (far entry f lives in word maxslots/8 - 1 - f/8), tfar[g] counts them, tnum[g] stays the total.
+// The pair kernels evaluate the near entries unconditionally and the far ones behind a cutoff
+// test that almost never fires, so that a warp does not run the expensive eam pair function for
+// the ~30 % of the stored partners that sit in the skin.  The SET of entries is unchanged.
+template <bool ONETYPE, bool FULLGHOST, bool SPLIT = false>
 __global__ void __launch_bounds__(512) k_tile_build(
     TileGeom G, FullStencil F, int nlocal, const double4 *__restrict__ xt,
     const int *__restrict__ ostart, const int *__restrict__ gstart,
     const int *__restrict__ atombin, const int *__restrict__ tile_ibase, int NI, int maxslots,
     double cut1, const double *__restrict__ cutneighsq, int ntypes,
     unsigned short *__restrict__ iloc, unsigned short *__restrict__ tnum, int *__restrict__ tgi,
-    uint4 *__restrict__ list, int *__restrict__ numneigh_half, int scap, int *__restrict__ tflags) {
+    uint4 *__restrict__ list, int *__restrict__ numneigh_half, int scap, int *__restrict__ tflags,
+    double splitsq = 0.0, unsigned short *__restrict__ tfar = nullptr) {
   extern __shared__ __align__(128) unsigned char tsm[];
   TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
   const TileS T = tile_carve(tsm, scap, false);
@@ -473,24 +481,38 @@ __global__ void __launch_bounds__(512) k_tile_build(
       const double *cut_i = ONETYPE ? nullptr : cutneighsq + (size_t)T.type[li] * n1;
       const int b = atombin[gi];
       const int bx = b % G.mbin[0], by = (b / G.mbin[0]) % G.mbin[1], bz = b / (G.mbin[0] * G.mbin[1]);
-      unsigned long long qlo = 0, qhi = 0;
-      auto push = [&](int s, unsigned flags) {
+      unsigned long long qlo = 0, qhi = 0, flo = 0, fhi = 0;
+      int nfar = 0;  // SPLIT: far entries so far (n counts the near ones until the row is done)
+      const int W = maxslots >> 3;
+      auto push = [&](int s, unsigned flags, bool isfar) {
         const unsigned long long e = (unsigned)s | flags;
+        nf += flags >> 15;
+        if (SPLIT && isfar) {
+          flo = (flo >> 16) | (fhi << 48);
+          fhi = (fhi >> 16) | (e << 48);
+          nfar++;
+          if ((nfar & 7) == 0 && (nfar >> 3) <= W)
+            list[(size_t)(W - (nfar >> 3)) * NI + g] = make_uint4((unsigned)flo, (unsigned)(flo >> 32),
+                                                                (unsigned)fhi, (unsigned)(fhi >> 32));
+          return;
+        }
         qlo = (qlo >> 16) | (qhi << 48);
         qhi = (qhi >> 16) | (e << 48);
         n++;
-        nf += flags >> 15;
         if ((n & 7) == 0 && n <= maxslots)
           list[(size_t)((n >> 3) - 1) * NI + g] = make_uint4((unsigned)qlo, (unsigned)(qlo >> 32),
                                                            (unsigned)qhi, (unsigned)(qhi >> 32));
       };
-      auto near = [&](int s) -> bool {  // the reference's test: rsq <= cutneighsq[itype][jtype]
+      auto dist = [&](int s) -> double {  // rsq in the reference's operation order
         const double3 pj = tile_pos3(T, s);
-        const double rsq = rsq_ref(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-        return rsq <= (ONETYPE ? cut1 : __ldg(cut_i + T.type[s]));
+        return rsq_ref(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+      };
+      auto cutof = [&](int s) -> double {  // the reference's test: rsq <= cutneighsq[itype][jtype]
+        return ONETYPE ? cut1 : __ldg(cut_i + T.type[s]);
       };
       auto test = [&](int s, unsigned flags) {
-        if (near(s)) push(s, flags);
+        const double rsq = dist(s);
+        if (rsq <= cutof(s)) push(s, flags, rsq > splitsq);
       };
       // a run of consecutive staged atoms with the same flags: two distance tests in flight
       // (four were measured slower: 2.71 vs 2.57 ms per build at 4 M atoms)
@@ -498,9 +520,9 @@ __global__ void __launch_bounds__(512) k_tile_build(
       auto run = [&](int lo, int hi, unsigned flags) {
         int s = lo;
         for (; s + 1 < hi; s += 2) {
-          const bool a = near(s), b = near(s + 1);
-          if (a) push(s, flags);
-          if (b) push(s + 1, flags);
+          const double ra = dist(s), rb = dist(s + 1);
+          if (ra <= cutof(s)) push(s, flags, ra > splitsq);
+          if (rb <= cutof(s + 1)) push(s + 1, flags, rb > splitsq);
         }
         if (s < hi) test(s, flags);
       };
@@ -546,11 +568,27 @@ __global__ void __launch_bounds__(512) k_tile_build(
         list[(size_t)(n >> 3) * NI + g] = make_uint4((unsigned)qlo, (unsigned)(qlo >> 32),
                                                    (unsigned)qhi, (unsigned)(qhi >> 32));
       }
+      if (SPLIT) {
+        if ((nfar & 7) && (nfar >> 3) < W) {
+          for (int k = nfar & 7; k < 8; k++) {
+            flo = (flo >> 16) | (fhi << 48);
+            fhi = (fhi >> 16) | ((unsigned long long)S << 48);
+          }
+          list[(size_t)(W - 1 - (nfar >> 3)) * NI + g] = make_uint4((unsigned)flo, (unsigned)(flo >> 32),
+                                                                 (unsigned)fhi, (unsigned)(fhi >> 32));
+        }
+        tfar[g] = (unsigned short)min(nfar, 65535);
+        // slots the row needs: whole words from both ends (the host grows maxslots to this)
+        const int need = (((n + 7) >> 3) + ((nfar + 7) >> 3)) << 3;
+        n += nfar;
+        wmax = max(wmax, need);
+      }
       iloc[g] = (unsigned short)li;
       tgi[g] = gi;
       numneigh_half[gi] = nf;
     } else {
       iloc[g] = (unsigned short)TILE_NOATOM;
+      if (SPLIT) tfar[g] = 0;
     }
     tnum[g] = (unsigned short)min(n, 65535);
     wmax = max(wmax, n);
@@ -572,7 +610,7 @@ __global__ void __launch_bounds__(512) k_tile_export(
     TileGeom G, int nlocal, const int *__restrict__ ostart, const int *__restrict__ gstart,
     const int *__restrict__ tile_ibase, int NI, int maxslots, const unsigned short *__restrict__ tnum,
     const uint4 *__restrict__ list, const long long *__restrict__ first, int *__restrict__ flat,
-    int scap) {
+    int scap, const unsigned short *__restrict__ tfar = nullptr) {
   extern __shared__ __align__(128) unsigned char tsm[];
   TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
   int *gmap = reinterpret_cast<int *>(tsm + TILE_HDR_BYTES);
@@ -593,8 +631,12 @@ __global__ void __launch_bounds__(512) k_tile_export(
     tile_own_atom(G, H, ti, gi);
     const int n = min((int)tnum[g], maxslots);
     long long o = first[gi];
-    for (int k = 0; k < n; k++) {
-      const uint4 q = list[(size_t)(k >> 3) * NI + g];
+    // (SPLIT rows: the last tfar[g] entries are stored from the end of the row downwards)
+    const int nfar = tfar ? min((int)tfar[g], n) : 0, W = maxslots >> 3;
+    for (int kk = 0; kk < n; kk++) {
+      const bool far = kk >= n - nfar;
+      const int k = far ? kk - (n - nfar) : kk;
+      const uint4 q = list[(size_t)(far ? W - 1 - (k >> 3) : (k >> 3)) * NI + g];
       const unsigned w = (k & 4) ? ((k & 2) ? q.w : q.z) : ((k & 2) ? q.y : q.x);
       const unsigned e = (w >> ((k & 1) * 16)) & 0xffffu;
       if (e & TILE_FWD) flat[o++] = gmap[e & TILE_IDX];

@@ -89,7 +89,9 @@ void VerletB200::init()
   thermo_on_device = 1;
   for (auto &c : modify->get_compute_list()) {
     const std::string style = c->style;
-    if (style == "temp/b200" || style == "pe" || style == "pressure") continue;
+    if (style == "temp/b200" || style == "pe" || style == "pressure" || style == "pe/b200" ||
+        style == "pressure/b200")
+      continue;
     thermo_on_device = 0;
   }
   for (auto &c : modify->get_compute_list())
