@@ -174,6 +174,15 @@ int b200_get_neighbor_list(b200_ctx *ctx, int *numneigh /*[nlocal]*/, int *neigh
 /*      EAM intermediates rho[], fp[] (pair_eam.h) for owned(+ghost) atoms */
 int b200_get_eam_rho_fp(b200_ctx *ctx, int with_ghosts, double *rho, double *fp);
 
+/* ---- per-atom energy / virial of the pair style: Pair::ev_tally's eatom[] and vatom[][6]
+ *      (pair.cpp:1087-1182, order xx,yy,zz,xy,xz,yz; what compute pe/atom and stress/atom read,
+ *      and what the reference's pair unit test requests, test_pair_style.cpp:143).  With Newton
+ *      on each atom of a pair receives half of the pair term; ghost shares are returned to their
+ *      owners (ComputePEAtom's reverse_comm).  nlocal values in current device order, like
+ *      b200_get_atoms.  Call right after a setup/step that tallied (eflag or vflag set); either
+ *      pointer may be NULL.  Collective over the sub-domains of a multi-GPU run. */
+int b200_pair_peratom(b200_ctx *ctx, double *eatom /*[nlocal]*/, double *vatom /*[nlocal][6]*/);
+
 /* ---- per-phase device timing (CUDA events recorded on the context's stream around each
  *      phase inside b200_run; replaces Timer::stamp of verlet.cpp:257-357).  Off by default. */
 enum {
@@ -235,6 +244,7 @@ int b200_group_set_atoms(b200_group *g, int n, int ntypes, const double *mass, c
                          const double *v, const int *type, const int *tag, const int *mask,
                          const int *image);
 int b200_group_count(b200_group *g, int *nlocal_total, int *nghost_total);
+int b200_group_pair_peratom(b200_group *g, double *eatom, double *vatom);
 int b200_group_get_atoms(b200_group *g, double *x, double *v, double *f, int *type, int *tag,
                          int *mask, int *image);
 int b200_group_setup(b200_group *g, int eflag, int vflag);

@@ -25,6 +25,7 @@
 #include "kernels_tile2.cuh"
 #include "kernels_eam2.cuh"
 #include "kernels_build2.cuh"
+#include "kernels_peratom.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -225,6 +226,7 @@ struct b200_ctx {
   bool eam2_active = false;     // the current list was built for those kernels
   double eam2_margin = 0.35;    // NEAR = stored within force cutoff + eam2_margin * skin (B200_EAM2_MARGIN)
   DBuf<unsigned short> tl_far;  // FAR entries per row (SPLIT rows)
+  DBuf<double> peratom;         // b200_pair_peratom: eatom + 6 vatom arrays over owned (+ ghost) atoms
   int lj2f[2] = {256, 4};       // k_tile_lj2f (mixed): threads, CTAs per SM (B200_LJ2F=threads,minb)
   DBuf<uint4> tl_list;
   int *tflags = nullptr;  // [8] device: max staged, max owned/tile, max entries, max FWD, owned total, overflow
@@ -1174,6 +1176,8 @@ static int tile_kernel_attrs(b200_ctx *ctx) {
   TRY(tile_attr(ctx, (k_tile_build<false, false>)));
   TRY(tile_attr(ctx, (k_tile_build<true, true, true>)));
   TRY(tile_attr(ctx, k_tile_export));
+  TRY(tile_attr(ctx, k_peratom_tile<1>));
+  TRY(tile_attr(ctx, k_peratom_tile<2>));
   // (k_tile_build2 also has 256 bytes of static shared memory: the opt-in limit covers both)
 #define B2A(K) CK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BUILD2_SMEM_MAX))
   B2A((k_tile_build2<true, true, false>));
@@ -2406,7 +2410,7 @@ void b200_destroy(b200_ctx *ctx) {
   F(ctx->neigh.p);
   F(ctx->numneigh.p); F(ctx->lj_tab.p); F(ctx->eam_i.p); F(ctx->eam_d.p); F(ctx->eam_one_d.p); F(ctx->ev); F(ctx->ke7); F(ctx->flags);
   F(ctx->cnt64);
-  F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p); F(ctx->tl_gi.p); F(ctx->tile_hdrs.p); F(ctx->tl_far.p);
+  F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p); F(ctx->tl_gi.p); F(ctx->tile_hdrs.p); F(ctx->tl_far.p); F(ctx->peratom.p);
   if (ctx->h_ev) cudaFreeHost(ctx->h_ev);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   for (auto &r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -3098,6 +3102,82 @@ int b200_get_eam_rho_fp(b200_ctx *ctx, int with_ghosts, double *rho, double *fp)
   return B200_OK;
 }
 
+// Per-atom energy and virial of the pair style for the positions, list and (eam) fp in force:
+// Pair::ev_tally's eatom / vatom (pair.cpp:1087-1182).  Call after a step or setup that tallied
+// (eflag/vflag set: then final_integrate has run and nothing is pending).  Collective over the
+// sub-domains when the list is a half list (the ghost shares travel back by the reverse halo).
+int b200_pair_peratom(b200_ctx *ctx, double *eatom, double *vatom) {
+  if (!ctx) return B200_EARG;
+  if (!ctx->setup_done) return ctx->fail(B200_EARG, "b200_pair_peratom before b200_setup");
+  if (ctx->ahead || ctx->pending_final)
+    return ctx->fail(B200_EARG, "per-atom tallies need a step that tallied (eflag/vflag) just before");
+  if (ctx->tiles_active && !ctx->full_ghost)
+    return ctx->fail(B200_EARG, "per-atom tallies are not available on the first-generation eam tile list");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const int nl = ctx->nlocal, ng = ctx->nghost, c = ctx->cur;
+  const bool flat = !ctx->tiles_active;
+  const size_t na = (size_t)std::max(flat ? nl + ng : nl, 1);
+  TRY(reserve(ctx, ctx->peratom, 7 * na));
+  PerAtomOut out;
+  out.e = ctx->peratom.p;
+  for (int k = 0; k < 6; k++) out.v[k] = ctx->peratom.p + (size_t)(1 + k) * na;
+  if (flat) CK(cudaMemsetAsync(ctx->peratom.p, 0, sizeof(double) * 7 * na, s));
+  const int st = ctx->pair_style;
+  if (st != 1 && st != 2) return ctx->fail(B200_EARG, "no pair style set");
+  if (nl > 0) {
+    if (flat) {
+      if (st == 1)
+        k_peratom_flat<1><<<cdiv(nl, 128), 128, 0, s>>>(nl, ctx->nstride, ctx->tpa, ctx->xt[c], nullptr,
+                                                        ctx->numneigh.p, ctx->neigh.p, ctx->lj_tab.p, ctx->eam,
+                                                        ctx->ntypes, out);
+      else
+        k_peratom_flat<2><<<cdiv(nl, 128), 128, 0, s>>>(nl, ctx->nstride, ctx->tpa, ctx->xt[c], ctx->fp,
+                                                        ctx->numneigh.p, ctx->neigh.p, nullptr, ctx->eam,
+                                                        ctx->ntypes, out);
+    } else {
+      const TileGeom &G = ctx->tg;
+      const size_t sm = tile_smem_bytes(ctx->tile_scap, G.srow_y * G.srow_z, G.sbx, false, true);
+      const int thr = std::max(32, std::min(352, cdiv(std::max(ctx->tile_maxown, 1), 32) * 32));
+      const unsigned short *tf = ctx->eam2_active ? ctx->tl_far.p : nullptr;
+      if (st == 1)
+        k_peratom_tile<1><<<G.ntiles, thr, sm, s>>>(G, nl, ctx->xt[c], nullptr, ctx->ostart.p, ctx->gstart.p,
+                                                    ctx->tile_ibase.p, ctx->tile_NI, ctx->tile_slots,
+                                                    ctx->tl_iloc.p, ctx->tl_num.p, tf, ctx->tl_list.p,
+                                                    ctx->lj_tab.p, ctx->eam, ctx->ntypes, out, ctx->tile_scap);
+      else
+        k_peratom_tile<2><<<G.ntiles, thr, sm, s>>>(G, nl, ctx->xt[c], ctx->fp, ctx->ostart.p, ctx->gstart.p,
+                                                    ctx->tile_ibase.p, ctx->tile_NI, ctx->tile_slots,
+                                                    ctx->tl_iloc.p, ctx->tl_num.p, tf, ctx->tl_list.p,
+                                                    nullptr, ctx->eam, ctx->ntypes, out, ctx->tile_scap);
+    }
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  if (flat)  // every sub-domain walks the same halos, even one without atoms
+    for (int k = 0; k < 7; k++) {
+      Vec3Ptr a{{ctx->peratom.p + (size_t)k * na, nullptr, nullptr}};
+      TRY(reverse_halo<1>(ctx, a));
+    }
+  if (st == 2 && nl > 0) {
+    k_peratom_embed<<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], ctx->eam, ctx->rho, out.e);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  CK(cudaStreamSynchronize(s));
+  if (nl > 0) {
+    if (eatom) CK(cudaMemcpy(eatom, out.e, sizeof(double) * nl, cudaMemcpyDeviceToHost));
+    if (vatom) {
+      std::vector<double> h((size_t)6 * nl);
+      for (int k = 0; k < 6; k++)
+        CK(cudaMemcpy(h.data() + (size_t)k * nl, out.v[k], sizeof(double) * nl, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < nl; i++)
+        for (int k = 0; k < 6; k++) vatom[(size_t)i * 6 + k] = h[(size_t)k * nl + i];
+    }
+  }
+  return B200_OK;
+}
+
 int b200_set_profiling(b200_ctx *ctx, int on) {
   if (!ctx) return B200_EARG;
   ph_collect(ctx);
@@ -3415,6 +3495,15 @@ int b200_group_get_atoms(b200_group *g, double *x, double *v, double *f, int *ty
     return b200_get_atoms(g->ctx[i], 0, x ? x + 3 * o : nullptr, v ? v + 3 * o : nullptr, f ? f + 3 * o : nullptr,
                           type ? type + o : nullptr, tag ? tag + o : nullptr, mask ? mask + o : nullptr,
                           image ? image + o : nullptr);
+  });
+}
+
+int b200_group_pair_peratom(b200_group *g, double *eatom, double *vatom) {
+  if (!g) return B200_EARG;
+  std::vector<size_t> off(g->n + 1, 0);
+  for (int i = 0; i < g->n; i++) off[i + 1] = off[i] + g->ctx[i]->nlocal;
+  return group_run(g, [&](int i) {
+    return b200_pair_peratom(g->ctx[i], eatom ? eatom + off[i] : nullptr, vatom ? vatom + 6 * off[i] : nullptr);
   });
 }
 
