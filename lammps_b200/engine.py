@@ -29,7 +29,8 @@ EXPORTS = [
     "b200_run", "b200_step", "b200_last_run_ms", "b200_initial_integrate", "b200_final_integrate", "b200_decide",
     "b200_forward_comm", "b200_reverse_comm", "b200_reneighbor", "b200_force_clear",
     "b200_pair_compute", "b200_get_tallies", "b200_ke_sum", "b200_get_stats",
-    "b200_get_neighbor_list", "b200_get_eam_rho_fp", "b200_set_profiling",
+    "b200_get_neighbor_list", "b200_get_eam_rho_fp", "b200_pair_peratom", "b200_group_pair_peratom",
+    "b200_set_profiling",
     "b200_get_phase_times", "b200_comm_unique_id", "b200_comm_init", "b200_neighbor_ranks",
     "b200_group_create", "b200_group_destroy", "b200_group_last_error", "b200_group_size",
     "b200_group_context", "b200_group_auto_grid", "b200_group_set_grid", "b200_group_set_atoms",
@@ -306,6 +307,14 @@ class Engine:
         self._chk(self.L.b200_get_eam_rho_fp(self.h, C.c_int(1 if ghosts else 0), _p(rho), _p(fp)))
         return rho, fp
 
+    def pair_peratom(self):
+        """Pair::ev_tally's eatom[nlocal], vatom[nlocal][6] (xx,yy,zz,xy,xz,yz) in device order;
+        call right after a setup/step that tallied"""
+        nl, _ = self.counts()
+        e, v = np.zeros(nl), np.zeros((nl, 6))
+        self._chk(self.L.b200_pair_peratom(self.h, _p(e), _p(v)))
+        return e, v
+
     def profiling(self, on=True):
         self._chk(self.L.b200_set_profiling(self.h, C.c_int(1 if on else 0)))
 
@@ -458,6 +467,13 @@ class EngineGroup:
         self._chk(self.L.b200_group_get_atoms(self.g, g("x"), g("v"), g("f"), g("type"), g("tag"),
                                               g("mask"), g("image")))
         return out
+
+    def pair_peratom(self):
+        """eatom[n], vatom[n][6] of all sub-domains, in the order get_atoms returns the atoms"""
+        n, _ = self.counts()
+        e, v = np.zeros(n), np.zeros((n, 6))
+        self._chk(self.L.b200_group_pair_peratom(self.g, _p(e), _p(v)))
+        return e, v
 
     def tallies(self):
         e = C.c_double(0)

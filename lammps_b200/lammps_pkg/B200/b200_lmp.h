@@ -22,6 +22,8 @@ class B200PairStyle {
  public:
   virtual ~B200PairStyle() noexcept(false) {}
   virtual int b200_upload(b200_ctx *ctx) = 0;
+  // Pair::ev_setup (protected): allocate and zero eatom / vatom for the atoms now on the host
+  virtual void b200_ev_setup(int eflag, int vflag) = 0;
 };
 
 // marker for the time-integration fix verlet/b200 knows how to run on the device

@@ -163,6 +163,11 @@ void FixB200::dev_tallies(double *eng_vdwl, double *virial)
   check(grp ? b200_group_get_tallies(grp, eng_vdwl, virial) : b200_get_tallies(ctx, eng_vdwl, virial), FLERR);
 }
 
+void FixB200::dev_peratom(double *eatom, double *vatom)
+{
+  check(grp ? b200_group_pair_peratom(grp, eatom, vatom) : b200_pair_peratom(ctx, eatom, vatom), FLERR);
+}
+
 void FixB200::dev_ke(int groupbit, double *mv2, double *tensor)
 {
   check(grp ? b200_group_ke_group(grp, groupbit, mv2, tensor) : b200_ke_group(ctx, groupbit, mv2, tensor),

@@ -46,6 +46,7 @@ class FixB200 : public Fix {
   void dev_setup(int eflag, int vflag);
   void dev_step(int eflag, int vflag, int *rebuilt);
   void dev_tallies(double *eng_vdwl, double *virial);
+  void dev_peratom(double *eatom, double *vatom);    // Pair::ev_tally's eatom / vatom, download order
   void dev_ke(int groupbit, double *mv2, double *tensor);
   void dev_counts(int *nlocal, int *nghost);
   void dev_stats(b200_stats *st);

@@ -27,6 +27,7 @@ class PairEAMB200 : public PairEAM, public B200PairStyle {
   void compute(int, int) override;
   void init_style() override;
   int b200_upload(b200_ctx *ctx) override;
+  void b200_ev_setup(int eflag, int vflag) override { ev_setup(eflag, vflag); }
 };
 
 // setfl / Finnis-Sinclair files: same device kernels, other file reader (PairEAM::fileformat)

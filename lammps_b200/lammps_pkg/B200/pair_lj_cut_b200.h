@@ -24,6 +24,7 @@ class PairLJCutB200 : public PairLJCut, public B200PairStyle {
   void compute(int, int) override;
   void init_style() override;
   int b200_upload(b200_ctx *ctx) override;
+  void b200_ev_setup(int eflag, int vflag) override { ev_setup(eflag, vflag); }
 };
 
 }    // namespace LAMMPS_NS

@@ -190,14 +190,36 @@ void VerletB200::fetch_tallies()
   pair->eng_coul = 0.0;
 }
 
-// compute pe/atom, stress/atom, centroid/stress/atom ask the pair style for per-atom tallies
-// (Pair::ev_tally eatom/vatom, pair.cpp:1087-1182): the device kernels do not keep them, and
-// handing back zeros would be silently wrong
+// compute centroid/stress/atom asks for Pair::cvatom (pair.cpp:1200-1350), which the device does
+// not compute: handing back zeros would be silently wrong
 void VerletB200::refuse_per_atom_tallies()
 {
-  if ((eflag & ENERGY_ATOM) || (vflag & (VIRIAL_ATOM | VIRIAL_CENTROID)))
-    error->all(FLERR, "run_style verlet/b200 does not provide per-atom energy or virial "
-                      "(compute pe/atom, stress/atom and friends need the CPU pair styles)");
+  if (vflag & VIRIAL_CENTROID)
+    error->all(FLERR, "run_style verlet/b200 does not provide the per-atom centroid virial "
+                      "(compute centroid/stress/atom needs the CPU pair styles)");
+}
+
+/* ----------------------------------------------------------------------
+   compute pe/atom, stress/atom and friends read Pair::eatom / Pair::vatom
+   (Pair::ev_tally, pair.cpp:1087-1182).  On a step that asks for them the
+   device computes both for its owned atoms (b200_pair_peratom: each atom's
+   half of every pair term, ghost shares already returned to their owners)
+   and they are stored in the pair style's own arrays, in the order the atoms
+   were just downloaded in.  The computes then run unchanged; their reverse
+   communication (ComputePEAtom::compute_peratom) needs the host's swap
+   lists to describe the current atoms, hence the borders() call: the host
+   ghosts it creates carry zeros.
+------------------------------------------------------------------------- */
+
+void VerletB200::fill_per_atom_tallies()
+{
+  if (!(eflag & ENERGY_ATOM) && !(vflag & VIRIAL_ATOM)) return;
+  Pair *pair = force->pair;
+  if (pkg->host_stale) download(0);
+  comm->borders();
+  bpair->b200_ev_setup(eflag, vflag);
+  pkg->dev_peratom((eflag & ENERGY_ATOM) ? pair->eatom : nullptr,
+                   (vflag & VIRIAL_ATOM) ? &pair->vatom[0][0] : nullptr);
 }
 
 /* ---------------------------------------------------------------------- */
@@ -235,6 +257,7 @@ void VerletB200::device_setup(int flag, int output_flag)
   pkg->dev_setup(eflag ? 1 : 0, vflag ? 1 : 0);
   resident = 1;
   download(0);
+  fill_per_atom_tallies();
   if (eflag || vflag) fetch_tallies();
   neighbor->ncalls = 0;
   neighbor->ndanger = 0;
@@ -337,6 +360,7 @@ void VerletB200::run(int n)
       const bool need_atoms = !thermo_on_device || ntimestep == output->next_dump_any ||
           ntimestep == output->next_restart;
       if (need_atoms) download(0);
+      fill_per_atom_tallies();
       if (eflag || vflag) fetch_tallies();
       if (!by_stage) timer->stamp(Timer::PAIR);
       output->write(ntimestep);

@@ -43,6 +43,7 @@ class VerletB200 : public Verlet {
   void device_setup(int flag, int output_flag);
   void publish_neighbor_stats();
   void refuse_per_atom_tallies();
+  void fill_per_atom_tallies();   // Pair::eatom / vatom <- device on steps that ask for them
   void step_by_stage(int eflag, int vflag);    // `package b200 profile yes`: Timer breakdown
 };
 

@@ -843,6 +843,94 @@ void orc_pair_compute(Orc *o, int eflag, int vflag) {
   else die("no pair style");
 }
 
+/* Per-atom energy and virial of the pair style for the positions, list and (eam) rho/fp in force:
+ * Pair::ev_tally with eflag_atom / vflag_atom and newton_pair on (pair.cpp:1087-1182: half of the
+ * pair energy and of del (x) del * fpair to each atom of the pair, ghosts included), the embedding
+ * energy of PairEAM::compute (pair_eam.cpp:219-231: eatom[i] += phi), then the reverse
+ * communication that ComputePEAtom / ComputeStressAtom apply (compute_pe_atom.cpp:141-145,
+ * compute_stress_atom.cpp:349-356: ghost shares are summed into their owners, last swap first).
+ * eatom[nlocal], vatom[nlocal][6] in the order xx,yy,zz,xy,xz,yz; call after a compute with eflag. */
+void orc_pair_peratom(Orc *o, double *eatom_out, double *vatom_out) {
+  int n1 = o->ntypes + 1, nall = o->nlocal + o->nghost;
+  double *x = o->x;
+  double *t = (double *)calloc((size_t)MAX(nall, 1) * 7, sizeof(double)); /* [nall][7]: e, v[6] */
+  for (int i = 0; i < o->inum; i++) {
+    double xtmp = x[3 * i], ytmp = x[3 * i + 1], ztmp = x[3 * i + 2];
+    int itype = o->type[i];
+    const int *jlist = &o->neigh[o->firstneigh[i]];
+    for (int jj = 0; jj < o->numneigh[i]; jj++) {
+      int j = jlist[jj] & 0x1FFFFFFF;
+      double delx = xtmp - x[3 * j], dely = ytmp - x[3 * j + 1], delz = ztmp - x[3 * j + 2];
+      double rsq = delx * delx + dely * dely + delz * delz;
+      int jtype = o->type[j];
+      double evdwl, fpair;
+      if (o->pair_style == 1) {
+        int tij = itype * n1 + jtype;
+        if (!(rsq < o->cutsq[tij])) continue;
+        double r2inv = 1.0 / rsq;
+        double r6inv = r2inv * r2inv * r2inv;
+        double forcelj = r6inv * (o->lj1[tij] * r6inv - o->lj2[tij]);
+        fpair = forcelj * r2inv;
+        evdwl = r6inv * (o->lj3[tij] * r6inv - o->lj4[tij]) - o->offset[tij];
+      } else {
+        if (!(rsq < o->cutforcesq)) continue;
+        int nr = o->nr;
+        double r = sqrt(rsq);
+        double p = r * o->rdr + 1.0;
+        int m = (int)p;
+        m = MIN(m, nr - 1);
+        p -= m;
+        p = MIN(p, 1.0);
+        const double *c = &o->rhor_spline[((size_t)o->type2rhor[itype * n1 + jtype] * (nr + 1) + m) * 7];
+        double rhoip = (c[0] * p + c[1]) * p + c[2];
+        c = &o->rhor_spline[((size_t)o->type2rhor[jtype * n1 + itype] * (nr + 1) + m) * 7];
+        double rhojp = (c[0] * p + c[1]) * p + c[2];
+        c = &o->z2r_spline[((size_t)o->type2z2r[itype * n1 + jtype] * (nr + 1) + m) * 7];
+        double z2p = (c[0] * p + c[1]) * p + c[2];
+        double z2 = ((c[3] * p + c[4]) * p + c[5]) * p + c[6];
+        double recip = 1.0 / r;
+        double phi = z2 * recip;
+        double phip = z2p * recip - phi * recip;
+        double psip = o->fp[i] * rhojp + o->fp[j] * rhoip + phip;
+        fpair = -o->scale[itype * n1 + jtype] * psip * recip;
+        evdwl = o->scale[itype * n1 + jtype] * phi;
+      }
+      double v[6] = {delx * delx * fpair, dely * dely * fpair, delz * delz * fpair,
+                     delx * dely * fpair, delx * delz * fpair, dely * delz * fpair};
+      t[7 * i] += 0.5 * evdwl;
+      t[7 * j] += 0.5 * evdwl;
+      for (int k = 0; k < 6; k++) {
+        t[7 * i + 1 + k] += 0.5 * v[k];
+        t[7 * j + 1 + k] += 0.5 * v[k];
+      }
+    }
+  }
+  if (o->pair_style == 2)
+    for (int i = 0; i < o->inum; i++) {
+      int nrho = o->nrho;
+      double p = o->rho[i] * o->rdrho + 1.0;
+      int m = (int)p;
+      m = MAX(1, MIN(m, nrho - 1));
+      p -= m;
+      p = MIN(p, 1.0);
+      const double *c = &o->frho_spline[((size_t)o->type2frho[o->type[i]] * (nrho + 1) + m) * 7];
+      double phi = ((c[3] * p + c[4]) * p + c[5]) * p + c[6];
+      if (o->rho[i] > o->rhomax) phi += o->fp[i] * (o->rho[i] - o->rhomax);
+      t[7 * i] += phi * o->scale[o->type[i] * n1 + o->type[i]];
+    }
+  for (int iswap = o->nswap - 1; iswap >= 0; iswap--) {
+    int first = o->firstrecv[iswap];
+    for (int k = 0; k < o->sendnum[iswap]; k++)
+      for (int q = 0; q < 7; q++) t[7 * o->sendlist[iswap][k] + q] += t[7 * (first + k) + q];
+  }
+  for (int i = 0; i < o->nlocal; i++) {
+    if (eatom_out) eatom_out[i] = t[7 * i];
+    if (vatom_out)
+      for (int k = 0; k < 6; k++) vatom_out[6 * i + k] = t[7 * i + 1 + k];
+  }
+  free(t);
+}
+
 /* ------------------------------------------------------------------ fix nve */
 
 /* fix_nve.cpp:68-108 */

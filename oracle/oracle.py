@@ -216,6 +216,14 @@ class Oracle:
         self.L.orc_get_rho_fp(self.h, C.c_int(n), _p(rho), _p(fp))
         return rho, fp
 
+    def pair_peratom(self):
+        """Pair::ev_tally's eatom[nlocal], vatom[nlocal][6] after the reverse communication of the
+        per-atom computes (orc_pair_peratom); call after a compute that tallied."""
+        e, v = np.zeros(self.nlocal), np.zeros((self.nlocal, 6))
+        self.L.orc_pair_peratom.restype = None
+        self.L.orc_pair_peratom(self.h, _p(e), _p(v))
+        return e, v
+
     def pairs(self):
         n = self.nneigh
         pi, pj = np.zeros(n, np.int32), np.zeros(n, np.int32)

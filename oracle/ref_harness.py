@@ -56,6 +56,8 @@ def _load():
         lib.lammps_has_error.argtypes = [C.c_void_p]
         lib.lammps_get_last_error_message.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         lib.lammps_extract_box.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+        lib.lammps_extract_compute.restype = C.c_void_p
+        lib.lammps_extract_compute.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         _lib = lib
     return _lib
 
@@ -123,6 +125,19 @@ class RefLammps:
         p = self.lib.lammps_extract_atom(self.h, name.encode())
         arr = C.cast(p, C.POINTER(C.c_int))
         return np.ctypeslib.as_array(arr, shape=(n,)).copy()
+
+    def compute_peratom(self, cid: str, n: int, ncols: int = 0) -> np.ndarray:
+        """per-atom vector (ncols = 0) or array of a compute, first n atoms (library.h:
+        LMP_STYLE_ATOM = 1, LMP_TYPE_VECTOR = 1, LMP_TYPE_ARRAY = 2); the compute must be current
+        (used by the thermo output of this step)"""
+        p = self.lib.lammps_extract_compute(self.h, cid.encode(), 1, 2 if ncols else 1)
+        self._check()
+        if not p:
+            raise RuntimeError(f"compute {cid} has no per-atom data")
+        if ncols:
+            rows = C.cast(p, C.POINTER(C.POINTER(C.c_double)))
+            return np.ctypeslib.as_array(rows[0], shape=(n * ncols,)).reshape(n, ncols).copy()
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,)).copy()
 
     def pair_extract_scalar(self, name: str) -> float:
         p = self.lib.lammps_extract_pair(self.h, name.encode())

@@ -318,13 +318,76 @@ run 10
             assert abs(u - v) <= 1e-9 * max(1.0, abs(u)), (x, y)
 
 
-def test_per_atom_tallies_are_refused_not_zero(tmp_path):
-    out = _run_b200(tmp_path, LJ_BODY + """
+@pytest.mark.parametrize("style", ["lj", "eam", "lj-subdomains"])
+def test_per_atom_energy_and_stress_match_reference_executable(tmp_path, style):
+    """compute pe/atom and compute stress/atom read Pair::eatom / Pair::vatom (pair.cpp:1087-1182):
+    under -sf b200 the device fills them on the steps that ask (b200_pair_peratom).  The dump of
+    both, sorted by id, must equal the reference executable's, at setup and during the run."""
+    import numpy as np
+    if style == "eam":
+        head = """
+units metal
+lattice fcc 3.615
+region box block 0 7 0 7 0 7
+create_box 1 box
+create_atoms 1 box
+pair_style eam
+pair_coeff 1 1 POT/Cu_u3.eam
+velocity all create 1600.0 376847 loop geom
+neighbor 1.0 bin
+neigh_modify every 1 delay 5 check yes
+fix 1 all nve
+timestep 0.005
+"""
+    else:
+        head = LJ_BODY
+    body = head + """
 compute pea all pe/atom
-dump 1 all custom 10 f.dump id c_pea
+compute sa all stress/atom NULL virial
+compute sk all stress/atom NULL
+compute pes all reduce sum c_pea
+thermo 10
+thermo_style custom step temp pe c_pes press
+thermo_modify format float %.12g
+dump 1 all custom 10 f.dump id c_pea c_sa[1] c_sa[2] c_sa[3] c_sa[4] c_sa[5] c_sa[6] c_sk[1] c_sk[4]
+dump_modify 1 sort id format float %.12g
+run 20
+"""
+    refexe = ROOT / "oracle" / "_ref" / "lmp_ref"
+    dumps = {}
+    extra = ["-pk", "b200", "subdomains", "8"] if style == "lj-subdomains" else []
+    for tag, exe, args in (("ref", refexe, []), ("b200", EXE, ["-sf", "b200", *extra])):
+        d = tmp_path / tag
+        d.mkdir()
+        (d / "in.t").write_text(body.replace("POT", str(ROOT / "oracle" / "_ref" / "potentials")))
+        r = subprocess.run([str(exe), *args, "-in", "in.t"], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        blocks = (d / "f.dump").read_text().split("ITEM: TIMESTEP")[1:]
+        assert len(blocks) == 3
+        per_step = []
+        for blk in blocks:
+            lines = blk.splitlines()
+            k = [i for i, ln in enumerate(lines) if ln.startswith("ITEM: ATOMS")][0]
+            per_step.append(np.array([[float(t) for t in ln.split()] for ln in lines[k + 1:] if ln.strip()]))
+        dumps[tag] = per_step
+    # scale of a column: its largest value over the three dumps, at least that of the diagonal
+    # stress (on the perfect lattice of step 0 the per-atom virial is a sum of O(1) pair terms that
+    # cancels to ~1e-7 -- eam -- or to rounding noise -- off-diagonal components)
+    allref = np.concatenate(dumps["ref"])
+    for a, b in zip(dumps["ref"], dumps["b200"]):
+        assert a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0])
+        for col in range(1, a.shape[1]):
+            scale = max(np.abs(allref[:, col]).max(), np.abs(allref[:, 2:5]).max() if col > 1 else 0.0)
+            assert np.abs(a[:, col] - b[:, col]).max() <= 1e-8 * scale, (style, col)
+
+
+def test_centroid_stress_is_refused_not_zero(tmp_path):
+    out = _run_b200(tmp_path, LJ_BODY + """
+compute cs all centroid/stress/atom NULL virial
+dump 1 all custom 10 f.dump id c_cs[1]
 run 10
 """, expect_fail=True)
-    assert "does not provide per-atom energy or virial" in out
+    assert "does not provide the per-atom centroid virial" in out
 
 
 def test_minimize_is_refused_not_silently_wrong(tmp_path):

@@ -120,3 +120,81 @@ def test_nve_on_a_sub_group_matches_the_compiled_reference():
     frozen = np.sort(tag)[300:] - 1                   # ids > 300 are outside the group
     (xs,) = by_tag(tag, x0)
     assert np.array_equal(xr[frozen], xs[frozen])     # they never moved
+
+
+PERATOM = """
+compute pea all pe/atom
+compute sa all stress/atom NULL virial
+compute pes all reduce sum c_pea
+compute sas all reduce sum c_sa[1] c_sa[2] c_sa[3] c_sa[4] c_sa[5] c_sa[6]
+thermo_style custom step pe c_pes c_sas[1] c_sas[2] c_sas[3] c_sas[4] c_sas[5] c_sas[6]
+run 0
+"""
+
+
+def _peratom_vs_reference(ref, s, nktv2p):
+    """oracle per-atom energy / virial (orc_pair_peratom) against compute pe/atom and
+    compute stress/atom NULL virial of the compiled reference (stress = -vatom * nktv2p)"""
+    n = ref.natoms()
+    tag = ref.atom_int("id", n)
+    e_ref = ref.compute_peratom("pea", n)
+    s_ref = ref.compute_peratom("sa", n, 6)
+    o = make_oracle(s)
+    o.setup(1, 1)
+    eo, vo = o.pair_peratom()
+    eo, vo = by_tag(o.tag(), eo, vo)
+    er, sr = by_tag(tag, e_ref, s_ref)
+    assert np.abs(eo - er).max() <= 1e-12 * np.abs(er).max()
+    assert np.abs(-vo * nktv2p - sr).max() <= 1e-12 * np.abs(sr).max()
+    # the per-atom values sum to the global tallies (pair.cpp:1087-1182)
+    assert abs(eo.sum() - o.eng_vdwl) <= 1e-11 * abs(o.eng_vdwl)
+    assert np.abs(vo.sum(axis=0) - o.virial).max() <= 1e-10 * np.abs(o.virial).max()
+
+
+def test_per_atom_energy_and_virial_lj_match_the_compiled_reference():
+    with R.RefLammps() as ref:
+        ref.commands(SETUP.format(nx=5, ny=6, nz=5, cross="pair_coeff 1 2 0.9 1.05 2.4", shift="yes",
+                                  neigh="delay 0 every 20 check no"))
+        ref.command("run 25")
+        ref.commands(PERATOM)
+        n = ref.natoms()
+        lo, hi = ref.box()
+        s = dict(kind="lj", units="lj", x=ref.atom_vec3("x", n), v=ref.atom_vec3("v", n),
+                 type=ref.atom_int("type", n), tag=ref.atom_int("id", n), mass=np.array([0.0, 1.0, 1.7]),
+                 lo=lo, hi=hi, skin=0.3, every=20, delay=0, check=False, dt=0.005,
+                 tables=pair_lj.lj_cut_tables(2, {(1, 1): (1.0, 1.0, 2.5), (2, 2): (0.8, 1.1, 2.2),
+                                                  (1, 2): (0.9, 1.05, 2.4)}, 2.5, offset_flag=True))
+        _peratom_vs_reference(ref, s, 1.0)
+
+
+def test_per_atom_energy_and_virial_eam_match_the_compiled_reference():
+    from common import eam_tables
+    from lammps_b200 import units
+    pot = R.LIB.parent / "potentials" / "Cu_u3.eam"
+    if not pot.exists():
+        pytest.skip("Cu_u3.eam not staged next to the compiled reference")
+    with R.RefLammps() as ref:
+        ref.commands(f"""
+units metal
+atom_style atomic
+lattice fcc 3.615
+region box block 0 6 0 5 0 5
+create_box 1 box
+create_atoms 1 box
+pair_style eam
+pair_coeff 1 1 {pot}
+velocity all create 1600.0 376847 loop geom
+neighbor 1.0 bin
+neigh_modify every 1 delay 5 check yes
+fix 1 all nve
+timestep 0.005
+run 30
+""")
+        ref.commands(PERATOM)
+        n = ref.natoms()
+        lo, hi = ref.box()
+        T = eam_tables()
+        s = dict(kind="eam", units="metal", x=ref.atom_vec3("x", n), v=ref.atom_vec3("v", n),
+                 type=ref.atom_int("type", n), tag=ref.atom_int("id", n), mass=T.mass, lo=lo, hi=hi,
+                 skin=1.0, every=1, delay=5, check=True, dt=0.005, tables=T.as_dict())
+        _peratom_vs_reference(ref, s, units.get("metal").nktv2p)
