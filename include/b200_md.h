@@ -59,6 +59,11 @@ int b200_set_rank_grid(b200_ctx *ctx, const int *grid2rank, int n);
  *      cutneighsq = (sqrt(cutsq)+skin)^2 is derived from the pair style's cutsq
  *      (neighbor.cpp:337-383), triggersq = (skin/2)^2 */
 int b200_set_neighbor(b200_ctx *ctx, double skin, int every, int delay, int dist_check, int one);
+/* neigh_modify once yes|no (Neighbor::decide never asks for a rebuild, neighbor.cpp:2420) and
+ * neigh_modify exclude type i j ... (NPair::exclusion, npair.cpp:244-248): ex_type is Neighbor's
+ * symmetric table of excluded type pairs, [(ntypes+1)^2] flags, NULL = no exclusions.  Group and
+ * molecule exclusions are not supported (the hosts refuse them). */
+int b200_neigh_modify(b200_ctx *ctx, int build_once, int ntypes, const int *ex_type);
 
 /* ---- atoms: Atom arrays (atom.h:72-75) + per-type mass (atom.cpp set_mass).
  *      mask/image may be NULL (all atoms in group `all`, image flags 0). */

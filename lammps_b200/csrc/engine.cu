@@ -124,6 +124,8 @@ struct b200_ctx {
   int every = 1, delay = 0, dist_check = 1, one = 2000;
   double cutneighmax = 0, cutneighmaxsq = 0, triggersq = 0, cutghost = 0;
   std::vector<double> cutneighsq_h;
+  std::vector<int> ex_type;  // neigh_modify exclude type: [(ntypes+1)^2] flags, empty = none
+  bool build_once = false;   // neigh_modify once yes: the list of setup is never rebuilt
   DBuf<double> cutneighsq_d;
   int64_t ago = 0, nbuilds = 0, ndanger = 0;
   Geom geom;
@@ -838,6 +840,14 @@ static int setup_geometry(b200_ctx *ctx) {
     }
   ctx->cutneighmaxsq = ctx->cutneighmax * ctx->cutneighmax;
   ctx->cutghost = ctx->cutneighmax;  // Comm::get_comm_cutoff, comm.cpp:683
+  // neigh_modify exclude type (NPair::exclusion, npair.cpp:244-248): an excluded type pair is
+  // never stored.  The build kernels test `rsq <= cutneighsq[itype][jtype]`; a negative entry
+  // makes that test fail for every distance, so the exclusion costs no extra instruction.  (Bins,
+  // stencil and ghost cutoff keep using the unmodified maximum, as the reference does.)
+  if ((int)ctx->ex_type.size() == n1 * n1)
+    for (int i = 1; i <= n; i++)
+      for (int j = 1; j <= n; j++)
+        if (ctx->ex_type[i * n1 + j]) ctx->cutneighsq_h[i * n1 + j] = -1.0;
   TRY(reserve(ctx, ctx->cutneighsq_d, (size_t)n1 * n1));
   CK(cudaMemcpyAsync(ctx->cutneighsq_d.p, ctx->cutneighsq_h.data(), sizeof(double) * n1 * n1,
                      cudaMemcpyHostToDevice, ctx->stream));
@@ -2215,6 +2225,7 @@ static int decide(b200_ctx *ctx, int *rebuild) {
   ctx->ago++;
   *rebuild = 0;
   if (ctx->ago >= ctx->delay && ctx->ago % ctx->every == 0) {
+    if (ctx->build_once) return B200_OK;  // neighbor.cpp:2420
     if (!ctx->dist_check) {
       *rebuild = 1;
       return B200_OK;
@@ -2243,7 +2254,7 @@ static int decide(b200_ctx *ctx, int *rebuild) {
 
 static bool check_due_next(const b200_ctx *ctx) {
   const int64_t a = ctx->ago + 1;
-  return ctx->dist_check && a >= ctx->delay && a % ctx->every == 0;
+  return ctx->dist_check && !ctx->build_once && a >= ctx->delay && a % ctx->every == 0;
 }
 
 static int ke_reduce(b200_ctx *ctx) {
@@ -2469,6 +2480,26 @@ int b200_set_neighbor(b200_ctx *ctx, double skin, int every, int delay, int dist
   ctx->delay = delay;
   ctx->dist_check = dist_check ? 1 : 0;
   if (one > 0) ctx->one = one;
+  ctx->geom_ready = false;
+  return B200_OK;
+}
+
+// neigh_modify once yes|no and exclude type (neighbor.cpp:2727-2790): ex_type is Neighbor's
+// symmetric table of excluded type pairs, [(ntypes+1)^2] flags, or NULL for none
+int b200_neigh_modify(b200_ctx *ctx, int build_once, int ntypes, const int *ex_type) {
+  if (!ctx) return B200_EARG;
+  drop_step_graph(ctx);
+  ctx->build_once = build_once != 0;
+  ctx->ex_type.clear();
+  if (ex_type) {
+    if (ntypes < 1) return ctx->fail(B200_EARG, "b200_neigh_modify: bad type count");
+    const int n1 = ntypes + 1;
+    ctx->ex_type.assign(ex_type, ex_type + n1 * n1);
+    for (int i = 1; i <= ntypes; i++)
+      for (int j = 1; j <= ntypes; j++)
+        if (ctx->ex_type[i * n1 + j] != ctx->ex_type[j * n1 + i])
+          return ctx->fail(B200_EARG, "b200_neigh_modify: the exclusion table must be symmetric");
+  }
   ctx->geom_ready = false;
   return B200_OK;
 }
@@ -2753,7 +2784,7 @@ static bool plain_step(const b200_ctx *ctx, int eflag, int vflag) {
       !ctx->pending_final || ctx->nlocal <= 0 || ctx->dist_check || ctx->ahead)
     return false;
   const int64_t a = ctx->ago + 1;
-  const bool due = a >= ctx->delay && a % ctx->every == 0;  // Neighbor::decide
+  const bool due = !ctx->build_once && a >= ctx->delay && a % ctx->every == 0;  // Neighbor::decide
   return !due;  // with `check yes` a due step needs the device vote; with `check no` it rebuilds
 }
 

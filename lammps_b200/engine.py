@@ -24,7 +24,8 @@ PHASES = ("initial_integrate", "final_integrate", "forward_comm", "reverse_comm"
 
 EXPORTS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_set_box",
-    "b200_set_decomposition", "b200_set_rank_grid", "b200_set_neighbor", "b200_set_atoms", "b200_get_atoms",
+    "b200_set_decomposition", "b200_set_rank_grid", "b200_set_neighbor", "b200_neigh_modify", "b200_set_atoms",
+    "b200_get_atoms",
     "b200_get_counts", "b200_pair_lj_cut", "b200_pair_eam", "b200_fix_nve", "b200_setup",
     "b200_run", "b200_step", "b200_last_run_ms", "b200_initial_integrate", "b200_final_integrate", "b200_decide",
     "b200_forward_comm", "b200_reverse_comm", "b200_reneighbor", "b200_force_clear",
@@ -143,6 +144,16 @@ class Engine:
         self._chk(self.L.b200_set_neighbor(self.h, C.c_double(skin), C.c_int(every),
                                            C.c_int(delay), C.c_int(1 if check else 0),
                                            C.c_int(one)))
+
+    def neigh_modify(self, once=False, exclude_types=(), ntypes=1):
+        """neigh_modify once yes|no, exclude type i j (pairs of types, made symmetric)"""
+        ex = None
+        if exclude_types:
+            n1 = ntypes + 1
+            ex = np.zeros(n1 * n1, np.int32)
+            for a, b in exclude_types:
+                ex[a * n1 + b] = ex[b * n1 + a] = 1
+        self._chk(self.L.b200_neigh_modify(self.h, C.c_int(1 if once else 0), C.c_int(ntypes), _p(ex)))
 
     def set_atoms(self, x, v, type, tag, mass, mask=None, image=None, natoms_total=None):
         x, v, type, tag, mass = _d(x), _d(v), _i(type), _i(tag), _d(mass)

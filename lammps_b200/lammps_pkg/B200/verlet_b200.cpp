@@ -128,6 +128,10 @@ void VerletB200::upload()
     B200_CHECK(pkg,
                b200_set_neighbor(c, neighbor->skin, neighbor->every, neighbor->delay,
                                  neighbor->dist_check, neighbor->oneatom));
+    // neigh_modify once / exclude type: Neighbor::init has built the symmetric ex_type table
+    B200_CHECK(pkg,
+               b200_neigh_modify(c, neighbor->build_once, atom->ntypes,
+                                 (neighbor->nex_type && neighbor->ex_type) ? &neighbor->ex_type[0][0] : nullptr));
   }
   const int nlocal = atom->nlocal;
   if (pkg->group()) {
@@ -244,7 +248,9 @@ void VerletB200::device_setup(int flag, int output_flag)
   refuse_per_atom_tallies();
   // list options of neigh_modify the device build does not implement (neighbor.cpp:2727-2940);
   // checked here because Neighbor::init() runs after Integrate::init()
-  if (neighbor->exclude) error->all(FLERR, "run_style verlet/b200 does not support neigh_modify exclude");
+  if (neighbor->nex_group || neighbor->nex_mol)
+    error->all(FLERR, "run_style verlet/b200 supports neigh_modify exclude type only "
+                      "(not exclude group or molecule)");
   if (neighbor->includegroup)
     error->all(FLERR, "run_style verlet/b200 does not support neigh_modify include");
   if (neighbor->style != Neighbor::BIN)

@@ -48,6 +48,8 @@ typedef struct {
   double skin, cutneighmax, cutneighmaxsq, triggersq;
   double *cutneighsq; /* [(ntypes+1)^2] */
   int every, delay, dist_check;
+  int build_once;  /* neigh_modify once yes (neighbor.cpp:2420) */
+  int *ex_type;    /* neigh_modify exclude type: [(ntypes+1)^2] flags or NULL (neighbor.h:66-68) */
   int ago, ncalls, ndanger;
   double *xhold;
   /* bins (nbin_standard.cpp) */
@@ -130,7 +132,7 @@ void orc_destroy(Orc *o) {
   free(o->firstneigh); free(o->neigh); free(o->cutsq); free(o->lj1); free(o->lj2);
   free(o->lj3); free(o->lj4); free(o->offset); free(o->type2frho); free(o->type2rhor);
   free(o->type2z2r); free(o->scale); free(o->frho_spline); free(o->rhor_spline);
-  free(o->z2r_spline); free(o->rho); free(o->fp); free(o->numforce);
+  free(o->z2r_spline); free(o->rho); free(o->fp); free(o->numforce); free(o->ex_type);
   for (int i = 0; i < MAXSWAP; i++) free(o->sendlist[i]);
   free(o);
 }
@@ -169,6 +171,19 @@ void orc_set_neighbor(Orc *o, double skin, int every, int delay, int dist_check)
   o->every = every;
   o->delay = delay;
   o->dist_check = dist_check;
+}
+
+/* neigh_modify once yes|no and exclude type i j ... (neighbor.cpp:2727-2790; Neighbor::init builds
+ * the symmetric ex_type table, neighbor.cpp:560-575).  ex_type: [(ntypes+1)^2] flags or NULL. */
+void orc_neigh_modify(Orc *o, int build_once, int ntypes, const int *ex_type) {
+  o->build_once = build_once;
+  free(o->ex_type);
+  o->ex_type = NULL;
+  if (ex_type) {
+    int n2 = (ntypes + 1) * (ntypes + 1);
+    o->ex_type = (int *)malloc(sizeof(int) * n2);
+    memcpy(o->ex_type, ex_type, sizeof(int) * n2);
+  }
 }
 
 void orc_fix_nve(Orc *o, double dt, double ftm2v, int groupbit) {
@@ -606,6 +621,8 @@ static void npair_build(Orc *o) {
           }
         }
         int jtype = o->type[j];
+        /* NPair::exclusion, npair.cpp:244-248 (type pairs; atomic systems have no molecules) */
+        if (o->ex_type && o->ex_type[itype * n1 + jtype]) continue;
         double delx = xtmp - o->x[3 * j];
         double dely = ytmp - o->x[3 * j + 1];
         double delz = ztmp - o->x[3 * j + 2];
@@ -640,6 +657,7 @@ void orc_neighbor_build(Orc *o) {
 int orc_decide(Orc *o) {
   o->ago++;
   if (o->ago >= o->delay && o->ago % o->every == 0) {
+    if (o->build_once) return 0;
     if (o->dist_check == 0) return 1;
     int flag = 0;
     for (int i = 0; i < o->nlocal; i++) {

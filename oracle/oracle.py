@@ -88,6 +88,17 @@ class Oracle:
         self.L.orc_set_neighbor(self.h, C.c_double(skin), C.c_int(every), C.c_int(delay),
                                 C.c_int(1 if check else 0))
 
+    def neigh_modify(self, once=False, exclude_types=(), ntypes=1):
+        """neigh_modify once yes|no, exclude type i j (pairs of types, symmetric)"""
+        ex = None
+        if exclude_types:
+            n1 = ntypes + 1
+            ex = np.zeros(n1 * n1, np.int32)
+            for i, j in exclude_types:
+                ex[i * n1 + j] = ex[j * n1 + i] = 1
+        self.L.orc_neigh_modify(self.h, C.c_int(1 if once else 0), C.c_int(ntypes),
+                                _p(ex) if ex is not None else None)
+
     def fix_nve(self, dt, ftm2v=1.0, groupbit=1):
         self.L.orc_fix_nve(self.h, C.c_double(dt), C.c_double(ftm2v), C.c_int(groupbit))
 

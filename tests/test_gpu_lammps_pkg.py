@@ -395,9 +395,43 @@ def test_minimize_is_refused_not_silently_wrong(tmp_path):
     assert "computes forces only inside run_style verlet/b200" in out
 
 
-def test_neigh_modify_exclude_is_refused(tmp_path):
-    out = _run_b200(tmp_path, LJ_BODY + "neigh_modify exclude type 1 1\nrun 5\n", expect_fail=True)
-    assert "does not support neigh_modify exclude" in out
+def test_neigh_modify_exclude_group_is_refused(tmp_path):
+    out = _run_b200(tmp_path, LJ_BODY + "group left id < 100\nneigh_modify exclude group left left\nrun 5\n",
+                    expect_fail=True)
+    assert "supports neigh_modify exclude type only" in out
+
+
+def test_neigh_modify_exclude_type_and_once_match_reference_executable(tmp_path):
+    """two atom types that do not see each other (exclude type 1 2), list built once"""
+    body = """
+units lj
+lattice fcc 0.8442
+region box block 0 8 0 8 0 8
+create_box 2 box
+create_atoms 1 box
+set type 1 type/ratio 2 0.4 4711
+mass 1 1.0
+mass 2 1.7
+velocity all create 1.44 87287 loop geom
+pair_style lj/cut 2.5
+pair_coeff 1 1 1.0 1.0 2.5
+pair_coeff 2 2 0.8 1.1 2.2
+pair_coeff 1 2 0.9 1.05 2.4
+neighbor 0.3 bin
+neigh_modify every 5 delay 0 check no exclude type 1 2
+fix 1 all nve
+thermo 10
+thermo_modify format float %.12g
+dump 1 all custom 20 f.dump id type fx fy fz
+dump_modify 1 sort id format float %.10g
+run 20
+"""
+    outs = _both(tmp_path, body, 20)
+    _compare(outs, ftol=1e-8, ttol=1e-9)
+    (tmp_path / "once").mkdir()
+    out = _run_b200(tmp_path / "once", body.replace("check no exclude type 1 2", "check no once yes")
+                    .replace("run 20", "run 10"))
+    assert "Neighbor list builds = 0" in out
 
 
 def test_neighbor_list_overflow_is_reported(tmp_path):

@@ -198,3 +198,46 @@ run 30
                  type=ref.atom_int("type", n), tag=ref.atom_int("id", n), mass=T.mass, lo=lo, hi=hi,
                  skin=1.0, every=1, delay=5, check=True, dt=0.005, tables=T.as_dict())
         _peratom_vs_reference(ref, s, units.get("metal").nktv2p)
+
+
+def test_neigh_modify_exclude_type_and_once_match_the_compiled_reference():
+    """neigh_modify exclude type 1 2 (NPair::exclusion, npair.cpp:244-248: the pair never enters
+    the list, so unlike atoms do not interact) and once yes (neighbor.cpp:2420: the list of setup
+    is kept for the whole run)"""
+    nsteps = 12
+    text = SETUP.format(nx=5, ny=5, nz=6, cross="pair_coeff 1 2 0.9 1.05 2.4", shift="no",
+                        neigh="delay 0 every 2 check no exclude type 1 2 once yes")
+    with R.RefLammps() as ref:
+        ref.commands(text)
+        n = ref.natoms()
+        lo, hi = ref.box()
+        x0, v0 = ref.atom_vec3("x", n), ref.atom_vec3("v", n)
+        typ, tag = ref.atom_int("type", n), ref.atom_int("id", n)
+        f0 = ref.atom_vec3("f", n)
+        nall = n + ref.setting("nghost")
+        pi, pj = ref.neighbor_pairs("lj/cut")
+        kref = canonical_pairs_box(pi, pj, ref.atom_int("id", nall), ref.atom_vec3("x", nall), lo, hi, nlocal=n)
+        ref.command(f"run {nsteps}")
+        x1, tag1 = ref.atom_vec3("x", n), ref.atom_int("id", n)
+    coeffs = {(1, 1): (1.0, 1.0, 2.5), (2, 2): (0.8, 1.1, 2.2), (1, 2): (0.9, 1.05, 2.4)}
+    s = dict(kind="lj", units="lj", x=x0, v=v0, type=typ, tag=tag, mass=np.array([0.0, 1.0, 1.7]),
+             lo=lo, hi=hi, skin=0.3, every=2, delay=0, check=False, dt=0.005,
+             tables=pair_lj.lj_cut_tables(2, coeffs, 2.5))
+    o = make_oracle(s)
+    o.neigh_modify(once=True, exclude_types=[(1, 2)], ntypes=2)
+    o.setup(1, 1)
+    pi, pj = o.pairs()
+    assert not np.any(o.type(True)[pi] != o.type(True)[pj]), "an excluded 1-2 pair is in the list"
+    kor = canonical_pairs_box(pi, pj, o.tag(True), o.x(True), lo, hi, nlocal=o.nlocal)
+    assert np.array_equal(kor, kref), "half-list pair sets differ"
+    (fo,) = by_tag(o.tag(), o.f())
+    (fr,) = by_tag(tag, f0)
+    assert np.abs(fo - fr).max() <= 1e-13 * np.abs(fr).max()
+    o.run(nsteps, 0, 0)
+    assert o.ncalls == 0, "once yes: no rebuild after setup"
+    (xo,) = by_tag(o.tag(), o.x())
+    (xr,) = by_tag(tag1, x1)
+    prd = hi - lo
+    d = xo - xr
+    d -= prd * np.rint(d / prd)
+    assert np.abs(d).max() <= 1e-12
