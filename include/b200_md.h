@@ -121,6 +121,13 @@ int b200_reverse_comm(b200_ctx *ctx);                 /* CommBrick::reverse_comm
 int b200_reneighbor(b200_ctx *ctx);                   /* pbc+exchange+borders+Neighbor::build */
 int b200_force_clear(b200_ctx *ctx);                  /* Verlet::force_clear verlet.cpp:376 */
 int b200_pair_compute(b200_ctx *ctx, int eflag, int vflag); /* Pair::compute pair.h:159 */
+/* ---- the per-atom loops of FixNH (fix nvt; fix_nh.cpp:916-1014, 2278-2352), for a host that runs
+ *      the Nose-Hoover chain itself (the package's fix nvt/b200 inherits the reference's FixNH):
+ *      nve_v: v += dtf/m f; nve_x: x += dtv v (+ the displacement check decide() reads);
+ *      nh_v_temp: v *= factor.  Atoms in groupbit only. */
+int b200_nve_v(b200_ctx *ctx, double dtf, int groupbit);
+int b200_nve_x(b200_ctx *ctx, double dtv, int groupbit);
+int b200_scale_v(b200_ctx *ctx, double factor, int groupbit);
 
 /* ---- tallies the host reads back: pair->eng_vdwl, pair->virial[6] (pair.h), and
  *      sum_i m_i v_i^2 (ComputeTemp::compute_scalar, compute_temp.cpp:73-97) */

@@ -2761,6 +2761,60 @@ int b200_final_integrate(b200_ctx *ctx) {
   TRY(flush_final(ctx));
   return final_integrate(ctx);
 }
+// ---- the per-atom loops of FixNH (fix nvt), driven stage by stage by the host's own FixNH code
+// (lammps_pkg/B200/fix_nvt_b200.cpp): see kernels_step.cuh
+static int staged_guard(b200_ctx *ctx) {
+  if (!ctx->setup_done) return ctx->fail(B200_EARG, "integrator stage before b200_setup");
+  if (ctx->ahead) return ctx->fail(B200_EARG, "integrator stage inside a fused run");
+  TRY(flush_final(ctx));
+  CK(cudaSetDevice(ctx->device));
+  return B200_OK;
+}
+
+int b200_nve_v(b200_ctx *ctx, double dtf, int groupbit) {
+  if (!ctx) return B200_EARG;
+  TRY(staged_guard(ctx));
+  const int nl = ctx->nlocal, c = ctx->cur;
+  if (nl > 0) {
+    k_nve_final<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2],
+                                                        ctx->f[0], ctx->f[1], ctx->f[2], ctx->mask[c],
+                                                        ctx->mass_d.p, dtf, groupbit);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  return B200_OK;
+}
+
+int b200_nve_x(b200_ctx *ctx, double dtv, int groupbit) {
+  if (!ctx) return B200_EARG;
+  TRY(staged_guard(ctx));
+  const int nl = ctx->nlocal, c = ctx->cur;
+  const int chk = check_due_next(ctx) ? 1 : 0;  // the vote decide() reads after this stage
+  CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
+  if (nl > 0) {
+    k_nve_x<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2],
+                                                    ctx->mask[c], dtv, groupbit, chk, ctx->xh[0], ctx->xh[1],
+                                                    ctx->xh[2], ctx->triggersq, ctx->flags);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  ctx->q_owned_valid = false;  // owned positions moved
+  return B200_OK;
+}
+
+int b200_scale_v(b200_ctx *ctx, double factor, int groupbit) {
+  if (!ctx) return B200_EARG;
+  TRY(staged_guard(ctx));
+  const int nl = ctx->nlocal, c = ctx->cur;
+  if (nl > 0) {
+    k_scale_v<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->mask[c],
+                                                      factor, groupbit);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  return B200_OK;
+}
+
 int b200_decide(b200_ctx *ctx, int *rebuild) { return (ctx && rebuild) ? decide(ctx, rebuild) : B200_EARG; }
 int b200_forward_comm(b200_ctx *ctx) { return ctx ? forward_comm(ctx) : B200_EARG; }
 int b200_reverse_comm(b200_ctx *ctx) { return ctx ? reverse_comm(ctx) : B200_EARG; }

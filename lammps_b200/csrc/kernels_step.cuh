@@ -55,6 +55,46 @@ __global__ void __launch_bounds__(256) k_nve_final(
   }
 }
 
+// The pieces of FixNH's integrator (fix nvt: fix_nh.cpp:916-1014) that loop over atoms.  The
+// Nose-Hoover chain itself is scalar host arithmetic and stays in the reference's own FixNH code
+// (the package's fix nvt/b200 inherits it); what runs here is
+//   nve_v     v += dtf/m * f           = k_nve_final above with the fix's dtf and group
+//   nve_x     x += dtv * v             (fix_nh.cpp:2278-2298) + Neighbor::check_distance when due
+//   nh_v_temp v *= factor_eta          (fix_nh.cpp:2338-2352, no bias)
+// each operation rounded separately like the reference loops.
+__global__ void __launch_bounds__(256) k_nve_x(
+    int nlocal, double4 *__restrict__ xt, const double *__restrict__ vx, const double *__restrict__ vy,
+    const double *__restrict__ vz, const int *__restrict__ mask, double dtv, int groupbit, int do_check,
+    const double *__restrict__ xhx, const double *__restrict__ xhy, const double *__restrict__ xhz,
+    double triggersq, int *__restrict__ moved) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  double4 p = xt[i];
+  if (mask[i] & groupbit) {
+    p.x = __dadd_rn(p.x, __dmul_rn(dtv, vx[i]));
+    p.y = __dadd_rn(p.y, __dmul_rn(dtv, vy[i]));
+    p.z = __dadd_rn(p.z, __dmul_rn(dtv, vz[i]));
+    xt[i] = p;
+  }
+  if (do_check) {
+    const double dx = p.x - xhx[i], dy = p.y - xhy[i], dz = p.z - xhz[i];
+    if (rsq_ref(dx, dy, dz) > triggersq) *moved = 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scale_v(int nlocal, double *__restrict__ vx,
+                                                 double *__restrict__ vy, double *__restrict__ vz,
+                                                 const int *__restrict__ mask, double factor,
+                                                 int groupbit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  if (mask[i] & groupbit) {
+    vx[i] = __dmul_rn(vx[i], factor);
+    vy[i] = __dmul_rn(vy[i], factor);
+    vz[i] = __dmul_rn(vz[i], factor);
+  }
+}
+
 // final_integrate of step n immediately followed by initial_integrate of step n+1 in ONE pass
 // over the atoms (both use the same forces f(n)): v += dtfm*f ; v += dtfm*f ; x += dtv*v, each
 // operation rounded separately exactly like the two reference loops.  Used whenever nothing

@@ -33,6 +33,15 @@ class B200NVEFix {
   virtual void b200_params(double &dtv, double &dtf, int &groupbit) = 0;
 };
 
+// a time-integration fix whose own initial_integrate / final_integrate run on the host and call
+// device kernels for the per-atom loops (fix nvt/b200): verlet/b200 then drives the timestep stage
+// by stage around them
+class B200StagedFix {
+ public:
+  virtual ~B200StagedFix() noexcept(false) {}
+  virtual void b200_params(double &dtv, double &dtf, int &groupbit) = 0;
+};
+
 }    // namespace LAMMPS_NS
 
 #endif

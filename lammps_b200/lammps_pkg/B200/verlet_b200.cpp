@@ -38,7 +38,8 @@ using namespace LAMMPS_NS;
 using namespace FixConst;
 
 VerletB200::VerletB200(LAMMPS *lmp, int narg, char **arg) :
-    Verlet(lmp, narg, arg), pkg(nullptr), ctx(nullptr), bpair(nullptr), bnve(nullptr), resident(0),
+    Verlet(lmp, narg, arg), pkg(nullptr), ctx(nullptr), bpair(nullptr), bnve(nullptr), bstaged(nullptr),
+    staged_fix(nullptr), resident(0),
     joined(0), thermo_on_device(0)
 {
 }
@@ -69,18 +70,24 @@ void VerletB200::init()
   const int stepmask = INITIAL_INTEGRATE | POST_INTEGRATE | PRE_EXCHANGE | PRE_NEIGHBOR |
       POST_NEIGHBOR | PRE_FORCE | PRE_REVERSE | POST_FORCE | FINAL_INTEGRATE | END_OF_STEP;
   bnve = nullptr;
+  bstaged = nullptr;
+  staged_fix = nullptr;
   for (auto &fix : modify->get_fix_list()) {
     auto *nve = dynamic_cast<B200NVEFix *>(fix);
-    if (nve) {
-      if (bnve) error->all(FLERR, "run_style verlet/b200 supports a single fix nve/b200");
+    auto *stg = dynamic_cast<B200StagedFix *>(fix);
+    if (nve || stg) {
+      if (bnve || bstaged)
+        error->all(FLERR, "run_style verlet/b200 supports a single time-integration fix (nve/b200 or nvt/b200)");
       bnve = nve;
+      bstaged = stg;
+      if (stg) staged_fix = fix;
       continue;
     }
     if (modify->get_fix_mask(fix) & stepmask)
       error->all(FLERR, "Fix {} (style {}) acts during the timestep and has no /b200 version", fix->id,
                  fix->style);
   }
-  if (!bnve) error->all(FLERR, "run_style verlet/b200 requires fix nve/b200");
+  if (!bnve && !bstaged) error->all(FLERR, "run_style verlet/b200 requires fix nve/b200 or fix nvt/b200");
   resident = 0;
   pkg->host_stale = 0;
 
@@ -121,7 +128,8 @@ void VerletB200::upload()
 {
   double dtv, dtf;
   int groupbit;
-  bnve->b200_params(dtv, dtf, groupbit);
+  if (bnve) bnve->b200_params(dtv, dtf, groupbit);
+  else bstaged->b200_params(dtv, dtf, groupbit);
   for (int i = 0; i < pkg->nctx(); i++) {
     b200_ctx *c = pkg->context(i);
     B200_CHECK(pkg, b200_set_box(c, domain->boxlo, domain->boxhi, domain->periodicity));
@@ -331,6 +339,34 @@ void VerletB200::step_by_stage(int ef, int vf)
 }
 
 /* ----------------------------------------------------------------------
+   a timestep whose integrator is a host fix with device loops (fix nvt/b200):
+   Verlet::run's sequence (verlet.cpp:257-355) with the fix's own
+   initial_integrate / final_integrate around the device stages
+------------------------------------------------------------------------- */
+
+void VerletB200::step_staged_fix(int ef, int vf)
+{
+  int nflag = 0;
+  staged_fix->initial_integrate(vflag);
+  timer->stamp(Timer::MODIFY);
+  B200_CHECK(pkg, b200_decide(ctx, &nflag));
+  if (nflag) {
+    B200_CHECK(pkg, b200_reneighbor(ctx));
+    timer->stamp(Timer::NEIGH);
+  } else {
+    B200_CHECK(pkg, b200_forward_comm(ctx));
+    timer->stamp(Timer::COMM);
+  }
+  B200_CHECK(pkg, b200_force_clear(ctx));
+  B200_CHECK(pkg, b200_pair_compute(ctx, ef, vf));
+  timer->stamp(Timer::PAIR);
+  B200_CHECK(pkg, b200_reverse_comm(ctx));
+  timer->stamp(Timer::COMM);
+  staged_fix->final_integrate();
+  timer->stamp(Timer::MODIFY);
+}
+
+/* ----------------------------------------------------------------------
    run for N steps
 ------------------------------------------------------------------------- */
 
@@ -353,7 +389,12 @@ void VerletB200::run(int n)
     // needs a word back (verlet.cpp:229-360 is the sequence it implements)
     timer->stamp();
     int rebuilt = 0;
-    if (by_stage)
+    // from here on the device copy of the atoms is the current one (compute temp/b200 inside a
+    // staged fix must already read the device sums on the first step of a run)
+    pkg->host_stale = 1;
+    if (bstaged)
+      step_staged_fix(eflag ? 1 : 0, vflag ? 1 : 0);
+    else if (by_stage)
       step_by_stage(eflag ? 1 : 0, vflag ? 1 : 0);
     else
       pkg->dev_step(eflag ? 1 : 0, vflag ? 1 : 0, &rebuilt);
@@ -368,7 +409,7 @@ void VerletB200::run(int n)
       if (need_atoms) download(0);
       fill_per_atom_tallies();
       if (eflag || vflag) fetch_tallies();
-      if (!by_stage) timer->stamp(Timer::PAIR);
+      if (!by_stage && !bstaged) timer->stamp(Timer::PAIR);
       output->write(ntimestep);
       timer->stamp(Timer::OUTPUT);
     }

@@ -33,6 +33,8 @@ class VerletB200 : public Verlet {
   b200_ctx *ctx;    // the context of this process (nullptr when the package drives a group)
   B200PairStyle *bpair;
   B200NVEFix *bnve;
+  B200StagedFix *bstaged;    // fix nvt/b200: the host fix drives its per-atom loops itself
+  class Fix *staged_fix;
   int resident;    // 1 once atoms have been handed to the device in this run
   int joined;      // 1 once this rank joined the NCCL communicator of the package
   int thermo_on_device;    // every compute a thermo step evaluates reads device sums or scalars
@@ -45,6 +47,7 @@ class VerletB200 : public Verlet {
   void refuse_per_atom_tallies();
   void fill_per_atom_tallies();   // Pair::eatom / vatom <- device on steps that ask for them
   void step_by_stage(int eflag, int vflag);    // `package b200 profile yes`: Timer breakdown
+  void step_staged_fix(int eflag, int vflag);  // a B200StagedFix integrates (fix nvt/b200)
 };
 
 }    // namespace LAMMPS_NS

@@ -452,3 +452,54 @@ def test_profile_fills_the_timer_breakdown(tmp_path):
     assert t["Pair"] > 0 and t["Neigh"] > 0 and t["Modify"] > 0
     assert t["Pair"] > t["Comm"], t
     assert "B200 device time by phase" in out
+
+
+@pytest.mark.parametrize("neigh", ["every 20 delay 0 check no", "every 1 delay 0 check yes"])
+def test_fix_nvt_matches_reference_executable(tmp_path, neigh):
+    """fix nvt under -sf b200 = fix nvt/b200: the reference's own Nose-Hoover chain (FixNH, inherited)
+    on the host, its per-atom loops (nve_v, nve_x, nh_v_temp) and the temperature sum on the device.
+    Thermo every step (temperature ramp 1.44 -> 0.8, chain of 3) and the final forces against
+    lmp_ref; with `check yes` the displacement vote comes from the nve_x kernel."""
+    body = LJ_BODY.replace("neigh_modify every 20 delay 0 check no", "neigh_modify " + neigh).replace(
+        "fix 1 all nve", "fix 1 all nvt temp 1.44 0.8 0.5 tchain 3") + """
+thermo 1
+thermo_style custom step temp pe etotal press ecouple
+thermo_modify format float %.12g
+dump 1 all custom 60 f.dump id x y z fx
+dump_modify 1 sort id format float %.10g
+run 60
+"""
+    refexe = ROOT / "oracle" / "_ref" / "lmp_ref"
+    import numpy as np
+    tabs = {}
+    for tag, exe, extra in (("ref", refexe, []), ("b200", EXE, ["-sf", "b200"])):
+        d = tmp_path / tag
+        d.mkdir()
+        (d / "in.t").write_text(body)
+        r = subprocess.run([str(exe), *extra, "-in", "in.t"], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        rows, on = [], False
+        for ln in r.stdout.splitlines():
+            if re.match(r"\s*Step\s+Temp\s+PotEng", ln):
+                on = True
+                continue
+            if ln.startswith("Loop time"):
+                on = False
+            f = ln.split()
+            if on and len(f) == 6 and re.fullmatch(r"\d+", f[0]):
+                rows.append([float(t) for t in f])
+        blocks = (d / "f.dump").read_text().split("ITEM: TIMESTEP")[1:]
+        last = blocks[-1].splitlines()
+        k = last.index([ln for ln in last if ln.startswith("ITEM: ATOMS")][0])
+        dump = np.array([[float(t) for t in ln.split()] for ln in last[k + 1:] if ln.strip()])
+        tabs[tag] = (np.array(rows), dump, r.stdout)
+    ta, tb = tabs["ref"][0], tabs["b200"][0]
+    assert ta.shape == tb.shape == (61, 6)
+    assert np.abs(ta - tb).max() <= 1e-9 * np.abs(ta).max(), np.abs(ta - tb).max(axis=0)
+    assert abs(ta[-1, 1] - 0.8) < 0.2                    # the thermostat did pull the temperature down
+    da, db = tabs["ref"][1], tabs["b200"][1]
+    assert np.array_equal(da[:, 0], db[:, 0])
+    assert np.abs(da[:, 1:4] - db[:, 1:4]).max() <= 1e-8
+    assert np.abs(da[:, 4] - db[:, 4]).max() <= 1e-8 * np.abs(da[:, 4]).max()
+    m = re.search(r"Neighbor list builds = (\d+)", tabs["ref"][2])
+    assert m and ("Neighbor list builds = " + m.group(1)) in tabs["b200"][2]
