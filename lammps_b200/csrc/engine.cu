@@ -2289,11 +2289,14 @@ static int fetch_ev(b200_ctx *ctx) {
   if (ctx->nranks > 1 && !ctx->grp && !ctx->local_tallies)
     NK(g_nccl.AllReduce(ctx->ev, ctx->ev, 8, ncclDouble, ncclSum, ctx->nccl, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_ev, ctx->ev, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  // the device error word rides along: a peer-memory halo that timed out (bit 8), a lost atom or a
+  // non-finite coordinate is reported on the next tally step, not only at the next rebuild
+  CK(cudaMemcpyAsync(ctx->h_flags + 1, ctx->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->grp && !ctx->local_tallies) TRY(group_sum(ctx, ctx->h_ev, 8));
   ctx->eng_vdwl = ctx->h_ev[0];
   for (int k = 0; k < 6; k++) ctx->virial[k] = ctx->h_ev[1 + k];
-  return B200_OK;
+  return check_err_flags(ctx, ctx->h_flags[1]);  // (after the group's collective: all members reach it)
 }
 
 // CUDA loads kernels lazily, on first launch.  The kernels that only run when atoms migrate
