@@ -112,6 +112,10 @@ int b200_run(b200_ctx *ctx, int nsteps, int64_t first_step, int thermo_every,
  *      calls every timestep.  Asynchronous unless dist_check needs the rebuild vote or
  *      eflag/vflag ask for tallies (then eng_vdwl/virial are current for b200_get_tallies). */
 int b200_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt);
+/* b200_step for a host that knows what comes next (Verlet::run does: i < n-1, output->next):
+ * more != 0 promises that another step follows before anything reads atoms, velocities or forces;
+ * the engine may then fuse the next step's FixNVE::initial_integrate into this step's pair kernel. */
+int b200_step_ahead(b200_ctx *ctx, int eflag, int vflag, int more, int *rebuilt);
 /*      stage-granular entry points (the same stages, one call each) */
 int b200_initial_integrate(b200_ctx *ctx);            /* FixNVE::initial_integrate fix_nve.cpp:68 */
 int b200_final_integrate(b200_ctx *ctx);              /* FixNVE::final_integrate  fix_nve.cpp:112 */
@@ -261,6 +265,7 @@ int b200_group_get_atoms(b200_group *g, double *x, double *v, double *f, int *ty
                          int *mask, int *image);
 int b200_group_setup(b200_group *g, int eflag, int vflag);
 int b200_group_step(b200_group *g, int eflag, int vflag, int *rebuilt);
+int b200_group_step_ahead(b200_group *g, int eflag, int vflag, int more, int *rebuilt);
 int b200_group_run(b200_group *g, int nsteps, int64_t first_step, int thermo_every,
                    double *thermo_out, int max_thermo, int *n_thermo);
 int b200_group_get_tallies(b200_group *g, double *eng_vdwl, double virial[6]);

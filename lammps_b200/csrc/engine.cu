@@ -276,7 +276,8 @@ struct b200_ctx {
   bool fuse_nve = true, ahead = false;
   bool fuse_now = false;   // the pair launches of the step being enqueued carry the integrator
   int fuse_check = 0;      // ... and the displacement check for the next step's decide()
-  int fuse_min_atoms = 65536;
+  int fuse_min_atoms = 0;  // (measured: fusing beats the CUDA graph of the unfused step even at 32 k atoms,
+                           //  1.03e9 vs 9.3e8 atom-steps/s on bench/in.lj; B200_FUSE_MIN raises the threshold)
   // tallies / flags
   double *ev = nullptr;   // [8] device: eng, virial[6], ke
   double *ke7 = nullptr;  // [7] device: b200_ke_group accumulators
@@ -2572,6 +2573,8 @@ int b200_get_counts(const b200_ctx *ctx, int *nlocal, int *nghost) {
 int b200_get_atoms(b200_ctx *ctx, int with_ghosts, double *x, double *v, double *f, int *type,
                    int *tag, int *mask, int *image) {
   if (!ctx) return B200_EARG;
+  if (ctx->ahead && (x || v || f))
+    return ctx->fail(B200_EARG, "atoms requested while the integrator runs ahead (b200_step_ahead with more != 0)");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   TRY(flush_final(ctx));
@@ -2949,9 +2952,18 @@ static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt, bool allo
 }
 
 int b200_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt) {
+  return b200_step_ahead(ctx, eflag, vflag, 0, rebuilt);
+}
+
+// b200_step for a host that knows what comes next: `more` != 0 promises that another step follows
+// before anything reads atoms, velocities or forces.  The engine may then apply the next step's
+// initial_integrate inside this step's pair kernel (NveFuse): the state it leaves is x(n+1),
+// v(n+1/2), no forces -- exactly what the next step starts from, and nothing a host may look at
+// (b200_get_atoms and the kinetic-energy sums refuse while the integrator runs ahead).
+int b200_step_ahead(b200_ctx *ctx, int eflag, int vflag, int more, int *rebuilt) {
   if (!ctx) return B200_EARG;
   if (!ctx->setup_done) return ctx->fail(B200_EARG, "b200_step before b200_setup");
-  TRY(one_step(ctx, eflag, vflag, rebuilt));
+  TRY(one_step(ctx, eflag, vflag, rebuilt, /*allow_fuse=*/more != 0));
   if (eflag || vflag) TRY(fetch_ev(ctx));  // the host is about to read eng_vdwl / virial
   return B200_OK;
 }
@@ -3015,6 +3027,7 @@ int b200_get_tallies(b200_ctx *ctx, double *eng_vdwl, double virial[6]) {
 
 int b200_ke_sum(b200_ctx *ctx, double *mv2) {
   if (!ctx || !mv2) return B200_EARG;
+  if (ctx->ahead) return ctx->fail(B200_EARG, "kinetic energy requested while the integrator runs ahead");
   TRY(flush_final(ctx));
   TRY(ke_reduce(ctx));
   if (ctx->nranks > 1 && !ctx->grp && !ctx->local_tallies)
@@ -3030,6 +3043,7 @@ int b200_ke_sum(b200_ctx *ctx, double *mv2) {
 // compute_temp.cpp:73-140); summed over all sub-domains unless tallies are local
 int b200_ke_group(b200_ctx *ctx, int groupbit, double *mv2, double tensor[6]) {
   if (!ctx) return B200_EARG;
+  if (ctx->ahead) return ctx->fail(B200_EARG, "kinetic energy requested while the integrator runs ahead");
   TRY(flush_final(ctx));
   CK(cudaSetDevice(ctx->device));
   const int nl = ctx->nlocal, c = ctx->cur;
@@ -3601,9 +3615,13 @@ int b200_group_setup(b200_group *g, int eflag, int vflag) {
 }
 
 int b200_group_step(b200_group *g, int eflag, int vflag, int *rebuilt) {
+  return b200_group_step_ahead(g, eflag, vflag, 0, rebuilt);
+}
+
+int b200_group_step_ahead(b200_group *g, int eflag, int vflag, int more, int *rebuilt) {
   if (!g) return B200_EARG;
   std::vector<int> rb(g->n, 0);
-  const int rc = group_run(g, [&](int i) { return b200_step(g->ctx[i], eflag, vflag, &rb[i]); });
+  const int rc = group_run(g, [&](int i) { return b200_step_ahead(g->ctx[i], eflag, vflag, more, &rb[i]); });
   if (rebuilt) *rebuilt = rb[0];
   return rc;
 }

@@ -153,9 +153,11 @@ void FixB200::dev_setup(int eflag, int vflag)
   check(grp ? b200_group_setup(grp, eflag, vflag) : b200_setup(ctx, eflag, vflag), FLERR);
 }
 
-void FixB200::dev_step(int eflag, int vflag, int *rebuilt)
+void FixB200::dev_step(int eflag, int vflag, int more, int *rebuilt)
 {
-  check(grp ? b200_group_step(grp, eflag, vflag, rebuilt) : b200_step(ctx, eflag, vflag, rebuilt), FLERR);
+  check(grp ? b200_group_step_ahead(grp, eflag, vflag, more, rebuilt)
+            : b200_step_ahead(ctx, eflag, vflag, more, rebuilt),
+        FLERR);
 }
 
 void FixB200::dev_tallies(double *eng_vdwl, double *virial)

@@ -44,7 +44,7 @@ class FixB200 : public Fix {
 
   // the calls that communicate between sub-domains, for one context or a group alike
   void dev_setup(int eflag, int vflag);
-  void dev_step(int eflag, int vflag, int *rebuilt);
+  void dev_step(int eflag, int vflag, int more, int *rebuilt);    // more: another step follows before any host read
   void dev_tallies(double *eng_vdwl, double *virial);
   void dev_peratom(double *eatom, double *vatom);    // Pair::ev_tally's eatom / vatom, download order
   void dev_ke(int groupbit, double *mv2, double *tensor);

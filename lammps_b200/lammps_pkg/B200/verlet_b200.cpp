@@ -396,8 +396,13 @@ void VerletB200::run(int n)
       step_staged_fix(eflag ? 1 : 0, vflag ? 1 : 0);
     else if (by_stage)
       step_by_stage(eflag ? 1 : 0, vflag ? 1 : 0);
-    else
-      pkg->dev_step(eflag ? 1 : 0, vflag ? 1 : 0, &rebuilt);
+    else {
+      // the device may run ahead (next step's initial_integrate inside this step's pair kernel)
+      // when nothing on the host looks at the atoms before the next step: not on the last step,
+      // not on an output step, not when a timeout may end the run here
+      const int more = (i < n - 1) && ntimestep != output->next && !timer->has_timeout();
+      pkg->dev_step(eflag ? 1 : 0, vflag ? 1 : 0, more, &rebuilt);
+    }
     resident = 1;
     pkg->host_stale = 1;
 

@@ -503,3 +503,45 @@ run 60
     assert np.abs(da[:, 4] - db[:, 4]).max() <= 1e-8 * np.abs(da[:, 4]).max()
     m = re.search(r"Neighbor list builds = (\d+)", tabs["ref"][2])
     assert m and ("Neighbor list builds = " + m.group(1)) in tabs["b200"][2]
+
+
+@pytest.mark.parametrize("extra", [[], ["-pk", "b200", "subdomains", "8"]], ids=["one-subdomain", "8-subdomains"])
+def test_running_ahead_inside_lmp_b200_never_leaks_into_host_reads(tmp_path, monkeypatch, extra):
+    """VerletB200::run tells the device when another step follows before any host read
+    (b200_step_ahead): the pair kernel then also integrates (fix nve fused, B200_FUSE_MIN=0 turns it
+    on at test sizes).  Dump-only steps (15, 30, 45: no thermo, so no tallies), thermo steps and the
+    end of the run must all see x(n), v(n), f(n) exactly as the reference executable does."""
+    monkeypatch.setenv("B200_FUSE_MIN", "0")
+    body = LJ_BODY + """
+thermo 20
+thermo_modify format float %.12g
+dump 1 all custom 15 f.dump id x y z vx fx
+dump_modify 1 sort id format float %.10g
+run 50
+"""
+    import numpy as np
+    refexe = ROOT / "oracle" / "_ref" / "lmp_ref"
+    res = {}
+    for tag, exe, args in (("ref", refexe, []), ("b200", EXE, ["-sf", "b200", *extra])):
+        d = tmp_path / tag
+        d.mkdir()
+        (d / "in.t").write_text(body)
+        r = subprocess.run([str(exe), *args, "-in", "in.t"], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        blocks = (d / "f.dump").read_text().split("ITEM: TIMESTEP")[1:]
+        assert [int(b.splitlines()[1]) for b in blocks] == [0, 15, 30, 45]
+        per = []
+        for blk in blocks:
+            lines = blk.splitlines()
+            k = [i for i, ln in enumerate(lines) if ln.startswith("ITEM: ATOMS")][0]
+            per.append(np.array([[float(t) for t in ln.split()] for ln in lines[k + 1:] if ln.strip()]))
+        res[tag] = (thermo_rows(r.stdout), per)
+    for x, y in zip(res["ref"][0], res["b200"][0]):
+        for u, v in zip(x, y):
+            assert abs(u - v) <= 1e-9 * max(1.0, abs(u)), (x, y)
+    assert len(res["b200"][0]) == 4
+    for a, b in zip(res["ref"][1], res["b200"][1]):
+        assert np.array_equal(a[:, 0], b[:, 0])
+        assert np.abs(a[:, 1:4] - b[:, 1:4]).max() <= 1e-8       # x
+        assert np.abs(a[:, 4] - b[:, 4]).max() <= 1e-8           # vx: full-step velocities, not half-kicked
+        assert np.abs(a[:, 5] - b[:, 5]).max() <= 1e-8 * max(np.abs(a[:, 5]).max(), 1.0)
