@@ -2607,6 +2607,13 @@ int b200_get_atoms(b200_ctx *ctx, int with_ghosts, double *x, double *v, double 
   if (tag) CK(cudaMemcpyAsync(tag, ctx->tag[c], sizeof(int) * n, cudaMemcpyDeviceToHost, s));
   if (mask) CK(cudaMemcpyAsync(mask, ctx->mask[c], sizeof(int) * n, cudaMemcpyDeviceToHost, s));
   if (image) CK(cudaMemcpyAsync(image, ctx->image[c], sizeof(int) * nl, cudaMemcpyDeviceToHost, s));
+  // The staging area was the other position buffer.  Its owned records are rewritten by whoever
+  // uses it next (the sort, the fused integrator), but its ghost records must keep the ghost
+  // TYPES: the fused integrator makes it the live buffer and the forward halo only writes x, y, z
+  // (k_ghost_place fills both buffers at a rebuild for the same reason).
+  if ((x || v || f) && ctx->nghost > 0)
+    CK(cudaMemcpyAsync(ctx->xt[c ^ 1] + nl, ctx->xt[c] + nl, sizeof(double4) * ctx->nghost,
+                       cudaMemcpyDeviceToDevice, s));
   CK(cudaStreamSynchronize(s));
   return B200_OK;
 }
