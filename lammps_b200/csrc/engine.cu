@@ -153,6 +153,9 @@ struct b200_ctx {
   DBuf<int> ostart, gstart, tilesum;
   // ghosts (index spaces p / q / g: see kernels_halo.cuh)
   DBuf<int> sendlist, gsrc, gbin, gslot, gtag_tmp, gsrc_tmp;
+  DBuf<int> okey;          // tags at the provisional sort slots (reproducible atom order, k_bin_keys)
+  DBuf<long long> gkey;    // (tag, direction) keys of the ghosts, likewise
+  bool stable_order = true;  // B200_STABLE=0: keep the arrival order of the atomics
   DBuf<unsigned char> senddir, gdir, gdir_tmp;
   DBuf<double4> gtmp;
   int *counts = nullptr;      // [32] device: per-direction counters [0,27), [27] error flags
@@ -1526,8 +1529,16 @@ static int reneighbor(b200_ctx *ctx) {
   // ---- counting sort of the owned atoms by bin (+ xhold)
   TRY(scan_inplace(ctx, ctx->ostart.p, g.mbins));
   if (ntot > 0) {
+    const int *okey = nullptr;
+    if (ctx->stable_order) {
+      TRY(reserve(ctx, ctx->okey, (size_t)ntot));
+      k_bin_keys<<<cdiv(ntot, 256), 256, 0, s>>>(ntot, ctx->atombin[c], ctx->slot, ctx->ostart.p, ctx->tag[c],
+                                                ctx->okey.p);
+      ctx->launches++;
+      okey = ctx->okey.p;
+    }
     k_permute_owned<<<cdiv(ntot, 256), 256, 0, s>>>(
-        ntot, ctx->atombin[c], ctx->slot, ctx->ostart.p, ctx->xt[c], ctx->xt[c ^ 1], ctx->v[c][0],
+        ntot, ctx->atombin[c], ctx->slot, okey, ctx->ostart.p, ctx->xt[c], ctx->xt[c ^ 1], ctx->v[c][0],
         ctx->v[c][1], ctx->v[c][2], ctx->v[c ^ 1][0], ctx->v[c ^ 1][1], ctx->v[c ^ 1][2], ctx->tag[c],
         ctx->tag[c ^ 1], ctx->mask[c], ctx->mask[c ^ 1], ctx->image[c], ctx->image[c ^ 1],
         ctx->atombin[c ^ 1], ctx->xh[0], ctx->xh[1], ctx->xh[2]);
@@ -1600,10 +1611,18 @@ static int reneighbor(b200_ctx *ctx) {
   }
   TRY(scan_inplace(ctx, ctx->gstart.p, g.mbins));
   if (ng > 0) {
+    const long long *gkey = nullptr;
+    if (ctx->stable_order) {
+      TRY(reserve(ctx, ctx->gkey, (size_t)ng));
+      k_ghost_keys<<<cdiv(ng, 256), 256, 0, s>>>(ng, ctx->gbin.p, ctx->gslot.p, ctx->gstart.p, ctx->gtag_tmp.p,
+                                                 ctx->gdir_tmp.p, ctx->gkey.p);
+      ctx->launches++;
+      gkey = ctx->gkey.p;
+    }
     k_ghost_place<<<cdiv(ng, 256), 256, 0, s>>>(ng, nl, ctx->gtmp.p, ctx->gtag_tmp.p, ctx->gsrc_tmp.p,
                                                 ctx->gbin.p, ctx->gslot.p, ctx->gdir_tmp.p,
                                                 ctx->gstart.p, ctx->xt[c], ctx->tag[c], ctx->mask[c],
-                                                ctx->gsrc.p, ctx->gdir.p, ctx->xt[c ^ 1]);
+                                                ctx->gsrc.p, ctx->gdir.p, ctx->xt[c ^ 1], gkey);
     ctx->launches++;
   }
   LAUNCH_CHECK();
@@ -2366,6 +2385,7 @@ int b200_create(b200_ctx **out, int device, int precision) {
     if (const char *e = getenv("B200_FUSE_MIN")) ctx->fuse_min_atoms = atoi(e);
     if (const char *e = getenv("B200_EAM2")) ctx->eam2 = strcmp(e, "auto") == 0 ? 2 : (atoi(e) != 0 ? 1 : 0);
     if (const char *e = getenv("B200_BUILD2")) ctx->build2 = atoi(e) != 0;
+    if (const char *e = getenv("B200_STABLE")) ctx->stable_order = atoi(e) != 0;
     if (const char *e = getenv("B200_EAM2_MARGIN")) ctx->eam2_margin = atof(e);
     if (const char *e = getenv("B200_LJ2F")) {
       int a[2];
@@ -2425,7 +2445,7 @@ void b200_destroy(b200_ctx *ctx) {
   F(ctx->neigh.p);
   F(ctx->numneigh.p); F(ctx->lj_tab.p); F(ctx->eam_i.p); F(ctx->eam_d.p); F(ctx->eam_one_d.p); F(ctx->ev); F(ctx->ke7); F(ctx->flags);
   F(ctx->cnt64);
-  F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p); F(ctx->tl_gi.p); F(ctx->tile_hdrs.p); F(ctx->tl_far.p); F(ctx->peratom.p);
+  F(ctx->tflags); F(ctx->tile_ibase.p); F(ctx->tl_iloc.p); F(ctx->tl_num.p); F(ctx->tl_list.p); F(ctx->tl_gi.p); F(ctx->tile_hdrs.p); F(ctx->tl_far.p); F(ctx->peratom.p); F(ctx->okey.p); F(ctx->gkey.p);
   if (ctx->h_ev) cudaFreeHost(ctx->h_ev);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   for (auto &r : ctx->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -173,6 +173,19 @@ __global__ void __launch_bounds__(256) k_ghost_make(
   gslot[q] = atomicAdd(&gbincount[b], 1);
 }
 
+// Reproducible ghost order (see k_bin_keys): a ghost is identified by (tag, direction it came
+// from); the ghosts of a bin are ranked by that key instead of by the order of the atomicAdd.
+__global__ void __launch_bounds__(256) k_ghost_keys(int nghost, const int *__restrict__ gbin,
+                                                    const int *__restrict__ gslot,
+                                                    const int *__restrict__ gstart,
+                                                    const int *__restrict__ gtag_tmp,
+                                                    const unsigned char *__restrict__ gdir_tmp,
+                                                    long long *__restrict__ gkey) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nghost) return;
+  gkey[gstart[gbin[q]] + gslot[q]] = ((long long)gtag_tmp[q] << 5) | gdir_tmp[q];
+}
+
 // Ghost creation, pass 2: place ghosts bin-sorted behind the owned atoms; gsrc/gdir are the
 // receiver-side equivalent of sendlist/firstrecv/pbc_flag of comm_brick, reused every step.
 __global__ void __launch_bounds__(256) k_ghost_place(
@@ -180,10 +193,18 @@ __global__ void __launch_bounds__(256) k_ghost_place(
     const int *__restrict__ gsrc_tmp, const int *__restrict__ gbin, const int *__restrict__ gslot,
     const unsigned char *__restrict__ gdir_tmp, const int *__restrict__ gstart,
     double4 *__restrict__ xt, int *__restrict__ tag, int *__restrict__ mask,
-    int *__restrict__ gsrc, unsigned char *__restrict__ gdir, double4 *__restrict__ xt_alt) {
+    int *__restrict__ gsrc, unsigned char *__restrict__ gdir, double4 *__restrict__ xt_alt,
+    const long long *__restrict__ gkey) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nghost) return;
-  const int gi = gstart[gbin[q]] + gslot[q];
+  int gi = gstart[gbin[q]] + gslot[q];
+  if (gkey) {
+    const int lo = gstart[gbin[q]], hi = gstart[gbin[q] + 1];
+    const long long mine = ((long long)gtag_tmp[q] << 5) | gdir_tmp[q];
+    int rank = 0;
+    for (int k = lo; k < hi; k++) rank += gkey[k] < mine;
+    gi = lo + rank;
+  }
   const int src = gsrc_tmp[q];
   xt[nlocal + gi] = gtmp[q];
   // the other position buffer takes the record too: a pair kernel with the fused integrator

@@ -177,11 +177,27 @@ __global__ void __launch_bounds__(256) k_pbc_bin(int nlocal, double4 *__restrict
   slot[i] = atomicAdd(&bincount[b], 1);
 }
 
+// The slot an atom takes inside its bin (atomicAdd in k_pbc_bin) depends on the order in which
+// thread blocks happen to run.  To make the atom order -- and with it the order of every list
+// row and of every force sum -- reproducible from run to run, the atoms of a bin are ranked by
+// their tag instead: pass 1 drops the tags at the provisional slots, pass 2 (k_permute_owned)
+// counts the smaller tags among the ~2 bin mates.  4 + 4 B/atom of extra traffic per rebuild.
+__global__ void __launch_bounds__(256) k_bin_keys(int n, const int *__restrict__ atombin,
+                                                  const int *__restrict__ slot,
+                                                  const int *__restrict__ binstart,
+                                                  const int *__restrict__ tag, int *__restrict__ okey) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = atombin[i];
+  if (b >= 0) okey[binstart[b] + slot[i]] = tag[i];
+}
+
 // Scatter pass of the counting sort: owned atoms are physically reordered by bin so that
 // every later gather (list build, pair kernels) walks nearly-contiguous memory.  xhold
 // (Neighbor::build prologue, neighbor.cpp:2520-2532) is written in the same pass.
 __global__ void __launch_bounds__(256) k_permute_owned(
     int nlocal, const int *__restrict__ atombin, const int *__restrict__ slot,
+    const int *__restrict__ okey,
     const int *__restrict__ binstart, const double4 *__restrict__ xt_in,
     double4 *__restrict__ xt_out, const double *__restrict__ vx_in, const double *__restrict__ vy_in,
     const double *__restrict__ vz_in, double *__restrict__ vx_out, double *__restrict__ vy_out,
@@ -193,7 +209,13 @@ __global__ void __launch_bounds__(256) k_permute_owned(
   if (i >= nlocal) return;
   const int b = atombin[i];
   if (b < 0) return;  // left for another sub-domain (k_pack_migrate shipped it)
-  const int d = binstart[b] + slot[i];
+  int d = binstart[b] + slot[i];
+  if (okey) {  // rank by tag among the atoms of the bin (tags are unique)
+    const int lo = binstart[b], hi = binstart[b + 1], mine = tag_in[i];
+    int rank = 0;
+    for (int q = lo; q < hi; q++) rank += okey[q] < mine;
+    d = lo + rank;
+  }
   const double4 p = xt_in[i];
   xt_out[d] = p;
   vx_out[d] = vx_in[i];
