@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(B2_WARPS * 32, B2_MINB) k_tile_build2(
             }
           }
           const double rsq = rsq_ref(pix - pxy.x, piy - pxy.y, piz - pz);
-          const double cut = ONETYPE ? cut1 : __ldg(cut_i + stype[s]);
+          const double cut = ONETYPE ? cut1 : (valid ? __ldg(cut_i + stype[s]) : 0.0);  // (slot S holds no type)
           const bool ok = valid && rsq <= cut;
           const bool isfar = SPLIT && rsq > splitsq;
           const unsigned mk = __ballot_sync(0xffffffffu, ok);
