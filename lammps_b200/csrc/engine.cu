@@ -1648,6 +1648,18 @@ static inline void shared_device_rendezvous(b200_ctx *ctx) {
   if (ctx->grp && ctx->grp->shared_dev) ctx->grp->barrier();
 }
 
+// Grid of a peer-memory halo kernel.  Every block of these kernels spins on flags another
+// sub-domain's kernel raises.  One device per sub-domain: one block per 256 records.  Sub-domains
+// SHARING a device: the spinning blocks of all of them (pack + unpack) must be resident together
+// with the kernels they wait for, or the device deadlocks until the spin limit (seen with 8
+// sub-domains of 500 k atoms each); the kernels are grid-stride, so the grid is capped to a share
+// of the 148 x 8 resident 256-thread blocks.
+static inline int p2p_grid(const b200_ctx *ctx, int n) {
+  int grid = cdiv(std::max(n, 1), 256);
+  if (ctx->grp && ctx->grp->shared_dev) grid = std::min(grid, std::max(1, 148 * 8 / (4 * std::max(ctx->grp->n, 1))));
+  return grid;
+}
+
 static int force_clear(b200_ctx *ctx) {
   const int ph3 = ph_begin(ctx, B200_PH_CLEAR);
   const int nall = ctx->nlocal + ctx->nghost;
@@ -1681,11 +1693,11 @@ static int forward_comm(b200_ctx *ctx) {
   if (ctx->p2p && ctx->remote_mask) {
     // pack + transfer in one kernel: records are stored straight into the neighbours' rbuf
     const long long seq = ++ctx->seqF;
-    k_p2p_pack_forward<0><<<cdiv(std::max(ctx->nsend, 1), 256), 256, 0, s>>>(
+    k_p2p_pack_forward<0><<<p2p_grid(ctx, ctx->nsend), 256, 0, s>>>(
         ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->diroffset, ctx->geom, ctx->xt[c], nullptr,
         ctx->fwdP, seq, ctx->p2p_counter + 0, (int *)ctx->p2p_counter + 4);
     shared_device_rendezvous(ctx);
-    k_p2p_unpack_forward<0><<<cdiv(std::max(ctx->nghost, 1), 256), 256, 0, s>>>(
+    k_p2p_unpack_forward<0><<<p2p_grid(ctx, ctx->nghost), 256, 0, s>>>(
         ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->geom, ctx->rbuf.p, ctx->xt[c], nullptr,
         ctx->fwdP, seq, ctx->p2p_counter + 1, (int *)ctx->p2p_counter + 4, fclear);
     shared_device_rendezvous(ctx);
@@ -1716,11 +1728,11 @@ static int reverse_halo(b200_ctx *ctx, Vec3Ptr a) {
   cudaStream_t s = ctx->stream;
   if (ctx->p2p && ctx->remote_mask) {
     const long long seq = ++ctx->seqR;
-    k_p2p_pack_reverse<W><<<cdiv(std::max(ctx->nghost, 1), 256), 256, 0, s>>>(
+    k_p2p_pack_reverse<W><<<p2p_grid(ctx, ctx->nghost), 256, 0, s>>>(
         ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->recvoffset, a, ctx->revP, seq,
         ctx->p2p_counter + 2, (int *)ctx->p2p_counter + 4);
     shared_device_rendezvous(ctx);
-    k_p2p_unpack_reverse<W><<<cdiv(std::max(ctx->nsend, 1), 256), 256, 0, s>>>(
+    k_p2p_unpack_reverse<W><<<p2p_grid(ctx, ctx->nsend), 256, 0, s>>>(
         ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->sbuf.p, a, ctx->revP, seq,
         ctx->p2p_counter + 3, (int *)ctx->p2p_counter + 4);
     shared_device_rendezvous(ctx);
@@ -1759,11 +1771,11 @@ static int forward_scalar(b200_ctx *ctx, double *a) {
   cudaStream_t s = ctx->stream;
   if (ctx->p2p && ctx->remote_mask) {
     const long long seq = ++ctx->seqF;
-    k_p2p_pack_forward<1><<<cdiv(std::max(ctx->nsend, 1), 256), 256, 0, s>>>(
+    k_p2p_pack_forward<1><<<p2p_grid(ctx, ctx->nsend), 256, 0, s>>>(
         ctx->nsend, ctx->sendlist.p, ctx->senddir.p, ctx->diroffset, ctx->geom, nullptr, a, ctx->fwdP,
         seq, ctx->p2p_counter + 0, (int *)ctx->p2p_counter + 4);
     shared_device_rendezvous(ctx);
-    k_p2p_unpack_forward<1><<<cdiv(std::max(ctx->nghost, 1), 256), 256, 0, s>>>(
+    k_p2p_unpack_forward<1><<<p2p_grid(ctx, ctx->nghost), 256, 0, s>>>(
         ctx->nghost, ctx->nlocal, ctx->gsrc.p, ctx->gdir.p, ctx->geom, ctx->rbuf.p, nullptr, a,
         ctx->fwdP, seq, ctx->p2p_counter + 1, (int *)ctx->p2p_counter + 4, Vec3Ptr{{nullptr, nullptr, nullptr}});
     shared_device_rendezvous(ctx);

@@ -406,8 +406,9 @@ __global__ void __launch_bounds__(256) k_p2p_pack_forward(
     const int *__restrict__ sendoffset, Geom g, const double4 *__restrict__ xt,
     const double *__restrict__ a, P2PMap pm, long long seq, unsigned *counter, int *err) {
   p2p_wait(pm.ack_in, pm.out_mask, seq - 1, err);
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < nsend) {
+  // (grid-stride: sub-domains that share a GPU launch these kernels with a capped grid so that
+  // every spinning block of every sub-domain is resident at once -- engine.cu p2p_grid)
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nsend; p += gridDim.x * blockDim.x) {
     const int dir = senddir[p];
     if ((pm.out_mask >> dir) & 1u) {
       const size_t q = (size_t)pm.dstoff[dir] + (p - sendoffset[dir]);
@@ -431,8 +432,7 @@ __global__ void __launch_bounds__(256) k_p2p_unpack_forward(
     Geom g, const double *__restrict__ rbuf, double4 *__restrict__ xt, double *__restrict__ a,
     P2PMap pm, long long seq, unsigned *counter, int *err, Vec3Ptr fclear) {
   p2p_wait(pm.flag_in, pm.in_mask, seq, err);
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < nghost) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nghost; k += gridDim.x * blockDim.x) {
     const int src = gsrc[k];
     if (MODE == 0 && fclear.a[0]) {
       fclear.a[0][nlocal + k] = 0.0;
@@ -468,8 +468,7 @@ __global__ void __launch_bounds__(256) k_p2p_pack_reverse(
     const int *__restrict__ recvoffset, Vec3Ptr f, P2PMap pm, long long seq, unsigned *counter,
     int *err) {
   p2p_wait(pm.ack_in, pm.out_mask, seq - 1, err);
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < nghost) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nghost; k += gridDim.x * blockDim.x) {
     const int src = gsrc[k];
     if (src >= 0) {
 #pragma unroll
@@ -491,8 +490,7 @@ __global__ void __launch_bounds__(256) k_p2p_unpack_reverse(
     const double *__restrict__ sbuf, Vec3Ptr f, P2PMap pm, long long seq, unsigned *counter,
     int *err) {
   p2p_wait(pm.flag_in, pm.in_mask, seq, err);
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < nsend) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nsend; p += gridDim.x * blockDim.x) {
     if ((pm.in_mask >> senddir[p]) & 1u) {
       const int i = sendlist[p];
       const double *r = sbuf + (size_t)W * p;

@@ -7,8 +7,8 @@ properties that do not depend on the size:
   * the stored list is the half list: every exported pair lies within the neighbour cutoff, no
     pair is stored twice, and the tile rows hold exactly two entries per owned-owned pair;
   * the lj/cut tile path sums forces in a fixed order: two runs are bit-identical;
-  * domain decomposition does not change the physics: 8 sub-domains sharing the GPU (500 k atoms)
-    end on the one-sub-domain trajectory (1e-9) with the same list builds and the same tallies;
+  * domain decomposition does not change the physics: 8 sub-domains sharing the GPU end on the
+    one-sub-domain trajectory (1e-9) with the same number of list builds and the same tallies;
   * intensive thermo quantities land on the reference's golden 32 k-atom log (same lattice, same
     state point, other random velocities): temperature, energy per atom and pressure after 100
     steps within the statistical scatter of the smaller system."""
@@ -92,12 +92,11 @@ def test_lj_4m_two_runs_are_bit_identical(lj4m):
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
 
 
-def test_lj_500k_eight_subdomains_follow_the_single_domain_trajectory():
-    """(500 k atoms, not 4 M: sub-domains that SHARE a GPU spin on each other's halo flags, and
-    eight 4 M-atom-sized halo kernels do not fit the device at once; with one GPU per sub-domain
-    the full sizes run in tools/gpu_scale.sh and the driver's scaling bench)"""
+def test_lj_4m_eight_subdomains_follow_the_single_domain_trajectory(lj4m):
+    """(sub-domains that share a GPU spin on each other's halo flags: their halo kernels run on a
+    capped, grid-stride grid so that all of them are resident at once -- engine.cu p2p_grid)"""
     from test_gpu_subdomains import _make_group
-    s = lj_system((50, 50, 50))
+    s = lj4m
     n = len(s["x"])
     e, th = _run(s, 60, 0)
     a = e.get_atoms(fields=("x", "tag"))
