@@ -343,11 +343,19 @@ def run_b200(args):
     t0 = time.perf_counter()
     e.step = 0
     configure(e, s, hx, hv, ht, hg, natoms)       # H2D: x,v (24 B each), type, tag (4 B each)
+    e.sync()
+    t1 = time.perf_counter()
     e.setup(1, 1)
+    e.sync()
+    t2 = time.perf_counter()
     th = e.run(e2e_steps, 100)                    # thermo tallies read back every 100 steps
+    t3 = time.perf_counter()
     got = e.get_atoms(fields=("x", "v", "f"), into=out)   # D2H: x,v,f into pinned host buffers
     barrier()
-    e2e_s = maxreduce(time.perf_counter() - t0)
+    t4 = time.perf_counter()
+    e2e_s = maxreduce(t4 - t0)
+    e2e_parts = {"upload_ms": (t1 - t0) * 1e3, "setup_ms": (t2 - t1) * 1e3, "run_ms": (t3 - t2) * 1e3,
+                 "download_ms": (t4 - t3) * 1e3}
     e2e_value = natoms * e2e_steps / e2e_s
     h2d = nown * (24 + 24 + 4 + 4)
     d2h = len(got["x"]) * 72 + len(th) * 80
@@ -444,7 +452,8 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d / e2e_steps,
                 "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps,
                 "includes": "pinned-host upload, Verlet setup (ghosts+list+forces), run, thermo "
-                            "read-back, x/v/f download"},
+                            "read-back, x/v/f download",
+                "parts_ms_rank0": {k: round(v, 2) for k, v in e2e_parts.items()}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
