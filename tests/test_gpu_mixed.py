@@ -12,8 +12,11 @@ pytestmark = pytest.mark.gpu
 
 FTOL = 1e-5   # max|df| / max|f|
 ETOL = 1e-6   # energy, virial trace (pressure)
-# 100-step drift of thermo quantities against the FP64 oracle: relative, per quantity
-DRIFT = {"temp": 2e-5, "e_pair": 2e-6, "toteng": 2e-6, "press": 5e-4}
+# 100-step drift of thermo quantities against the FP64 oracle: relative, per quantity.  Measured
+# (tools/mixed_drift_probe.py, FP32 pair math with FP64 accumulation): lj temp 4e-9, e_pair 9e-9,
+# toteng 1e-8, press 4e-7; eam temp 1.5e-7, e_pair 5e-9, toteng 2e-10, press 3e-7 -- the 1e-7 level
+# of the reference's own accelerator regression tolerance, with a margin of 5-7x.
+DRIFT = {"temp": 1e-6, "e_pair": 1e-7, "toteng": 1e-7, "press": 2e-6}
 
 
 def _static(s):
