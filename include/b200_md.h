@@ -265,6 +265,17 @@ int b200_group_get_atoms(b200_group *g, double *x, double *v, double *f, int *ty
                          int *mask, int *image);
 int b200_group_setup(b200_group *g, int eflag, int vflag);
 int b200_group_step(b200_group *g, int eflag, int vflag, int *rebuilt);
+/* the stages of a timestep one by one (b200_decide ... b200_reverse_comm, b200_nve_v / _x /
+ * b200_scale_v) for every sub-domain of the group, in step */
+int b200_group_decide(b200_group *g, int *rebuild);
+int b200_group_reneighbor(b200_group *g);
+int b200_group_forward_comm(b200_group *g);
+int b200_group_force_clear(b200_group *g);
+int b200_group_pair_compute(b200_group *g, int eflag, int vflag);
+int b200_group_reverse_comm(b200_group *g);
+int b200_group_nve_v(b200_group *g, double dtf, int groupbit);
+int b200_group_nve_x(b200_group *g, double dtv, int groupbit);
+int b200_group_scale_v(b200_group *g, double factor, int groupbit);
 int b200_group_step_ahead(b200_group *g, int eflag, int vflag, int more, int *rebuilt);
 int b200_group_run(b200_group *g, int nsteps, int64_t first_step, int thermo_every,
                    double *thermo_out, int max_thermo, int *n_thermo);

@@ -2324,11 +2324,15 @@ static int fetch_ev(b200_ctx *ctx) {
   // the device error word rides along: a peer-memory halo that timed out (bit 8), a lost atom or a
   // non-finite coordinate is reported on the next tally step, not only at the next rebuild
   CK(cudaMemcpyAsync(ctx->h_flags + 1, ctx->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->h_flags[40] = 0;
+  if (ctx->p2p && ctx->p2p_counter)
+    CK(cudaMemcpyAsync(ctx->h_flags + 40, ctx->p2p_counter + 4, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->grp && !ctx->local_tallies) TRY(group_sum(ctx, ctx->h_ev, 8));
   ctx->eng_vdwl = ctx->h_ev[0];
   for (int k = 0; k < 6; k++) ctx->virial[k] = ctx->h_ev[1 + k];
-  return check_err_flags(ctx, ctx->h_flags[1]);  // (after the group's collective: all members reach it)
+  // (after the group's collective: all members reach it)
+  return check_err_flags(ctx, ctx->h_flags[1] | (ctx->h_flags[40] ? 8 : 0));
 }
 
 // CUDA loads kernels lazily, on first launch.  The kernels that only run when atoms migrate
@@ -3110,8 +3114,18 @@ int b200_sync(b200_ctx *ctx) {
   if (!ctx) return B200_EARG;
   CK(cudaSetDevice(ctx->device));
   if (ctx->stream2) CK(cudaStreamSynchronize(ctx->stream2));
+  // the device error word comes back with the sync: a peer-memory halo that gave up waiting for a
+  // neighbour (P2P_SPIN_LIMIT), a lost atom, a non-finite coordinate
+  if (!(ctx->flags && ctx->h_flags)) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+  }
+  CK(cudaMemcpyAsync(ctx->h_flags + 1, ctx->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->h_flags[40] = 0;
+  if (ctx->p2p && ctx->p2p_counter)  // the peer-memory halo kernels keep their own error word
+    CK(cudaMemcpyAsync(ctx->h_flags + 40, ctx->p2p_counter + 4, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  return B200_OK;
+  return check_err_flags(ctx, ctx->h_flags[1] | (ctx->h_flags[40] ? 8 : 0));
 }
 
 // run-time knobs by name (the `package b200` keywords; the B200_* environment variables set the
@@ -3637,6 +3651,31 @@ int b200_group_get_atoms(b200_group *g, double *x, double *v, double *f, int *ty
                           type ? type + o : nullptr, tag ? tag + o : nullptr, mask ? mask + o : nullptr,
                           image ? image + o : nullptr);
   });
+}
+
+// ---- the stages of a timestep, one by one, for a host whose integrator is its own fix
+// (fix nvt/b200 under `package b200 gpus N`): every sub-domain runs the stage, in step
+#define GROUP_STAGE(NAME, ARGS, CALL)                                        \
+  int b200_group_##NAME ARGS {                                               \
+    if (!g) return B200_EARG;                                                \
+    return group_run(g, [&](int i) { b200_ctx *c = g->ctx[i]; return CALL; }); \
+  }
+GROUP_STAGE(nve_v, (b200_group *g, double dtf, int groupbit), b200_nve_v(c, dtf, groupbit))
+GROUP_STAGE(nve_x, (b200_group *g, double dtv, int groupbit), b200_nve_x(c, dtv, groupbit))
+GROUP_STAGE(scale_v, (b200_group *g, double factor, int groupbit), b200_scale_v(c, factor, groupbit))
+GROUP_STAGE(reneighbor, (b200_group *g), b200_reneighbor(c))
+GROUP_STAGE(forward_comm, (b200_group *g), b200_forward_comm(c))
+GROUP_STAGE(force_clear, (b200_group *g), b200_force_clear(c))
+GROUP_STAGE(pair_compute, (b200_group *g, int eflag, int vflag), b200_pair_compute(c, eflag, vflag))
+GROUP_STAGE(reverse_comm, (b200_group *g), b200_reverse_comm(c))
+#undef GROUP_STAGE
+
+int b200_group_decide(b200_group *g, int *rebuild) {
+  if (!g || !rebuild) return B200_EARG;
+  std::vector<int> rb(g->n, 0);
+  const int rc = group_run(g, [&](int i) { return b200_decide(g->ctx[i], &rb[i]); });
+  *rebuild = rb[0];  // (the vote is the group's: every member holds the same answer)
+  return rc;
 }
 
 int b200_group_pair_peratom(b200_group *g, double *eatom, double *vatom) {

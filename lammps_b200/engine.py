@@ -27,7 +27,9 @@ EXPORTS = [
     "b200_set_decomposition", "b200_set_rank_grid", "b200_set_neighbor", "b200_neigh_modify", "b200_set_atoms",
     "b200_get_atoms",
     "b200_get_counts", "b200_pair_lj_cut", "b200_pair_eam", "b200_fix_nve", "b200_setup",
-    "b200_run", "b200_step", "b200_step_ahead", "b200_group_step_ahead", "b200_last_run_ms", "b200_initial_integrate", "b200_final_integrate", "b200_decide",
+    "b200_run", "b200_step", "b200_step_ahead", "b200_group_step_ahead", "b200_group_decide", "b200_group_reneighbor", "b200_group_forward_comm",
+    "b200_group_force_clear", "b200_group_pair_compute", "b200_group_reverse_comm", "b200_group_nve_v",
+    "b200_group_nve_x", "b200_group_scale_v", "b200_last_run_ms", "b200_initial_integrate", "b200_final_integrate", "b200_decide",
     "b200_forward_comm", "b200_reverse_comm", "b200_reneighbor", "b200_force_clear",
     "b200_pair_compute", "b200_nve_v", "b200_nve_x", "b200_scale_v", "b200_get_tallies", "b200_ke_sum", "b200_get_stats",
     "b200_get_neighbor_list", "b200_get_eam_rho_fp", "b200_pair_peratom", "b200_group_pair_peratom",

@@ -176,6 +176,31 @@ void FixB200::dev_ke(int groupbit, double *mv2, double *tensor)
         FLERR);
 }
 
+void FixB200::dev_decide(int *rebuild)
+{
+  check(grp ? b200_group_decide(grp, rebuild) : b200_decide(ctx, rebuild), FLERR);
+}
+void FixB200::dev_reneighbor() { check(grp ? b200_group_reneighbor(grp) : b200_reneighbor(ctx), FLERR); }
+void FixB200::dev_forward_comm() { check(grp ? b200_group_forward_comm(grp) : b200_forward_comm(ctx), FLERR); }
+void FixB200::dev_force_clear() { check(grp ? b200_group_force_clear(grp) : b200_force_clear(ctx), FLERR); }
+void FixB200::dev_pair_compute(int eflag, int vflag)
+{
+  check(grp ? b200_group_pair_compute(grp, eflag, vflag) : b200_pair_compute(ctx, eflag, vflag), FLERR);
+}
+void FixB200::dev_reverse_comm() { check(grp ? b200_group_reverse_comm(grp) : b200_reverse_comm(ctx), FLERR); }
+void FixB200::dev_nve_v(double dtf, int groupbit)
+{
+  check(grp ? b200_group_nve_v(grp, dtf, groupbit) : b200_nve_v(ctx, dtf, groupbit), FLERR);
+}
+void FixB200::dev_nve_x(double dtv, int groupbit)
+{
+  check(grp ? b200_group_nve_x(grp, dtv, groupbit) : b200_nve_x(ctx, dtv, groupbit), FLERR);
+}
+void FixB200::dev_scale_v(double factor, int groupbit)
+{
+  check(grp ? b200_group_scale_v(grp, factor, groupbit) : b200_scale_v(ctx, factor, groupbit), FLERR);
+}
+
 void FixB200::dev_counts(int *nlocal, int *nghost)
 {
   check(grp ? b200_group_count(grp, nlocal, nghost) : b200_get_counts(ctx, nlocal, nghost), FLERR);

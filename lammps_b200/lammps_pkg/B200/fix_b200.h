@@ -49,6 +49,16 @@ class FixB200 : public Fix {
   void dev_peratom(double *eatom, double *vatom);    // Pair::ev_tally's eatom / vatom, download order
   void dev_ke(int groupbit, double *mv2, double *tensor);
   void dev_counts(int *nlocal, int *nghost);
+  // the stages of a timestep one by one (a host fix integrates: fix nvt/b200)
+  void dev_decide(int *rebuild);
+  void dev_reneighbor();
+  void dev_forward_comm();
+  void dev_force_clear();
+  void dev_pair_compute(int eflag, int vflag);
+  void dev_reverse_comm();
+  void dev_nve_v(double dtf, int groupbit);
+  void dev_nve_x(double dtv, int groupbit);
+  void dev_scale_v(double factor, int groupbit);
   void dev_stats(b200_stats *st);
 
   // the package fix of this LAMMPS instance; issues "package b200" defaults if absent

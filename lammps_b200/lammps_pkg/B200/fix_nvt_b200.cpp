@@ -23,8 +23,6 @@ void FixNVTB200::init()
   if (atom->rmass_flag) error->all(FLERR, "Fix nvt/b200 requires per-type masses");
   if (strcmp(update->integrate_style, "verlet/b200") != 0)
     error->all(FLERR, "Fix nvt/b200 requires run_style verlet/b200");
-  if (pkg->group())
-    error->all(FLERR, "Fix nvt/b200 runs on one sub-domain per process (not with package b200 gpus/subdomains)");
   if (which != 0)    // NOBIAS (fix_nh.cpp enum): a bias would need per-atom host work in nh_v_temp
     error->all(FLERR, "Fix nvt/b200 does not support temperature computes with a bias");
   // the chain reads the temperature every step: it must come from the device sum
@@ -42,22 +40,19 @@ void FixNVTB200::b200_params(double &dtv_, double &dtf_, int &groupbit_)
 /* FixNH::nve_v, fix_nh.cpp:2300-2336 (per-type masses) */
 void FixNVTB200::nve_v()
 {
-  FixB200 *pkg = FixB200::instance(lmp);
-  B200_CHECK(pkg, b200_nve_v(pkg->context(), dtf, groupbit));
+  FixB200::instance(lmp)->dev_nve_v(dtf, groupbit);
 }
 
 /* FixNH::nve_x, fix_nh.cpp:2278-2298 */
 void FixNVTB200::nve_x()
 {
-  FixB200 *pkg = FixB200::instance(lmp);
-  B200_CHECK(pkg, b200_nve_x(pkg->context(), dtv, groupbit));
+  FixB200::instance(lmp)->dev_nve_x(dtv, groupbit);
 }
 
 /* FixNH::nh_v_temp, fix_nh.cpp:2338-2352 (no bias) */
 void FixNVTB200::nh_v_temp()
 {
-  FixB200 *pkg = FixB200::instance(lmp);
-  // FixNH::setup() runs the chain once before the atoms are on the device? No: setup only
-  // computes t_current; the first scaling happens in initial_integrate of the first step.
-  B200_CHECK(pkg, b200_scale_v(pkg->context(), factor_eta, groupbit));
+  // (FixNH::setup only computes t_current on the host; the first scaling happens in
+  // initial_integrate of the first step, when the atoms are on the device)
+  FixB200::instance(lmp)->dev_scale_v(factor_eta, groupbit);
 }

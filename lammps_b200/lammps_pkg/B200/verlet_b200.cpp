@@ -349,18 +349,18 @@ void VerletB200::step_staged_fix(int ef, int vf)
   int nflag = 0;
   staged_fix->initial_integrate(vflag);
   timer->stamp(Timer::MODIFY);
-  B200_CHECK(pkg, b200_decide(ctx, &nflag));
+  pkg->dev_decide(&nflag);
   if (nflag) {
-    B200_CHECK(pkg, b200_reneighbor(ctx));
+    pkg->dev_reneighbor();
     timer->stamp(Timer::NEIGH);
   } else {
-    B200_CHECK(pkg, b200_forward_comm(ctx));
+    pkg->dev_forward_comm();
     timer->stamp(Timer::COMM);
   }
-  B200_CHECK(pkg, b200_force_clear(ctx));
-  B200_CHECK(pkg, b200_pair_compute(ctx, ef, vf));
+  pkg->dev_force_clear();
+  pkg->dev_pair_compute(ef, vf);
   timer->stamp(Timer::PAIR);
-  B200_CHECK(pkg, b200_reverse_comm(ctx));
+  pkg->dev_reverse_comm();
   timer->stamp(Timer::COMM);
   staged_fix->final_integrate();
   timer->stamp(Timer::MODIFY);

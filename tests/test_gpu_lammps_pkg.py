@@ -454,8 +454,10 @@ def test_profile_fills_the_timer_breakdown(tmp_path):
     assert "B200 device time by phase" in out
 
 
-@pytest.mark.parametrize("neigh", ["every 20 delay 0 check no", "every 1 delay 0 check yes"])
-def test_fix_nvt_matches_reference_executable(tmp_path, neigh):
+@pytest.mark.parametrize("neigh,extra", [("every 20 delay 0 check no", []), ("every 1 delay 0 check yes", []),
+                                         ("every 5 delay 0 check yes", ["-pk", "b200", "subdomains", "8"])],
+                         ids=["check-no", "check-yes", "8-subdomains"])
+def test_fix_nvt_matches_reference_executable(tmp_path, neigh, extra):
     """fix nvt under -sf b200 = fix nvt/b200: the reference's own Nose-Hoover chain (FixNH, inherited)
     on the host, its per-atom loops (nve_v, nve_x, nh_v_temp) and the temperature sum on the device.
     Thermo every step (temperature ramp 1.44 -> 0.8, chain of 3) and the final forces against
@@ -472,11 +474,11 @@ run 60
     refexe = ROOT / "oracle" / "_ref" / "lmp_ref"
     import numpy as np
     tabs = {}
-    for tag, exe, extra in (("ref", refexe, []), ("b200", EXE, ["-sf", "b200"])):
+    for tag, exe, args in (("ref", refexe, []), ("b200", EXE, ["-sf", "b200", *extra])):
         d = tmp_path / tag
         d.mkdir()
         (d / "in.t").write_text(body)
-        r = subprocess.run([str(exe), *extra, "-in", "in.t"], cwd=d, capture_output=True, text=True, timeout=600)
+        r = subprocess.run([str(exe), *args, "-in", "in.t"], cwd=d, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         rows, on = [], False
         for ln in r.stdout.splitlines():

@@ -34,3 +34,53 @@ def test_eight_ranks_match_oracle():
     if _ngpu() < 8:
         pytest.skip("needs 8 GPUs")
     _run(8, "lj", 16, 100, 29532)
+
+
+def test_peer_memory_halo_gives_up_instead_of_hanging():
+    """the spin-wait of the peer-memory halo (k_p2p_unpack_forward) has a limit (P2P_SPIN_LIMIT,
+    ~2 s): a sub-domain whose neighbour never sends reports B200_ECUDA "timed out" at the next
+    sync instead of hanging the GPU.  Two sub-domains on two devices in one process; only one of
+    them is stepped."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import ctypes as C
+    sys.path.insert(0, str(ROOT / "tests"))
+    from common import lj_system
+    from lammps_b200.engine import B200Error, EngineGroup
+    s = lj_system((10, 10, 10))
+    g = EngineGroup([0, 1], "double", s["units"])
+    g.set_box(s["lo"], s["hi"])
+    g.set_atoms(s["x"], s["v"], s["type"], s["tag"], s["mass"])
+    g.neighbor(s["skin"], every=20, delay=0, check=False)
+    g.fix_nve(s["dt"])
+    g.pair_lj_cut(s["tables"])
+    g.setup(1, 1)
+    e0 = g.sub[0]
+    e0.sync()                                                      # (selects device 0 in this thread)
+    e0._chk(e0.L.b200_step(e0.h, C.c_int(0), C.c_int(0), None))   # the neighbour stays silent
+    with pytest.raises(B200Error, match="timed out"):
+        e0.sync()
+
+
+def test_lmp_b200_package_drives_two_gpus_from_one_process():
+    """`lmp_b200 -sf b200 -pk b200 gpus 2 -in bench/in.lj` (unmodified input): one LAMMPS process,
+    one brick sub-domain per GPU, peer access instead of MPI.  The thermo output must be the golden
+    log's (tests/golden/ref_lj_32k.json) and the list statistics the reference's."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+    import re
+    sys.path.insert(0, str(ROOT / "tests"))
+    from test_gpu_lammps_pkg import BENCH, GOLDEN, close_to_printed, run_lmp, thermo_rows
+    out = run_lmp(["-sf", "b200", "-pk", "b200", "gpus", "2", "-in", "in.lj"], cwd=BENCH)
+    assert "2 sub-domains on 2 GPU(s)" in out
+    g = json.loads((GOLDEN / "ref_lj_32k.json").read_text())["published_log"]
+    rows = thermo_rows(out)
+    assert [int(r[0]) for r in rows] == [int(r[0]) for r in g["thermo"]]
+    for got, ref in zip(rows, g["thermo"]):
+        for a, b in zip(got[1:], ref[1:]):
+            assert close_to_printed(a, b), (got, ref)
+    m = re.search(r"Total # of neighbors = (\d+)", out)
+    assert m and int(m.group(1)) == g["neighbors"]
+    m = re.search(r"Neighbor list builds = (\d+)", out)
+    assert m and int(m.group(1)) == g["builds"]
