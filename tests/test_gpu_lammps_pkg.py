@@ -547,3 +547,22 @@ run 50
         assert np.abs(a[:, 1:4] - b[:, 1:4]).max() <= 1e-8       # x
         assert np.abs(a[:, 4] - b[:, 4]).max() <= 1e-8           # vx: full-step velocities, not half-kicked
         assert np.abs(a[:, 5] - b[:, 5]).max() <= 1e-8 * max(np.abs(a[:, 5]).max(), 1.0)
+
+
+def test_run_continuation_pre_no_keeps_the_device_state(tmp_path):
+    """`run N pre no` (run.cpp:169-172): no init, no setup -- Verlet::run continues from the state
+    the previous run left, including the age of the neighbour list.  The device keeps atoms, list
+    and `ago` across runs, so the rebuild schedule and the trajectory are the reference's; a third
+    run with `pre yes` goes through setup again."""
+    body = LJ_BODY + """
+thermo 15
+thermo_modify format float %.12g
+run 30
+run 30 pre no post no
+dump 1 all custom 5 f.dump id x y z fx
+dump_modify 1 sort id format float %.10g
+run 25
+"""
+    outs = _both(tmp_path, body, 85)
+    _compare(outs, ftol=1e-8, ttol=1e-9)
+    assert len(outs["b200"][0]) == len(outs["ref"][0]) >= 8
