@@ -132,6 +132,14 @@ int b200_pair_compute(b200_ctx *ctx, int eflag, int vflag); /* Pair::compute pai
 int b200_nve_v(b200_ctx *ctx, double dtf, int groupbit);
 int b200_nve_x(b200_ctx *ctx, double dtv, int groupbit);
 int b200_scale_v(b200_ctx *ctx, double factor, int groupbit);
+/* fix npt / nph (FixNH with a barostat, orthogonal box): nh_v_press (fix_nh.cpp:2227-2252: each
+ * velocity component scaled twice by factor[d]) and remap (fix_nh.cpp:1156-1300): owned atoms of
+ * groupbit are dilated from the old box into the new one (Domain::x2lamda / lamda2x) and the
+ * device adopts the new box -- halo shifts at once, bins / stencil / sub-domain bounds at the next
+ * rebuild, the displacement check's trigger shrinks with the box corners (neighbor.cpp:2443). */
+int b200_scale_v3(b200_ctx *ctx, const double factor[3], int groupbit);
+int b200_remap(b200_ctx *ctx, const double oldlo[3], const double oldhi[3], const double newlo[3],
+               const double newhi[3], int groupbit);
 
 /* ---- tallies the host reads back: pair->eng_vdwl, pair->virial[6] (pair.h), and
  *      sum_i m_i v_i^2 (ComputeTemp::compute_scalar, compute_temp.cpp:73-97) */
@@ -276,6 +284,9 @@ int b200_group_reverse_comm(b200_group *g);
 int b200_group_nve_v(b200_group *g, double dtf, int groupbit);
 int b200_group_nve_x(b200_group *g, double dtv, int groupbit);
 int b200_group_scale_v(b200_group *g, double factor, int groupbit);
+int b200_group_scale_v3(b200_group *g, const double factor[3], int groupbit);
+int b200_group_remap(b200_group *g, const double oldlo[3], const double oldhi[3], const double newlo[3],
+                     const double newhi[3], int groupbit);
 int b200_group_step_ahead(b200_group *g, int eflag, int vflag, int more, int *rebuilt);
 int b200_group_run(b200_group *g, int nsteps, int64_t first_step, int thermo_every,
                    double *thermo_out, int max_thermo, int *n_thermo);

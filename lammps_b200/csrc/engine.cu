@@ -126,6 +126,10 @@ struct b200_ctx {
   std::vector<double> cutneighsq_h;
   std::vector<int> ex_type;  // neigh_modify exclude type: [(ntypes+1)^2] flags, empty = none
   bool build_once = false;   // neigh_modify once yes: the list of setup is never rebuilt
+  // a box that changes during the run (fix npt/b200 -> b200_remap): the displacement check moves
+  // into decide() and its trigger distance shrinks with the box corners (neighbor.cpp:2443-2455)
+  bool box_changes = false;
+  double boxlo_hold[3] = {0, 0, 0}, boxhi_hold[3] = {0, 0, 0}, deltasq = 0.0;
   DBuf<double> cutneighsq_d;
   int64_t ago = 0, nbuilds = 0, ndanger = 0;
   Geom geom;
@@ -1455,6 +1459,13 @@ static void drop_step_graph(b200_ctx *ctx) {
 static int reneighbor(b200_ctx *ctx) {
   drop_step_graph(ctx);
   if (!ctx->geom_ready) TRY(setup_geometry(ctx));
+  if (ctx->box_changes) {  // Neighbor::build: boxlo_hold / boxhi_hold (neighbor.cpp:2533-2541)
+    for (int d = 0; d < 3; d++) {
+      ctx->boxlo_hold[d] = ctx->boxlo[d];
+      ctx->boxhi_hold[d] = ctx->boxhi[d];
+    }
+    ctx->deltasq = ctx->triggersq;
+  }
   const int ph2 = ph_begin(ctx, B200_PH_NEIGH);
   const Geom &g = ctx->geom;
   const bool multi = ctx->nranks > 1;
@@ -2262,6 +2273,15 @@ static int decide(b200_ctx *ctx, int *rebuild) {
       *rebuild = 1;
       return B200_OK;
     }
+    if (ctx->box_changes) {  // the check was not fused into an integrate kernel: take it now
+      CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
+      if (ctx->nlocal > 0) {
+        k_check_distance<<<cdiv(ctx->nlocal, 256), 256, 0, ctx->stream>>>(
+            ctx->nlocal, ctx->xt[ctx->cur], ctx->xh[0], ctx->xh[1], ctx->xh[2], ctx->deltasq, ctx->flags);
+        ctx->launches++;
+        LAUNCH_CHECK();
+      }
+    }
     // Neighbor::check_distance: MPI_Allreduce(MAX) of the moved flag (neighbor.cpp:2487)
     if (ctx->nranks > 1 && !ctx->grp)
       NK(g_nccl.AllReduce(ctx->flags, ctx->flags, 1, ncclInt, ncclMax, ctx->nccl, ctx->stream));
@@ -2838,7 +2858,8 @@ int b200_nve_x(b200_ctx *ctx, double dtv, int groupbit) {
   if (!ctx) return B200_EARG;
   TRY(staged_guard(ctx));
   const int nl = ctx->nlocal, c = ctx->cur;
-  const int chk = check_due_next(ctx) ? 1 : 0;  // the vote decide() reads after this stage
+  // the vote decide() reads after this stage (with a changing box decide() takes it itself)
+  const int chk = (check_due_next(ctx) && !ctx->box_changes) ? 1 : 0;
   CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
   if (nl > 0) {
     k_nve_x<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2],
@@ -2861,6 +2882,76 @@ int b200_scale_v(b200_ctx *ctx, double factor, int groupbit) {
     ctx->launches++;
     LAUNCH_CHECK();
   }
+  return B200_OK;
+}
+
+int b200_scale_v3(b200_ctx *ctx, const double factor[3], int groupbit) {
+  if (!ctx || !factor) return B200_EARG;
+  TRY(staged_guard(ctx));
+  const int nl = ctx->nlocal, c = ctx->cur;
+  if (nl > 0) {
+    k_scale_v3<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->mask[c],
+                                                       factor[0], factor[1], factor[2], groupbit);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  return B200_OK;
+}
+
+// The box follows the barostat.  Owned atoms of `groupbit` are dilated with it (FixNH::remap,
+// fix_nh.cpp:1156-1300: x2lamda in the old box, lamda2x in the new one); then the new box is
+// adopted: periodic shifts of the halo at once (ghosts follow at the next forward halo), bins,
+// stencil, slabs and sub-domain bounds at the next rebuild (Verlet::run, verlet.cpp:300-304).
+int b200_remap(b200_ctx *ctx, const double oldlo[3], const double oldhi[3], const double newlo[3],
+               const double newhi[3], int groupbit) {
+  if (!ctx || !oldlo || !oldhi || !newlo || !newhi) return B200_EARG;
+  TRY(staged_guard(ctx));
+  if (!ctx->geom_ready && !ctx->box_changes) return ctx->fail(B200_EARG, "b200_remap before b200_setup");
+  RemapBox B;
+  for (int d = 0; d < 3; d++) {
+    if (!(newhi[d] > newlo[d])) return ctx->fail(B200_EARG, "box hi <= lo in dim %d", d);
+    B.oldlo[d] = oldlo[d];
+    B.oldhinv[d] = 1.0 / (oldhi[d] - oldlo[d]);  // Domain::set_global_box: h_inv = 1/prd
+    B.newlo[d] = newlo[d];
+    B.newh[d] = newhi[d] - newlo[d];
+  }
+  const int nl = ctx->nlocal, c = ctx->cur;
+  if (nl > 0) {
+    k_remap<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->xt[c], ctx->mask[c], groupbit, B);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  ctx->q_owned_valid = false;
+  drop_step_graph(ctx);
+  if (!ctx->box_changes) {  // first call: the box the list in force was built in
+    for (int d = 0; d < 3; d++) {
+      ctx->boxlo_hold[d] = ctx->boxlo[d];
+      ctx->boxhi_hold[d] = ctx->boxhi[d];
+    }
+    ctx->box_changes = true;
+  }
+  Geom &g = ctx->geom;
+  for (int d = 0; d < 3; d++) {
+    ctx->boxlo[d] = newlo[d];
+    ctx->boxhi[d] = newhi[d];
+    ctx->prd[d] = newhi[d] - newlo[d];
+    g.boxlo[d] = ctx->boxlo[d];
+    g.boxhi[d] = ctx->boxhi[d];
+    g.prd[d] = ctx->prd[d];
+    for (int dir = 0; dir < NDIR; dir++)
+      if (g.shift[dir][d] != 0.0) g.shift[dir][d] = g.shift[dir][d] > 0.0 ? ctx->prd[d] : -ctx->prd[d];
+  }
+  ctx->geom_ready = false;  // bins, stencil, slabs, sub-domain bounds: at the next rebuild
+  // Neighbor::check_distance, neighbor.cpp:2443-2455: the trigger shrinks by the corner motion
+  double d1 = 0.0, d2 = 0.0;
+  for (int d = 0; d < 3; d++) {
+    const double a = ctx->boxlo[d] - ctx->boxlo_hold[d], b = ctx->boxhi[d] - ctx->boxhi_hold[d];
+    d1 += a * a;
+    d2 += b * b;
+  }
+  double delta = 0.5 * (ctx->skin - (std::sqrt(d1) + std::sqrt(d2)));
+  if (delta < 0.0) delta = 0.0;
+  ctx->deltasq = delta * delta;
   return B200_OK;
 }
 
@@ -3663,6 +3754,9 @@ int b200_group_get_atoms(b200_group *g, double *x, double *v, double *f, int *ty
 GROUP_STAGE(nve_v, (b200_group *g, double dtf, int groupbit), b200_nve_v(c, dtf, groupbit))
 GROUP_STAGE(nve_x, (b200_group *g, double dtv, int groupbit), b200_nve_x(c, dtv, groupbit))
 GROUP_STAGE(scale_v, (b200_group *g, double factor, int groupbit), b200_scale_v(c, factor, groupbit))
+GROUP_STAGE(scale_v3, (b200_group *g, const double factor[3], int groupbit), b200_scale_v3(c, factor, groupbit))
+GROUP_STAGE(remap, (b200_group *g, const double oldlo[3], const double oldhi[3], const double newlo[3],
+                    const double newhi[3], int groupbit), b200_remap(c, oldlo, oldhi, newlo, newhi, groupbit))
 GROUP_STAGE(reneighbor, (b200_group *g), b200_reneighbor(c))
 GROUP_STAGE(forward_comm, (b200_group *g), b200_forward_comm(c))
 GROUP_STAGE(force_clear, (b200_group *g), b200_force_clear(c))

@@ -95,6 +95,55 @@ __global__ void __launch_bounds__(256) k_scale_v(int nlocal, double *__restrict_
   }
 }
 
+// fix npt / nph (FixNH with a barostat, orthogonal box): nh_v_press scales the velocity components
+// twice by exp(-dt4 (omega_dot + mtk_term2)) (fix_nh.cpp:2227-2252), remap() dilates the atoms
+// with the box: x -> lamda in the old box (Domain::x2lamda, domain.cpp) -> x in the new box
+// (Domain::lamda2x), same operations, each rounded separately.
+__global__ void __launch_bounds__(256) k_scale_v3(int nlocal, double *__restrict__ vx,
+                                                  double *__restrict__ vy, double *__restrict__ vz,
+                                                  const int *__restrict__ mask, double f0, double f1,
+                                                  double f2, int groupbit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  if (mask[i] & groupbit) {
+    vx[i] = __dmul_rn(__dmul_rn(vx[i], f0), f0);
+    vy[i] = __dmul_rn(__dmul_rn(vy[i], f1), f1);
+    vz[i] = __dmul_rn(__dmul_rn(vz[i], f2), f2);
+  }
+}
+
+struct RemapBox {
+  double oldlo[3], oldhinv[3], newlo[3], newh[3];
+};
+
+__global__ void __launch_bounds__(256) k_remap(int nlocal, double4 *__restrict__ xt,
+                                               const int *__restrict__ mask, int groupbit, RemapBox B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  if (!(mask[i] & groupbit)) return;
+  double4 p = xt[i];
+  const double l0 = __dmul_rn(B.oldhinv[0], __dadd_rn(p.x, -B.oldlo[0]));
+  const double l1 = __dmul_rn(B.oldhinv[1], __dadd_rn(p.y, -B.oldlo[1]));
+  const double l2 = __dmul_rn(B.oldhinv[2], __dadd_rn(p.z, -B.oldlo[2]));
+  p.x = __dadd_rn(__dmul_rn(B.newh[0], l0), B.newlo[0]);
+  p.y = __dadd_rn(__dmul_rn(B.newh[1], l1), B.newlo[1]);
+  p.z = __dadd_rn(__dmul_rn(B.newh[2], l2), B.newlo[2]);
+  xt[i] = p;
+}
+
+// Neighbor::check_distance on its own (neighbor.cpp:2438-2490): with a changing box the trigger
+// distance shrinks with the box corners and the test must see the positions decide() sees
+__global__ void __launch_bounds__(256) k_check_distance(int nlocal, const double4 *__restrict__ xt,
+                                                        const double *__restrict__ xhx,
+                                                        const double *__restrict__ xhy,
+                                                        const double *__restrict__ xhz, double deltasq,
+                                                        int *__restrict__ moved) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  const double4 p = xt[i];
+  if (rsq_ref(p.x - xhx[i], p.y - xhy[i], p.z - xhz[i]) > deltasq) *moved = 1;
+}
+
 // final_integrate of step n immediately followed by initial_integrate of step n+1 in ONE pass
 // over the atoms (both use the same forces f(n)): v += dtfm*f ; v += dtfm*f ; x += dtv*v, each
 // operation rounded separately exactly like the two reference loops.  Used whenever nothing

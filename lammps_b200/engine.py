@@ -31,7 +31,8 @@ EXPORTS = [
     "b200_group_force_clear", "b200_group_pair_compute", "b200_group_reverse_comm", "b200_group_nve_v",
     "b200_group_nve_x", "b200_group_scale_v", "b200_last_run_ms", "b200_initial_integrate", "b200_final_integrate", "b200_decide",
     "b200_forward_comm", "b200_reverse_comm", "b200_reneighbor", "b200_force_clear",
-    "b200_pair_compute", "b200_nve_v", "b200_nve_x", "b200_scale_v", "b200_get_tallies", "b200_ke_sum", "b200_get_stats",
+    "b200_pair_compute", "b200_nve_v", "b200_nve_x", "b200_scale_v", "b200_scale_v3", "b200_remap", "b200_group_scale_v3",
+    "b200_group_remap", "b200_get_tallies", "b200_ke_sum", "b200_get_stats",
     "b200_get_neighbor_list", "b200_get_eam_rho_fp", "b200_pair_peratom", "b200_group_pair_peratom",
     "b200_set_profiling",
     "b200_get_phase_times", "b200_comm_unique_id", "b200_comm_init", "b200_neighbor_ranks",

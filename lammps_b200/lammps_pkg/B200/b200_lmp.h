@@ -40,6 +40,7 @@ class B200StagedFix {
  public:
   virtual ~B200StagedFix() noexcept(false) {}
   virtual void b200_params(double &dtv, double &dtf, int &groupbit) = 0;
+  virtual bool b200_box_change() { return false; }    // the fix moves the box itself (barostat)
 };
 
 }    // namespace LAMMPS_NS

@@ -201,6 +201,18 @@ void FixB200::dev_scale_v(double factor, int groupbit)
   check(grp ? b200_group_scale_v(grp, factor, groupbit) : b200_scale_v(ctx, factor, groupbit), FLERR);
 }
 
+void FixB200::dev_scale_v3(const double *factor, int groupbit)
+{
+  check(grp ? b200_group_scale_v3(grp, factor, groupbit) : b200_scale_v3(ctx, factor, groupbit), FLERR);
+}
+void FixB200::dev_remap(const double *oldlo, const double *oldhi, const double *newlo, const double *newhi,
+                        int groupbit)
+{
+  check(grp ? b200_group_remap(grp, oldlo, oldhi, newlo, newhi, groupbit)
+            : b200_remap(ctx, oldlo, oldhi, newlo, newhi, groupbit),
+        FLERR);
+}
+
 void FixB200::dev_counts(int *nlocal, int *nghost)
 {
   check(grp ? b200_group_count(grp, nlocal, nghost) : b200_get_counts(ctx, nlocal, nghost), FLERR);

@@ -59,6 +59,8 @@ class FixB200 : public Fix {
   void dev_nve_v(double dtf, int groupbit);
   void dev_nve_x(double dtv, int groupbit);
   void dev_scale_v(double factor, int groupbit);
+  void dev_scale_v3(const double *factor, int groupbit);
+  void dev_remap(const double *oldlo, const double *oldhi, const double *newlo, const double *newhi, int groupbit);
   void dev_stats(b200_stats *st);
 
   // the package fix of this LAMMPS instance; issues "package b200" defaults if absent

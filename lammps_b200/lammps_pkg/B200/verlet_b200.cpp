@@ -60,7 +60,6 @@ void VerletB200::init()
   if (force->kspace || force->bond || force->angle || force->dihedral || force->improper)
     error->all(FLERR, "run_style verlet/b200 supports pairwise short-range forces only");
   if (!force->newton_pair) error->all(FLERR, "run_style verlet/b200 requires newton pair on");
-  if (domain->box_change) error->all(FLERR, "run_style verlet/b200 requires a fixed box");
 
   bpair = dynamic_cast<B200PairStyle *>(force->pair);
   if (!bpair)
@@ -87,7 +86,11 @@ void VerletB200::init()
       error->all(FLERR, "Fix {} (style {}) acts during the timestep and has no /b200 version", fix->id,
                  fix->style);
   }
-  if (!bnve && !bstaged) error->all(FLERR, "run_style verlet/b200 requires fix nve/b200 or fix nvt/b200");
+  if (!bnve && !bstaged)
+    error->all(FLERR, "run_style verlet/b200 requires fix nve/b200, nvt/b200, npt/b200 or nph/b200");
+  // the only thing that may change the box is a barostat whose device version moves the atoms too
+  if (domain->box_change && !(bstaged && bstaged->b200_box_change()))
+    error->all(FLERR, "run_style verlet/b200 requires a fixed box (or fix npt/b200, nph/b200)");
   resident = 0;
   pkg->host_stale = 0;
 
@@ -362,6 +365,8 @@ void VerletB200::step_staged_fix(int ef, int vf)
   timer->stamp(Timer::PAIR);
   pkg->dev_reverse_comm();
   timer->stamp(Timer::COMM);
+  // a barostat reads the pressure of this step (pair virial) inside final_integrate
+  if (ef || vf) fetch_tallies();
   staged_fix->final_integrate();
   timer->stamp(Timer::MODIFY);
 }

@@ -566,3 +566,61 @@ run 25
     outs = _both(tmp_path, body, 85)
     _compare(outs, ftol=1e-8, ttol=1e-9)
     assert len(outs["b200"][0]) == len(outs["ref"][0]) >= 8
+
+
+@pytest.mark.parametrize("fix,neigh", [
+    ("npt temp 1.44 1.0 0.5 iso 0.5 2.0 5.0", "every 20 delay 0 check no"),
+    ("npt temp 1.2 1.2 0.5 aniso 1.0 1.0 4.0 tchain 2 pchain 2", "every 1 delay 0 check yes"),
+    ("nph x 0.0 1.0 5.0 z 2.0 0.0 5.0", "every 2 delay 0 check yes"),
+], ids=["npt-iso", "npt-aniso-check-yes", "nph-xz"])
+def test_fix_npt_nph_match_reference_executable(tmp_path, fix, neigh):
+    """fix npt / nph under -sf b200: FixNH's thermostat chain, barostat equations and box update run
+    as the reference's own host code; its per-atom loops (nve_v, nve_x, nh_v_temp, nh_v_press, remap)
+    on the device, which adopts the changing box (halo shifts at once, bins at the next rebuild, the
+    displacement trigger shrinking with the box corners).  Thermo every step -- temperature, energy,
+    pressure, volume, the conserved quantity's coupling term -- and the final state against lmp_ref."""
+    body = LJ_BODY.replace("neigh_modify every 20 delay 0 check no", "neigh_modify " + neigh).replace(
+        "fix 1 all nve", "fix 1 all " + fix) + """
+thermo 1
+thermo_style custom step temp pe press vol lx lz ecouple
+thermo_modify format float %.12g
+dump 1 all custom 50 f.dump id x y z vx fx
+dump_modify 1 sort id format float %.10g
+run 50
+"""
+    import numpy as np
+    refexe = ROOT / "oracle" / "_ref" / "lmp_ref"
+    tabs = {}
+    for tag, exe, args in (("ref", refexe, []), ("b200", EXE, ["-sf", "b200"])):
+        d = tmp_path / tag
+        d.mkdir()
+        (d / "in.t").write_text(body)
+        r = subprocess.run([str(exe), *args, "-in", "in.t"], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        rows, on = [], False
+        for ln in r.stdout.splitlines():
+            if re.match(r"\s*Step\s+Temp\s+PotEng", ln):
+                on = True
+                continue
+            if ln.startswith("Loop time"):
+                on = False
+            f = ln.split()
+            if on and len(f) == 8 and re.fullmatch(r"\d+", f[0]):
+                rows.append([float(t) for t in f])
+        blocks = (d / "f.dump").read_text().split("ITEM: TIMESTEP")[1:]
+        last = blocks[-1].splitlines()
+        k = last.index([ln for ln in last if ln.startswith("ITEM: ATOMS")][0])
+        dump = np.array([[float(t) for t in ln.split()] for ln in last[k + 1:] if ln.strip()])
+        tabs[tag] = (np.array(rows), dump, r.stdout)
+    ta, tb = tabs["ref"][0], tabs["b200"][0]
+    assert ta.shape == tb.shape == (51, 8)
+    scale = np.maximum(np.abs(ta).max(axis=0), 1e-3)
+    assert (np.abs(ta - tb).max(axis=0) <= 1e-9 * scale).all(), np.abs(ta - tb).max(axis=0) / scale
+    assert abs(ta[-1, 4] - ta[0, 4]) > 1e-3 * ta[0, 4]    # the box did move
+    da, db = tabs["ref"][1], tabs["b200"][1]
+    assert np.array_equal(da[:, 0], db[:, 0])
+    assert np.abs(da[:, 1:4] - db[:, 1:4]).max() <= 1e-8
+    assert np.abs(da[:, 4] - db[:, 4]).max() <= 1e-8
+    assert np.abs(da[:, 5] - db[:, 5]).max() <= 1e-8 * np.abs(da[:, 5]).max()
+    m = re.search(r"Neighbor list builds = (\d+)", tabs["ref"][2])
+    assert m and ("Neighbor list builds = " + m.group(1)) in tabs["b200"][2]
