@@ -141,6 +141,21 @@ int b200_scale_v3(b200_ctx *ctx, const double factor[3], int groupbit);
 int b200_remap(b200_ctx *ctx, const double oldlo[3], const double oldhi[3], const double newlo[3],
                const double newhi[3], int groupbit);
 
+/* fix langevin (FixLangevin::post_force, fix_langevin.cpp:383-507; constant or equal-style target,
+ * per-type masses, no bias / tally): on the stored forces of this step, for atoms in groupbit,
+ *   f += gfactor1[type] v + gfactor2_tsqrt[type] (u - 0.5)
+ * with the per-type prefactors [ntypes+1] of FixLangevin::init (:268-280), the second already
+ * multiplied by sqrt(t_target).  u: three uniforms per atom and step from the device's
+ * counter-based stream (Philox-4x32-10, key = seed, counter = (tag, step): independent of atom
+ * order and of the number of sub-domains) -- or, when uniforms_by_tag != NULL, u =
+ * uniforms_by_tag[3 (tag-1) + d] drawn by the host (verification against the reference's
+ * sequential RanMars stream).  fsum != NULL: returns the summed random force of the group
+ * (zero yes, :481-497; the host subtracts fsum/count with b200_add_force). */
+int b200_langevin(b200_ctx *ctx, int ntypes, const double *gfactor1, const double *gfactor2_tsqrt,
+                  int groupbit, uint64_t seed, int64_t step, const double *uniforms_by_tag,
+                  int64_t nuniform, double *fsum);
+int b200_add_force(b200_ctx *ctx, const double df[3], int groupbit);
+
 /* ---- tallies the host reads back: pair->eng_vdwl, pair->virial[6] (pair.h), and
  *      sum_i m_i v_i^2 (ComputeTemp::compute_scalar, compute_temp.cpp:73-97) */
 int b200_get_tallies(b200_ctx *ctx, double *eng_vdwl, double virial[6]);
@@ -285,6 +300,10 @@ int b200_group_nve_v(b200_group *g, double dtf, int groupbit);
 int b200_group_nve_x(b200_group *g, double dtv, int groupbit);
 int b200_group_scale_v(b200_group *g, double factor, int groupbit);
 int b200_group_scale_v3(b200_group *g, const double factor[3], int groupbit);
+int b200_group_langevin(b200_group *g, int ntypes, const double *gfactor1, const double *gfactor2_tsqrt,
+                        int groupbit, uint64_t seed, int64_t step, const double *uniforms_by_tag,
+                        int64_t nuniform, double *fsum);
+int b200_group_add_force(b200_group *g, const double df[3], int groupbit);
 int b200_group_remap(b200_group *g, const double oldlo[3], const double oldhi[3], const double newlo[3],
                      const double newhi[3], int groupbit);
 int b200_group_step_ahead(b200_group *g, int eflag, int vflag, int more, int *rebuilt);

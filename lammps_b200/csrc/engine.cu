@@ -140,6 +140,8 @@ struct b200_ctx {
   int ntypes = 0, nlocal = 0, nghost = 0, nmax = 0;
   std::vector<double> mass_h;
   DBuf<double> mass_d;
+  DBuf<double> lang_d, lang_u;  // fix langevin: per-type prefactors (+ 3 sums), host-drawn uniforms
+  std::vector<double> lang_h;
   double4 *xt[2] = {nullptr, nullptr};
   // mixed precision: sub-domain-wide fixed-point records {qx,qy,qz,type} of all atoms (k_tile_lj2f
   // stages them with one cp.async each); [cur] is live like xt[cur]; kept current by the fused
@@ -290,7 +292,7 @@ struct b200_ctx {
   double *ke7 = nullptr;  // [7] device: b200_ke_group accumulators
   int *flags = nullptr;   // [4] device: moved, err, maxcount, grand_total
   unsigned long long *cnt64 = nullptr;
-  double *h_ev = nullptr; // pinned [8]
+  double *h_ev = nullptr; // pinned [24]: tallies [0,8), ke_group [8,15), langevin sums [16,19)
   int *h_flags = nullptr; // pinned [32]
   double eng_vdwl = 0, virial[6] = {0, 0, 0, 0, 0, 0};
   bool setup_done = false;
@@ -2448,7 +2450,7 @@ int b200_create(b200_ctx **out, int device, int precision) {
   memset(&ctx->owner, 0, sizeof ctx->owner);
   TRY(dalloc(ctx, &ctx->diroffset, NDIR + 1));
   TRY(dalloc(ctx, &ctx->cnt64, 1));
-  CK(cudaMallocHost((void **)&ctx->h_ev, 16 * sizeof(double)));
+  CK(cudaMallocHost((void **)&ctx->h_ev, 24 * sizeof(double)));
   CK(cudaMallocHost((void **)&ctx->h_flags, 64 * sizeof(int)));
   CK(cudaMemsetAsync(ctx->ev, 0, 8 * sizeof(double), ctx->stream));
   CK(cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), ctx->stream));
@@ -2470,7 +2472,7 @@ void b200_destroy(b200_ctx *ctx) {
   }
   for (int d = 0; d < 3; d++) { F(ctx->f[d]); F(ctx->xh[d]); }
   F(ctx->slot); F(ctx->rho); F(ctx->fp); F(ctx->ff); F(ctx->lj_tabf.p); F(ctx->eam_f.p);
-  F(ctx->cutneighsq_d.p); F(ctx->mass_d.p); F(ctx->ostart.p); F(ctx->gstart.p); F(ctx->tilesum.p);
+  F(ctx->cutneighsq_d.p); F(ctx->mass_d.p); F(ctx->lang_d.p); F(ctx->lang_u.p); F(ctx->ostart.p); F(ctx->gstart.p); F(ctx->tilesum.p);
   F(ctx->sendlist.p); F(ctx->gsrc.p); F(ctx->gbin.p); F(ctx->gslot.p); F(ctx->gdir.p);
   F(ctx->gdir_tmp.p); F(ctx->gtmp.p); F(ctx->counts); F(ctx->diroffset); F(ctx->recvoffset); F(ctx->allcounts);
   F(ctx->senddir.p); F(ctx->gtag_tmp.p); F(ctx->gsrc_tmp.p); F(ctx->arena); F(ctx->pflags); F(ctx->p2p_counter);
@@ -2892,6 +2894,62 @@ int b200_scale_v3(b200_ctx *ctx, const double factor[3], int groupbit) {
   if (nl > 0) {
     k_scale_v3<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->mask[c],
                                                        factor[0], factor[1], factor[2], groupbit);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  return B200_OK;
+}
+
+// FixLangevin::post_force (fix_langevin.cpp:383-507) on the stored forces of this step: see
+// k_langevin.  gfactor1 / gfactor2_tsqrt: per-type prefactors [ntypes+1] as FixLangevin::init
+// computes them, the second already multiplied by sqrt(t_target) of this step.  fsum (nullable):
+// the group's summed random force comes back (zero yes).
+int b200_langevin(b200_ctx *ctx, int ntypes, const double *gfactor1, const double *gfactor2_tsqrt, int groupbit,
+                  uint64_t seed, int64_t step, const double *uniforms_by_tag, int64_t nuniform, double *fsum) {
+  if (!ctx || !gfactor1 || !gfactor2_tsqrt) return B200_EARG;
+  TRY(staged_guard(ctx));
+  if (ntypes != ctx->ntypes) return ctx->fail(B200_EARG, "b200_langevin: ntypes %d != %d", ntypes, ctx->ntypes);
+  const int nl = ctx->nlocal, c = ctx->cur;
+  cudaStream_t s = ctx->stream;
+  const size_t nt = (size_t)ntypes + 1;
+  TRY(reserve(ctx, ctx->lang_d, 2 * nt + 4));
+  ctx->lang_h.assign(2 * nt, 0.0);
+  memcpy(ctx->lang_h.data(), gfactor1, nt * sizeof(double));
+  memcpy(ctx->lang_h.data() + nt, gfactor2_tsqrt, nt * sizeof(double));
+  CK(cudaMemcpyAsync(ctx->lang_d.p, ctx->lang_h.data(), 2 * nt * sizeof(double), cudaMemcpyHostToDevice, s));
+  double *dsum = fsum ? ctx->lang_d.p + 2 * nt : nullptr;
+  if (dsum) CK(cudaMemsetAsync(dsum, 0, 3 * sizeof(double), s));
+  const double *duni = nullptr;
+  if (uniforms_by_tag && nuniform > 0) {
+    TRY(reserve(ctx, ctx->lang_u, (size_t)nuniform));
+    CK(cudaMemcpyAsync(ctx->lang_u.p, uniforms_by_tag, sizeof(double) * nuniform, cudaMemcpyHostToDevice, s));
+    duni = ctx->lang_u.p;
+  }
+  if (nl > 0) {
+    k_langevin<<<std::min(cdiv(nl, 256), 148 * 8), 256, 0, s>>>(
+        nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->f[0], ctx->f[1], ctx->f[2], ctx->tag[c],
+        ctx->mask[c], groupbit, ntypes, ctx->lang_d.p, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step,
+        (uint32_t)((uint64_t)step >> 32), duni, (long long)nuniform, dsum);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  if (fsum) {
+    CK(cudaMemcpyAsync(ctx->h_ev + 16, dsum, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(fsum, ctx->h_ev + 16, 3 * sizeof(double));
+  } else if (duni)
+    CK(cudaStreamSynchronize(s));  // the caller's uniforms may be reused
+  return B200_OK;
+}
+
+// f_i += df for the owned atoms of a group (FixLangevin zero yes, fix_langevin.cpp:481-497)
+int b200_add_force(b200_ctx *ctx, const double df[3], int groupbit) {
+  if (!ctx || !df) return B200_EARG;
+  TRY(staged_guard(ctx));
+  const int nl = ctx->nlocal, c = ctx->cur;
+  if (nl > 0) {
+    k_add_force<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->f[0], ctx->f[1], ctx->f[2], ctx->mask[c], groupbit,
+                                                        df[0], df[1], df[2]);
     ctx->launches++;
     LAUNCH_CHECK();
   }
@@ -3757,12 +3815,32 @@ GROUP_STAGE(scale_v, (b200_group *g, double factor, int groupbit), b200_scale_v(
 GROUP_STAGE(scale_v3, (b200_group *g, const double factor[3], int groupbit), b200_scale_v3(c, factor, groupbit))
 GROUP_STAGE(remap, (b200_group *g, const double oldlo[3], const double oldhi[3], const double newlo[3],
                     const double newhi[3], int groupbit), b200_remap(c, oldlo, oldhi, newlo, newhi, groupbit))
+GROUP_STAGE(add_force, (b200_group *g, const double df[3], int groupbit), b200_add_force(c, df, groupbit))
 GROUP_STAGE(reneighbor, (b200_group *g), b200_reneighbor(c))
 GROUP_STAGE(forward_comm, (b200_group *g), b200_forward_comm(c))
 GROUP_STAGE(force_clear, (b200_group *g), b200_force_clear(c))
 GROUP_STAGE(pair_compute, (b200_group *g, int eflag, int vflag), b200_pair_compute(c, eflag, vflag))
 GROUP_STAGE(reverse_comm, (b200_group *g), b200_reverse_comm(c))
 #undef GROUP_STAGE
+
+// fix langevin over all sub-domains; fsum (nullable) = the random force summed over the whole group
+int b200_group_langevin(b200_group *g, int ntypes, const double *gfactor1, const double *gfactor2_tsqrt,
+                        int groupbit, uint64_t seed, int64_t step, const double *uniforms_by_tag,
+                        int64_t nuniform, double *fsum) {
+  if (!g) return B200_EARG;
+  std::vector<double> part(3 * (size_t)g->n, 0.0);
+  int rc = group_run(g, [&](int i) {
+    return b200_langevin(g->ctx[i], ntypes, gfactor1, gfactor2_tsqrt, groupbit, seed, step, uniforms_by_tag,
+                         nuniform, fsum ? &part[3 * (size_t)i] : nullptr);
+  });
+  if (rc != B200_OK) return rc;
+  if (fsum)
+    for (int d = 0; d < 3; d++) {
+      fsum[d] = 0.0;
+      for (int i = 0; i < g->n; i++) fsum[d] += part[3 * (size_t)i + d];
+    }
+  return B200_OK;
+}
 
 int b200_group_decide(b200_group *g, int *rebuild) {
   if (!g || !rebuild) return B200_EARG;

@@ -229,6 +229,85 @@ __global__ void __launch_bounds__(256) k_ke_group(int nlocal, const double4 *__r
     for (int k = 0; k < 7; k++) atomicAdd(&out[k], v[k]);
 }
 
+// fix langevin (FixLangevin::post_force_templated<0,0,0,0,ZERO>, fix_langevin.cpp:383-507: constant
+// or equal-style target temperature, per-type masses, no bias, no tally):
+//   f_i += gfactor1[type] v_i + gfactor2[type] sqrt(T) (u - 0.5),  u uniform in (0,1), three per atom,
+// each operation rounded separately like the reference loop.  The reference draws u from one
+// sequential Marsaglia stream in host atom order, an order a bin-sorted, multi-sub-domain device
+// layout does not have; the device's own stream is counter based instead -- Philox-4x32-10 keyed
+// by the fix's seed with the counter (atom tag, timestep): one block of four 32-bit words per
+// atom and step, independent of atom order, sub-domain count and launch shape.  For verification
+// against the reference a host may hand in the uniforms itself (`uni`, indexed by tag), e.g. drawn
+// from the reference's RanMars in tag order.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// gf[t] = gfactor1[t], gf[ntypes+1+t] = gfactor2[t]*tsqrt.  fsum (nullable) += sum of the random
+// forces of the group (zero yes: the host subtracts the group mean afterwards, k_add_force).
+__global__ void __launch_bounds__(256) k_langevin(
+    int nlocal, const double4 *__restrict__ xt, const double *__restrict__ vx, const double *__restrict__ vy,
+    const double *__restrict__ vz, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
+    const int *__restrict__ tag, const int *__restrict__ mask, int groupbit, int ntypes,
+    const double *__restrict__ gf, uint32_t seed_lo, uint32_t seed_hi, uint32_t step_lo, uint32_t step_hi,
+    const double *__restrict__ uni, long long nuni, double *__restrict__ fsum) {
+  double s[3] = {0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
+    if (!(mask[i] & groupbit)) continue;
+    const int t = d2type(reinterpret_cast<const double *>(xt)[4 * (size_t)i + 3]);
+    const double g1 = gf[t], g2 = gf[ntypes + 1 + t];
+    double u[3];
+    const long long k = 3LL * (tag[i] - 1);
+    if (uni && k + 2 < nuni) {
+      u[0] = uni[k]; u[1] = uni[k + 1]; u[2] = uni[k + 2];
+    } else {
+      uint32_t r[4];
+      philox4x32_10((uint32_t)tag[i], step_lo, step_hi, 0u, seed_lo, seed_hi, r);
+#pragma unroll
+      for (int d = 0; d < 3; d++) u[d] = ((double)r[d] + 0.5) * 2.3283064365386963e-10;  // 2^-32
+    }
+    const double fr0 = __dmul_rn(g2, __dadd_rn(u[0], -0.5));
+    const double fr1 = __dmul_rn(g2, __dadd_rn(u[1], -0.5));
+    const double fr2 = __dmul_rn(g2, __dadd_rn(u[2], -0.5));
+    fx[i] = __dadd_rn(fx[i], __dadd_rn(__dmul_rn(g1, vx[i]), fr0));
+    fy[i] = __dadd_rn(fy[i], __dadd_rn(__dmul_rn(g1, vy[i]), fr1));
+    fz[i] = __dadd_rn(fz[i], __dadd_rn(__dmul_rn(g1, vz[i]), fr2));
+    s[0] += fr0; s[1] += fr1; s[2] += fr2;
+  }
+  if (fsum) {  // uniform branch: fsum is a kernel argument
+    __shared__ double red[3 * 32];
+    block_sum<3>(s, red);
+    if (threadIdx.x == 0)
+      for (int d = 0; d < 3; d++) atomicAdd(&fsum[d], s[d]);
+  }
+}
+
+// f_i += df for the atoms of a group (fix langevin zero yes: df = -sum(fran)/count, :481-497)
+__global__ void __launch_bounds__(256) k_add_force(int nlocal, double *__restrict__ fx,
+                                                   double *__restrict__ fy, double *__restrict__ fz,
+                                                   const int *__restrict__ mask, int groupbit, double d0,
+                                                   double d1, double d2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  if (mask[i] & groupbit) {
+    fx[i] = __dadd_rn(fx[i], d0);
+    fy[i] = __dadd_rn(fy[i], d1);
+    fz[i] = __dadd_rn(fz[i], d2);
+  }
+}
+
 // host array <-> device layout converters (b200_set_atoms / b200_get_atoms)
 __global__ void __launch_bounds__(256) k_pack_xt(int n, const double *__restrict__ x3,
                                                  const int *__restrict__ type,

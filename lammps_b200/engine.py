@@ -41,6 +41,7 @@ EXPORTS = [
     "b200_group_count", "b200_group_get_atoms", "b200_group_setup", "b200_group_step",
     "b200_group_run", "b200_group_get_tallies", "b200_group_ke_sum", "b200_group_last_run_ms",
     "b200_group_get_stats", "b200_group_ke_group", "b200_ke_group", "b200_sync", "b200_set_option",
+    "b200_langevin", "b200_add_force", "b200_group_langevin", "b200_group_add_force",
 ]
 
 
@@ -238,6 +239,28 @@ class Engine:
 
     def pair_compute(self, eflag=1, vflag=1):
         self._chk(self.L.b200_pair_compute(self.h, C.c_int(eflag), C.c_int(vflag)))
+
+    def nve_v(self, dtf: float, groupbit: int = 1):
+        self._chk(self.L.b200_nve_v(self.h, C.c_double(dtf), C.c_int(groupbit)))
+
+    def nve_x(self, dtv: float, groupbit: int = 1):
+        self._chk(self.L.b200_nve_x(self.h, C.c_double(dtv), C.c_int(groupbit)))
+
+    def langevin(self, gfactor1, gfactor2_tsqrt, seed: int, step: int, groupbit: int = 1,
+                 uniforms_by_tag=None, want_fsum=False):
+        """FixLangevin::post_force (fix_langevin.cpp:383-507) on the stored forces; per-type
+        prefactors are indexed by type (entry 0 unused) like the reference's gfactor arrays."""
+        g1, g2 = _d(gfactor1), _d(gfactor2_tsqrt)
+        assert g1.shape == g2.shape
+        u = None if uniforms_by_tag is None else _d(uniforms_by_tag).ravel()
+        fs = np.zeros(3) if want_fsum else None
+        self._chk(self.L.b200_langevin(self.h, C.c_int(g1.shape[0] - 1), _p(g1), _p(g2), C.c_int(groupbit),
+                                       C.c_uint64(seed), C.c_int64(step), _p(u),
+                                       C.c_int64(0 if u is None else u.shape[0]), _p(fs)))
+        return fs
+
+    def add_force(self, df, groupbit: int = 1):
+        self._chk(self.L.b200_add_force(self.h, _p(_d(df)), C.c_int(groupbit)))
 
     # ------------------------------------------------------------ results
     def counts(self):

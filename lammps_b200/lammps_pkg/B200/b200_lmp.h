@@ -43,6 +43,14 @@ class B200StagedFix {
   virtual bool b200_box_change() { return false; }    // the fix moves the box itself (barostat)
 };
 
+// a fix that changes the forces after the pair stage (fix langevin/b200): its own post_force()
+// launches device kernels on the stored forces; verlet/b200 then steps stage by stage and calls
+// it where Verlet::run calls Modify::post_force (verlet.cpp:340-350)
+class B200PostForceFix {
+ public:
+  virtual ~B200PostForceFix() noexcept(false) {}
+};
+
 }    // namespace LAMMPS_NS
 
 #endif

@@ -12,6 +12,8 @@
      list tile|flat|auto neighbour list layout      tile tx ty tz   bins per tile
      overlap yes|no      interior tiles beside the halo          graph yes|no  CUDA graph
      tpa 1|2|4|8         lanes per atom of the flat kernels      mixed_fx yes|no
+     langevin_rng device|host   fix langevin/b200: counter-based device stream (default) or
+                         the reference's RanMars drawn on the host in tag order (verification)
    The device contexts are created here and destroyed with the fix, like the
    GPU package ties its devices to fix GPU (precedent: src/GPU/fix_gpu.cpp).
 ------------------------------------------------------------------------- */
@@ -32,7 +34,7 @@ using namespace LAMMPS_NS;
 
 FixB200::FixB200(LAMMPS *lmp, int narg, char **arg) :
     Fix(lmp, narg, arg), host_stale(0), ctx(nullptr), grp(nullptr), nsub(1), device(0),
-    prec(B200_PREC_DOUBLE), profile_flag(0)
+    prec(B200_PREC_DOUBLE), profile_flag(0), lang_rng_host(0)
 {
   if (const char *lr = getenv("LOCAL_RANK")) device = atoi(lr);
 
@@ -59,6 +61,10 @@ FixB200::FixB200(LAMMPS *lmp, int narg, char **arg) :
       else error->all(FLERR, "Illegal package b200 prec value: {}", arg[iarg + 1]);
     } else if (key == "profile") {
       profile_flag = utils::logical(FLERR, arg[iarg + 1], false, lmp);
+    } else if (key == "langevin_rng") {
+      if (strcmp(arg[iarg + 1], "host") == 0) lang_rng_host = 1;
+      else if (strcmp(arg[iarg + 1], "device") == 0) lang_rng_host = 0;
+      else error->all(FLERR, "Illegal package b200 langevin_rng value: {}", arg[iarg + 1]);
     } else if (key == "tile") {
       if (iarg + 4 > narg) error->all(FLERR, "Illegal package b200 command: tile needs three values");
       options.emplace_back("tile", std::string(arg[iarg + 1]) + "," + arg[iarg + 2] + "," + arg[iarg + 3]);
@@ -211,6 +217,21 @@ void FixB200::dev_remap(const double *oldlo, const double *oldhi, const double *
   check(grp ? b200_group_remap(grp, oldlo, oldhi, newlo, newhi, groupbit)
             : b200_remap(ctx, oldlo, oldhi, newlo, newhi, groupbit),
         FLERR);
+}
+
+void FixB200::dev_langevin(int ntypes, const double *gfactor1, const double *gfactor2_tsqrt, int groupbit,
+                           uint64_t seed, int64_t step, const double *uniforms_by_tag, int64_t nuniform,
+                           double *fsum)
+{
+  check(grp ? b200_group_langevin(grp, ntypes, gfactor1, gfactor2_tsqrt, groupbit, seed, step, uniforms_by_tag,
+                                  nuniform, fsum)
+            : b200_langevin(ctx, ntypes, gfactor1, gfactor2_tsqrt, groupbit, seed, step, uniforms_by_tag, nuniform,
+                            fsum),
+        FLERR);
+}
+void FixB200::dev_add_force(const double *df, int groupbit)
+{
+  check(grp ? b200_group_add_force(grp, df, groupbit) : b200_add_force(ctx, df, groupbit), FLERR);
 }
 
 void FixB200::dev_counts(int *nlocal, int *nghost)

@@ -61,7 +61,12 @@ class FixB200 : public Fix {
   void dev_scale_v(double factor, int groupbit);
   void dev_scale_v3(const double *factor, int groupbit);
   void dev_remap(const double *oldlo, const double *oldhi, const double *newlo, const double *newhi, int groupbit);
+  void dev_langevin(int ntypes, const double *gfactor1, const double *gfactor2_tsqrt, int groupbit, uint64_t seed,
+                    int64_t step, const double *uniforms_by_tag, int64_t nuniform, double *fsum);
+  void dev_add_force(const double *df, int groupbit);
   void dev_stats(b200_stats *st);
+  // `package b200 langevin_rng host`: fix langevin/b200 draws its uniforms on the host (verification)
+  int langevin_rng_host() const { return lang_rng_host; }
 
   // the package fix of this LAMMPS instance; issues "package b200" defaults if absent
   static FixB200 *instance(class LAMMPS *);
@@ -69,7 +74,7 @@ class FixB200 : public Fix {
  private:
   b200_ctx *ctx;
   b200_group *grp;
-  int nsub, device, prec, profile_flag;
+  int nsub, device, prec, profile_flag, lang_rng_host;
 };
 
 }    // namespace LAMMPS_NS

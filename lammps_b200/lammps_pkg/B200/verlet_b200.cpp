@@ -71,7 +71,12 @@ void VerletB200::init()
   bnve = nullptr;
   bstaged = nullptr;
   staged_fix = nullptr;
+  post_fixes.clear();
   for (auto &fix : modify->get_fix_list()) {
+    if (dynamic_cast<B200PostForceFix *>(fix)) {
+      post_fixes.push_back(fix);
+      continue;
+    }
     auto *nve = dynamic_cast<B200NVEFix *>(fix);
     auto *stg = dynamic_cast<B200StagedFix *>(fix);
     if (nve || stg) {
@@ -280,6 +285,8 @@ void VerletB200::device_setup(int flag, int output_flag)
   neighbor->ndanger = 0;
 
   modify->setup(vflag);
+  // a post-force fix (fix langevin/b200) has just changed the forces on the device (Fix::setup)
+  if (pkg->host_stale) download(0);
   if (output_flag >= 0) output->setup(output_flag);
   update->setupflag = 0;
 }
@@ -365,9 +372,44 @@ void VerletB200::step_staged_fix(int ef, int vf)
   timer->stamp(Timer::PAIR);
   pkg->dev_reverse_comm();
   timer->stamp(Timer::COMM);
+  for (auto &fix : post_fixes) fix->post_force(vflag);
   // a barostat reads the pressure of this step (pair virial) inside final_integrate
   if (ef || vf) fetch_tallies();
   staged_fix->final_integrate();
+  timer->stamp(Timer::MODIFY);
+}
+
+/* ----------------------------------------------------------------------
+   fix nve/b200 with fixes that act on the forces after the pair stage (fix
+   langevin/b200): the integrator cannot live inside the pair kernel, so the
+   timestep runs stage by stage -- FixNVE::initial_integrate as its two loops
+   (v += dtf/m f, then x += dtv v: fix_nve.cpp:92-101), Modify::post_force
+   where Verlet::run has it (verlet.cpp:340-350), FixNVE::final_integrate
+------------------------------------------------------------------------- */
+
+void VerletB200::step_nve_post_force(int ef, int vf)
+{
+  int nflag = 0, groupbit;
+  double dtv, dtf;
+  bnve->b200_params(dtv, dtf, groupbit);
+  pkg->dev_nve_v(dtf, groupbit);
+  pkg->dev_nve_x(dtv, groupbit);
+  timer->stamp(Timer::MODIFY);
+  pkg->dev_decide(&nflag);
+  if (nflag) {
+    pkg->dev_reneighbor();
+    timer->stamp(Timer::NEIGH);
+  } else {
+    pkg->dev_forward_comm();
+    timer->stamp(Timer::COMM);
+  }
+  pkg->dev_force_clear();
+  pkg->dev_pair_compute(ef, vf);
+  timer->stamp(Timer::PAIR);
+  pkg->dev_reverse_comm();
+  timer->stamp(Timer::COMM);
+  for (auto &fix : post_fixes) fix->post_force(vflag);
+  pkg->dev_nve_v(dtf, groupbit);
   timer->stamp(Timer::MODIFY);
 }
 
@@ -399,6 +441,8 @@ void VerletB200::run(int n)
     pkg->host_stale = 1;
     if (bstaged)
       step_staged_fix(eflag ? 1 : 0, vflag ? 1 : 0);
+    else if (!post_fixes.empty())
+      step_nve_post_force(eflag ? 1 : 0, vflag ? 1 : 0);
     else if (by_stage)
       step_by_stage(eflag ? 1 : 0, vflag ? 1 : 0);
     else {
@@ -419,7 +463,7 @@ void VerletB200::run(int n)
       if (need_atoms) download(0);
       fill_per_atom_tallies();
       if (eflag || vflag) fetch_tallies();
-      if (!by_stage && !bstaged) timer->stamp(Timer::PAIR);
+      if (!by_stage && !bstaged && post_fixes.empty()) timer->stamp(Timer::PAIR);
       output->write(ntimestep);
       timer->stamp(Timer::OUTPUT);
     }

@@ -16,6 +16,8 @@ IntegrateStyle(verlet/b200,VerletB200);
 #include "b200_lmp.h"
 #include "verlet.h"
 
+#include <vector>
+
 namespace LAMMPS_NS {
 
 class VerletB200 : public Verlet {
@@ -35,6 +37,7 @@ class VerletB200 : public Verlet {
   B200NVEFix *bnve;
   B200StagedFix *bstaged;    // fix nvt/b200: the host fix drives its per-atom loops itself
   class Fix *staged_fix;
+  std::vector<class Fix *> post_fixes;    // B200PostForceFix instances (fix langevin/b200), in fix order
   int resident;    // 1 once atoms have been handed to the device in this run
   int joined;      // 1 once this rank joined the NCCL communicator of the package
   int thermo_on_device;    // every compute a thermo step evaluates reads device sums or scalars
@@ -48,6 +51,7 @@ class VerletB200 : public Verlet {
   void fill_per_atom_tallies();   // Pair::eatom / vatom <- device on steps that ask for them
   void step_by_stage(int eflag, int vflag);    // `package b200 profile yes`: Timer breakdown
   void step_staged_fix(int eflag, int vflag);  // a B200StagedFix integrates (fix nvt/b200)
+  void step_nve_post_force(int eflag, int vflag);    // fix nve/b200 + post-force fixes (fix langevin/b200)
 };
 
 }    // namespace LAMMPS_NS

@@ -286,3 +286,64 @@ def canonical_pairs_box(pi, pj, tag, x, boxlo, boxhi, nlocal=None):
     key = np.stack([a, b, s[:, 0], s[:, 1], s[:, 2]], axis=1)
     order = np.lexsort(key.T[::-1])
     return key[order]
+
+
+# ---- fix langevin (test infrastructure like everything in this file) --------------------------
+def langevin_prefactors(mass, t_period, dt, boltz, ftm2v, mvv2e, ratio=None):
+    """FixLangevin::init, fix_langevin.cpp:268-280: gfactor1[t], gfactor2[t] (index 0 unused)."""
+    mass = np.asarray(mass, np.float64)
+    g1 = np.zeros_like(mass)
+    g2 = np.zeros_like(mass)
+    for t in range(1, len(mass)):
+        r = 1.0 if ratio is None else ratio[t]
+        g1[t] = -mass[t] / t_period / ftm2v
+        g2[t] = np.sqrt(mass[t]) / ftm2v
+        g2[t] *= np.sqrt(24.0 * boltz / t_period / dt / mvv2e)
+        g1[t] *= 1.0 / r
+        g2[t] *= 1.0 / np.sqrt(r)
+    return g1, g2
+
+
+def langevin_post_force(f, v, type, g1, g2, tsqrt, uniforms, zero=False):
+    """FixLangevin::post_force_templated<0,0,0,0,ZERO>, fix_langevin.cpp:424-497, group all:
+    f += gamma1 v + gamma2 (u - 0.5), each operation rounded separately (numpy float64 does);
+    `uniforms` [n,3] are the three draws of each atom.  Returns the new forces."""
+    gamma1 = g1[type][:, None]
+    gamma2 = (g2[type] * tsqrt)[:, None]
+    fran = gamma2 * (uniforms - 0.5)
+    fdrag = gamma1 * v
+    out = f + (fdrag + fran)
+    if zero:
+        fsum = np.zeros(3)
+        for i in range(len(f)):           # the reference's sequential sum
+            fsum += fran[i]
+        out = out - fsum / len(f)
+    return out
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox-4x32-10 (Salmon et al., SC'11) on numpy uint32 arrays: the counter-based stream of
+    the product's fix langevin kernel (kernels_step.cuh), restated to check it word for word."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    c0, c1, c2, c3 = (np.asarray(a, np.uint32).copy() for a in (c0, c1, c2, c3))
+    k0 = np.uint32(k0)
+    k1 = np.uint32(k1)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c0.astype(np.uint64)
+        p1 = M1 * c2.astype(np.uint64)
+        hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & mask).astype(np.uint32)
+        hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), (p1 & mask).astype(np.uint32)
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = np.uint32((int(k0) + 0x9E3779B9) & 0xFFFFFFFF)
+        k1 = np.uint32((int(k1) + 0xBB67AE85) & 0xFFFFFFFF)
+    return c0, c1, c2, c3
+
+
+def langevin_device_uniforms(tag, seed, step):
+    """u[n,3] of the device stream: key = seed (lo, hi), counter = (tag, step lo, step hi, 0)."""
+    tag = np.asarray(tag, np.uint32)
+    z = np.zeros_like(tag)
+    r = philox4x32_10(tag, z + np.uint32(step & 0xFFFFFFFF), z + np.uint32((step >> 32) & 0xFFFFFFFF), z,
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    return np.stack([(w.astype(np.float64) + 0.5) * 2.0 ** -32 for w in r[:3]], axis=1)
