@@ -50,6 +50,14 @@ int b200_device_count(void);
  *      (comm.cpp:505); sub-box = boxlo + prd*myloc/procgrid, last one closed at boxhi */
 int b200_set_box(b200_ctx *ctx, const double boxlo[3], const double boxhi[3],
                  const int periodicity[3]);
+/*      triclinic box (Domain::set_global_box domain.cpp:263-290: tilt factors xy, xz, yz;
+ *      Domain::x2lamda / lamda2x :2347-2390): periodic wrap, migration and ghost slabs are decided
+ *      in lamda coordinates (verlet.cpp:293-313, comm_brick.cpp:177-237), bins cover the bounding
+ *      box (nbin_standard.cpp:86-112), the stencil is full and the half list follows the tag rule
+ *      of NPairBin<HALF,NEWTON,TRI> (npair_bin.cpp:133-155; angstrom = Force::angstrom for its
+ *      0.01 angstrom tolerance).  Sub-domains are bricks in lamda coordinates. */
+int b200_set_box_triclinic(b200_ctx *ctx, const double boxlo[3], const double boxhi[3], double xy,
+                           double xz, double yz, const int periodicity[3], double angstrom);
 int b200_set_decomposition(b200_ctx *ctx, const int procgrid[3], const int myloc[3]);
 /*      optional: which rank owns grid location (ix,iy,iz), n = px*py*pz entries indexed
  *      (ix*py+iy)*pz+iz -- Comm::grid2proc (comm.h); default = that index itself (MPI_Cart order) */

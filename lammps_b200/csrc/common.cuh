@@ -16,25 +16,65 @@
 #define IMGBITS 10
 #define IMG2BITS 20
 #define B200_SMALL 1.0e-6 /* nbin_standard.cpp:27 */
-#define MAXROWS 32        /* stencil rows (dz,dy) of the half stencil: 13 for sx=sy=sz=2 */
+#define MAXROWS 64        /* stencil rows (dz,dy): 13 of the half stencil for sx=sy=sz=2, 25..49 of the
+                             full stencil a triclinic box uses (nstencil_bin.cpp:36-62) */
 #define NDIR 27
 
 // Geometry of the box, the sub-domain, the bins and the ghost slabs; passed to kernels by value.
+// Everything that decides where an atom belongs -- periodic wrap, sub-domain ownership, ghost
+// slabs, the shift a ghost gets when it is created -- lives in the "comm frame": box coordinates
+// for an orthogonal box, lamda (0-1) coordinates for a triclinic one (comm_brick.cpp:177-237,
+// verlet.cpp:293-313: x2lamda before pbc/exchange/borders, lamda2x after).  Bins are always in box
+// coordinates, over the box (orthogonal) or its bounding box (triclinic, nbin_standard.cpp:86-112).
 struct Geom {
-  double boxlo[3], boxhi[3], prd[3];
-  double sublo[3], subhi[3];
+  double boxlo[3], boxhi[3], prd[3];  // comm frame: the box, or (0,1,1) in lamda coordinates
+  double sublo[3], subhi[3];          // comm frame
   int periodic[3];
   // bins: nbin_standard.cpp:82-214
+  double binlo[3], binhi[3];  // NBin::bboxlo / bboxhi: boxlo/boxhi, or boxlo_bound/boxhi_bound
   int nbin[3];
   double bininv[3];
   int mbinlo[3], mbin[3];
   int mbins;
   // ghost slabs: comm_brick.cpp:389-420 (slabhi of the "send left" swap, slablo of "send right")
-  double slab_left_hi[3], slab_right_lo[3];
+  double slab_left_hi[3], slab_right_lo[3];  // comm frame
   int send_left[3], send_right[3];
-  // per direction (dz+1)*9+(dy+1)*3+(dx+1): periodic shift added to a ghost's position
+  // per direction (dz+1)*9+(dy+1)*3+(dx+1): periodic shift added to a ghost's position when it is
+  // created at a rebuild (comm frame: pbc * prd, or pbc in lamda units, atom_vec.cpp:796-830)
   double shift[NDIR][3];
+  // ... and on every forward halo (box coordinates, AtomVec::pack_comm atom_vec.cpp:354-440): the
+  // reference moves a ghost through up to three swaps, each adding its own offset with its own
+  // rounding: x swap (pbc[0] xprd), y swap (pbc[5] xy, pbc[1] yprd), z swap (pbc[4] xz, pbc[3] yz,
+  // pbc[2] zprd).  fshift = the diagonal terms, tilt = {xy, xz, yz} terms; zero in an orthogonal box.
+  double fshift[NDIR][3];
+  double tilt[NDIR][3];
+  // triclinic box (domain.cpp:263-290): h = {xprd, yprd, zprd, yz, xz, xy}, h_inv, lamda origin
+  int tri;
+  double h[6], h_inv[6], origin[3];
 };
+
+// ghost position on a forward halo = owner + the offsets of the swaps it travels through, each
+// added and rounded separately in the reference's order (x, then y, then z swap)
+__device__ __forceinline__ void halo_shift(const Geom &g, int dir, double qx, double qy, double qz,
+                                           double *o) {
+  o[0] = __dadd_rn(__dadd_rn(__dadd_rn(qx, g.fshift[dir][0]), g.tilt[dir][0]), g.tilt[dir][1]);
+  o[1] = __dadd_rn(__dadd_rn(qy, g.fshift[dir][1]), g.tilt[dir][2]);
+  o[2] = __dadd_rn(qz, g.fshift[dir][2]);
+}
+
+// Domain::x2lamda / lamda2x (domain.cpp:2347-2390), every operation rounded separately
+__device__ __forceinline__ void x2lamda(const Geom &g, double &x, double &y, double &z) {
+  const double d0 = __dadd_rn(x, -g.origin[0]), d1 = __dadd_rn(y, -g.origin[1]), d2 = __dadd_rn(z, -g.origin[2]);
+  x = __dadd_rn(__dadd_rn(__dmul_rn(g.h_inv[0], d0), __dmul_rn(g.h_inv[5], d1)), __dmul_rn(g.h_inv[4], d2));
+  y = __dadd_rn(__dmul_rn(g.h_inv[1], d1), __dmul_rn(g.h_inv[3], d2));
+  z = __dmul_rn(g.h_inv[2], d2);
+}
+__device__ __forceinline__ void lamda2x(const Geom &g, double &x, double &y, double &z) {
+  const double l0 = x, l1 = y, l2 = z;
+  x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.h[0], l0), __dmul_rn(g.h[5], l1)), __dmul_rn(g.h[4], l2)), g.origin[0]);
+  y = __dadd_rn(__dadd_rn(__dmul_rn(g.h[1], l1), __dmul_rn(g.h[3], l2)), g.origin[1]);
+  z = __dadd_rn(__dmul_rn(g.h[2], l2), g.origin[2]);
+}
 
 // Half stencil as rows of x-contiguous bins: nstencil_bin.cpp:28-67 regrouped by (dz,dy).
 struct Stencil {
@@ -73,9 +113,9 @@ __device__ __forceinline__ int coord2bin_dim(double x, double lo, double hi, dou
 }
 
 __device__ __forceinline__ int coord2bin(const Geom &g, double x, double y, double z) {
-  int ix = coord2bin_dim(x, g.boxlo[0], g.boxhi[0], g.bininv[0], g.nbin[0]);
-  int iy = coord2bin_dim(y, g.boxlo[1], g.boxhi[1], g.bininv[1], g.nbin[1]);
-  int iz = coord2bin_dim(z, g.boxlo[2], g.boxhi[2], g.bininv[2], g.nbin[2]);
+  int ix = coord2bin_dim(x, g.binlo[0], g.binhi[0], g.bininv[0], g.nbin[0]);
+  int iy = coord2bin_dim(y, g.binlo[1], g.binhi[1], g.bininv[1], g.nbin[1]);
+  int iz = coord2bin_dim(z, g.binlo[2], g.binhi[2], g.bininv[2], g.nbin[2]);
   ix -= g.mbinlo[0];
   iy -= g.mbinlo[1];
   iz -= g.mbinlo[2];

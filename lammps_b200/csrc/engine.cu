@@ -118,7 +118,9 @@ struct b200_ctx {
   double boxlo[3], boxhi[3], prd[3];
   int periodic[3] = {1, 1, 1};
   int procgrid[3] = {1, 1, 1}, myloc[3] = {0, 0, 0};
-  double sublo[3], subhi[3];
+  double sublo[3], subhi[3];  // comm frame (lamda coordinates in a triclinic box)
+  bool tri = false;           // triclinic box: tilt factors, Force::angstrom for the list rule's delta
+  double xy = 0.0, xz = 0.0, yz = 0.0, angstrom = 1.0;
   // neighbor settings
   double skin = 0.3;
   int every = 1, delay = 0, dist_check = 1, one = 2000;
@@ -864,38 +866,74 @@ static int setup_geometry(b200_ctx *ctx) {
 
   Geom &g = ctx->geom;
   memset(&g, 0, sizeof g);
+  // the comm frame (see Geom): the box itself, or the unit cube of lamda coordinates
+  // (Domain::set_lamda_box, domain.cpp: boxlo_lamda = 0, boxhi_lamda = 1, prd_lamda = 1)
+  const bool tri = ctx->tri;
+  double flo[3], fhi[3], fprd[3], fcut[3];
+  g.tri = tri ? 1 : 0;
+  {
+    // Domain::set_global_box, domain.cpp:263-290
+    double *h = g.h, *hi = g.h_inv;
+    h[0] = ctx->prd[0]; h[1] = ctx->prd[1]; h[2] = ctx->prd[2];
+    hi[0] = 1.0 / h[0]; hi[1] = 1.0 / h[1]; hi[2] = 1.0 / h[2];
+    h[3] = tri ? ctx->yz : 0.0; h[4] = tri ? ctx->xz : 0.0; h[5] = tri ? ctx->xy : 0.0;
+    hi[3] = -h[3] / (h[1] * h[2]);
+    hi[4] = (h[3] * h[5] - h[1] * h[4]) / (h[0] * h[1] * h[2]);
+    hi[5] = -h[5] / (h[0] * h[1]);
+    // CommBrick::setup, comm_brick.cpp:225-237: the ghost cutoff as a distance between lamda planes
+    const double len[3] = {std::sqrt(hi[0] * hi[0] + hi[5] * hi[5] + hi[4] * hi[4]),
+                           std::sqrt(hi[1] * hi[1] + hi[3] * hi[3]), hi[2]};
+    for (int d = 0; d < 3; d++) {
+      g.origin[d] = ctx->boxlo[d];
+      flo[d] = tri ? 0.0 : ctx->boxlo[d];
+      fhi[d] = tri ? 1.0 : ctx->boxhi[d];
+      fprd[d] = tri ? 1.0 : ctx->prd[d];
+      fcut[d] = tri ? ctx->cutghost * len[d] : ctx->cutghost;
+    }
+  }
+  if (tri && ctx->box_changes) return ctx->fail(B200_EARG, "a changing triclinic box is not supported");
   for (int d = 0; d < 3; d++) {
-    g.boxlo[d] = ctx->boxlo[d];
-    g.boxhi[d] = ctx->boxhi[d];
-    g.prd[d] = ctx->prd[d];
+    g.boxlo[d] = flo[d];
+    g.boxhi[d] = fhi[d];
+    g.prd[d] = fprd[d];
     g.periodic[d] = ctx->periodic[d];
-    // Domain::set_local_box (domain.cpp), uniform grid: xsplit[i] = i * 1.0/procgrid
+    // Domain::set_local_box / set_lamda_box (domain.cpp), uniform grid: xsplit[i] = i * 1.0/procgrid
     const int P = ctx->procgrid[d], me = ctx->myloc[d];
-    ctx->sublo[d] = ctx->boxlo[d] + ctx->prd[d] * (me * 1.0 / P);
-    ctx->subhi[d] = (me < P - 1) ? ctx->boxlo[d] + ctx->prd[d] * ((me + 1) * 1.0 / P) : ctx->boxhi[d];
+    ctx->sublo[d] = flo[d] + fprd[d] * (me * 1.0 / P);
+    ctx->subhi[d] = (me < P - 1) ? flo[d] + fprd[d] * ((me + 1) * 1.0 / P) : fhi[d];
+    if (tri) {  // set_lamda_box: sublo_lamda = xsplit[myloc], subhi_lamda = xsplit[myloc+1] (= 1.0 at the end)
+      ctx->sublo[d] = me * 1.0 / P;
+      ctx->subhi[d] = (me < P - 1) ? (me + 1) * 1.0 / P : 1.0;
+    }
     g.sublo[d] = ctx->sublo[d];
     g.subhi[d] = ctx->subhi[d];
     // comm_brick.cpp:268-270 maxneed; only one layer of neighbours is supported
     const double sub = ctx->subhi[d] - ctx->sublo[d];
-    int maxneed = (int)(ctx->cutghost * P / ctx->prd[d]) + 1;
+    int maxneed = (int)(fcut[d] * P / fprd[d]) + 1;
     if (!ctx->periodic[d]) maxneed = std::min(maxneed, P - 1);
     if (maxneed > 1)
       return ctx->fail(B200_EARG,
                        "sub-domain edge %g in dim %d is shorter than the ghost cutoff %g "
-                       "(multi-layer halos are not supported)", sub, d, ctx->cutghost);
-    g.slab_left_hi[d] = ctx->sublo[d] + ctx->cutghost;
-    g.slab_right_lo[d] = ctx->subhi[d] - ctx->cutghost;
+                       "(multi-layer halos are not supported)", sub, d, fcut[d]);
+    g.slab_left_hi[d] = ctx->sublo[d] + fcut[d];
+    g.slab_right_lo[d] = ctx->subhi[d] - fcut[d];
     g.send_left[d] = (maxneed >= 1) && (ctx->periodic[d] || me > 0);
     g.send_right[d] = (maxneed >= 1) && (ctx->periodic[d] || me < P - 1);
   }
   for (int dir = 0; dir < NDIR; dir++) {
     const int dv[3] = {dir % 3 - 1, (dir / 3) % 3 - 1, dir / 9 - 1};
+    int pbc[3];  // pbc[iswap][dim], comm_brick.cpp:389-420: set when the sender sits at the box edge
     for (int d = 0; d < 3; d++) {
-      double s = 0.0;  // pbc[iswap][dim] * prd, comm_brick.cpp:396-399, 414-417
-      if (dv[d] < 0 && ctx->myloc[d] == 0) s = 1 * ctx->prd[d];
-      if (dv[d] > 0 && ctx->myloc[d] == ctx->procgrid[d] - 1) s = -1 * ctx->prd[d];
-      g.shift[dir][d] = s;
+      pbc[d] = 0;
+      if (dv[d] < 0 && ctx->myloc[d] == 0) pbc[d] = 1;
+      if (dv[d] > 0 && ctx->myloc[d] == ctx->procgrid[d] - 1) pbc[d] = -1;
+      g.shift[dir][d] = pbc[d] * fprd[d];        // border time: box or lamda units (atom_vec.cpp:796-830)
+      g.fshift[dir][d] = pbc[d] * ctx->prd[d];   // forward halo: box units (atom_vec.cpp:354-440)
     }
+    // the y swap carries pbc[5] = pbc[1] (xy), the z swap pbc[4] = pbc[3] = pbc[2] (xz, yz)
+    g.tilt[dir][0] = tri ? pbc[1] * ctx->xy : 0.0;
+    g.tilt[dir][1] = tri ? pbc[2] * ctx->xz : 0.0;
+    g.tilt[dir][2] = tri ? pbc[2] * ctx->yz : 0.0;
   }
   // ---- neighbour sub-domains: rank numbering as MPI_Cart (last dimension fastest,
   //      procmap.cpp:361-374), periodic wrap of the grid location, -1 beyond an open boundary
@@ -931,6 +969,11 @@ static int setup_geometry(b200_ctx *ctx) {
     Owner &o = ctx->owner;
     memset(&o, 0, sizeof o);
     auto bounds = [&](int d, int l, double &lo, double &hi) {
+      if (tri) {
+        lo = l * 1.0 / P[d];
+        hi = (l < P[d] - 1) ? (l + 1) * 1.0 / P[d] : 1.0;
+        return;
+      }
       lo = ctx->boxlo[d] + ctx->prd[d] * (l * 1.0 / P[d]);
       hi = (l < P[d] - 1) ? ctx->boxlo[d] + ctx->prd[d] * ((l + 1) * 1.0 / P[d]) : ctx->boxhi[d];
     };
@@ -954,8 +997,41 @@ static int setup_geometry(b200_ctx *ctx) {
   for (int d = 0; d < 3; d++) {
     bsublo[d] = ctx->sublo[d] - ctx->cutghost;
     bsubhi[d] = ctx->subhi[d] + ctx->cutghost;
-    bbox[d] = ctx->boxhi[d] - ctx->boxlo[d];
+    g.binlo[d] = ctx->boxlo[d];
+    g.binhi[d] = ctx->boxhi[d];
   }
+  if (tri) {
+    // NBin::bboxlo/hi = Domain::boxlo_bound / boxhi_bound (domain.cpp:282-290); the sub-domain's
+    // extent = bounding box of its lamda brick +- cutghost (Domain::bbox, domain.cpp:2467-2530)
+    g.binlo[0] = std::min(ctx->boxlo[0], ctx->boxlo[0] + ctx->xy);
+    g.binlo[0] = std::min(g.binlo[0], g.binlo[0] + ctx->xz);
+    g.binlo[1] = std::min(ctx->boxlo[1], ctx->boxlo[1] + ctx->yz);
+    g.binlo[2] = ctx->boxlo[2];
+    g.binhi[0] = std::max(ctx->boxhi[0], ctx->boxhi[0] + ctx->xy);
+    g.binhi[0] = std::max(g.binhi[0], g.binhi[0] + ctx->xz);
+    g.binhi[1] = std::max(ctx->boxhi[1], ctx->boxhi[1] + ctx->yz);
+    g.binhi[2] = ctx->boxhi[2];
+    double lo[3], hi[3];
+    for (int d = 0; d < 3; d++) {
+      lo[d] = ctx->sublo[d] - fcut[d];
+      hi[d] = ctx->subhi[d] + fcut[d];
+      bsublo[d] = 1.0e20;
+      bsubhi[d] = -1.0e20;
+    }
+    // corners in the order Domain::bbox visits them (min/max do not depend on it)
+    for (int cz = 0; cz < 2; cz++)
+      for (int cy = 0; cy < 2; cy++)
+        for (int cx = 0; cx < 2; cx++) {
+          const double l[3] = {cx ? hi[0] : lo[0], cy ? hi[1] : lo[1], cz ? hi[2] : lo[2]};
+          const double x[3] = {g.h[0] * l[0] + g.h[5] * l[1] + g.h[4] * l[2] + ctx->boxlo[0],
+                               g.h[1] * l[1] + g.h[3] * l[2] + ctx->boxlo[1], g.h[2] * l[2] + ctx->boxlo[2]};
+          for (int d = 0; d < 3; d++) {
+            bsublo[d] = std::min(bsublo[d], x[d]);
+            bsubhi[d] = std::max(bsubhi[d], x[d]);
+          }
+        }
+  }
+  for (int d = 0; d < 3; d++) bbox[d] = g.binhi[d] - g.binlo[d];
   double binsize_optimal = 0.5 * ctx->cutneighmax;
   if (binsize_optimal == 0.0) binsize_optimal = bbox[0];
   const double binsizeinv = 1.0 / binsize_optimal;
@@ -967,10 +1043,10 @@ static int setup_geometry(b200_ctx *ctx) {
     binsize[d] = bbox[d] / g.nbin[d];
     g.bininv[d] = 1.0 / binsize[d];
     double coord = bsublo[d] - B200_SMALL * bbox[d];
-    int lo = (int)((coord - ctx->boxlo[d]) * g.bininv[d]);
-    if (coord < ctx->boxlo[d]) lo = lo - 1;
+    int lo = (int)((coord - g.binlo[d]) * g.bininv[d]);
+    if (coord < g.binlo[d]) lo = lo - 1;
     coord = bsubhi[d] + B200_SMALL * bbox[d];
-    int hi = (int)((coord - ctx->boxlo[d]) * g.bininv[d]);
+    int hi = (int)((coord - g.binlo[d]) * g.bininv[d]);
     lo -= 1;
     hi += 1;
     g.mbinlo[d] = lo;
@@ -1006,7 +1082,31 @@ static int setup_geometry(b200_ctx *ctx) {
   st.rowoff[0] = 0;
   st.dxlo[0] = 0;
   st.dxhi[0] = 0;
-  for (int k = 0; k <= s[2]; k++)
+  if (tri) {
+    // NStencilBin<HALF=1,DIM_3D=1,TRI=1>::create (nstencil_bin.cpp:36-62): full in all three
+    // dimensions, no separate central bin; every (dz,dy) row is a contiguous x range
+    ctx->nstencil = 0;
+    st.nrows = 0;
+    for (int k = -s[2]; k <= s[2]; k++)
+      for (int j = -s[1]; j <= s[1]; j++) {
+        int lo = 1 << 30, hi = -(1 << 30), cnt = 0;
+        for (int i = -s[0]; i <= s[0]; i++)
+          if (bin_distance(i, j, k) < ctx->cutneighmaxsq) {
+            lo = std::min(lo, i);
+            hi = std::max(hi, i);
+            cnt++;
+          }
+        if (!cnt) continue;
+        if (cnt != hi - lo + 1) return ctx->fail(B200_EARG, "stencil row is not contiguous");
+        if (st.nrows >= MAXROWS) return ctx->fail(B200_EARG, "too many stencil rows");
+        ctx->nstencil += cnt;
+        st.rowoff[st.nrows] = k * g.mbin[1] * g.mbin[0] + j * g.mbin[0];
+        st.dxlo[st.nrows] = lo;
+        st.dxhi[st.nrows] = hi;
+        st.nrows++;
+      }
+  }
+  for (int k = 0; !tri && k <= s[2]; k++)
     for (int j = -s[1]; j <= s[1]; j++) {
       int lo = 1 << 30, hi = -(1 << 30), cnt = 0;
       for (int i = -s[0]; i <= s[0]; i++) {
@@ -1036,7 +1136,8 @@ static int setup_geometry(b200_ctx *ctx) {
   {
     FullStencil &fs = ctx->fst;
     memset(&fs, 0, sizeof fs);
-    bool ok = s[0] <= 3 && s[1] <= 3 && s[2] <= 3;
+    // (a triclinic box runs on the flat half list: the tile kernels' FWD rule is the orthogonal one)
+    bool ok = !tri && s[0] <= 3 && s[1] <= 3 && s[2] <= 3;
     for (int k = -s[2]; ok && k <= s[2]; k++)
       for (int j = -s[1]; j <= s[1]; j++) {
         int lo = 1 << 30, hi = -(1 << 30), cnt = 0;
@@ -1057,7 +1158,7 @@ static int setup_geometry(b200_ctx *ctx) {
         fs.dxhi[fs.nrows] = (signed char)hi;
         fs.nrows++;
       }
-    if (!ok) ctx->use_tiles = false;  // unusual stencil: the flat list handles it
+    ctx->use_tiles = ok;  // unusual stencil or triclinic box: the flat list handles it
     {
       // Order in which the build walks the stencil rows = order of the entries in a list row.  Any
       // order that does not put the rows of neighbouring z-planes next to each other makes the
@@ -1086,9 +1187,9 @@ static int setup_geometry(b200_ctx *ctx) {
     }
     auto host_bin = [&](double x, int d) {  // NBin::coord2bin, nbin.cpp:141-173
       int ix;
-      if (x >= g.boxhi[d]) ix = (int)((x - g.boxhi[d]) * g.bininv[d]) + g.nbin[d];
-      else if (x >= g.boxlo[d]) ix = std::min((int)((x - g.boxlo[d]) * g.bininv[d]), g.nbin[d] - 1);
-      else ix = (int)((x - g.boxlo[d]) * g.bininv[d]) - 1;
+      if (x >= g.binhi[d]) ix = (int)((x - g.binhi[d]) * g.bininv[d]) + g.nbin[d];
+      else if (x >= g.binlo[d]) ix = std::min((int)((x - g.binlo[d]) * g.bininv[d]), g.nbin[d] - 1);
+      else ix = (int)((x - g.binlo[d]) * g.bininv[d]) - 1;
       return ix - g.mbinlo[d];
     };
     for (int d = 0; d < 3; d++) {
@@ -1420,7 +1521,19 @@ static int build_list(b200_ctx *ctx) {
     const int ph1 = ph_begin(ctx, B200_PH_BUILD);
     if (nl > 0) {
       const int n1 = ctx->ntypes + 1;
-      if (ctx->ntypes == 1)
+      if (ctx->tri) {
+        const double delta = 0.01 * ctx->angstrom;  // npair_bin.cpp:59
+        if (ctx->ntypes == 1)
+          k_build_half_tri<true><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
+              nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->tag[c], ctx->atombin[c], ctx->ostart.p,
+              ctx->gstart.p, ctx->stencil, ctx->cutneighsq_h[n1 + 1], ctx->cutneighsq_d.p, ctx->ntypes, delta,
+              ctx->numneigh.p, ctx->neigh.p, ctx->flags + 2);
+        else
+          k_build_half_tri<false><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
+              nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->tag[c], ctx->atombin[c], ctx->ostart.p,
+              ctx->gstart.p, ctx->stencil, 0.0, ctx->cutneighsq_d.p, ctx->ntypes, delta, ctx->numneigh.p,
+              ctx->neigh.p, ctx->flags + 2);
+      } else if (ctx->ntypes == 1)
         k_build_half<true><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
             nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->atombin[c], ctx->ostart.p,
             ctx->gstart.p, ctx->stencil, ctx->cutneighsq_h[n1 + 1], ctx->cutneighsq_d.p,
@@ -1554,7 +1667,7 @@ static int reneighbor(b200_ctx *ctx) {
         ntot, ctx->atombin[c], ctx->slot, okey, ctx->ostart.p, ctx->xt[c], ctx->xt[c ^ 1], ctx->v[c][0],
         ctx->v[c][1], ctx->v[c][2], ctx->v[c ^ 1][0], ctx->v[c ^ 1][1], ctx->v[c ^ 1][2], ctx->tag[c],
         ctx->tag[c ^ 1], ctx->mask[c], ctx->mask[c ^ 1], ctx->image[c], ctx->image[c ^ 1],
-        ctx->atombin[c ^ 1], ctx->xh[0], ctx->xh[1], ctx->xh[2]);
+        ctx->atombin[c ^ 1], ctx->xh[0], ctx->xh[1], ctx->xh[2], g);
     ctx->launches++;
   }
   c ^= 1;
@@ -1636,6 +1749,10 @@ static int reneighbor(b200_ctx *ctx) {
                                                 ctx->gbin.p, ctx->gslot.p, ctx->gdir_tmp.p,
                                                 ctx->gstart.p, ctx->xt[c], ctx->tag[c], ctx->mask[c],
                                                 ctx->gsrc.p, ctx->gdir.p, ctx->xt[c ^ 1], gkey);
+    ctx->launches++;
+  }
+  if (g.tri && nl > 0) {  // owned atoms back to box coordinates (the ghosts were converted as made)
+    k_lamda2x<<<cdiv(nl, 256), 256, 0, s>>>(nl, ctx->xt[c], g);
     ctx->launches++;
   }
   LAUNCH_CHECK();
@@ -2509,8 +2626,31 @@ int b200_set_box(b200_ctx *ctx, const double boxlo[3], const double boxhi[3], co
     ctx->prd[d] = boxhi[d] - boxlo[d];
     ctx->periodic[d] = per ? per[d] : 1;
   }
+  ctx->tri = false;
+  ctx->xy = ctx->xz = ctx->yz = 0.0;
   ctx->have_box = true;
   ctx->geom_ready = false;
+  return B200_OK;
+}
+
+// Triclinic box (Domain::set_global_box, domain.cpp:263-290): boxlo/boxhi as above plus the tilt
+// factors; `angstrom` = Force::angstrom of the unit style (the list rule's tolerance is
+// 0.01 angstrom, npair_bin.cpp:59).  Runs on the flat half list (NPairBin<1,1,1,0,1>).
+int b200_set_box_triclinic(b200_ctx *ctx, const double boxlo[3], const double boxhi[3], double xy, double xz,
+                           double yz, const int per[3], double angstrom) {
+  if (!ctx) return B200_EARG;
+  TRY(b200_set_box(ctx, boxlo, boxhi, per));
+  if (!std::isfinite(xy) || !std::isfinite(xz) || !std::isfinite(yz) || !(angstrom > 0.0))
+    return ctx->fail(B200_EARG, "b200_set_box_triclinic: bad tilt factors");
+  if (per) {  // Domain::set_initial_box, domain.cpp:203-206
+    if ((xy != 0.0 && !per[0]) || (xz != 0.0 && !per[0]) || (yz != 0.0 && !per[1]))
+      return ctx->fail(B200_EARG, "Triclinic box must be periodic in skewed dimensions");
+  }
+  ctx->tri = true;
+  ctx->xy = xy;
+  ctx->xz = xz;
+  ctx->yz = yz;
+  ctx->angstrom = angstrom;
   return B200_OK;
 }
 
@@ -2965,6 +3105,7 @@ int b200_remap(b200_ctx *ctx, const double oldlo[3], const double oldhi[3], cons
   if (!ctx || !oldlo || !oldhi || !newlo || !newhi) return B200_EARG;
   TRY(staged_guard(ctx));
   if (!ctx->geom_ready && !ctx->box_changes) return ctx->fail(B200_EARG, "b200_remap before b200_setup");
+  if (ctx->tri) return ctx->fail(B200_EARG, "b200_remap: a changing triclinic box is not supported");
   RemapBox B;
   for (int d = 0; d < 3; d++) {
     if (!(newhi[d] > newlo[d])) return ctx->fail(B200_EARG, "box hi <= lo in dim %d", d);
@@ -2996,8 +3137,10 @@ int b200_remap(b200_ctx *ctx, const double oldlo[3], const double oldhi[3], cons
     g.boxlo[d] = ctx->boxlo[d];
     g.boxhi[d] = ctx->boxhi[d];
     g.prd[d] = ctx->prd[d];
-    for (int dir = 0; dir < NDIR; dir++)
+    for (int dir = 0; dir < NDIR; dir++) {
       if (g.shift[dir][d] != 0.0) g.shift[dir][d] = g.shift[dir][d] > 0.0 ? ctx->prd[d] : -ctx->prd[d];
+      g.fshift[dir][d] = g.shift[dir][d];
+    }
   }
   ctx->geom_ready = false;  // bins, stencil, slabs, sub-domain bounds: at the next rebuild
   // Neighbor::check_distance, neighbor.cpp:2443-2455: the trigger shrinks by the corner motion
@@ -3746,14 +3889,33 @@ int b200_group_set_atoms(b200_group *g, int n, int ntypes, const double *mass, c
   if (!c0->have_box) return group_fail(g, B200_EARG, "b200_set_box before b200_group_set_atoms");
   std::vector<std::vector<int>> idx(g->n);
   const int *P = g->grid;
+  // triclinic: sub-domains are bricks in lamda coordinates (Domain::x2lamda, domain.cpp:2376-2390)
+  const bool tri = c0->tri;
+  double hinv[6] = {0, 0, 0, 0, 0, 0};
+  if (tri) {
+    const double h0 = c0->prd[0], h1 = c0->prd[1], h2 = c0->prd[2];
+    hinv[0] = 1.0 / h0; hinv[1] = 1.0 / h1; hinv[2] = 1.0 / h2;
+    hinv[3] = -c0->yz / (h1 * h2);
+    hinv[4] = (c0->yz * c0->xy - h1 * c0->xz) / (h0 * h1 * h2);
+    hinv[5] = -c0->xy / (h0 * h1);
+  }
   for (int i = 0; i < n; i++) {
     int loc[3];
+    double lam[3] = {0, 0, 0};
+    if (tri) {
+      const double d0 = x[3 * (size_t)i] - c0->boxlo[0], d1 = x[3 * (size_t)i + 1] - c0->boxlo[1],
+                   d2 = x[3 * (size_t)i + 2] - c0->boxlo[2];
+      lam[0] = hinv[0] * d0 + hinv[5] * d1 + hinv[4] * d2;
+      lam[1] = hinv[1] * d1 + hinv[3] * d2;
+      lam[2] = hinv[2] * d2;
+    }
     for (int d = 0; d < 3; d++) {
-      const double c = x[3 * (size_t)i + d];
-      int l = (int)((c - c0->boxlo[d]) / c0->prd[d] * P[d]);
+      const double c = tri ? lam[d] : x[3 * (size_t)i + d];
+      const double blo = tri ? 0.0 : c0->boxlo[d], bprd = tri ? 1.0 : c0->prd[d];
+      int l = (int)((c - blo) / bprd * P[d]);
       l = std::min(std::max(l, 0), P[d] - 1);
       // the exact bounds of setup_geometry (boxlo + prd * l / P, last one closed at boxhi)
-      auto lo = [&](int q) { return c0->boxlo[d] + c0->prd[d] * (q * 1.0 / P[d]); };
+      auto lo = [&](int q) { return tri ? q * 1.0 / P[d] : c0->boxlo[d] + c0->prd[d] * (q * 1.0 / P[d]); };
       while (l > 0 && c < lo(l)) l--;
       while (l < P[d] - 1 && c >= lo(l + 1)) l++;
       loc[d] = l;

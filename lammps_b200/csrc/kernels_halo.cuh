@@ -92,7 +92,9 @@ __global__ void __launch_bounds__(256) k_unpack_migrate(
   image[i] = a;
   if (owner_dim(own, 0, p.x) != 0 || owner_dim(own, 1, p.y) != 0 || owner_dim(own, 2, p.z) != 0)
     atomicOr(err, 2);  // arrived at the wrong sub-domain: moved more than one sub-domain
-  int b = coord2bin(g, p.x, p.y, p.z);
+  double bx = p.x, by = p.y, bz = p.z;
+  if (g.tri) lamda2x(g, bx, by, bz);  // arrivals are in lamda coordinates like everybody else
+  int b = coord2bin(g, bx, by, bz);
   if (b < 0) {
     atomicOr(err, 2);
     b = 0;
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(256) k_ghost_make(
     r.z = r.z + g.shift[dir][2];
     t = tag[src];
   }
+  if (g.tri) lamda2x(g, r.x, r.y, r.z);  // Domain::lamda2x(nlocal+nghost), verlet.cpp:313
   int b = coord2bin(g, r.x, r.y, r.z);
   if (b < 0) {
     atomicOr(err, 2);
@@ -232,9 +235,7 @@ __global__ void __launch_bounds__(256) k_pack_forward(int nsend, const int *__re
   if (!((remote_mask >> dir) & 1u)) return;
   const double4 q = xt[sendlist[p]];
   double *o = buf + 3 * (size_t)p;
-  o[0] = q.x + g.shift[dir][0];
-  o[1] = q.y + g.shift[dir][1];
-  o[2] = q.z + g.shift[dir][2];
+  halo_shift(g, dir, q.x, q.y, q.z, o);
 }
 
 struct Vec3Ptr {
@@ -261,9 +262,7 @@ __global__ void __launch_bounds__(256) k_unpack_forward(int nghost, int nlocal,
   if (src >= 0) {
     const int dir = gdir[k];
     const double4 q = xt[src];
-    o[0] = q.x + g.shift[dir][0];
-    o[1] = q.y + g.shift[dir][1];
-    o[2] = q.z + g.shift[dir][2];
+    halo_shift(g, dir, q.x, q.y, q.z, o);
   } else {
     const double *r = rbuf + 3 * (size_t)(-1 - src);
     o[0] = r[0];
@@ -415,9 +414,7 @@ __global__ void __launch_bounds__(256) k_p2p_pack_forward(
       if (MODE == 0) {
         const double4 r = xt[sendlist[p]];
         double *o = pm.dst[dir] + 3 * q;
-        o[0] = r.x + g.shift[dir][0];
-        o[1] = r.y + g.shift[dir][1];
-        o[2] = r.z + g.shift[dir][2];
+        halo_shift(g, dir, r.x, r.y, r.z, o);
       } else {
         pm.dst[dir][q] = a[sendlist[p]];
       }
@@ -444,9 +441,7 @@ __global__ void __launch_bounds__(256) k_p2p_unpack_forward(
       if (src >= 0) {
         const int dir = gdir[k];
         const double4 q = xt[src];
-        o[0] = q.x + g.shift[dir][0];
-        o[1] = q.y + g.shift[dir][1];
-        o[2] = q.z + g.shift[dir][2];
+        halo_shift(g, dir, q.x, q.y, q.z, o);
       } else {
         const double *r = rbuf + 3 * (size_t)(-1 - src);
         o[0] = __ldcv(r);

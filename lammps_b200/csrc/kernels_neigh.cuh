@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(256) k_pbc_bin(int nlocal, double4 *__restrict
     slot[i] = atomicAdd(&bincount[0], 1);
     return;
   }
+  // triclinic: wrap, ownership and (later) the ghost slabs are decided in lamda coordinates; the
+  // atom stays in lamda coordinates until the ghosts exist (Domain::x2lamda, verlet.cpp:293)
+  if (g.tri) x2lamda(g, p.x, p.y, p.z);
   int idim, otherdims;
   if (g.periodic[0]) {
     if (p.x < g.boxlo[0]) {
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(256) k_pbc_bin(int nlocal, double4 *__restrict
       return;
     }
   }
+  if (g.tri) lamda2x(g, p.x, p.y, p.z);  // the position it will have when it is binned (verlet.cpp:313)
   int b = coord2bin(g, p.x, p.y, p.z);
   if (b < 0) {
     atomicOr(err, 2);
@@ -175,6 +179,16 @@ __global__ void __launch_bounds__(256) k_pbc_bin(int nlocal, double4 *__restrict
   }
   atombin[i] = b;
   slot[i] = atomicAdd(&bincount[b], 1);
+}
+
+// Domain::lamda2x over the owned atoms once the ghosts have been created from their lamda
+// coordinates (verlet.cpp:313); the ghosts were converted as they were made (k_ghost_make)
+__global__ void __launch_bounds__(256) k_lamda2x(int n, double4 *__restrict__ xt, Geom g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = xt[i];
+  lamda2x(g, p.x, p.y, p.z);
+  xt[i] = p;
 }
 
 // The slot an atom takes inside its bin (atomicAdd in k_pbc_bin) depends on the order in which
@@ -204,7 +218,7 @@ __global__ void __launch_bounds__(256) k_permute_owned(
     double *__restrict__ vz_out, const int *__restrict__ tag_in, int *__restrict__ tag_out,
     const int *__restrict__ mask_in, int *__restrict__ mask_out, const int *__restrict__ image_in,
     int *__restrict__ image_out, int *__restrict__ bin_out, double *__restrict__ xhx,
-    double *__restrict__ xhy, double *__restrict__ xhz) {
+    double *__restrict__ xhy, double *__restrict__ xhz, Geom g) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nlocal) return;
   const int b = atombin[i];
@@ -225,9 +239,11 @@ __global__ void __launch_bounds__(256) k_permute_owned(
   mask_out[d] = mask_in[i];
   image_out[d] = image_in[i];
   bin_out[d] = b;
-  xhx[d] = p.x;
-  xhy[d] = p.y;
-  xhz[d] = p.z;
+  double hx = p.x, hy = p.y, hz = p.z;
+  if (g.tri) lamda2x(g, hx, hy, hz);  // xhold is taken after lamda2x (neighbor.cpp:2520-2532)
+  xhx[d] = hx;
+  xhy[d] = hy;
+  xhz[d] = hz;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -344,6 +360,73 @@ __global__ void __launch_bounds__(128) k_build_half(
     numneigh[i] = n;
   }
   // one atomicMax per warp
+  int m = n;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxcount, m);
+}
+
+// ---------------------------------------------------------------------------------------
+// NPairBin<HALF=1,NEWTON=1,TRI=1,SIZE=0,ATOMONLY=1>::build (npair_bin.cpp:52-253, active branch
+// :133-155): triclinic box.  The stencil is full in all three dimensions (nstencil_bin.cpp:36-62;
+// `st` holds every (dz,dy) row, the row (0,0) includes the own bin).  An owned j is stored when it
+// comes after i in the local order (each owned pair once); a ghost j is stored by the parity of
+// itag+jtag (itag > jtag: odd sums, itag < jtag: even sums), a ghost image of i itself by the
+// (z,y,x) comparison with the reference's tolerance `delta`.  Which of two owned atoms holds a pair
+// depends on the local order, which is the reference's business as much as ours; the SET of pairs
+// (as unordered tag pairs + image) does not, and that is what parity compares.
+// ---------------------------------------------------------------------------------------
+template <bool ONETYPE>
+__global__ void __launch_bounds__(128) k_build_half_tri(
+    int nlocal, int nstride, int maxneigh, int T, const double4 *__restrict__ xt,
+    const int *__restrict__ tag, const int *__restrict__ atombin, const int *__restrict__ ostart,
+    const int *__restrict__ gstart, Stencil st, double cutneighsq_one,
+    const double *__restrict__ cutneighsq, int ntypes, double delta, int *__restrict__ numneigh,
+    int *__restrict__ neigh, int *__restrict__ maxcount) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = 0;
+  if (i < nlocal) {
+    const double4 pi = xt[i];
+    const int itype = d2type(pi.w), itag = tag[i];
+    const int b = atombin[i];
+    const double *cut_i = ONETYPE ? nullptr : cutneighsq + (size_t)itype * (ntypes + 1);
+
+    auto test = [&](int j, const double4 &pj) {
+      const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
+      const double rsq = rsq_ref(delx, dely, delz);
+      const double c = ONETYPE ? cutneighsq_one : cut_i[d2type(pj.w)];
+      if (rsq <= c) {
+        if (n < maxneigh) neigh[list_index(n, i, nstride, T)] = j;
+        n++;
+      }
+    };
+
+    for (int r = 0; r < st.nrows; r++) {
+      const int b0 = b + st.rowoff[r] + st.dxlo[r];
+      const int b1 = b + st.rowoff[r] + st.dxhi[r] + 1;
+      for (int j = max(ostart[b0], i + 1); j < ostart[b1]; j++) test(j, ld_xt(xt + j));
+      for (int gj = gstart[b0]; gj < gstart[b1]; gj++) {
+        const int j = nlocal + gj;
+        const int jtag = tag[j];
+        const double4 pj = ld_xt(xt + j);
+        if (itag > jtag) {
+          if ((itag + jtag) % 2 == 0) continue;
+        } else if (itag < jtag) {
+          if ((itag + jtag) % 2 == 1) continue;
+        } else {
+          if (fabs(pj.z - pi.z) > delta) {
+            if (pj.z < pi.z) continue;
+          } else if (fabs(pj.y - pi.y) > delta) {
+            if (pj.y < pi.y) continue;
+          } else {
+            if (pj.x < pi.x) continue;
+          }
+        }
+        test(j, pj);
+      }
+    }
+    numneigh[i] = n;
+  }
   int m = n;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));

@@ -42,6 +42,7 @@ EXPORTS = [
     "b200_group_run", "b200_group_get_tallies", "b200_group_ke_sum", "b200_group_last_run_ms",
     "b200_group_get_stats", "b200_group_ke_group", "b200_ke_group", "b200_sync", "b200_set_option",
     "b200_langevin", "b200_add_force", "b200_group_langevin", "b200_group_add_force",
+    "b200_set_box_triclinic",
 ]
 
 
@@ -138,6 +139,12 @@ class Engine:
         lo, hi, per = _d(lo), _d(hi), _i(periodic)
         self.boxlo, self.boxhi = lo.copy(), hi.copy()
         self._chk(self.L.b200_set_box(self.h, _p(lo), _p(hi), _p(per)))
+
+    def set_box_triclinic(self, lo, hi, xy, xz, yz, periodic=(1, 1, 1), angstrom=1.0):
+        lo, hi, per = _d(lo), _d(hi), _i(periodic)
+        self.boxlo, self.boxhi = lo.copy(), hi.copy()
+        self._chk(self.L.b200_set_box_triclinic(self.h, _p(lo), _p(hi), C.c_double(xy), C.c_double(xz),
+                                                C.c_double(yz), _p(per), C.c_double(angstrom)))
 
     def set_decomposition(self, procgrid, myloc):
         pg, ml = _i(procgrid), _i(myloc)
@@ -443,6 +450,11 @@ class EngineGroup:
             grid = tuple(int(v) for v in g3)
         self.grid = tuple(grid)
         self._chk(self.L.b200_group_set_grid(self.g, _p(_i(self.grid))))
+
+    def set_box_triclinic(self, lo, hi, xy, xz, yz, periodic=(1, 1, 1), angstrom=1.0):
+        self.set_box(lo, hi, periodic)
+        for e in self.sub:
+            e.set_box_triclinic(lo, hi, xy, xz, yz, periodic, angstrom)
 
     def neighbor(self, *a, **k):
         for e in self.sub:

@@ -53,7 +53,6 @@ void VerletB200::init()
   pkg = FixB200::instance(lmp);
   ctx = pkg->group() ? nullptr : pkg->context();
 
-  if (domain->triclinic) error->all(FLERR, "run_style verlet/b200 requires an orthogonal box");
   if (domain->dimension != 3) error->all(FLERR, "run_style verlet/b200 requires a 3d system");
   if (atom->molecular != Atom::ATOMIC || atom->rmass_flag)
     error->all(FLERR, "run_style verlet/b200 requires atom_style atomic with per-type masses");
@@ -140,7 +139,12 @@ void VerletB200::upload()
   else bstaged->b200_params(dtv, dtf, groupbit);
   for (int i = 0; i < pkg->nctx(); i++) {
     b200_ctx *c = pkg->context(i);
-    B200_CHECK(pkg, b200_set_box(c, domain->boxlo, domain->boxhi, domain->periodicity));
+    if (domain->triclinic)
+      B200_CHECK(pkg,
+                 b200_set_box_triclinic(c, domain->boxlo, domain->boxhi, domain->xy, domain->xz, domain->yz,
+                                        domain->periodicity, force->angstrom));
+    else
+      B200_CHECK(pkg, b200_set_box(c, domain->boxlo, domain->boxhi, domain->periodicity));
     B200_CHECK(pkg,
                b200_set_neighbor(c, neighbor->skin, neighbor->every, neighbor->delay,
                                  neighbor->dist_check, neighbor->oneatom));
@@ -236,7 +240,9 @@ void VerletB200::fill_per_atom_tallies()
   if (!(eflag & ENERGY_ATOM) && !(vflag & VIRIAL_ATOM)) return;
   Pair *pair = force->pair;
   if (pkg->host_stale) download(0);
+  if (domain->triclinic) domain->x2lamda(atom->nlocal);
   comm->borders();
+  if (domain->triclinic) domain->lamda2x(atom->nlocal + atom->nghost);
   bpair->b200_ev_setup(eflag, vflag);
   pkg->dev_peratom((eflag & ENERGY_ATOM) ? pair->eatom : nullptr,
                    (vflag & VIRIAL_ATOM) ? &pair->vatom[0][0] : nullptr);
@@ -253,11 +259,17 @@ void VerletB200::device_setup(int flag, int output_flag)
   if (flag) {
     atom->setup();
     modify->setup_pre_exchange();
-    domain->pbc();
+    // triclinic: the reference wraps and migrates in lamda coordinates, once (Verlet::setup,
+    // verlet.cpp:111-128).  One process: the device does exactly that in its own setup, so the
+    // host leaves the atoms alone (a second x -> lamda -> x round trip would move them by an ulp).
+    const int tri_on_device = domain->triclinic && comm->nprocs == 1;
+    if (domain->triclinic && !tri_on_device) domain->x2lamda(atom->nlocal);
+    if (!tri_on_device) domain->pbc();
     domain->reset_box();
     comm->setup();
     if (neighbor->style) neighbor->setup_bins();
-    comm->exchange();
+    if (!tri_on_device) comm->exchange();
+    if (domain->triclinic && !tri_on_device) domain->lamda2x(atom->nlocal);
   }
   force->setup();
   ev_set(update->ntimestep);
