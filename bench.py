@@ -198,12 +198,17 @@ def also_block(args, local_rank):
     from lammps_b200.engine import Engine
     res = {}
 
-    def quick(workload, precision, steps=100):
+    def quick(workload, precision, steps=100, tilt=None):
         kind, cells1, _ = WORKLOADS[workload]
         s = build_system(kind, (cells1,) * 3)
         n = len(s["x"])
         e = Engine(local_rank, precision, s["units"])
         configure(e, s, s["x"], s["v"], s["type"], np.arange(1, n + 1, dtype=np.int32), n)
+        if tilt is not None:
+            # the same crystal in a sheared box: tilt factors are whole lattice constants, so the
+            # lattice stays periodic; atoms outside the parallelepiped are wrapped at setup
+            a = (s["hi"][0] - s["lo"][0]) / cells1
+            e.set_box_triclinic(s["lo"], s["hi"], tilt[0] * a, tilt[1] * a, tilt[2] * a)
         e.setup(1, 1)
         e.run(20, 0)
         e.run(steps, 0)
@@ -223,6 +228,11 @@ def also_block(args, local_rank):
             res[name] = quick(wl, prec)
         except Exception as ex:  # a side measurement must not take the headline down
             res[name] = {"error": str(ex)[:200]}
+    try:  # triclinic box (flat half list by the tag rule, k_build_half_tri + k_pair_lj)
+        res["lj4m_triclinic_double"] = quick("lj4m", "double", tilt=(2.0, -1.0, 3.0))
+        res["lj4m_triclinic_double"]["note"] = "prism box, tilt (2, -1, 3) lattice constants"
+    except Exception as ex:
+        res["lj4m_triclinic_double"] = {"error": str(ex)[:200]}
     # the reference's own small inputs, unmodified, through the LAMMPS package
     exe = ROOT / "lammps_b200" / "lammps_pkg" / "lmp_b200"
     inputs = ROOT / "lammps_b200" / "lammps_pkg" / "bench_inputs"
@@ -236,6 +246,25 @@ def also_block(args, local_rank):
             t, nst, nat = float(m.group(1)), int(m.group(2)), int(m.group(3))
             res[name] = {"value": nat * nst / t, "unit": "atom-steps/s", "natoms": nat, "steps": nst,
                          "note": "unmodified bench input, lmp_b200 -sf b200, LAMMPS loop time"}
+        except Exception as ex:
+            res[name] = {"error": str(ex)[:200]}
+    # thermostatted 4 M-atom melts through the LAMMPS package (stage-by-stage timestep: the
+    # integrator cannot live inside the pair kernel when a fix acts between the two half-kicks)
+    for name, fixes in (("lj4m_nvt_lmp_b200", "fix 1 all nvt temp 1.44 1.44 0.5"),
+                        ("lj4m_langevin_lmp_b200", "fix 1 all nve\nfix 2 all langevin 1.44 1.44 1.0 48279")):
+        if not exe.exists():
+            continue
+        try:
+            script = ("units lj\nlattice fcc 0.8442\nregion box block 0 100 0 100 0 100\ncreate_box 1 box\n"
+                      "create_atoms 1 box\nmass 1 1.0\nvelocity all create 1.44 87287 loop geom\n"
+                      "pair_style lj/cut 2.5\npair_coeff 1 1 1.0 1.0 2.5\nneighbor 0.3 bin\n"
+                      "neigh_modify delay 0 every 20 check no\n" + fixes + "\nthermo 100\nrun 20\nrun 100\n")
+            out = subprocess.run([str(exe), "-sf", "b200", "-echo", "none"], input=script, capture_output=True,
+                                 text=True, timeout=300).stdout
+            m = re.findall(r"Loop time of ([0-9.eE+-]+) on \d+ procs for (\d+) steps with (\d+) atoms", out)[-1]
+            t, nst, nat = float(m[0]), int(m[1]), int(m[2])
+            res[name] = {"value": nat * nst / t, "unit": "atom-steps/s", "natoms": nat, "steps": nst,
+                         "note": fixes.replace("\n", "; ") + ", lmp_b200 -sf b200, LAMMPS loop time"}
         except Exception as ex:
             res[name] = {"error": str(ex)[:200]}
     return res
