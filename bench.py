@@ -228,7 +228,7 @@ def also_block(args, local_rank):
             res[name] = quick(wl, prec)
         except Exception as ex:  # a side measurement must not take the headline down
             res[name] = {"error": str(ex)[:200]}
-    try:  # triclinic box (flat half list by the tag rule, k_build_half_tri + k_pair_lj)
+    try:  # triclinic box (bin tiles, half list by the tag rule: k_tile_build<...,TRI>)
         res["lj4m_triclinic_double"] = quick("lj4m", "double", tilt=(2.0, -1.0, 3.0))
         res["lj4m_triclinic_double"]["note"] = "prism box, tilt (2, -1, 3) lattice constants"
     except Exception as ex:

@@ -119,6 +119,7 @@ struct b200_ctx {
   int periodic[3] = {1, 1, 1};
   int procgrid[3] = {1, 1, 1}, myloc[3] = {0, 0, 0};
   double sublo[3], subhi[3];  // comm frame (lamda coordinates in a triclinic box)
+  double osublo[3], osubhi[3];  // extent of the sub-domain in box coordinates (bounding box if triclinic)
   bool tri = false;           // triclinic box: tilt factors, Force::angstrom for the list rule's delta
   double xy = 0.0, xz = 0.0, yz = 0.0, angstrom = 1.0;
   // neighbor settings
@@ -1136,8 +1137,7 @@ static int setup_geometry(b200_ctx *ctx) {
   {
     FullStencil &fs = ctx->fst;
     memset(&fs, 0, sizeof fs);
-    // (a triclinic box runs on the flat half list: the tile kernels' FWD rule is the orthogonal one)
-    bool ok = !tri && s[0] <= 3 && s[1] <= 3 && s[2] <= 3;
+    bool ok = s[0] <= 3 && s[1] <= 3 && s[2] <= 3;
     for (int k = -s[2]; ok && k <= s[2]; k++)
       for (int j = -s[1]; j <= s[1]; j++) {
         int lo = 1 << 30, hi = -(1 << 30), cnt = 0;
@@ -1192,9 +1192,40 @@ static int setup_geometry(b200_ctx *ctx) {
       else ix = (int)((x - g.binlo[d]) * g.bininv[d]) - 1;
       return ix - g.mbinlo[d];
     };
+    // extent of the sub-domain in box coordinates: the brick itself, or the bounding box of the
+    // lamda brick (some of its bins then hold no owned atom, only ghosts: tiles with ni = 0)
     for (int d = 0; d < 3; d++) {
-      const int lo = std::max(host_bin(ctx->sublo[d], d), 0);
-      const int hi = std::min(host_bin(std::nextafter(ctx->subhi[d], -1.0e300), d), g.mbin[d] - 1);
+      ctx->osublo[d] = ctx->sublo[d];
+      ctx->osubhi[d] = ctx->subhi[d];
+    }
+    if (tri) {
+      for (int d = 0; d < 3; d++) {
+        ctx->osublo[d] = 1.0e300;
+        ctx->osubhi[d] = -1.0e300;
+      }
+      for (int cz = 0; cz < 2; cz++)
+        for (int cy = 0; cy < 2; cy++)
+          for (int cx = 0; cx < 2; cx++) {
+            const double l[3] = {cx ? ctx->subhi[0] : ctx->sublo[0], cy ? ctx->subhi[1] : ctx->sublo[1],
+                                 cz ? ctx->subhi[2] : ctx->sublo[2]};
+            const double x[3] = {g.h[0] * l[0] + g.h[5] * l[1] + g.h[4] * l[2] + ctx->boxlo[0],
+                                 g.h[1] * l[1] + g.h[3] * l[2] + ctx->boxlo[1], g.h[2] * l[2] + ctx->boxlo[2]};
+            for (int d = 0; d < 3; d++) {
+              ctx->osublo[d] = std::min(ctx->osublo[d], x[d]);
+              ctx->osubhi[d] = std::max(ctx->osubhi[d], x[d]);
+            }
+          }
+      // lamda2x of an owned atom may land an ulp outside the exact corners: one bin of slack
+      for (int d = 0; d < 3; d++) {
+        const double pad = 1.0e-9 * (g.binhi[d] - g.binlo[d]);
+        ctx->osublo[d] -= pad;
+        ctx->osubhi[d] += pad;
+      }
+    }
+    for (int d = 0; d < 3; d++) {
+      const int lo = std::max(host_bin(ctx->osublo[d], d), 0);
+      const int hi = std::min(host_bin(tri ? ctx->osubhi[d] : std::nextafter(ctx->subhi[d], -1.0e300), d),
+                              g.mbin[d] - 1);
       ctx->ibin_lo[d] = lo;
       ctx->ibin_n[d] = std::max(hi - lo + 1, 1);
       ctx->tg.s[d] = s[d];
@@ -1206,10 +1237,10 @@ static int setup_geometry(b200_ctx *ctx) {
     // ghost shell, 30 bits over the largest extent, power-of-two scale
     double ext = 0.0;
     const double margin = ctx->cutghost + 2.0 * ctx->skin;
-    for (int d = 0; d < 3; d++) ext = std::max(ext, ctx->subhi[d] - ctx->sublo[d] + 2.0 * margin);
-    ctx->qgeom.ox = ctx->sublo[0] - margin;
-    ctx->qgeom.oy = ctx->sublo[1] - margin;
-    ctx->qgeom.oz = ctx->sublo[2] - margin;
+    for (int d = 0; d < 3; d++) ext = std::max(ext, ctx->osubhi[d] - ctx->osublo[d] + 2.0 * margin);
+    ctx->qgeom.ox = ctx->osublo[0] - margin;
+    ctx->qgeom.oy = ctx->osublo[1] - margin;
+    ctx->qgeom.oz = ctx->osublo[2] - margin;
     ctx->qgeom.scale = std::ldexp(1.0, (int)std::floor(std::log2(1073741824.0 / ext)));
     double cmin = 1.0e300;
     for (int i = 1; i <= n; i++)
@@ -1265,8 +1296,8 @@ static void set_tile_geom(b200_ctx *ctx, const int t[3]) {
     G.nib[d] = ctx->ibin_n[d];
     G.mbin[d] = ctx->geom.mbin[d];
     G.ntiles *= G.nt[d];
-    G.bsize[d] = ctx->prd[d] / ctx->geom.nbin[d];
-    G.bin0[d] = ctx->boxlo[d] + ctx->geom.mbinlo[d] * G.bsize[d];
+    G.bsize[d] = (ctx->geom.binhi[d] - ctx->geom.binlo[d]) / ctx->geom.nbin[d];
+    G.bin0[d] = ctx->geom.binlo[d] + ctx->geom.mbinlo[d] * G.bsize[d];
 
   }
   {
@@ -1296,6 +1327,9 @@ static int tile_kernel_attrs(b200_ctx *ctx) {
   TRY(tile_attr(ctx, (k_tile_build<true, false>)));
   TRY(tile_attr(ctx, (k_tile_build<false, false>)));
   TRY(tile_attr(ctx, (k_tile_build<true, true, true>)));
+  TRY(tile_attr(ctx, (k_tile_build<true, true, false, true>)));
+  TRY(tile_attr(ctx, (k_tile_build<false, true, false, true>)));
+  TRY(tile_attr(ctx, (k_tile_build<true, true, true, true>)));
   TRY(tile_attr(ctx, k_tile_export));
   TRY(tile_attr(ctx, k_peratom_tile<1>));
   TRY(tile_attr(ctx, k_peratom_tile<2>));
@@ -1358,6 +1392,9 @@ static int build_tiles(b200_ctx *ctx) {
   const bool eam = ctx->pair_style == 2;
   const bool eam2 = eam && eam2_usable(ctx);
   ctx->eam2_active = false;
+  // triclinic: the tile rows that hold every ghost partner (lj/cut, eam2) carry the tag rule; the
+  // first-generation eam tile kernels (FWD ghosts + scatter) stay orthogonal-only -> flat list
+  if (ctx->tri && eam && !eam2) return B200_OK;
   if (ctx->tile_level < 0) {
     // first build for this geometry: the largest tile that still gives every SM several CTAs
     int lvl = 0;
@@ -1455,7 +1492,18 @@ static int build_tiles(b200_ctx *ctx) {
       ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p, ctx->tl_num.p,          \
       ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags, rs * rs,             \
       eam2 ? ctx->tl_far.p : nullptr)
-    if (ctx->build2 && smem2 <= BUILD2_SMEM_MAX) {
+    const double tdelta = 0.01 * ctx->angstrom;  // npair_bin.cpp:59
+#define TBT(ONE, SPL)                                                                                  \
+  k_tile_build<ONE, true, SPL, true><<<G.ntiles, ctx->tile_threads, smem, s>>>(                       \
+      G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,   \
+      ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,           \
+      ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags,       \
+      SPL ? rs * rs : 0.0, SPL ? ctx->tl_far.p : nullptr, ctx->tag[c], tdelta)
+    if (ctx->tri) {
+      if (eam2) TBT(true, true);
+      else if (one) TBT(true, false);
+      else TBT(false, false);
+    } else if (ctx->build2 && smem2 <= BUILD2_SMEM_MAX) {
       if (eam2) TB2(true, true, true);
       else if (!eam) { if (one) TB2(true, true, false); else TB2(false, true, false); }
       else           { if (one) TB2(true, false, false); else TB2(false, false, false); }
@@ -1470,6 +1518,7 @@ static int build_tiles(b200_ctx *ctx) {
     else      { if (one) TB(true, false); else TB(false, false); }
 #undef TB
 #undef TB2
+#undef TBT
     ctx->launches++;
     LAUNCH_CHECK();
     ph_end(ctx, ph1);

@@ -423,7 +423,13 @@ __global__ void __launch_bounds__(256) k_tile_split(int ntiles, const int *__res
 // The pair kernels evaluate the near entries unconditionally and the far ones behind a cutoff
 // test that almost never fires, so that a warp does not run the expensive eam pair function for
 // the ~30 % of the stored partners that sit in the skin.  The SET of entries is unchanged.
-template <bool ONETYPE, bool FULLGHOST, bool SPLIT = false>
+// TRI (triclinic box, npair_bin.cpp:133-155): the half list is not cut out by stencil halves and
+// coordinates but by the local order (owned j after owned i: here the global index, any
+// antisymmetric order stores each owned pair once) and, for a ghost j, by the parity of
+// itag + jtag; a ghost image of i itself by the (z,y,x) comparison with tolerance `tri_delta`.
+// The rule is antisymmetric between the two owners of a boundary pair, so FULLGHOST rows flag
+// the pair FWD on exactly one side, as in the orthogonal case.
+template <bool ONETYPE, bool FULLGHOST, bool SPLIT = false, bool TRI = false>
 __global__ void __launch_bounds__(512) k_tile_build(
     TileGeom G, FullStencil F, int nlocal, const double4 *__restrict__ xt,
     const int *__restrict__ ostart, const int *__restrict__ gstart,
@@ -431,7 +437,8 @@ __global__ void __launch_bounds__(512) k_tile_build(
     double cut1, const double *__restrict__ cutneighsq, int ntypes,
     unsigned short *__restrict__ iloc, unsigned short *__restrict__ tnum, int *__restrict__ tgi,
     uint4 *__restrict__ list, int *__restrict__ numneigh_half, int scap, int *__restrict__ tflags,
-    double splitsq = 0.0, unsigned short *__restrict__ tfar = nullptr) {
+    double splitsq = 0.0, unsigned short *__restrict__ tfar = nullptr,
+    const int *__restrict__ tag = nullptr, double tri_delta = 0.0) {
   extern __shared__ __align__(128) unsigned char tsm[];
   TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
   const TileS T = tile_carve(tsm, scap, false);
@@ -531,6 +538,26 @@ __global__ void __launch_bounds__(512) k_tile_build(
         const int srow = (by + dy - ys) + (bz + dz - zs) * G.srow_y;
         const unsigned short *bo = sbo + srow * ncol, *bg = sbg + srow * ncol;
         const int ca = bx + F.dxlo[r] - xs, cb = bx + F.dxhi[r] + 1 - xs;
+        if (TRI) {
+          const int itag = tag[gi];
+          for (int s = bo[ca]; s < bo[cb]; s++)
+            if (s != li) test(s, T.gmap[s] > gi ? TILE_FWD : 0u);
+          for (int s = bg[ca]; s < bg[cb]; s++) {
+            const int jtag = tag[T.gmap[s]];
+            bool member = true;
+            if (itag > jtag) member = ((itag + jtag) % 2) != 0;
+            else if (itag < jtag) member = ((itag + jtag) % 2) != 1;
+            else {
+              const double3 pj = tile_pos3(T, s);
+              if (fabs(pj.z - pi.z) > tri_delta) member = !(pj.z < pi.z);
+              else if (fabs(pj.y - pi.y) > tri_delta) member = !(pj.y < pi.y);
+              else member = !(pj.x < pi.x);
+            }
+            if (member) test(s, TILE_FWD | TILE_GHOST);
+            else if (FULLGHOST) test(s, TILE_GHOST);
+          }
+          continue;
+        }
         if (dz > 0 || (dz == 0 && dy > 0)) {  // upper half stencil: members of i's half list
           run(bo[ca], bo[cb], TILE_FWD);
           run(bg[ca], bg[cb], TILE_FWD | TILE_GHOST);

@@ -94,9 +94,11 @@ def _reference_state(script, nsteps):
     return st
 
 
-@pytest.mark.parametrize("tilt,subdomains", [("2.0 -1.0 3.0", 1), ("-3.0 2.5 1.5", 1), ("2.0 -1.0 3.0", 8)],
-                         ids=["tilt-a", "tilt-b", "tilt-a-8-subdomains"])
-def test_triclinic_list_forces_energy_equal_the_reference(tilt, subdomains):
+@pytest.mark.parametrize("tilt,subdomains,mode", [
+    ("2.0 -1.0 3.0", 1, "flat"), ("2.0 -1.0 3.0", 1, "tile"), ("-3.0 2.5 1.5", 1, "tile"),
+    ("2.0 -1.0 3.0", 8, "flat"), ("2.0 -1.0 3.0", 8, "tile")],
+    ids=["tilt-a-flat", "tilt-a-tile", "tilt-b-tile", "tilt-a-8-subdomains-flat", "tilt-a-8-subdomains-tile"])
+def test_triclinic_list_forces_energy_equal_the_reference(tilt, subdomains, mode):
     from lammps_b200 import pair_lj
     from lammps_b200.engine import Engine, EngineGroup
     st = _reference_state(_script(LJ_TRI, 8, tilt, "every 1 delay 0 check yes"), 50)
@@ -108,10 +110,12 @@ def test_triclinic_list_forces_energy_equal_the_reference(tilt, subdomains):
     e.neighbor(0.3, every=1, delay=0, check=True)
     e.fix_nve(0.005)
     e.pair_lj_cut(pair_lj.lj_cut_tables(1, {(1, 1): (1.0, 1.0, 2.5)}, 2.5))
+    for sub in ([e] if subdomains == 1 else e.sub):
+        sub.set_option("list", mode)
     e.setup(1, 1)
     want = _pair_keys(*st["pairs"], st["tag"], st["x"])
     if subdomains == 1:
-        assert e.stats()["list_kind"] == 0           # flat half list
+        assert e.stats()["list_kind"] == (1 if mode == "tile" else 0)
         a = e.get_atoms(ghosts=True, fields=("x", "tag"))
         _, pi, pj = e.neighbor_list()
         got = _pair_keys(pi, pj, a["tag"], a["x"])
@@ -135,6 +139,34 @@ def test_triclinic_list_forces_energy_equal_the_reference(tilt, subdomains):
     eng, vir = e.tallies()
     assert abs(eng / st["natoms"] - st["pe"]) <= 1e-12 * abs(st["pe"])
     e.close()
+
+
+def test_triclinic_fused_run_on_tiles_equals_flat_list_run():
+    """100 steps through b200_run: bin tiles with the integrator inside the pair kernel against the
+    flat half list stage by stage -- same rebuilds, positions to 1e-9"""
+    from lammps_b200 import pair_lj
+    from lammps_b200.engine import Engine
+    st = _reference_state(_script(LJ_TRI, 8, "2.0 -1.0 3.0", "every 1 delay 0 check yes"), 20)
+    nl = st["nlocal"]
+    res = {}
+    for mode in ("tile", "flat"):
+        e = Engine(0, "double", "lj")
+        e.set_box_triclinic(st["lo"], st["hi"], st["xy"], st["xz"], st["yz"])
+        e.set_atoms(st["x"][:nl], st["v"], st["type"], st["tag"][:nl], np.array([0.0, 1.0]), image=st["image"])
+        e.neighbor(0.3, every=1, delay=0, check=True)
+        e.fix_nve(0.005)
+        e.pair_lj_cut(pair_lj.lj_cut_tables(1, {(1, 1): (1.0, 1.0, 2.5)}, 2.5))
+        e.set_option("list", mode)
+        e.setup(1, 1)
+        th = e.run(100, 50)
+        a = e.get_atoms(fields=("x", "v", "tag"))
+        o = np.argsort(a["tag"])
+        res[mode] = (th, a["x"][o], a["v"][o], e.stats()["nbuilds"])
+        e.close()
+    assert res["tile"][3] == res["flat"][3] > 3
+    assert np.abs(res["tile"][1] - res["flat"][1]).max() < 1e-9
+    assert np.abs(res["tile"][2] - res["flat"][2]).max() < 1e-9
+    assert np.abs(res["tile"][0] - res["flat"][0]).max() <= 1e-9 * np.abs(res["flat"][0]).max()
 
 
 def _run(exe, args, d, body, ncols):
@@ -164,7 +196,10 @@ def _run(exe, args, d, body, ncols):
     ("lj", 10, "2.0 -1.0 3.0", "every 2 delay 0 check yes", ["-pk", "b200", "subdomains", "8"]),
     ("eam", 8, "1.5 -2.0 1.0", "every 1 delay 5 check yes", []),
     ("eam", 8, "1.5 -2.0 1.0", "every 1 delay 5 check yes", ["-pk", "b200", "subdomains", "4"]),
-], ids=["lj-check-no", "lj-check-yes", "lj-8-subdomains", "eam", "eam-4-subdomains"])
+    ("lj", 10, "-4.0 3.0 -2.0", "every 1 delay 0 check yes", ["-pk", "b200", "list", "flat"]),
+    ("eam", 8, "1.5 -2.0 1.0", "every 1 delay 5 check yes", ["-pk", "b200", "list", "flat"]),
+], ids=["lj-check-no", "lj-check-yes", "lj-8-subdomains", "eam", "eam-4-subdomains", "lj-flat-list",
+        "eam-flat-list"])
 def test_triclinic_run_matches_reference_executable(tmp_path, kind, cells, tilt, neigh, extra):
     body = _script(LJ_TRI if kind == "lj" else EAM_TRI, cells, tilt, neigh) + """
 compute pea all pe/atom
