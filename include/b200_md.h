@@ -58,6 +58,11 @@ int b200_set_box(b200_ctx *ctx, const double boxlo[3], const double boxhi[3],
  *      0.01 angstrom tolerance).  Sub-domains are bricks in lamda coordinates. */
 int b200_set_box_triclinic(b200_ctx *ctx, const double boxlo[3], const double boxhi[3], double xy,
                            double xz, double yz, const int periodicity[3], double angstrom);
+/*      `newton off` (Force::newton_pair = 0, force.cpp; list rule NPairBin<HALF,!NEWTON>
+ *      npair_bin.cpp:126-131): owned-ghost pairs are stored and evaluated by both owners, nothing
+ *      is scattered onto ghosts or sent back.  Runs on the bin-tile rows that hold every ghost
+ *      partner (lj/cut, single-element eam); default is on. */
+int b200_set_newton(b200_ctx *ctx, int newton_pair);
 int b200_set_decomposition(b200_ctx *ctx, const int procgrid[3], const int myloc[3]);
 /*      optional: which rank owns grid location (ix,iy,iz), n = px*py*pz entries indexed
  *      (ix*py+iy)*pz+iz -- Comm::grid2proc (comm.h); default = that index itself (MPI_Cart order) */

@@ -233,6 +233,7 @@ struct b200_ctx {
   // eam on tiles, second generation (kernels_eam2.cuh): FULLGHOST + NEAR/FAR split rows, density
   // and embedding in one kernel, fix nve fused into the force kernel.  Single-element potentials
   // in FP64 (B200_EAM2=0 / `package b200 eam2 no` selects the flat half list kernels).
+  int newton = 1;               // Force::newton_pair; 0: lists hold every owned-ghost pair on both sides
   int eam2 = 2;                 // 0 never, 1 whenever usable, 2 auto: small sub-domains (see eam2_usable)
   long long eam2_max_bins = 60000;
   bool build2 = false;          // warp-per-bin list build (kernels_build2.cuh; B200_BUILD2=1): measured slower
@@ -1379,7 +1380,7 @@ static bool eam2_usable(const b200_ctx *ctx) {
   if (!(ctx->eam2 && ctx->pair_style == 2 && ctx->eam_one_ok && ctx->ntypes == 1 &&
         ctx->prec == B200_PREC_DOUBLE))
     return false;
-  if (ctx->eam2 == 1) return true;
+  if (ctx->eam2 == 1 || !ctx->newton) return true;  // newton off lives on the FULLGHOST tile rows
   const long long bins = (long long)ctx->geom.nbin[0] * ctx->geom.nbin[1] * ctx->geom.nbin[2];
   return bins / std::max(ctx->nranks, 1) <= ctx->eam2_max_bins;
 }
@@ -1482,7 +1483,8 @@ static int build_tiles(b200_ctx *ctx) {
   k_tile_build<ONE, FULL><<<G.ntiles, ctx->tile_threads, smem, s>>>(                                  \
       G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,   \
       ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,           \
-      ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags)
+      ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags, 0.0,  \
+      nullptr, nullptr, 0.0, ctx->newton ? 0 : 1)
     // lj/cut: every ghost partner is stored (no scatter, no reverse halo); eam: FWD ghosts only
     const size_t smem2 = build2_smem_bytes(ctx->tile_scap, rows, G.sbx, !one, ctx->tile_slots);
     const double rs = eam2 ? std::max(0.0, std::sqrt(ctx->eam.cutforcesq) + ctx->eam2_margin * ctx->skin) : 0.0;
@@ -1498,12 +1500,13 @@ static int build_tiles(b200_ctx *ctx) {
       G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,   \
       ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,           \
       ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags,       \
-      SPL ? rs * rs : 0.0, SPL ? ctx->tl_far.p : nullptr, ctx->tag[c], tdelta)
+      SPL ? rs * rs : 0.0, SPL ? ctx->tl_far.p : nullptr, ctx->tag[c], tdelta, ctx->newton ? 0 : 1)
+    if (!ctx->newton && eam && !eam2) return B200_OK;  // no FULLGHOST rows: build_list reports it
     if (ctx->tri) {
       if (eam2) TBT(true, true);
       else if (one) TBT(true, false);
       else TBT(false, false);
-    } else if (ctx->build2 && smem2 <= BUILD2_SMEM_MAX) {
+    } else if (ctx->build2 && ctx->newton && smem2 <= BUILD2_SMEM_MAX) {
       if (eam2) TB2(true, true, true);
       else if (!eam) { if (one) TB2(true, true, false); else TB2(false, true, false); }
       else           { if (one) TB2(true, false, false); else TB2(false, false, false); }
@@ -1513,7 +1516,7 @@ static int build_tiles(b200_ctx *ctx) {
           G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,
           ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,
           ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags,
-          rs * rs, ctx->tl_far.p);
+          rs * rs, ctx->tl_far.p, nullptr, 0.0, ctx->newton ? 0 : 1);
     } else if (!eam) { if (one) TB(true, true); else TB(false, true); }
     else      { if (one) TB(true, false); else TB(false, false); }
 #undef TB
@@ -1553,10 +1556,17 @@ static int build_list(b200_ctx *ctx) {
   // flat half list stays the default for it
   const bool want_tiles = ctx->list_mode == 1 ||
                           (ctx->list_mode == 0 && (ctx->pair_style == 1 || (ctx->pair_style == 2 && eam2_usable(ctx))));
-  if (ctx->use_tiles && want_tiles && nl > 0) {
+  if (ctx->use_tiles && (want_tiles || (!ctx->newton && ctx->list_mode != 2)) && nl > 0) {
     TRY(build_tiles(ctx));
-    if (ctx->tiles_active) return B200_OK;
+    if (ctx->tiles_active && (ctx->newton || ctx->full_ghost)) return B200_OK;
   }
+  // newton off (force.cpp newton_pair = 0): every boundary pair is evaluated by both owners and
+  // nothing is sent back -- which is what the tile rows holding every ghost partner do anyway
+  // (k_tile_build FULLGHOST).  The flat half list scatters onto ghosts and returns their forces:
+  // a Newton-on scheme with no newton-off variant.
+  if (!ctx->newton && nl > 0)
+    return ctx->fail(B200_EARG, "newton off needs the bin-tile list: lj/cut, or single-element eam in double "
+                                "precision (package b200 list flat / multi-element eam are newton-on only)");
   ctx->tiles_active = false;
   ctx->full_ghost = false;
   ctx->eam2_active = false;
@@ -2703,6 +2713,16 @@ int b200_set_box_triclinic(b200_ctx *ctx, const double boxlo[3], const double bo
   return B200_OK;
 }
 
+// Force::newton_pair (force.cpp, `newton` command).  off: the neighbour list holds every
+// owned-ghost pair on both of its owners (npair_bin.cpp:126-131) and no force returns from ghosts.
+int b200_set_newton(b200_ctx *ctx, int newton_pair) {
+  if (!ctx) return B200_EARG;
+  drop_step_graph(ctx);
+  ctx->newton = newton_pair ? 1 : 0;
+  ctx->geom_ready = false;
+  return B200_OK;
+}
+
 int b200_set_decomposition(b200_ctx *ctx, const int procgrid[3], const int myloc[3]) {
   if (!ctx) return B200_EARG;
   for (int d = 0; d < 3; d++) {
@@ -3577,7 +3597,8 @@ int b200_get_neighbor_list(b200_ctx *ctx, int *numneigh, int *neigh, int64_t cap
     k_tile_export<<<G.ntiles, 256, sm, ctx->stream>>>(G, nl, ctx->ostart.p, ctx->gstart.p, ctx->tile_ibase.p,
                                                      ctx->tile_NI, ctx->tile_slots, ctx->tl_num.p,
                                                      ctx->tl_list.p, dfirst, dflat, ctx->tile_scap,
-                                                     ctx->eam2_active ? ctx->tl_far.p : nullptr);
+                                                     ctx->eam2_active ? ctx->tl_far.p : nullptr,
+                                                     ctx->newton ? 0 : 1);
   } else
     k_export_csr<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->nstride, ctx->tpa, ctx->numneigh.p,
                                                          ctx->neigh.p, dfirst, dflat);

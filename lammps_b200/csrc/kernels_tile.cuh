@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(512) k_tile_build(
     unsigned short *__restrict__ iloc, unsigned short *__restrict__ tnum, int *__restrict__ tgi,
     uint4 *__restrict__ list, int *__restrict__ numneigh_half, int scap, int *__restrict__ tflags,
     double splitsq = 0.0, unsigned short *__restrict__ tfar = nullptr,
-    const int *__restrict__ tag = nullptr, double tri_delta = 0.0) {
+    const int *__restrict__ tag = nullptr, double tri_delta = 0.0, int newtoff = 0) {
   extern __shared__ __align__(128) unsigned char tsm[];
   TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
   const TileS T = tile_carve(tsm, scap, false);
@@ -493,7 +493,10 @@ __global__ void __launch_bounds__(512) k_tile_build(
       const int W = maxslots >> 3;
       auto push = [&](int s, unsigned flags, bool isfar) {
         const unsigned long long e = (unsigned)s | flags;
-        nf += flags >> 15;
+        // members of the reference's list: the FWD entries -- or, with newton off
+        // (NPairBin<HALF,!NEWTON>, npair_bin.cpp:126-131: "stores own/ghost pairs on both procs"),
+        // the FWD owned partners and EVERY ghost partner
+        nf += (newtoff && (flags & TILE_GHOST)) ? 1 : (flags >> 15);
         if (SPLIT && isfar) {
           flo = (flo >> 16) | (fhi << 48);
           fhi = (fhi >> 16) | (e << 48);
@@ -637,7 +640,7 @@ __global__ void __launch_bounds__(512) k_tile_export(
     TileGeom G, int nlocal, const int *__restrict__ ostart, const int *__restrict__ gstart,
     const int *__restrict__ tile_ibase, int NI, int maxslots, const unsigned short *__restrict__ tnum,
     const uint4 *__restrict__ list, const long long *__restrict__ first, int *__restrict__ flat,
-    int scap, const unsigned short *__restrict__ tfar = nullptr) {
+    int scap, const unsigned short *__restrict__ tfar = nullptr, int newtoff = 0) {
   extern __shared__ __align__(128) unsigned char tsm[];
   TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
   int *gmap = reinterpret_cast<int *>(tsm + TILE_HDR_BYTES);
@@ -666,7 +669,8 @@ __global__ void __launch_bounds__(512) k_tile_export(
       const uint4 q = list[(size_t)(far ? W - 1 - (k >> 3) : (k >> 3)) * NI + g];
       const unsigned w = (k & 4) ? ((k & 2) ? q.w : q.z) : ((k & 2) ? q.y : q.x);
       const unsigned e = (w >> ((k & 1) * 16)) & 0xffffu;
-      if (e & TILE_FWD) flat[o++] = gmap[e & TILE_IDX];
+      if ((e & TILE_FWD) || (newtoff && (e & TILE_GHOST) && (e & TILE_IDX) != (unsigned)S))
+        flat[o++] = gmap[e & TILE_IDX];
     }
   }
 }

@@ -130,8 +130,7 @@ int FixB200::setmask()
 
 void FixB200::init()
 {
-  if (!force->newton_pair)
-    error->all(FLERR, "The B200 package requires newton pair on (half neighbor lists)");
+  // newton pair on or off: off runs on the tile rows that hold every ghost partner (b200_set_newton)
 }
 
 double FixB200::memory_usage()

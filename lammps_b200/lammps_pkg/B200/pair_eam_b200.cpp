@@ -36,7 +36,6 @@ void PairEAMB200::init_style()
 {
   PairEAM::init_style();    // file2array() + array2spline()
   FixB200::instance(lmp);
-  if (!force->newton_pair) error->all(FLERR, "Pair style eam/b200 requires newton pair on");
   if (he_flag) error->all(FLERR, "Pair style eam/b200 does not support eam/he tables");
 }
 

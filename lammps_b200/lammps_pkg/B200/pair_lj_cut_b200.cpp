@@ -24,7 +24,6 @@ void PairLJCutB200::init_style()
 {
   PairLJCut::init_style();
   FixB200::instance(lmp);
-  if (!force->newton_pair) error->all(FLERR, "Pair style lj/cut/b200 requires newton pair on");
   if (atom->molecular != Atom::ATOMIC)
     error->all(FLERR, "Pair style lj/cut/b200 requires an atomic system (no special bonds)");
 }

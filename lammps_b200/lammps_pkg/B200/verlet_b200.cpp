@@ -58,7 +58,6 @@ void VerletB200::init()
     error->all(FLERR, "run_style verlet/b200 requires atom_style atomic with per-type masses");
   if (force->kspace || force->bond || force->angle || force->dihedral || force->improper)
     error->all(FLERR, "run_style verlet/b200 supports pairwise short-range forces only");
-  if (!force->newton_pair) error->all(FLERR, "run_style verlet/b200 requires newton pair on");
 
   bpair = dynamic_cast<B200PairStyle *>(force->pair);
   if (!bpair)
@@ -145,6 +144,7 @@ void VerletB200::upload()
                                         domain->periodicity, force->angstrom));
     else
       B200_CHECK(pkg, b200_set_box(c, domain->boxlo, domain->boxhi, domain->periodicity));
+    B200_CHECK(pkg, b200_set_newton(c, force->newton_pair));
     B200_CHECK(pkg,
                b200_set_neighbor(c, neighbor->skin, neighbor->every, neighbor->delay,
                                  neighbor->dist_check, neighbor->oneatom));
