@@ -74,9 +74,12 @@ int b200_set_rank_grid(b200_ctx *ctx, const int *grid2rank, int n);
 int b200_set_neighbor(b200_ctx *ctx, double skin, int every, int delay, int dist_check, int one);
 /* neigh_modify once yes|no (Neighbor::decide never asks for a rebuild, neighbor.cpp:2420) and
  * neigh_modify exclude type i j ... (NPair::exclusion, npair.cpp:244-248): ex_type is Neighbor's
- * symmetric table of excluded type pairs, [(ntypes+1)^2] flags, NULL = no exclusions.  Group and
- * molecule exclusions are not supported (the hosts refuse them). */
+ * symmetric table of excluded type pairs, [(ntypes+1)^2] flags, NULL = no exclusions.
+ * neigh_modify exclude group g1 g2 (npair.cpp:249-254): n pairs of group bits (Neighbor::ex1_bit,
+ * ex2_bit; n <= 8); the group masks of ghosts owned by other sub-domains then travel with the
+ * border exchange.  Molecule exclusions need molecule ids, which atomic systems do not have. */
 int b200_neigh_modify(b200_ctx *ctx, int build_once, int ntypes, const int *ex_type);
+int b200_neigh_modify_groups(b200_ctx *ctx, int n, const int *bit1, const int *bit2);
 
 /* ---- atoms: Atom arrays (atom.h:72-75) + per-type mass (atom.cpp set_mass).
  *      mask/image may be NULL (all atoms in group `all`, image flags 0). */

@@ -53,6 +53,21 @@ struct Geom {
   double h[6], h_inv[6], origin[3];
 };
 
+// neigh_modify exclude group g1 g2 (NPair::exclusion, npair.cpp:249-254): a pair is never stored when
+// one atom is in the first group and the other in the second
+#define MAXEXGROUP 8
+struct ExGroups {
+  int n;
+  int bit1[MAXEXGROUP], bit2[MAXEXGROUP];
+};
+__device__ __forceinline__ bool ex_group(const ExGroups &ex, int mi, int mj) {
+  for (int m = 0; m < ex.n; m++) {
+    if ((mi & ex.bit1[m]) && (mj & ex.bit2[m])) return true;
+    if ((mi & ex.bit2[m]) && (mj & ex.bit1[m])) return true;
+  }
+  return false;
+}
+
 // ghost position on a forward halo = owner + the offsets of the swaps it travels through, each
 // added and rounded separately in the reference's order (x, then y, then z swap)
 __device__ __forceinline__ void halo_shift(const Geom &g, int dir, double qx, double qy, double qz,

@@ -233,6 +233,8 @@ struct b200_ctx {
   // eam on tiles, second generation (kernels_eam2.cuh): FULLGHOST + NEAR/FAR split rows, density
   // and embedding in one kernel, fix nve fused into the force kernel.  Single-element potentials
   // in FP64 (B200_EAM2=0 / `package b200 eam2 no` selects the flat half list kernels).
+  ExGroups exg = ExGroups{0, {0}, {0}};  // neigh_modify exclude group
+  DBuf<double> mask_s, mask_r;          // group masks of border atoms / remote ghosts (only with exg)
   int newton = 1;               // Force::newton_pair; 0: lists hold every owned-ghost pair on both sides
   int eam2 = 2;                 // 0 never, 1 whenever usable, 2 auto: small sub-domains (see eam2_usable)
   long long eam2_max_bins = 60000;
@@ -1484,7 +1486,7 @@ static int build_tiles(b200_ctx *ctx) {
       G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,   \
       ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,           \
       ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags, 0.0,  \
-      nullptr, nullptr, 0.0, ctx->newton ? 0 : 1)
+      nullptr, nullptr, 0.0, ctx->newton ? 0 : 1, ctx->exg, ctx->mask[c])
     // lj/cut: every ghost partner is stored (no scatter, no reverse halo); eam: FWD ghosts only
     const size_t smem2 = build2_smem_bytes(ctx->tile_scap, rows, G.sbx, !one, ctx->tile_slots);
     const double rs = eam2 ? std::max(0.0, std::sqrt(ctx->eam.cutforcesq) + ctx->eam2_margin * ctx->skin) : 0.0;
@@ -1500,13 +1502,14 @@ static int build_tiles(b200_ctx *ctx) {
       G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,   \
       ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,           \
       ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags,       \
-      SPL ? rs * rs : 0.0, SPL ? ctx->tl_far.p : nullptr, ctx->tag[c], tdelta, ctx->newton ? 0 : 1)
+      SPL ? rs * rs : 0.0, SPL ? ctx->tl_far.p : nullptr, ctx->tag[c], tdelta, ctx->newton ? 0 : 1, ctx->exg,  \
+      ctx->mask[c])
     if (!ctx->newton && eam && !eam2) return B200_OK;  // no FULLGHOST rows: build_list reports it
     if (ctx->tri) {
       if (eam2) TBT(true, true);
       else if (one) TBT(true, false);
       else TBT(false, false);
-    } else if (ctx->build2 && ctx->newton && smem2 <= BUILD2_SMEM_MAX) {
+    } else if (ctx->build2 && ctx->newton && !ctx->exg.n && smem2 <= BUILD2_SMEM_MAX) {
       if (eam2) TB2(true, true, true);
       else if (!eam) { if (one) TB2(true, true, false); else TB2(false, true, false); }
       else           { if (one) TB2(true, false, false); else TB2(false, false, false); }
@@ -1516,7 +1519,7 @@ static int build_tiles(b200_ctx *ctx) {
           G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,
           ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,
           ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags,
-          rs * rs, ctx->tl_far.p, nullptr, 0.0, ctx->newton ? 0 : 1);
+          rs * rs, ctx->tl_far.p, nullptr, 0.0, ctx->newton ? 0 : 1, ctx->exg, ctx->mask[c]);
     } else if (!eam) { if (one) TB(true, true); else TB(false, true); }
     else      { if (one) TB(true, false); else TB(false, false); }
 #undef TB
@@ -1586,22 +1589,22 @@ static int build_list(b200_ctx *ctx) {
           k_build_half_tri<true><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
               nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->tag[c], ctx->atombin[c], ctx->ostart.p,
               ctx->gstart.p, ctx->stencil, ctx->cutneighsq_h[n1 + 1], ctx->cutneighsq_d.p, ctx->ntypes, delta,
-              ctx->numneigh.p, ctx->neigh.p, ctx->flags + 2);
+              ctx->numneigh.p, ctx->neigh.p, ctx->flags + 2, ctx->exg, ctx->mask[c]);
         else
           k_build_half_tri<false><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
               nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->tag[c], ctx->atombin[c], ctx->ostart.p,
               ctx->gstart.p, ctx->stencil, 0.0, ctx->cutneighsq_d.p, ctx->ntypes, delta, ctx->numneigh.p,
-              ctx->neigh.p, ctx->flags + 2);
+              ctx->neigh.p, ctx->flags + 2, ctx->exg, ctx->mask[c]);
       } else if (ctx->ntypes == 1)
         k_build_half<true><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
             nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->atombin[c], ctx->ostart.p,
             ctx->gstart.p, ctx->stencil, ctx->cutneighsq_h[n1 + 1], ctx->cutneighsq_d.p,
-            ctx->ntypes, ctx->numneigh.p, ctx->neigh.p, ctx->flags + 2);
+            ctx->ntypes, ctx->numneigh.p, ctx->neigh.p, ctx->flags + 2, ctx->exg, ctx->mask[c]);
       else
         k_build_half<false><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
             nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->atombin[c], ctx->ostart.p,
             ctx->gstart.p, ctx->stencil, 0.0, ctx->cutneighsq_d.p, ctx->ntypes, ctx->numneigh.p,
-            ctx->neigh.p, ctx->flags + 2);
+            ctx->neigh.p, ctx->flags + 2, ctx->exg, ctx->mask[c]);
       ctx->launches++;
       LAUNCH_CHECK();
     }
@@ -1794,6 +1797,21 @@ static int reneighbor(b200_ctx *ctx) {
         ctx->gsrc_tmp.p, ctx->gbin.p, ctx->gslot.p, ctx->gdir_tmp.p, ctx->gstart.p, ctx->flags + 1);
     ctx->launches++;
   }
+  // neigh_modify exclude group reads the group mask of every list candidate: ghosts owned by
+  // another sub-domain get theirs through one more exchange in the order of the border records
+  const double *rmask = nullptr;
+  if (multi && ctx->exg.n) {
+    TRY(reserve(ctx, ctx->mask_s, (size_t)std::max(nsend, 1)));
+    TRY(reserve(ctx, ctx->mask_r, (size_t)std::max(ng, 1)));
+    if (nsend > 0) {
+      k_pack_mask<<<cdiv(nsend, 256), 256, 0, s>>>(nsend, ctx->sendlist.p, ctx->senddir.p, ctx->remote_mask,
+                                                   ctx->mask[c], ctx->mask_s.p);
+      ctx->launches++;
+    }
+    LAUNCH_CHECK();
+    TRY(halo_exchange(ctx, ctx->mask_s.p, ctx->sendoff, ctx->mask_r.p, ctx->recvoff, 1, false));
+    rmask = ctx->mask_r.p;
+  }
   TRY(scan_inplace(ctx, ctx->gstart.p, g.mbins));
   if (ng > 0) {
     const long long *gkey = nullptr;
@@ -1807,7 +1825,7 @@ static int reneighbor(b200_ctx *ctx) {
     k_ghost_place<<<cdiv(ng, 256), 256, 0, s>>>(ng, nl, ctx->gtmp.p, ctx->gtag_tmp.p, ctx->gsrc_tmp.p,
                                                 ctx->gbin.p, ctx->gslot.p, ctx->gdir_tmp.p,
                                                 ctx->gstart.p, ctx->xt[c], ctx->tag[c], ctx->mask[c],
-                                                ctx->gsrc.p, ctx->gdir.p, ctx->xt[c ^ 1], gkey);
+                                                ctx->gsrc.p, ctx->gdir.p, ctx->xt[c ^ 1], gkey, rmask);
     ctx->launches++;
   }
   if (g.tri && nl > 0) {  // owned atoms back to box coordinates (the ghosts were converted as made)
@@ -2648,7 +2666,7 @@ void b200_destroy(b200_ctx *ctx) {
   }
   for (int d = 0; d < 3; d++) { F(ctx->f[d]); F(ctx->xh[d]); }
   F(ctx->slot); F(ctx->rho); F(ctx->fp); F(ctx->ff); F(ctx->lj_tabf.p); F(ctx->eam_f.p);
-  F(ctx->cutneighsq_d.p); F(ctx->mass_d.p); F(ctx->lang_d.p); F(ctx->lang_u.p); F(ctx->ostart.p); F(ctx->gstart.p); F(ctx->tilesum.p);
+  F(ctx->cutneighsq_d.p); F(ctx->mass_d.p); F(ctx->lang_d.p); F(ctx->lang_u.p); F(ctx->mask_s.p); F(ctx->mask_r.p); F(ctx->ostart.p); F(ctx->gstart.p); F(ctx->tilesum.p);
   F(ctx->sendlist.p); F(ctx->gsrc.p); F(ctx->gbin.p); F(ctx->gslot.p); F(ctx->gdir.p);
   F(ctx->gdir_tmp.p); F(ctx->gtmp.p); F(ctx->counts); F(ctx->diroffset); F(ctx->recvoffset); F(ctx->allcounts);
   F(ctx->senddir.p); F(ctx->gtag_tmp.p); F(ctx->gsrc_tmp.p); F(ctx->arena); F(ctx->pflags); F(ctx->p2p_counter);
@@ -2770,6 +2788,22 @@ int b200_neigh_modify(b200_ctx *ctx, int build_once, int ntypes, const int *ex_t
       for (int j = 1; j <= ntypes; j++)
         if (ctx->ex_type[i * n1 + j] != ctx->ex_type[j * n1 + i])
           return ctx->fail(B200_EARG, "b200_neigh_modify: the exclusion table must be symmetric");
+  }
+  ctx->geom_ready = false;
+  return B200_OK;
+}
+
+// neigh_modify exclude group g1 g2 (NPair::exclusion, npair.cpp:249-254): n pairs of group bits
+// (Neighbor::ex1_bit / ex2_bit); n = 0 clears them
+int b200_neigh_modify_groups(b200_ctx *ctx, int n, const int *bit1, const int *bit2) {
+  if (!ctx || n < 0 || (n && (!bit1 || !bit2))) return B200_EARG;
+  if (n > MAXEXGROUP) return ctx->fail(B200_EARG, "neigh_modify exclude group: at most %d group pairs", MAXEXGROUP);
+  drop_step_graph(ctx);
+  ctx->exg = ExGroups{0, {0}, {0}};
+  ctx->exg.n = n;
+  for (int m = 0; m < n; m++) {
+    ctx->exg.bit1[m] = bit1[m];
+    ctx->exg.bit2[m] = bit2[m];
   }
   ctx->geom_ready = false;
   return B200_OK;

@@ -126,6 +126,18 @@ __global__ void __launch_bounds__(256) k_pack_border(int nsend, const int *__res
   buf[p] = q;
 }
 
+// group masks of the border atoms, one double each, same order as the border records
+// (AtomVec::pack_border sends mask with every ghost, atom_vec.cpp:796-830; here only on request)
+__global__ void __launch_bounds__(256) k_pack_mask(int nsend, const int *__restrict__ sendlist,
+                                                   const unsigned char *__restrict__ senddir,
+                                                   unsigned remote_mask, const int *__restrict__ mask,
+                                                   double *__restrict__ buf) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nsend) return;
+  if (!((remote_mask >> senddir[p]) & 1u)) return;
+  buf[p] = (double)mask[sendlist[p]];
+}
+
 // Ghost creation, pass 1 over recv order q: take the ghost from the local owner (self image)
 // or from the received border record, bin it, take a slot in the ghost histogram.
 __global__ void __launch_bounds__(256) k_ghost_make(
@@ -197,7 +209,7 @@ __global__ void __launch_bounds__(256) k_ghost_place(
     const unsigned char *__restrict__ gdir_tmp, const int *__restrict__ gstart,
     double4 *__restrict__ xt, int *__restrict__ tag, int *__restrict__ mask,
     int *__restrict__ gsrc, unsigned char *__restrict__ gdir, double4 *__restrict__ xt_alt,
-    const long long *__restrict__ gkey) {
+    const long long *__restrict__ gkey, const double *__restrict__ rmask) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nghost) return;
   int gi = gstart[gbin[q]] + gslot[q];
@@ -214,7 +226,8 @@ __global__ void __launch_bounds__(256) k_ghost_place(
   // writes owned positions there and the halo then refreshes x,y,z only -- the type must be in place
   xt_alt[nlocal + gi] = gtmp[q];
   tag[nlocal + gi] = gtag_tmp[q];
-  mask[nlocal + gi] = src >= 0 ? mask[src] : 1;
+  // (group masks of ghosts owned elsewhere travel only when a list rule reads them: k_pack_mask)
+  mask[nlocal + gi] = src >= 0 ? mask[src] : (rmask ? (int)rmask[q] : 1);
   gsrc[gi] = src;
   gdir[gi] = gdir_tmp[q];
 }

@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(128) k_build_half(
     const int *__restrict__ atombin, const int *__restrict__ ostart,
     const int *__restrict__ gstart, Stencil st, double cutneighsq_one,
     const double *__restrict__ cutneighsq, int ntypes, int *__restrict__ numneigh,
-    int *__restrict__ neigh, int *__restrict__ maxcount) {
+    int *__restrict__ neigh, int *__restrict__ maxcount, ExGroups ex, const int *__restrict__ mask) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int n = 0;
   if (i < nlocal) {
@@ -322,8 +322,10 @@ __global__ void __launch_bounds__(128) k_build_half(
     const int itype = d2type(pi.w);
     const int b = atombin[i];
     const double *cut_i = ONETYPE ? nullptr : cutneighsq + (size_t)itype * (ntypes + 1);
+    const int mi = ex.n ? mask[i] : 0;
 
     auto test = [&](int j) {
+      if (ex.n && ex_group(ex, mi, mask[j])) return;
       const double4 pj = ld_xt(xt + j);
       const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
       const double rsq = rsq_ref(delx, dely, delz);
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(128) k_build_half_tri(
     const int *__restrict__ tag, const int *__restrict__ atombin, const int *__restrict__ ostart,
     const int *__restrict__ gstart, Stencil st, double cutneighsq_one,
     const double *__restrict__ cutneighsq, int ntypes, double delta, int *__restrict__ numneigh,
-    int *__restrict__ neigh, int *__restrict__ maxcount) {
+    int *__restrict__ neigh, int *__restrict__ maxcount, ExGroups ex, const int *__restrict__ mask) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int n = 0;
   if (i < nlocal) {
@@ -390,8 +392,10 @@ __global__ void __launch_bounds__(128) k_build_half_tri(
     const int itype = d2type(pi.w), itag = tag[i];
     const int b = atombin[i];
     const double *cut_i = ONETYPE ? nullptr : cutneighsq + (size_t)itype * (ntypes + 1);
+    const int mi = ex.n ? mask[i] : 0;
 
     auto test = [&](int j, const double4 &pj) {
+      if (ex.n && ex_group(ex, mi, mask[j])) return;
       const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
       const double rsq = rsq_ref(delx, dely, delz);
       const double c = ONETYPE ? cutneighsq_one : cut_i[d2type(pj.w)];

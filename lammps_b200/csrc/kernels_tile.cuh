@@ -438,7 +438,8 @@ __global__ void __launch_bounds__(512) k_tile_build(
     unsigned short *__restrict__ iloc, unsigned short *__restrict__ tnum, int *__restrict__ tgi,
     uint4 *__restrict__ list, int *__restrict__ numneigh_half, int scap, int *__restrict__ tflags,
     double splitsq = 0.0, unsigned short *__restrict__ tfar = nullptr,
-    const int *__restrict__ tag = nullptr, double tri_delta = 0.0, int newtoff = 0) {
+    const int *__restrict__ tag = nullptr, double tri_delta = 0.0, int newtoff = 0,
+    ExGroups ex = ExGroups{0, {0}, {0}}, const int *__restrict__ mask = nullptr) {
   extern __shared__ __align__(128) unsigned char tsm[];
   TileHdr *H = reinterpret_cast<TileHdr *>(tsm);
   const TileS T = tile_carve(tsm, scap, false);
@@ -517,7 +518,10 @@ __global__ void __launch_bounds__(512) k_tile_build(
         const double3 pj = tile_pos3(T, s);
         return rsq_ref(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
       };
+      const int mi = ex.n ? mask[gi] : 0;
       auto cutof = [&](int s) -> double {  // the reference's test: rsq <= cutneighsq[itype][jtype]
+        // (neigh_modify exclude group: an excluded partner fails the test at every distance)
+        if (ex.n && ex_group(ex, mi, mask[T.gmap[s]])) return -1.0;
         return ONETYPE ? cut1 : __ldg(cut_i + T.type[s]);
       };
       auto test = [&](int s, unsigned flags) {

@@ -42,7 +42,7 @@ EXPORTS = [
     "b200_group_run", "b200_group_get_tallies", "b200_group_ke_sum", "b200_group_last_run_ms",
     "b200_group_get_stats", "b200_group_ke_group", "b200_ke_group", "b200_sync", "b200_set_option",
     "b200_langevin", "b200_add_force", "b200_group_langevin", "b200_group_add_force",
-    "b200_set_box_triclinic", "b200_set_newton",
+    "b200_set_box_triclinic", "b200_set_newton", "b200_neigh_modify_groups",
 ]
 
 
@@ -145,6 +145,13 @@ class Engine:
         self.boxlo, self.boxhi = lo.copy(), hi.copy()
         self._chk(self.L.b200_set_box_triclinic(self.h, _p(lo), _p(hi), C.c_double(xy), C.c_double(xz),
                                                 C.c_double(yz), _p(per), C.c_double(angstrom)))
+
+    def neigh_modify_groups(self, pairs=()):
+        """neigh_modify exclude group: pairs of group BITS (1 << igroup)"""
+        b1 = _i([p[0] for p in pairs])
+        b2 = _i([p[1] for p in pairs])
+        self._chk(self.L.b200_neigh_modify_groups(self.h, C.c_int(len(pairs)), _p(b1) if len(pairs) else None,
+                                                  _p(b2) if len(pairs) else None))
 
     def set_newton(self, newton_pair: bool):
         self._chk(self.L.b200_set_newton(self.h, C.c_int(1 if newton_pair else 0)))

@@ -145,6 +145,7 @@ void VerletB200::upload()
     else
       B200_CHECK(pkg, b200_set_box(c, domain->boxlo, domain->boxhi, domain->periodicity));
     B200_CHECK(pkg, b200_set_newton(c, force->newton_pair));
+    B200_CHECK(pkg, b200_neigh_modify_groups(c, neighbor->nex_group, neighbor->ex1_bit, neighbor->ex2_bit));
     B200_CHECK(pkg,
                b200_set_neighbor(c, neighbor->skin, neighbor->every, neighbor->delay,
                                  neighbor->dist_check, neighbor->oneatom));
@@ -276,9 +277,9 @@ void VerletB200::device_setup(int flag, int output_flag)
   refuse_per_atom_tallies();
   // list options of neigh_modify the device build does not implement (neighbor.cpp:2727-2940);
   // checked here because Neighbor::init() runs after Integrate::init()
-  if (neighbor->nex_group || neighbor->nex_mol)
-    error->all(FLERR, "run_style verlet/b200 supports neigh_modify exclude type only "
-                      "(not exclude group or molecule)");
+  if (neighbor->nex_mol)
+    error->all(FLERR, "run_style verlet/b200 supports neigh_modify exclude type and group "
+                      "(not molecule: atomic systems carry no molecule ids)");
   if (neighbor->includegroup)
     error->all(FLERR, "run_style verlet/b200 does not support neigh_modify include");
   if (neighbor->style != Neighbor::BIN)

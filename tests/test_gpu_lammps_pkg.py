@@ -395,10 +395,39 @@ def test_minimize_is_refused_not_silently_wrong(tmp_path):
     assert "computes forces only inside run_style verlet/b200" in out
 
 
-def test_neigh_modify_exclude_group_is_refused(tmp_path):
-    out = _run_b200(tmp_path, LJ_BODY + "group left id < 100\nneigh_modify exclude group left left\nrun 5\n",
-                    expect_fail=True)
-    assert "supports neigh_modify exclude type only" in out
+@pytest.mark.parametrize("extra", [[], ["-pk", "b200", "list", "flat"], ["-pk", "b200", "subdomains", "8"]],
+                         ids=["tiles", "flat-list", "8-subdomains"])
+def test_neigh_modify_exclude_group_matches_reference_executable(tmp_path, extra):
+    """neigh_modify exclude group (NPair::exclusion, npair.cpp:249-254): two interleaved groups that
+    do not see each other plus a group excluded from itself; with 8 sub-domains the group masks of
+    remote ghosts travel with the border exchange.  Thermo, forces and the neighbour count vs lmp_ref."""
+    body = LJ_BODY.replace("fix 1 all nve", """group odd id 1:4000:2
+group even id 2:4000:2
+group slab id 1:600
+neigh_modify exclude group odd even
+neigh_modify exclude group slab slab
+fix 1 all nve""") + """
+thermo 10
+thermo_modify format float %.12g
+dump 1 all custom 40 f.dump id type fx fy fz
+dump_modify 1 sort id format float %.10g
+run 40
+"""
+    refexe = ROOT / "oracle" / "_ref" / "lmp_ref"
+    outs, texts = {}, {}
+    for tag, exe, args in (("ref", refexe, []), ("b200", EXE, ["-sf", "b200", *extra])):
+        d = tmp_path / tag
+        d.mkdir()
+        (d / "in.t").write_text(body)
+        r = subprocess.run([str(exe), *args, "-in", "in.t"], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        last = (d / "f.dump").read_text().split("ITEM: TIMESTEP")[-1].splitlines()
+        k = last.index([ln for ln in last if ln.startswith("ITEM: ATOMS")][0])
+        outs[tag] = (thermo_rows(r.stdout), [[float(t) for t in ln.split()] for ln in last[k + 1:] if ln.strip()])
+        texts[tag] = r.stdout
+    _compare(outs, ftol=1e-8, ttol=1e-9)
+    m = re.search(r"Total # of neighbors = (\d+)", texts["ref"])
+    assert m and m.group(0) in texts["b200"]
 
 
 def test_neigh_modify_exclude_type_and_once_match_reference_executable(tmp_path):
