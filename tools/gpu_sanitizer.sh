@@ -36,6 +36,28 @@ elif which == "eam":
         os.environ["B200_EAM2"] = env
         e = make_engine(eam_system((6, 6, 6))); e.setup(1, 1); e.run(12, 6); e.pair_peratom()
         print(env, e.stats()["list_kind"], e.stats()["npairs"]); e.close()
+elif which == "new":
+    # round-2 additions: triclinic box (bin tiles, flat list, 4 lamda bricks), newton off,
+    # neigh_modify exclude group, fix langevin (device stream, host uniforms, zero yes)
+    from lammps_b200.engine import EngineGroup
+    s = lj_system((8, 8, 8)); n = len(s["x"])
+    a = (s["hi"][0] - s["lo"][0]) / 8
+    mask = (1 | np.where(np.arange(n) % 2 == 0, 2, 4)).astype(np.int32)
+    for mode in ("tile", "flat"):
+        e = make_engine(s); e.set_box_triclinic(s["lo"], s["hi"], 2 * a, -a, 3 * a); e.set_option("list", mode)
+        e.set_atoms(s["x"], s["v"], s["type"], s["tag"], s["mass"], mask=mask)
+        e.neigh_modify_groups([(2, 4)])
+        if mode == "tile": e.set_newton(False)
+        e.setup(1, 1); e.run(25, 10)
+        g1 = np.array([0.0, -1.0]); g2 = np.array([0.0, 3.0])
+        e.langevin(g1, g2, 77, 5, want_fsum=True); e.langevin(g1, g2, 77, 6, uniforms_by_tag=np.random.rand(n, 3))
+        e.add_force(np.array([1e-3, 0, 0])); e.nve_v(0.0025)
+        print("tri", mode, e.stats()["npairs"], e.stats()["list_kind"]); e.close()
+    g = EngineGroup([0] * 4, "double", s["units"]); g.set_box_triclinic(s["lo"], s["hi"], 2 * a, -a, 3 * a)
+    g.set_atoms(s["x"], s["v"], s["type"], s["tag"], s["mass"], mask=mask)
+    g.neighbor(s["skin"], every=5, delay=0, check=True); g.fix_nve(s["dt"]); g.pair_lj_cut(s["tables"])
+    for sub in g.sub: sub.neigh_modify_groups([(2, 4)])
+    g.setup(1, 1); g.run(25, 0); print("tri group", g.stats()["npairs"], g.counts()); g.close()
 else:
     from lammps_b200.engine import EngineGroup
     s = lj_system((10, 10, 10)); n = len(s["x"])
@@ -45,7 +67,7 @@ else:
     g.setup(1, 1); g.run(25, 0); g.pair_peratom(); print(g.stats()["npairs"], g.counts()); g.close()
 PY
 for tool in memcheck racecheck; do
-  for c in lj eam group; do
+  for c in ${2:-lj eam group new}; do
     timeout 600 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py $c > gpurun_out/${tag}_sanitizer_${tool}_${c}.txt 2>&1
     echo "== $tool $c: $(grep -E "ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/${tag}_sanitizer_${tool}_${c}.txt | tail -1)"
   done
