@@ -1240,10 +1240,21 @@ static int setup_geometry(b200_ctx *ctx) {
     // ghost shell, 30 bits over the largest extent, power-of-two scale
     double ext = 0.0;
     const double margin = ctx->cutghost + 2.0 * ctx->skin;
-    for (int d = 0; d < 3; d++) ext = std::max(ext, ctx->osubhi[d] - ctx->osublo[d] + 2.0 * margin);
-    ctx->qgeom.ox = ctx->osublo[0] - margin;
-    ctx->qgeom.oy = ctx->osublo[1] - margin;
-    ctx->qgeom.oz = ctx->osublo[2] - margin;
+    double qlo[3], qhi[3];
+    for (int d = 0; d < 3; d++) {
+      qlo[d] = ctx->osublo[d] - margin;
+      qhi[d] = ctx->osubhi[d] + margin;
+      if (tri) {
+        // the ghost shell is cutghost wide between lamda planes: along a tilted direction its box
+        // extent is larger than cutghost; bsublo/bsubhi = bounding box of the brick +- that shell
+        qlo[d] = bsublo[d] - 2.0 * ctx->skin;
+        qhi[d] = bsubhi[d] + 2.0 * ctx->skin;
+      }
+      ext = std::max(ext, qhi[d] - qlo[d]);
+    }
+    ctx->qgeom.ox = qlo[0];
+    ctx->qgeom.oy = qlo[1];
+    ctx->qgeom.oz = qlo[2];
     ctx->qgeom.scale = std::ldexp(1.0, (int)std::floor(std::log2(1073741824.0 / ext)));
     double cmin = 1.0e300;
     for (int i = 1; i <= n; i++)

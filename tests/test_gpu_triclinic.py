@@ -169,6 +169,37 @@ def test_triclinic_fused_run_on_tiles_equals_flat_list_run():
     assert np.abs(res["tile"][0] - res["flat"][0]).max() <= 1e-9 * np.abs(res["flat"][0]).max()
 
 
+def test_triclinic_mixed_precision_meets_the_mixed_tolerances():
+    """FP32 pair math (fixed-point staged positions, sub-domain-wide records) in a prism box:
+    forces <= 1e-5, energy <= 1e-6 against the double-precision path (north_star's mixed bar)"""
+    from lammps_b200 import pair_lj
+    from lammps_b200.engine import Engine
+    st = _reference_state(_script(LJ_TRI, 10, "-4.0 3.0 -2.0", "every 1 delay 0 check yes"), 40)
+    nl = st["nlocal"]
+    res = {}
+    for prec in ("double", "mixed"):
+        e = Engine(0, prec, "lj")
+        e.set_box_triclinic(st["lo"], st["hi"], st["xy"], st["xz"], st["yz"])
+        e.set_atoms(st["x"][:nl], st["v"], st["type"], st["tag"][:nl], np.array([0.0, 1.0]), image=st["image"])
+        e.neighbor(0.3, every=1, delay=0, check=True)
+        e.fix_nve(0.005)
+        e.pair_lj_cut(pair_lj.lj_cut_tables(1, {(1, 1): (1.0, 1.0, 2.5)}, 2.5))
+        e.setup(1, 1)
+        assert e.stats()["list_kind"] == 1
+        a = e.get_atoms(fields=("f", "tag"))
+        eng, vir = e.tallies()
+        th = e.run(40, 20)
+        res[prec] = (a["f"][np.argsort(a["tag"])], eng, vir, th)
+        e.close()
+    fd, fm = res["double"][0], res["mixed"][0]
+    assert np.abs(fd - fm).max() / np.abs(fd).max() <= 1e-5
+    assert abs(res["double"][1] - res["mixed"][1]) <= 1e-6 * abs(res["double"][1])
+    assert np.abs(res["double"][2] - res["mixed"][2]).max() <= 1e-6 * np.abs(res["double"][2]).max()
+    td, tm = res["double"][3], res["mixed"][3]
+    scale = np.maximum(np.abs(td).max(axis=0), 1e-3)
+    assert (np.abs(td - tm).max(axis=0) <= 1e-5 * scale).all(), np.abs(td - tm).max(axis=0) / scale
+
+
 def _run(exe, args, d, body, ncols):
     d.mkdir()
     (d / "in.t").write_text(body)
