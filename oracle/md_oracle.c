@@ -4,8 +4,9 @@
  * lammps_b200/csrc.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
  * leg may load it; the product path never does.
  *
- * Scope: one process, orthogonal box, atom_style atomic, newton on, half/bin/atomonly/newton
- * list, pair lj/cut or eam (funcfl / setfl / fs tables built by lammps_b200/eam.py), fix nve.  Each function cites the reference
+ * Scope: one process, orthogonal or triclinic box, atom_style atomic, newton on or off, the
+ * half/bin/atomonly lists (newton, newton/tri, newtoff), neigh_modify exclude type / group, pair
+ * lj/cut or eam (funcfl / setfl / fs tables built by lammps_b200/eam.py), fix nve.  Each function cites the reference
  * file:line (relative to /root/reference/src) whose arithmetic it restates.  The code keeps
  * the reference's operation ORDER (atom order, swap order, neighbour order) so that results
  * can be compared bit-for-bit with oracle/_ref (the compiled reference).
@@ -15,6 +16,8 @@
  * published bench logs (bench/log.15Jul25.{lj,eam}.fixed.g++.1), against
  * unittest/cplusplus/test_neighbor_class.cpp:235-269, and against the reference's known-answer
  * vectors unittest/force-styles/tests/atomic-pair-eam{,_alloy,_fs}.yaml at their own epsilon.
+ * Triclinic boxes, newton off and group exclusions are pinned against oracle/_ref live
+ * (tests/test_oracle_tri_newton_live.py: pair sets, forces, energy, pxy, 40-step trajectories).
  *
  * Build: gcc -O2 -fPIC -shared -ffp-contract=off -o oracle/libmd_oracle.so oracle/md_oracle.c -lm
  * (-ffp-contract=off: the reference is built for baseline x86-64, i.e. without FMA contraction)
@@ -39,6 +42,13 @@ typedef struct {
   /* domain (domain.h) */
   double boxlo[3], boxhi[3], prd[3];
   int periodic[3];
+  /* triclinic box (domain.cpp:263-290): tilt factors, h = {xprd,yprd,zprd,yz,xz,xy}, its inverse,
+     the bounding box of the tilted cell; angstrom = Force::angstrom (npair_bin.cpp:59) */
+  int triclinic;
+  double xy, xz, yz, h[6], h_inv[6], boxlo_bound[3], boxhi_bound[3], angstrom;
+  /* Force::newton_pair (force.cpp); neigh_modify exclude group (neighbor.h:70-72) */
+  int newton_pair;
+  int nex_group, ex1_bit[8], ex2_bit[8];
   /* atoms (atom.h:72-75) */
   int nlocal, nghost, nmax, ntypes;
   double *x, *v, *f; /* [nmax][3] row-major */
@@ -61,7 +71,8 @@ typedef struct {
   int nstencil, *stencil;
   /* comm (comm_brick.cpp) single proc: every swap is with self */
   double cutghost;
-  int nswap, sendnum[MAXSWAP], firstrecv[MAXSWAP], pbc_flag[MAXSWAP], pbc[MAXSWAP][3];
+  double cutghost3[3]; /* CommBrick::cutghost[]: box units, or lamda units in a triclinic box */
+  int nswap, sendnum[MAXSWAP], firstrecv[MAXSWAP], pbc_flag[MAXSWAP], pbc[MAXSWAP][6];
   double slablo[MAXSWAP], slabhi[MAXSWAP];
   int *sendlist[MAXSWAP], maxsendlist[MAXSWAP];
   /* neighbor list (neigh_list.h:53-57) in CSR form */
@@ -122,7 +133,11 @@ static void grow_atoms(Orc *o, int n) {
 
 /* ------------------------------------------------------------------ API: lifetime */
 
-Orc *orc_create(void) { return (Orc *)calloc(1, sizeof(Orc)); }
+Orc *orc_create(void) {
+  Orc *o = (Orc *)calloc(1, sizeof(Orc));
+  if (o) { o->newton_pair = 1; o->angstrom = 1.0; }
+  return o;
+}
 
 void orc_destroy(Orc *o) {
   if (!o) return;
@@ -144,6 +159,66 @@ void orc_set_box(Orc *o, const double *lo, const double *hi, const int *periodic
     o->prd[d] = hi[d] - lo[d]; /* domain.cpp set_global_box: xprd = boxhi - boxlo */
     o->periodic[d] = periodic[d];
   }
+  o->triclinic = 0;
+  o->xy = o->xz = o->yz = 0.0;
+}
+
+/* Domain::set_global_box for a triclinic cell, domain.cpp:263-290 */
+void orc_set_box_triclinic(Orc *o, const double *lo, const double *hi, double xy, double xz, double yz,
+                           const int *periodic, double angstrom) {
+  orc_set_box(o, lo, hi, periodic);
+  o->triclinic = 1;
+  o->xy = xy; o->xz = xz; o->yz = yz;
+  o->angstrom = angstrom;
+  double *h = o->h, *h_inv = o->h_inv;
+  h[0] = o->prd[0]; h[1] = o->prd[1]; h[2] = o->prd[2];
+  h_inv[0] = 1.0 / h[0]; h_inv[1] = 1.0 / h[1]; h_inv[2] = 1.0 / h[2];
+  h[3] = yz; h[4] = xz; h[5] = xy;
+  h_inv[3] = -h[3] / (h[1] * h[2]);
+  h_inv[4] = (h[3] * h[5] - h[1] * h[4]) / (h[0] * h[1] * h[2]);
+  h_inv[5] = -h[5] / (h[0] * h[1]);
+  o->boxlo_bound[0] = MIN(o->boxlo[0], o->boxlo[0] + xy);
+  o->boxlo_bound[0] = MIN(o->boxlo_bound[0], o->boxlo_bound[0] + xz);
+  o->boxlo_bound[1] = MIN(o->boxlo[1], o->boxlo[1] + yz);
+  o->boxlo_bound[2] = o->boxlo[2];
+  o->boxhi_bound[0] = MAX(o->boxhi[0], o->boxhi[0] + xy);
+  o->boxhi_bound[0] = MAX(o->boxhi_bound[0], o->boxhi_bound[0] + xz);
+  o->boxhi_bound[1] = MAX(o->boxhi[1], o->boxhi[1] + yz);
+  o->boxhi_bound[2] = o->boxhi[2];
+}
+
+/* the `newton` command (force.cpp): newton_pair on (default) or off */
+void orc_set_newton(Orc *o, int newton_pair) { o->newton_pair = newton_pair ? 1 : 0; }
+
+/* neigh_modify exclude group: n pairs of group bits (Neighbor::ex1_bit / ex2_bit) */
+void orc_neigh_modify_groups(Orc *o, int n, const int *bit1, const int *bit2) {
+  if (n > 8) die("too many group exclusions");
+  o->nex_group = n;
+  for (int m = 0; m < n; m++) { o->ex1_bit[m] = bit1[m]; o->ex2_bit[m] = bit2[m]; }
+}
+
+/* Domain::x2lamda / lamda2x for the first n atoms, domain.cpp:2347-2390 */
+static void x2lamda(Orc *o, int n) {
+  const double *h_inv = o->h_inv, *boxlo = o->boxlo;
+  for (int i = 0; i < n; i++) {
+    double *x = &o->x[3 * i], delta[3];
+    delta[0] = x[0] - boxlo[0];
+    delta[1] = x[1] - boxlo[1];
+    delta[2] = x[2] - boxlo[2];
+    x[0] = h_inv[0] * delta[0] + h_inv[5] * delta[1] + h_inv[4] * delta[2];
+    x[1] = h_inv[1] * delta[1] + h_inv[3] * delta[2];
+    x[2] = h_inv[2] * delta[2];
+  }
+}
+static void lamda2x_one(const Orc *o, const double *lamda, double *x) {
+  const double *h = o->h, *boxlo = o->boxlo;
+  double l0 = lamda[0], l1 = lamda[1], l2 = lamda[2];
+  x[0] = h[0] * l0 + h[5] * l1 + h[4] * l2 + boxlo[0];
+  x[1] = h[1] * l1 + h[3] * l2 + boxlo[1];
+  x[2] = h[2] * l2 + boxlo[2];
+}
+static void lamda2x(Orc *o, int n) {
+  for (int i = 0; i < n; i++) lamda2x_one(o, &o->x[3 * i], &o->x[3 * i]);
 }
 
 void orc_set_atoms(Orc *o, int n, int ntypes, const double *mass, const double *x,
@@ -270,6 +345,10 @@ static void neighbor_init(Orc *o) {
 /* domain.cpp:769-887 Domain::pbc (orthogonal, no deform) */
 void orc_pbc(Orc *o) {
   double *lo = o->boxlo, *hi = o->boxhi, *period = o->prd;
+  /* triclinic: atoms are in lamda coordinates here (verlet.cpp:293); boxlo_lamda = 0,
+     boxhi_lamda = 1, prd_lamda = 1 (Domain::set_lamda_box) */
+  static double lo_lamda[3] = {0.0, 0.0, 0.0}, hi_lamda[3] = {1.0, 1.0, 1.0}, prd_lamda[3] = {1.0, 1.0, 1.0};
+  if (o->triclinic) { lo = lo_lamda; hi = hi_lamda; period = prd_lamda; }
   for (int i = 0; i < o->nlocal; i++) {
     double *x = &o->x[3 * i];
     int idim, otherdims;
@@ -337,25 +416,49 @@ void orc_pbc(Orc *o) {
    pair, restricted to one half of the sub-box (slab bound at its middle, :385-411). */
 static void comm_setup(Orc *o) {
   o->cutghost = o->cutneighmax; /* comm.cpp:683 with no user cutoff */
+  /* comm_brick.cpp:220-237: box coordinates, or for a triclinic box lamda coordinates with the
+     cutoff as a distance between lamda planes */
+  double prd[3], lo3[3], hi3[3];
+  for (int d = 0; d < 3; d++) {
+    prd[d] = o->triclinic ? 1.0 : o->prd[d];
+    lo3[d] = o->triclinic ? 0.0 : o->boxlo[d];
+    hi3[d] = o->triclinic ? 1.0 : o->boxhi[d];
+    o->cutghost3[d] = o->cutghost;
+  }
+  if (o->triclinic) {
+    const double *h_inv = o->h_inv;
+    double length0 = sqrt(h_inv[0] * h_inv[0] + h_inv[5] * h_inv[5] + h_inv[4] * h_inv[4]);
+    o->cutghost3[0] = o->cutghost * length0;
+    double length1 = sqrt(h_inv[1] * h_inv[1] + h_inv[3] * h_inv[3]);
+    o->cutghost3[1] = o->cutghost * length1;
+    double length2 = h_inv[2];
+    o->cutghost3[2] = o->cutghost * length2;
+  }
   int iswap = 0;
   for (int dim = 0; dim < 3; dim++) {
-    int maxneed = (int)(o->cutghost * 1 / o->prd[dim]) + 1;
+    int maxneed = (int)(o->cutghost3[dim] * 1 / prd[dim]) + 1;
     if (!o->periodic[dim]) maxneed = MIN(maxneed, 0);
     if (iswap + 2 * maxneed > MAXSWAP) die("box edge much shorter than the ghost cutoff: too many swaps");
-    double sublo = o->boxlo[dim], subhi = o->boxhi[dim];
+    double sublo = lo3[dim], subhi = hi3[dim];
     for (int ineed = 0; ineed < 2 * maxneed; ineed++) {
       o->pbc_flag[iswap] = 0;
-      o->pbc[iswap][0] = o->pbc[iswap][1] = o->pbc[iswap][2] = 0;
+      for (int k = 0; k < 6; k++) o->pbc[iswap][k] = 0;
+      int sign;
       if (ineed % 2 == 0) {
         o->slablo[iswap] = ineed < 2 ? -BIG : 0.5 * (sublo + subhi);
-        o->slabhi[iswap] = sublo + o->cutghost;
+        o->slabhi[iswap] = sublo + o->cutghost3[dim];
         o->pbc_flag[iswap] = 1; /* myloc == 0 */
-        o->pbc[iswap][dim] = 1;
+        sign = 1;
       } else {
-        o->slablo[iswap] = subhi - o->cutghost;
+        o->slablo[iswap] = subhi - o->cutghost3[dim];
         o->slabhi[iswap] = ineed < 2 ? BIG : 0.5 * (sublo + subhi);
         o->pbc_flag[iswap] = 1; /* myloc == procgrid-1 */
-        o->pbc[iswap][dim] = -1;
+        sign = -1;
+      }
+      o->pbc[iswap][dim] = sign;
+      if (o->triclinic) { /* comm_brick.cpp:396-420 */
+        if (dim == 1) o->pbc[iswap][5] = sign;
+        else if (dim == 2) o->pbc[iswap][4] = o->pbc[iswap][3] = sign;
       }
       iswap++;
     }
@@ -368,6 +471,25 @@ static int swap_dim(const Orc *o, int iswap) {
   for (int d = 0; d < 3; d++)
     if (o->pbc[iswap][d]) return d;
   return -1;
+}
+
+/* offsets a ghost gets from swap iswap: AtomVec::pack_comm (atom_vec.cpp:369-377, box units, with
+   the tilt terms of a triclinic box) or pack_border (:813-821: lamda units if triclinic) */
+static void swap_shift(const Orc *o, int iswap, int border, double *d) {
+  const int *pbc = o->pbc[iswap];
+  if (!o->triclinic) {
+    d[0] = pbc[0] * o->prd[0];
+    d[1] = pbc[1] * o->prd[1];
+    d[2] = pbc[2] * o->prd[2];
+  } else if (border) {
+    d[0] = pbc[0];
+    d[1] = pbc[1];
+    d[2] = pbc[2];
+  } else {
+    d[0] = pbc[0] * o->prd[0] + pbc[5] * o->xy + pbc[4] * o->xz;
+    d[1] = pbc[1] * o->prd[1] + pbc[3] * o->yz;
+    d[2] = pbc[2] * o->prd[2];
+  }
 }
 
 /* comm_brick.cpp:720-899 CommBrick::borders + atom_vec.cpp:796-830 pack_border /
@@ -397,9 +519,9 @@ void orc_borders(Orc *o) {
       }
     int first = o->nlocal + o->nghost;
     grow_atoms(o, first + nsend);
-    double dx = o->pbc[iswap][0] * o->prd[0];
-    double dy = o->pbc[iswap][1] * o->prd[1];
-    double dz = o->pbc[iswap][2] * o->prd[2];
+    double sh[3];
+    swap_shift(o, iswap, 1, sh);
+    const double dx = sh[0], dy = sh[1], dz = sh[2];
     for (int k = 0; k < nsend; k++) {
       int j = o->sendlist[iswap][k], g = first + k;
       o->x[3 * g + 0] = o->x[3 * j + 0] + dx;
@@ -418,9 +540,9 @@ void orc_borders(Orc *o) {
 /* comm_brick.cpp:485-538 forward_comm + atom_vec.cpp:354-440 pack_comm (self copy) */
 void orc_forward_comm(Orc *o) {
   for (int iswap = 0; iswap < o->nswap; iswap++) {
-    double dx = o->pbc[iswap][0] * o->prd[0];
-    double dy = o->pbc[iswap][1] * o->prd[1];
-    double dz = o->pbc[iswap][2] * o->prd[2];
+    double sh[3];
+    swap_shift(o, iswap, 0, sh);
+    const double dx = sh[0], dy = sh[1], dz = sh[2];
     int first = o->firstrecv[iswap];
     for (int k = 0; k < o->sendnum[iswap]; k++) {
       int j = o->sendlist[iswap][k], g = first + k;
@@ -465,11 +587,32 @@ static void forward_comm_fp(Orc *o) {
 /* nbin_standard.cpp:82-214 NBinStandard::setup_bins (style BIN, orthogonal, 3d) */
 void orc_setup_bins(Orc *o) {
   double bbox[3], bsubboxlo[3], bsubboxhi[3];
+  const double *bboxlo = o->triclinic ? o->boxlo_bound : o->boxlo; /* NBin::bboxlo/bboxhi */
+  const double *bboxhi = o->triclinic ? o->boxhi_bound : o->boxhi;
   for (int d = 0; d < 3; d++) {
     bsubboxlo[d] = o->boxlo[d] - o->cutghost;
     bsubboxhi[d] = o->boxhi[d] + o->cutghost;
-    bbox[d] = o->boxhi[d] - o->boxlo[d];
   }
+  if (o->triclinic) {
+    /* nbin_standard.cpp:103-111 + Domain::bbox (domain.cpp:2467-2530): bounding box of the lamda
+       sub-box (0..1 here) extended by the lamda ghost cutoff */
+    double lo[3], hi[3];
+    for (int d = 0; d < 3; d++) {
+      lo[d] = 0.0 - o->cutghost3[d];
+      hi[d] = 1.0 + o->cutghost3[d];
+      bsubboxlo[d] = BIG;
+      bsubboxhi[d] = -BIG;
+    }
+    for (int c = 0; c < 8; c++) {
+      double l[3] = {(c & 1) ? hi[0] : lo[0], (c & 2) ? hi[1] : lo[1], (c & 4) ? hi[2] : lo[2]}, x[3];
+      lamda2x_one(o, l, x);
+      for (int d = 0; d < 3; d++) {
+        bsubboxlo[d] = MIN(bsubboxlo[d], x[d]);
+        bsubboxhi[d] = MAX(bsubboxhi[d], x[d]);
+      }
+    }
+  }
+  for (int d = 0; d < 3; d++) bbox[d] = bboxhi[d] - bboxlo[d];
   double binsize_optimal = 0.5 * o->cutneighmax;
   if (binsize_optimal == 0.0) binsize_optimal = bbox[0];
   double binsizeinv = 1.0 / binsize_optimal;
@@ -489,22 +632,22 @@ void orc_setup_bins(Orc *o) {
   int mbinxhi, mbinyhi, mbinzhi;
   double coord;
   coord = bsubboxlo[0] - SMALL * bbox[0];
-  o->mbinxlo = (int)((coord - o->boxlo[0]) * o->bininvx);
-  if (coord < o->boxlo[0]) o->mbinxlo = o->mbinxlo - 1;
+  o->mbinxlo = (int)((coord - bboxlo[0]) * o->bininvx);
+  if (coord < bboxlo[0]) o->mbinxlo = o->mbinxlo - 1;
   coord = bsubboxhi[0] + SMALL * bbox[0];
-  mbinxhi = (int)((coord - o->boxlo[0]) * o->bininvx);
+  mbinxhi = (int)((coord - bboxlo[0]) * o->bininvx);
 
   coord = bsubboxlo[1] - SMALL * bbox[1];
-  o->mbinylo = (int)((coord - o->boxlo[1]) * o->bininvy);
-  if (coord < o->boxlo[1]) o->mbinylo = o->mbinylo - 1;
+  o->mbinylo = (int)((coord - bboxlo[1]) * o->bininvy);
+  if (coord < bboxlo[1]) o->mbinylo = o->mbinylo - 1;
   coord = bsubboxhi[1] + SMALL * bbox[1];
-  mbinyhi = (int)((coord - o->boxlo[1]) * o->bininvy);
+  mbinyhi = (int)((coord - bboxlo[1]) * o->bininvy);
 
   coord = bsubboxlo[2] - SMALL * bbox[2];
-  o->mbinzlo = (int)((coord - o->boxlo[2]) * o->bininvz);
-  if (coord < o->boxlo[2]) o->mbinzlo = o->mbinzlo - 1;
+  o->mbinzlo = (int)((coord - bboxlo[2]) * o->bininvz);
+  if (coord < bboxlo[2]) o->mbinzlo = o->mbinzlo - 1;
   coord = bsubboxhi[2] + SMALL * bbox[2];
-  mbinzhi = (int)((coord - o->boxlo[2]) * o->bininvz);
+  mbinzhi = (int)((coord - bboxlo[2]) * o->bininvz);
 
   o->mbinxlo -= 1; mbinxhi += 1; o->mbinx = mbinxhi - o->mbinxlo + 1;
   o->mbinylo -= 1; mbinyhi += 1; o->mbiny = mbinyhi - o->mbinylo + 1;
@@ -521,28 +664,30 @@ void orc_setup_bins(Orc *o) {
 /* nbin.cpp:141-173 NBin::coord2bin */
 static int coord2bin(const Orc *o, const double *x) {
   int ix, iy, iz;
+  const double *bboxlo = o->triclinic ? o->boxlo_bound : o->boxlo;
+  const double *bboxhi = o->triclinic ? o->boxhi_bound : o->boxhi;
   if (!isfinite(x[0]) || !isfinite(x[1]) || !isfinite(x[2])) die("non-numeric positions");
-  if (x[0] >= o->boxhi[0])
-    ix = (int)((x[0] - o->boxhi[0]) * o->bininvx) + o->nbinx;
-  else if (x[0] >= o->boxlo[0]) {
-    ix = (int)((x[0] - o->boxlo[0]) * o->bininvx);
+  if (x[0] >= bboxhi[0])
+    ix = (int)((x[0] - bboxhi[0]) * o->bininvx) + o->nbinx;
+  else if (x[0] >= bboxlo[0]) {
+    ix = (int)((x[0] - bboxlo[0]) * o->bininvx);
     ix = MIN(ix, o->nbinx - 1);
   } else
-    ix = (int)((x[0] - o->boxlo[0]) * o->bininvx) - 1;
-  if (x[1] >= o->boxhi[1])
-    iy = (int)((x[1] - o->boxhi[1]) * o->bininvy) + o->nbiny;
-  else if (x[1] >= o->boxlo[1]) {
-    iy = (int)((x[1] - o->boxlo[1]) * o->bininvy);
+    ix = (int)((x[0] - bboxlo[0]) * o->bininvx) - 1;
+  if (x[1] >= bboxhi[1])
+    iy = (int)((x[1] - bboxhi[1]) * o->bininvy) + o->nbiny;
+  else if (x[1] >= bboxlo[1]) {
+    iy = (int)((x[1] - bboxlo[1]) * o->bininvy);
     iy = MIN(iy, o->nbiny - 1);
   } else
-    iy = (int)((x[1] - o->boxlo[1]) * o->bininvy) - 1;
-  if (x[2] >= o->boxhi[2])
-    iz = (int)((x[2] - o->boxhi[2]) * o->bininvz) + o->nbinz;
-  else if (x[2] >= o->boxlo[2]) {
-    iz = (int)((x[2] - o->boxlo[2]) * o->bininvz);
+    iy = (int)((x[1] - bboxlo[1]) * o->bininvy) - 1;
+  if (x[2] >= bboxhi[2])
+    iz = (int)((x[2] - bboxhi[2]) * o->bininvz) + o->nbinz;
+  else if (x[2] >= bboxlo[2]) {
+    iz = (int)((x[2] - bboxlo[2]) * o->bininvz);
     iz = MIN(iz, o->nbinz - 1);
   } else
-    iz = (int)((x[2] - o->boxlo[2]) * o->bininvz) - 1;
+    iz = (int)((x[2] - bboxlo[2]) * o->bininvz) - 1;
   return (iz - o->mbinzlo) * o->mbiny * o->mbinx + (iy - o->mbinylo) * o->mbinx + (ix - o->mbinxlo);
 }
 
@@ -584,11 +729,15 @@ void orc_create_stencil(Orc *o) {
   int smax = (2 * sx + 1) * (2 * sy + 1) * (2 * sz + 1);
   o->stencil = xrealloc(o->stencil, sizeof(int) * smax);
   int n = 0;
-  o->stencil[n++] = 0;
-  for (int k = 0; k <= sz; k++)
+  /* half/newton/orthogonal: central bin first, then the upper half.  half/newton/triclinic
+     (NStencilBin<1,1,1>) and half/newtoff (NStencilBin<0,1,0>, the full stencil): every bin, in
+     loop order, no separate central bin (nstencil_bin.cpp:36-62) */
+  const int full = o->triclinic || !o->newton_pair;
+  if (!full) o->stencil[n++] = 0;
+  for (int k = full ? -sz : 0; k <= sz; k++)
     for (int j = -sy; j <= sy; j++)
       for (int i = -sx; i <= sx; i++) {
-        if (k <= 0 && j <= 0 && (j != 0 || i <= 0)) continue;
+        if (!full && k <= 0 && j <= 0 && (j != 0 || i <= 0)) continue;
         if (bin_distance(o, i, j, k) < o->cutneighmaxsq)
           o->stencil[n++] = k * o->mbiny * o->mbinx + j * o->mbinx + i;
       }
@@ -600,6 +749,8 @@ void orc_create_stencil(Orc *o) {
 /* npair_bin.cpp:52-253 NPairBin<HALF=1,NEWTON=1,TRI=0,SIZE=0,ATOMONLY=1>::build */
 static void npair_build(Orc *o) {
   int nlocal = o->nlocal, n1 = o->ntypes + 1;
+  const int newton = o->newton_pair, tri = o->triclinic;
+  const double delta = 0.01 * o->angstrom; /* npair_bin.cpp:59 */
   int64_t total = 0;
   for (int i = 0; i < nlocal; i++) {
     int itype = o->type[i];
@@ -607,11 +758,35 @@ static void npair_build(Orc *o) {
     int ibin = o->atom2bin[i];
     o->firstneigh[i] = total;
     int n = 0;
+    const int itag = o->tag[i];
     for (int k = 0; k < o->nstencil; k++) {
       int bin_start = o->binhead[ibin + o->stencil[k]];
-      if (k == 0) bin_start = o->bins[i];
+      if (newton && !tri && k == 0) bin_start = o->bins[i];
       for (int j = bin_start; j >= 0; j = o->bins[j]) {
-        if (k == 0) {
+        if (!newton) {
+          /* half list, newton off (npair_bin.cpp:126-131): own/own pairs once, own/ghost pairs
+             on both procs */
+          if (j <= i) continue;
+        } else if (tri) {
+          /* npair_bin.cpp:133-155 */
+          if (j <= i) continue;
+          if (j >= nlocal) {
+            int jtag = o->tag[j];
+            if (itag > jtag) {
+              if ((itag + jtag) % 2 == 0) continue;
+            } else if (itag < jtag) {
+              if ((itag + jtag) % 2 == 1) continue;
+            } else {
+              if (fabs(o->x[3 * j + 2] - ztmp) > delta) {
+                if (o->x[3 * j + 2] < ztmp) continue;
+              } else if (fabs(o->x[3 * j + 1] - ytmp) > delta) {
+                if (o->x[3 * j + 1] < ytmp) continue;
+              } else {
+                if (o->x[3 * j] < xtmp) continue;
+              }
+            }
+          }
+        } else if (k == 0) {
           if (j >= nlocal) {
             if (o->x[3 * j + 2] < ztmp) continue;
             if (o->x[3 * j + 2] == ztmp) {
@@ -621,8 +796,17 @@ static void npair_build(Orc *o) {
           }
         }
         int jtype = o->type[j];
-        /* NPair::exclusion, npair.cpp:244-248 (type pairs; atomic systems have no molecules) */
+        /* NPair::exclusion, npair.cpp:244-254 (type pairs, group pairs; atomic systems have no
+           molecules) */
         if (o->ex_type && o->ex_type[itype * n1 + jtype]) continue;
+        if (o->nex_group) {
+          int ex = 0;
+          for (int m = 0; m < o->nex_group; m++) {
+            if ((o->mask[i] & o->ex1_bit[m]) && (o->mask[j] & o->ex2_bit[m])) ex = 1;
+            if ((o->mask[i] & o->ex2_bit[m]) && (o->mask[j] & o->ex1_bit[m])) ex = 1;
+          }
+          if (ex) continue;
+        }
         double delx = xtmp - o->x[3 * j];
         double dely = ytmp - o->x[3 * j + 1];
         double delz = ztmp - o->x[3 * j + 2];
@@ -694,10 +878,37 @@ static void virial_fdotr(Orc *o) {
   }
 }
 
+/* Pair::ev_tally, pair.cpp:1087-1150, global tallies with newton_pair off: energy and the pairwise
+   virial del (x) del * fpair go half to each LOCAL atom of the pair (with newton off the virial
+   is tallied pair by pair, integrate.cpp:81-82 VIRIAL_PAIR, not by virial_fdotr_compute) */
+static void ev_tally_newtoff(Orc *o, int i, int j, int eflag, int vflag, double evdwl, double fpair,
+                             double delx, double dely, double delz) {
+  const int nlocal = o->nlocal;
+  if (eflag) {
+    double evdwlhalf = 0.5 * evdwl;
+    if (i < nlocal) o->eng_vdwl += evdwlhalf;
+    if (j < nlocal) o->eng_vdwl += evdwlhalf;
+  }
+  if (vflag) {
+    double v[6];
+    v[0] = delx * delx * fpair;
+    v[1] = dely * dely * fpair;
+    v[2] = delz * delz * fpair;
+    v[3] = delx * dely * fpair;
+    v[4] = delx * delz * fpair;
+    v[5] = dely * delz * fpair;
+    if (i < nlocal)
+      for (int k = 0; k < 6; k++) o->virial[k] += 0.5 * v[k];
+    if (j < nlocal)
+      for (int k = 0; k < 6; k++) o->virial[k] += 0.5 * v[k];
+  }
+}
+
 /* pair_lj_cut.cpp:71-141 PairLJCut::compute; ev_tally (pair.cpp:1087-1182) reduced to the
    global-energy branch with newton_pair on: eng_vdwl += evdwl */
 static void lj_compute(Orc *o, int eflag, int vflag) {
   int n1 = o->ntypes + 1;
+  const int newton_pair = o->newton_pair, nlocal = o->nlocal;
   double *x = o->x, *f = o->f;
   for (int i = 0; i < o->inum; i++) {
     double xtmp = x[3 * i], ytmp = x[3 * i + 1], ztmp = x[3 * i + 2];
@@ -721,19 +932,24 @@ static void lj_compute(Orc *o, int eflag, int vflag) {
         f[3 * i + 0] += delx * fpair;
         f[3 * i + 1] += dely * fpair;
         f[3 * i + 2] += delz * fpair;
-        f[3 * j + 0] -= delx * fpair;
-        f[3 * j + 1] -= dely * fpair;
-        f[3 * j + 2] -= delz * fpair;
-        if (eflag) {
-          double evdwl = r6inv * (o->lj3[itype * n1 + jtype] * r6inv - o->lj4[itype * n1 + jtype]) -
-                         o->offset[itype * n1 + jtype];
-          evdwl *= factor_lj;
-          o->eng_vdwl += evdwl;
+        if (newton_pair || j < nlocal) {
+          f[3 * j + 0] -= delx * fpair;
+          f[3 * j + 1] -= dely * fpair;
+          f[3 * j + 2] -= delz * fpair;
         }
+        double evdwl = 0.0;
+        if (eflag) {
+          evdwl = r6inv * (o->lj3[itype * n1 + jtype] * r6inv - o->lj4[itype * n1 + jtype]) -
+                  o->offset[itype * n1 + jtype];
+          evdwl *= factor_lj;
+          if (newton_pair) o->eng_vdwl += evdwl;
+        }
+        if (!newton_pair && (eflag || vflag))
+          ev_tally_newtoff(o, i, j, eflag, vflag, evdwl, fpair, delx, dely, delz);
       }
     }
   }
-  if (vflag) virial_fdotr(o);
+  if (vflag && newton_pair) virial_fdotr(o);
 }
 
 /* pair_eam.cpp:124-327 PairEAM::compute + :338-366 compute_embedding<0> + pair_eam.h:146-169 */
@@ -745,7 +961,8 @@ static void eam_compute(Orc *o, int eflag, int vflag) {
 #define RHOR(t, m) (&o->rhor_spline[((size_t)(t) * (nr + 1) + (m)) * 7])
 #define Z2R(t, m) (&o->z2r_spline[((size_t)(t) * (nr + 1) + (m)) * 7])
 #define FRHO(t, m) (&o->frho_spline[((size_t)(t) * (nrho + 1) + (m)) * 7])
-  for (int i = 0; i < nall; i++) rho[i] = 0.0;
+  const int newton_pair = o->newton_pair;
+  for (int i = 0; i < (newton_pair ? nall : nlocal); i++) rho[i] = 0.0; /* pair_eam.cpp:149-153 */
   for (int i = 0; i < o->inum; i++) {
     double xtmp = x[3 * i], ytmp = x[3 * i + 1], ztmp = x[3 * i + 2];
     int itype = o->type[i];
@@ -767,13 +984,15 @@ static void eam_compute(Orc *o, int eflag, int vflag) {
         p = MIN(p, 1.0);
         const double *coeff = RHOR(o->type2rhor[jtype * n1 + itype], m);
         rhotmp += ((coeff[3] * p + coeff[4]) * p + coeff[5]) * p + coeff[6];
-        coeff = RHOR(o->type2rhor[itype * n1 + jtype], m);
-        rho[j] += ((coeff[3] * p + coeff[4]) * p + coeff[5]) * p + coeff[6];
+        if (newton_pair || j < nlocal) {
+          coeff = RHOR(o->type2rhor[itype * n1 + jtype], m);
+          rho[j] += ((coeff[3] * p + coeff[4]) * p + coeff[5]) * p + coeff[6];
+        }
       }
     }
     rho[i] = rhotmp;
   }
-  reverse_comm_rho(o);
+  if (newton_pair) reverse_comm_rho(o); /* pair_eam.cpp:215 */
 
   int beyond_rhomax = 0;
   for (int i = 0; i < o->inum; i++) {
@@ -833,10 +1052,16 @@ static void eam_compute(Orc *o, int eflag, int vflag) {
         fxtmp += delx * fpair;
         fytmp += dely * fpair;
         fztmp += delz * fpair;
-        f[3 * j + 0] -= delx * fpair;
-        f[3 * j + 1] -= dely * fpair;
-        f[3 * j + 2] -= delz * fpair;
-        if (eflag) o->eng_vdwl += o->scale[itype * n1 + jtype] * phi;
+        if (newton_pair || j < nlocal) {
+          f[3 * j + 0] -= delx * fpair;
+          f[3 * j + 1] -= dely * fpair;
+          f[3 * j + 2] -= delz * fpair;
+        }
+        if (newton_pair) {
+          if (eflag) o->eng_vdwl += o->scale[itype * n1 + jtype] * phi;
+        } else if (eflag || vflag)
+          ev_tally_newtoff(o, i, j, eflag, vflag, eflag ? o->scale[itype * n1 + jtype] * phi : 0.0, fpair, delx,
+                           dely, delz);
       }
     }
     o->numforce[i] = nforce;
@@ -845,8 +1070,7 @@ static void eam_compute(Orc *o, int eflag, int vflag) {
     f[3 * i + 2] = fztmp;
   }
   if (eflag && beyond_rhomax) o->exceeded_rhomax = 1;
-  (void)nlocal;
-  if (vflag) virial_fdotr(o);
+  if (vflag && newton_pair) virial_fdotr(o);
 #undef RHOR
 #undef Z2R
 #undef FRHO
@@ -869,6 +1093,7 @@ void orc_pair_compute(Orc *o, int eflag, int vflag) {
  * compute_stress_atom.cpp:349-356: ghost shares are summed into their owners, last swap first).
  * eatom[nlocal], vatom[nlocal][6] in the order xx,yy,zz,xy,xz,yz; call after a compute with eflag. */
 void orc_pair_peratom(Orc *o, double *eatom_out, double *vatom_out) {
+  if (!o->newton_pair) die("per-atom tallies are restated for newton_pair on only");
   int n1 = o->ntypes + 1, nall = o->nlocal + o->nghost;
   double *x = o->x;
   double *t = (double *)calloc((size_t)MAX(nall, 1) * 7, sizeof(double)); /* [nall][7]: e, v[6] */
@@ -981,18 +1206,20 @@ void orc_final_integrate(Orc *o) {
 /* verlet.cpp:93-162 Verlet::setup (atom->sort() is skipped: it only permutes atoms) */
 void orc_setup(Orc *o, int eflag, int vflag) {
   neighbor_init(o);
+  if (o->triclinic) x2lamda(o, o->nlocal); /* verlet.cpp:111 */
   orc_pbc(o);
   comm_setup(o);
   orc_setup_bins(o);
   orc_create_stencil(o);
   /* comm->exchange(): single proc, nothing migrates after pbc() */
   orc_borders(o);
+  if (o->triclinic) lamda2x(o, o->nlocal + o->nghost); /* verlet.cpp:121 */
   orc_neighbor_build(o);
   o->ncalls = 0;
   o->ndanger = 0;
   orc_force_clear(o);
   orc_pair_compute(o, eflag, vflag);
-  orc_reverse_comm(o);
+  if (o->newton_pair) orc_reverse_comm(o); /* verlet.cpp:147: if (force->newton) */
 }
 
 /* one iteration of verlet.cpp:229-360 Verlet::run; returns 1 if the list was rebuilt */
@@ -1002,13 +1229,15 @@ int orc_step(Orc *o, int eflag, int vflag) {
   if (nflag == 0) {
     orc_forward_comm(o);
   } else {
+    if (o->triclinic) x2lamda(o, o->nlocal); /* verlet.cpp:293 */
     orc_pbc(o);
     orc_borders(o);
+    if (o->triclinic) lamda2x(o, o->nlocal + o->nghost); /* verlet.cpp:313 */
     orc_neighbor_build(o);
   }
   orc_force_clear(o);
   orc_pair_compute(o, eflag, vflag);
-  orc_reverse_comm(o);
+  if (o->newton_pair) orc_reverse_comm(o); /* verlet.cpp:345: if (force->newton) */
   orc_final_integrate(o);
   return nflag;
 }

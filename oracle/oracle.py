@@ -54,7 +54,7 @@ def _p(a):
 
 
 class Oracle:
-    """One periodic orthogonal box on one process, driven like the reference's Verlet."""
+    """One periodic box (orthogonal or triclinic) on one process, driven like the reference's Verlet."""
 
     def __init__(self):
         self.L = lib()
@@ -73,6 +73,18 @@ class Oracle:
     def set_box(self, lo, hi, periodic=(1, 1, 1)):
         lo, hi, per = _d(lo), _d(hi), _i(periodic)
         self.L.orc_set_box(self.h, _p(lo), _p(hi), _p(per))
+
+    def set_box_triclinic(self, lo, hi, xy, xz, yz, periodic=(1, 1, 1), angstrom=1.0):
+        lo, hi, per = _d(lo), _d(hi), _i(periodic)
+        self.L.orc_set_box_triclinic(self.h, _p(lo), _p(hi), C.c_double(xy), C.c_double(xz), C.c_double(yz),
+                                     _p(per), C.c_double(angstrom))
+
+    def set_newton(self, newton_pair):
+        self.L.orc_set_newton(self.h, C.c_int(1 if newton_pair else 0))
+
+    def neigh_modify_groups(self, pairs=()):
+        b1, b2 = _i([p[0] for p in pairs]), _i([p[1] for p in pairs])
+        self.L.orc_neigh_modify_groups(self.h, C.c_int(len(pairs)), _p(b1), _p(b2))
 
     def set_atoms(self, x, v, type, tag, mass, mask=None, image=None):
         x, v, type, tag, mass = _d(x), _d(v), _i(type), _i(tag), _d(mass)

@@ -169,6 +169,71 @@ def test_triclinic_fused_run_on_tiles_equals_flat_list_run():
     assert np.abs(res["tile"][0] - res["flat"][0]).max() <= 1e-9 * np.abs(res["flat"][0]).max()
 
 
+@pytest.mark.parametrize("variant", ["triclinic", "triclinic-newton-off", "newton-off-exclude-group", "eam-triclinic"])
+def test_engine_equals_oracle_restatement(variant):
+    """the CUDA path against md_oracle.c (itself pinned to the compiled reference in
+    tests/test_oracle_tri_newton_live.py) on a melted state: pair sets exact, forces, energy and
+    virial 1e-12, then 60 steps of both (positions 1e-9, same rebuild count)"""
+    from common import eam_system, lj_system, make_engine, make_oracle
+    eam = variant.startswith("eam")
+    s = eam_system((6, 6, 6)) if eam else lj_system((8, 8, 8))
+    n = len(s["x"])
+    a = (s["hi"][0] - s["lo"][0]) / (6 if eam else 8)
+    # tilt factors of whole lattice constants keep the crystal periodic in the sheared cell
+    tilt = (2 * a, -a, 3 * a) if "triclinic" in variant else None
+    mask = (1 | np.where(np.arange(n) % 2 == 0, 2, 4)).astype(np.int32)
+    # melt it in that cell first (forces of a perfect lattice are ~1e-13: nothing to compare)
+    o0 = make_oracle(s)
+    if tilt:
+        o0.set_box_triclinic(s["lo"], s["hi"], *tilt)
+        o0.set_atoms(s["x"], s["v"], s["type"], s["tag"], s["mass"])
+    o0.setup(0, 0)
+    o0.run(40)
+    order = np.argsort(o0.tag())
+    s = dict(s, x=o0.x()[order], v=o0.v()[order], image=o0.image()[order])
+    objs = []
+    for make in (make_oracle, make_engine):
+        o = make(s)
+        if tilt:
+            o.set_box_triclinic(s["lo"], s["hi"], *tilt)
+        o.set_atoms(s["x"], s["v"], s["type"], s["tag"], s["mass"], mask=mask, image=s.get("image"))
+        if "newton-off" in variant:
+            o.set_newton(False)
+        if "exclude-group" in variant:
+            o.neigh_modify_groups([(2, 4)])
+        o.setup(1, 1)
+        objs.append(o)
+    o, e = objs
+    ae = e.get_atoms(ghosts=True, fields=("x", "tag"))
+    _, pi, pj = e.neighbor_list()
+    kor = _pair_keys(*o.pairs(), o.tag(True), o.x(True))
+    keng = _pair_keys(pi, pj, ae["tag"], ae["x"])
+    assert kor.shape == keng.shape and np.array_equal(kor, keng)
+    assert e.counts() == (o.nlocal, o.nghost)
+
+    def state(obj, is_engine):
+        if is_engine:
+            g = obj.get_atoms(fields=("x", "f", "tag"))
+            order = np.argsort(g["tag"])
+            eng, vir = obj.tallies()
+            return g["x"][order], g["f"][order], eng, vir, obj.stats()["nbuilds"]
+        order = np.argsort(obj.tag())
+        return obj.x()[order], obj.f()[order], obj.eng_vdwl, obj.virial, obj.ncalls
+
+    for nsteps, xtol, ftol, etol in ((0, 1e-13, 1e-12, 1e-12), (60, 1e-9, 1e-8, 1e-10)):
+        if nsteps:
+            o.run(nsteps, 0, nsteps)
+            e.run(nsteps, nsteps)
+        xo, fo, eo, vo, bo = state(o, False)
+        xe, fe, ee, ve, be = state(e, True)
+        assert np.abs(xo - xe).max() <= xtol
+        assert np.abs(fo - fe).max() <= ftol * np.abs(fo).max()
+        assert abs(eo - ee) <= etol * abs(eo)
+        assert np.abs(vo - ve).max() <= max(etol, 1e-11) * np.abs(vo).max()
+        assert bo == be
+    e.close()
+
+
 def test_triclinic_mixed_precision_meets_the_mixed_tolerances():
     """FP32 pair math (fixed-point staged positions, sub-domain-wide records) in a prism box:
     forces <= 1e-5, energy <= 1e-6 against the double-precision path (north_star's mixed bar)"""
