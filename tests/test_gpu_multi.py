@@ -84,3 +84,42 @@ def test_lmp_b200_package_drives_two_gpus_from_one_process():
     assert m and int(m.group(1)) == g["neighbors"]
     m = re.search(r"Neighbor list builds = (\d+)", out)
     assert m and int(m.group(1)) == g["builds"]
+
+
+@pytest.mark.parametrize("variant", ["triclinic-langevin-exclude", "newton-off-eam-triclinic"])
+def test_round2_features_on_two_gpus_match_reference_executable(tmp_path, variant):
+    """the round-2 additions across two real devices (`package b200 gpus 2`: peer stores over
+    NVLink instead of copies inside one GPU): a prism box cut into two lamda bricks, group masks
+    of remote ghosts, fix langevin with zero yes (the reference's random stream drawn on the host,
+    summed random force over both sub-domains), newton off, eam -- thermo every step against lmp_ref"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import re
+    import numpy as np
+    sys.path.insert(0, str(ROOT / "tests"))
+    from test_gpu_triclinic import EAM_TRI, LJ_TRI, REF, EXE, _run, _script
+    if variant == "triclinic-langevin-exclude":
+        body = "atom_modify sort 0 0\n" + _script(LJ_TRI, 10, "2.0 -1.0 3.0", "every 2 delay 0 check yes").replace(
+            "fix 1 all nve", "group odd id 1:4000:2\ngroup even id 2:4000:2\nneigh_modify exclude group odd even\n"
+                             "fix 1 all nve\nfix 2 all langevin 1.2 0.9 0.5 33 zero yes")
+        extra = ["-pk", "b200", "gpus", "2", "langevin_rng", "host"]
+    else:
+        body = "newton off\n" + _script(EAM_TRI, 8, "1.5 -2.0 1.0", "every 1 delay 5 check yes")
+        extra = ["-pk", "b200", "gpus", "2"]
+    body += """
+thermo 1
+thermo_style custom step temp pe etotal press pxy pxz pyz
+thermo_modify format float %.12g
+dump 1 all custom 60 f.dump id x y z vx fx fy fz
+dump_modify 1 sort id format float %.10g
+run 60
+"""
+    ta, da, oa = _run(REF, [], tmp_path / "ref", body, 8)
+    tb, db, ob = _run(EXE, ["-sf", "b200", *extra], tmp_path / "b200", body, 8)
+    assert "2 sub-domains on 2 GPU(s)" in ob
+    assert ta.shape == tb.shape == (61, 8)
+    scale = np.maximum(np.abs(ta).max(axis=0), 1e-3)
+    assert (np.abs(ta - tb).max(axis=0) <= 1e-9 * scale).all(), np.abs(ta - tb).max(axis=0) / scale
+    assert np.abs(da[:, 5:8] - db[:, 5:8]).max() <= 1e-8 * np.abs(da[:, 5:8]).max()
+    m = re.search(r"Neighbor list builds = (\d+)", oa)
+    assert m and m.group(0) in ob
