@@ -359,3 +359,56 @@ def langevin_device_uniforms(tag, seed, step):
     r = philox4x32_10(tag, z + np.uint32(step & 0xFFFFFFFF), z + np.uint32((step >> 32) & 0xFFFFFFFF), z,
                       seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     return np.stack([(w.astype(np.float64) + 0.5) * 2.0 ** -32 for w in r[:3]], axis=1)
+
+
+class RanMars:
+    """RanMars (random_mars.cpp:32-100): the Marsaglia generator fix langevin draws from, restated
+    so that a test can rebuild the reference's uniform stream (seed + comm->me, one draw consumed
+    by the constructor)."""
+
+    def __init__(self, seed):
+        assert 0 < seed <= 900000000
+        ij = (seed - 1) // 30082
+        kl = (seed - 1) - 30082 * ij
+        i = (ij // 177) % 177 + 2
+        j = ij % 177 + 2
+        k = (kl // 169) % 178 + 1
+        l = kl % 169
+        self.u = [0.0] * 98
+        for ii in range(1, 98):
+            s, t = 0.0, 0.5
+            for _ in range(24):
+                m = ((i * j) % 179) * k % 179
+                i, j, k = j, k, m
+                l = (53 * l + 1) % 169
+                if (l * m) % 64 >= 32:
+                    s = s + t
+                t = 0.5 * t
+            self.u[ii] = s
+        self.c = 362436.0 / 16777216.0
+        self.cd = 7654321.0 / 16777216.0
+        self.cm = 16777213.0 / 16777216.0
+        self.i97, self.j97 = 97, 33
+        self.uniform()
+
+    def uniform(self):
+        uni = self.u[self.i97] - self.u[self.j97]
+        if uni < 0.0:
+            uni += 1.0
+        self.u[self.i97] = uni
+        self.i97 -= 1
+        if self.i97 == 0:
+            self.i97 = 97
+        self.j97 -= 1
+        if self.j97 == 0:
+            self.j97 = 97
+        self.c -= self.cd
+        if self.c < 0.0:
+            self.c += self.cm
+        uni -= self.c
+        if uni < 0.0:
+            uni += 1.0
+        return uni
+
+    def uniforms(self, n):
+        return np.array([self.uniform() for _ in range(n)])
