@@ -62,8 +62,9 @@ void FixLangevinB200::post_force(int /*vflag*/)
   if (pkg->langevin_rng_host()) {
     // the reference's stream, consumed in tag order: three draws per atom of the group, atom
     // after atom (what its loop does when the host order is the tag order and the group is all)
-    if (comm->nprocs > 1 || igroup != 0 || atom->natoms > MAXSMALLINT / 3)
-      error->all(FLERR, "package b200 langevin_rng host needs one process, group all and < 7e8 atoms");
+    if (comm->nprocs > 1 || igroup != 0 || atom->natoms > MAXSMALLINT / 3 || !atom->tag_consecutive())
+      error->all(FLERR, "package b200 langevin_rng host needs one process, group all, consecutive atom IDs "
+                        "and < 7e8 atoms");
     nu = 3 * atom->natoms;
     uni.resize(nu);
     for (bigint k = 0; k < nu; k++) uni[k] = random->uniform();
