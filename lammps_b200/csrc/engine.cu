@@ -1341,9 +1341,12 @@ static int tile_kernel_attrs(b200_ctx *ctx) {
   TRY(tile_attr(ctx, (k_tile_build<true, false>)));
   TRY(tile_attr(ctx, (k_tile_build<false, false>)));
   TRY(tile_attr(ctx, (k_tile_build<true, true, true>)));
-  TRY(tile_attr(ctx, (k_tile_build<true, true, false, true>)));
-  TRY(tile_attr(ctx, (k_tile_build<false, true, false, true>)));
-  TRY(tile_attr(ctx, (k_tile_build<true, true, true, true>)));
+  TRY(tile_attr(ctx, (k_tile_build<true, true, false, true, true>)));
+  TRY(tile_attr(ctx, (k_tile_build<false, true, false, true, true>)));
+  TRY(tile_attr(ctx, (k_tile_build<true, true, true, true, true>)));
+  TRY(tile_attr(ctx, (k_tile_build<true, true, false, false, true>)));
+  TRY(tile_attr(ctx, (k_tile_build<false, true, false, false, true>)));
+  TRY(tile_attr(ctx, (k_tile_build<true, true, true, false, true>)));
   TRY(tile_attr(ctx, k_tile_export));
   TRY(tile_attr(ctx, k_peratom_tile<1>));
   TRY(tile_attr(ctx, k_peratom_tile<2>));
@@ -1496,8 +1499,7 @@ static int build_tiles(b200_ctx *ctx) {
   k_tile_build<ONE, FULL><<<G.ntiles, ctx->tile_threads, smem, s>>>(                                  \
       G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,   \
       ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,           \
-      ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags, 0.0,  \
-      nullptr, nullptr, 0.0, ctx->newton ? 0 : 1, ctx->exg, ctx->mask[c])
+      ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags)
     // lj/cut: every ghost partner is stored (no scatter, no reverse halo); eam: FWD ghosts only
     const size_t smem2 = build2_smem_bytes(ctx->tile_scap, rows, G.sbx, !one, ctx->tile_slots);
     const double rs = eam2 ? std::max(0.0, std::sqrt(ctx->eam.cutforcesq) + ctx->eam2_margin * ctx->skin) : 0.0;
@@ -1508,19 +1510,27 @@ static int build_tiles(b200_ctx *ctx) {
       ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags, rs * rs,             \
       eam2 ? ctx->tl_far.p : nullptr)
     const double tdelta = 0.01 * ctx->angstrom;  // npair_bin.cpp:59
-#define TBT(ONE, SPL)                                                                                  \
-  k_tile_build<ONE, true, SPL, true><<<G.ntiles, ctx->tile_threads, smem, s>>>(                       \
+#define TBT(ONE, SPL, TRI)                                                                             \
+  k_tile_build<ONE, true, SPL, TRI, true><<<G.ntiles, ctx->tile_threads, smem, s>>>(                  \
       G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,   \
       ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,           \
       ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags,       \
       SPL ? rs * rs : 0.0, SPL ? ctx->tl_far.p : nullptr, ctx->tag[c], tdelta, ctx->newton ? 0 : 1, ctx->exg,  \
       ctx->mask[c])
     if (!ctx->newton && eam && !eam2) return B200_OK;  // no FULLGHOST rows: build_list reports it
+    // triclinic boxes, newton off and group exclusions: the instantiations that carry those rules
+    // (always on rows holding every ghost partner: lj/cut, eam2)
+    const bool extra = !ctx->newton || ctx->exg.n > 0;
+    if ((ctx->tri || extra) && eam && !eam2) return B200_OK;  // flat list instead (build_list)
     if (ctx->tri) {
-      if (eam2) TBT(true, true);
-      else if (one) TBT(true, false);
-      else TBT(false, false);
-    } else if (ctx->build2 && ctx->newton && !ctx->exg.n && smem2 <= BUILD2_SMEM_MAX) {
+      if (eam2) TBT(true, true, true);
+      else if (one) TBT(true, false, true);
+      else TBT(false, false, true);
+    } else if (extra) {
+      if (eam2) TBT(true, true, false);
+      else if (one) TBT(true, false, false);
+      else TBT(false, false, false);
+    } else if (ctx->build2 && smem2 <= BUILD2_SMEM_MAX) {
       if (eam2) TB2(true, true, true);
       else if (!eam) { if (one) TB2(true, true, false); else TB2(false, true, false); }
       else           { if (one) TB2(true, false, false); else TB2(false, false, false); }
@@ -1530,7 +1540,7 @@ static int build_tiles(b200_ctx *ctx) {
           G, ctx->fst, nl, ctx->xt[c], ctx->ostart.p, ctx->gstart.p, ctx->atombin[c], ctx->tile_ibase.p,
           ctx->tile_NI, ctx->tile_slots, cut1, ctx->cutneighsq_d.p, ctx->ntypes, ctx->tl_iloc.p,
           ctx->tl_num.p, ctx->tl_gi.p, ctx->tl_list.p, ctx->numneigh.p, ctx->tile_scap, ctx->tflags,
-          rs * rs, ctx->tl_far.p, nullptr, 0.0, ctx->newton ? 0 : 1, ctx->exg, ctx->mask[c]);
+          rs * rs, ctx->tl_far.p);
     } else if (!eam) { if (one) TB(true, true); else TB(false, true); }
     else      { if (one) TB(true, false); else TB(false, false); }
 #undef TB

@@ -429,7 +429,9 @@ __global__ void __launch_bounds__(256) k_tile_split(int ntiles, const int *__res
 // itag + jtag; a ghost image of i itself by the (z,y,x) comparison with tolerance `tri_delta`.
 // The rule is antisymmetric between the two owners of a boundary pair, so FULLGHOST rows flag
 // the pair FWD on exactly one side, as in the orthogonal case.
-template <bool ONETYPE, bool FULLGHOST, bool SPLIT = false, bool TRI = false>
+// EXTRA: the rarely used list rules (newton off membership, neigh_modify exclude group) are compiled
+// into separate instantiations so that the default build carries none of their tests.
+template <bool ONETYPE, bool FULLGHOST, bool SPLIT = false, bool TRI = false, bool EXTRA = false>
 __global__ void __launch_bounds__(512) k_tile_build(
     TileGeom G, FullStencil F, int nlocal, const double4 *__restrict__ xt,
     const int *__restrict__ ostart, const int *__restrict__ gstart,
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(512) k_tile_build(
         // members of the reference's list: the FWD entries -- or, with newton off
         // (NPairBin<HALF,!NEWTON>, npair_bin.cpp:126-131: "stores own/ghost pairs on both procs"),
         // the FWD owned partners and EVERY ghost partner
-        nf += (newtoff && (flags & TILE_GHOST)) ? 1 : (flags >> 15);
+        nf += (EXTRA && newtoff && (flags & TILE_GHOST)) ? 1 : (flags >> 15);
         if (SPLIT && isfar) {
           flo = (flo >> 16) | (fhi << 48);
           fhi = (fhi >> 16) | (e << 48);
@@ -518,10 +520,10 @@ __global__ void __launch_bounds__(512) k_tile_build(
         const double3 pj = tile_pos3(T, s);
         return rsq_ref(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
       };
-      const int mi = ex.n ? mask[gi] : 0;
+      const int mi = (EXTRA && ex.n) ? mask[gi] : 0;
       auto cutof = [&](int s) -> double {  // the reference's test: rsq <= cutneighsq[itype][jtype]
         // (neigh_modify exclude group: an excluded partner fails the test at every distance)
-        if (ex.n && ex_group(ex, mi, mask[T.gmap[s]])) return -1.0;
+        if (EXTRA && ex.n && ex_group(ex, mi, mask[T.gmap[s]])) return -1.0;
         return ONETYPE ? cut1 : __ldg(cut_i + T.type[s]);
       };
       auto test = [&](int s, unsigned flags) {
