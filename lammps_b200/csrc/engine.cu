@@ -1616,16 +1616,17 @@ static int build_list(b200_ctx *ctx) {
               nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->tag[c], ctx->atombin[c], ctx->ostart.p,
               ctx->gstart.p, ctx->stencil, 0.0, ctx->cutneighsq_d.p, ctx->ntypes, delta, ctx->numneigh.p,
               ctx->neigh.p, ctx->flags + 2, ctx->exg, ctx->mask[c]);
-      } else if (ctx->ntypes == 1)
-        k_build_half<true><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
-            nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->atombin[c], ctx->ostart.p,
-            ctx->gstart.p, ctx->stencil, ctx->cutneighsq_h[n1 + 1], ctx->cutneighsq_d.p,
-            ctx->ntypes, ctx->numneigh.p, ctx->neigh.p, ctx->flags + 2, ctx->exg, ctx->mask[c]);
-      else
-        k_build_half<false><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(
-            nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->atombin[c], ctx->ostart.p,
-            ctx->gstart.p, ctx->stencil, 0.0, ctx->cutneighsq_d.p, ctx->ntypes, ctx->numneigh.p,
-            ctx->neigh.p, ctx->flags + 2, ctx->exg, ctx->mask[c]);
+      } else {
+#define BH(ONE, EXG)                                                                                   \
+  k_build_half<ONE, EXG><<<cdiv(nl, 128), 128, 0, ctx->stream>>>(                                      \
+      nl, ctx->nstride, ctx->maxneigh, ctx->tpa, ctx->xt[c], ctx->atombin[c], ctx->ostart.p, ctx->gstart.p, \
+      ctx->stencil, ONE ? ctx->cutneighsq_h[n1 + 1] : 0.0, ctx->cutneighsq_d.p, ctx->ntypes, ctx->numneigh.p, \
+      ctx->neigh.p, ctx->flags + 2, ctx->exg, ctx->mask[c])
+        const bool one = ctx->ntypes == 1;
+        if (ctx->exg.n) { if (one) BH(true, true); else BH(false, true); }
+        else            { if (one) BH(true, false); else BH(false, false); }
+#undef BH
+      }
       ctx->launches++;
       LAUNCH_CHECK();
     }

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) k_border(int nlocal, const double4 *__res
 // numneigh[i] = full count even when it
 // exceeds maxneigh (then nothing past maxneigh is written and the host regrows the list).
 // ---------------------------------------------------------------------------------------
-template <bool ONETYPE>
+template <bool ONETYPE, bool EXG = false>
 __global__ void __launch_bounds__(128) k_build_half(
     int nlocal, int nstride, int maxneigh, int T, const double4 *__restrict__ xt,
     const int *__restrict__ atombin, const int *__restrict__ ostart,
@@ -322,10 +322,10 @@ __global__ void __launch_bounds__(128) k_build_half(
     const int itype = d2type(pi.w);
     const int b = atombin[i];
     const double *cut_i = ONETYPE ? nullptr : cutneighsq + (size_t)itype * (ntypes + 1);
-    const int mi = ex.n ? mask[i] : 0;
+    const int mi = (EXG && ex.n) ? mask[i] : 0;
 
     auto test = [&](int j) {
-      if (ex.n && ex_group(ex, mi, mask[j])) return;
+      if (EXG && ex.n && ex_group(ex, mi, mask[j])) return;
       const double4 pj = ld_xt(xt + j);
       const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
       const double rsq = rsq_ref(delx, dely, delz);
