@@ -235,6 +235,9 @@ struct b200_ctx {
   // in FP64 (B200_EAM2=0 / `package b200 eam2 no` selects the flat half list kernels).
   ExGroups exg = ExGroups{0, {0}, {0}};  // neigh_modify exclude group
   DBuf<double> mask_s, mask_r;          // group masks of border atoms / remote ghosts (only with exg)
+  VOps vops = VOps{};         // deferred per-atom integrator operations (k_vops), in issue order
+  int vops_chk = 0;           // the queued drift also takes the displacement vote
+  bool lazy_ops = true;       // package b200 lazy yes|no: queue them (default) or run each at once
   int newton = 1;               // Force::newton_pair; 0: lists hold every owned-ghost pair on both sides
   int eam2 = 2;                 // 0 never, 1 whenever usable, 2 auto: small sub-domains (see eam2_usable)
   long long eam2_max_bins = 60000;
@@ -1653,9 +1656,39 @@ static void drop_step_graph(b200_ctx *ctx) {
   }
 }
 
+// ------------------------------------------------------------------ deferred integrator operations
+// b200_scale_v / _v3, b200_nve_v, b200_nve_x queue their per-atom loop (VOps, kernels_step.cuh);
+// whoever next reads or writes x, v or f -- the rebuild vote, halo, rebuild, pair stage, a
+// temperature sum, a download, another force term -- first runs the queue in one pass.  With
+// ke_out the pass also leaves ComputeTemp's sums of the updated velocities there (7 doubles).
+static int flush_vops(b200_ctx *ctx, int ke_groupbit = 0, double *ke_out = nullptr) {
+  if (ctx->vops.n == 0 && !ke_out) return B200_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int nl = ctx->nlocal, c = ctx->cur;
+  if (nl > 0) {
+    const int grid = ke_out ? std::min(cdiv(nl, 256), 148 * 8) : cdiv(nl, 256);
+    if (ke_out)
+      k_vops<true><<<grid, 256, 0, ctx->stream>>>(nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->f[0],
+                                                  ctx->f[1], ctx->f[2], ctx->mask[c], ctx->mass_d.p, ctx->vops,
+                                                  ctx->vops_chk, ctx->xh[0], ctx->xh[1], ctx->xh[2], ctx->triggersq,
+                                                  ctx->flags, ke_groupbit, ke_out);
+    else
+      k_vops<false><<<grid, 256, 0, ctx->stream>>>(nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->f[0],
+                                                   ctx->f[1], ctx->f[2], ctx->mask[c], ctx->mass_d.p, ctx->vops,
+                                                   ctx->vops_chk, ctx->xh[0], ctx->xh[1], ctx->xh[2], ctx->triggersq,
+                                                   ctx->flags, 0, nullptr);
+    ctx->launches++;
+    LAUNCH_CHECK();
+  }
+  ctx->vops.n = 0;
+  ctx->vops_chk = 0;
+  return B200_OK;
+}
+
 // ------------------------------------------------------------------ reneighbor
 // Verlet::run rebuild branch (verlet.cpp:268-297): pbc, exchange, borders, neighbor->build.
 static int reneighbor(b200_ctx *ctx) {
+  TRY(flush_vops(ctx));
   drop_step_graph(ctx);
   if (!ctx->geom_ready) TRY(setup_geometry(ctx));
   if (ctx->box_changes) {  // Neighbor::build: boxlo_hold / boxhi_hold (neighbor.cpp:2533-2541)
@@ -1890,6 +1923,7 @@ static inline int p2p_grid(const b200_ctx *ctx, int n) {
 }
 
 static int force_clear(b200_ctx *ctx) {
+  TRY(flush_vops(ctx));  // a queued half-kick reads the forces this is about to clear
   const int ph3 = ph_begin(ctx, B200_PH_CLEAR);
   const int nall = ctx->nlocal + ctx->nghost;
   // mixed mode: the pair kernel stores f_i and k_merge_ff writes the ghosts; only the float4
@@ -1909,6 +1943,7 @@ static int force_clear(b200_ctx *ctx) {
 }
 
 static int forward_comm(b200_ctx *ctx) {
+  TRY(flush_vops(ctx));
   ctx->q_ghost_valid = false;  // ghost positions change: their fixed-point records follow in q_refresh
   const int ph4 = ph_begin(ctx, B200_PH_FORWARD);
   const int c = ctx->cur;
@@ -1986,6 +2021,7 @@ static int reverse_halo(b200_ctx *ctx, Vec3Ptr a) {
 }
 
 static int reverse_comm(b200_ctx *ctx) {
+  TRY(flush_vops(ctx));
   // lj/cut on tiles evaluates boundary pairs on both sides: no ghost forces to return
   if (ctx->tiles_active && ctx->full_ghost) return B200_OK;
   const int ph5 = ph_begin(ctx, B200_PH_REVERSE);
@@ -2232,6 +2268,7 @@ static int pair_interior_async(b200_ctx *ctx, int eflag, int vflag) {
 // tiles were forked by pair_interior_async, which also cleared the tallies); the join happens
 // before the virial (it reads every force) or is left to the caller (*joined = false)
 static int pair_compute(b200_ctx *ctx, int eflag, int vflag, int part = 0, bool *joined = nullptr) {
+  TRY(flush_vops(ctx));
   const int nl = ctx->nlocal, ng = ctx->nghost, c = ctx->cur;
   cudaStream_t s = ctx->stream;
   const bool ev = eflag || vflag;
@@ -2434,6 +2471,7 @@ static int pair_compute(b200_ctx *ctx, int eflag, int vflag, int part = 0, bool 
 }
 
 static int initial_integrate(b200_ctx *ctx, int do_check) {
+  TRY(flush_vops(ctx));
   if (!ctx->have_nve) return ctx->fail(B200_EARG, "b200_fix_nve has not been called");
   const int ph8 = ph_begin(ctx, B200_PH_INITIAL);
   const int nl = ctx->nlocal, c = ctx->cur;
@@ -2458,6 +2496,7 @@ static int initial_integrate(b200_ctx *ctx, int do_check) {
 }
 
 static int final_integrate(b200_ctx *ctx) {
+  TRY(flush_vops(ctx));
   const int ph9 = ph_begin(ctx, B200_PH_FINAL);
   const int nl = ctx->nlocal, c = ctx->cur;
   if (nl > 0) {
@@ -2476,6 +2515,7 @@ static int final_integrate(b200_ctx *ctx) {
 static int flush_final(b200_ctx *ctx) {
   if (ctx->ahead)
     return ctx->fail(B200_EARG, "atoms are one half-step ahead (fused integrator): a run did not end on a tallied step");
+  TRY(flush_vops(ctx));  // queued operations were issued before whatever asks now
   if (!ctx->pending_final) return B200_OK;
   ctx->pending_final = false;
   return final_integrate(ctx);
@@ -2483,6 +2523,7 @@ static int flush_final(b200_ctx *ctx) {
 
 // Neighbor::decide (neighbor.cpp:2408-2424); `moved` is the device vote of check_distance
 static int decide(b200_ctx *ctx, int *rebuild) {
+  TRY(flush_vops(ctx));  // the queued drift carries the displacement vote
   ctx->ago++;
   *rebuild = 0;
   if (ctx->ago >= ctx->delay && ctx->ago % ctx->every == 0) {
@@ -2841,6 +2882,8 @@ int b200_set_atoms(b200_ctx *ctx, int nlocal, int ntypes, const double *mass, co
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   ctx->ntypes = ntypes;
+  ctx->vops.n = 0;  // queued integrator operations belonged to the previous atoms
+  ctx->vops_chk = 0;
   ctx->mass_h.assign(mass, mass + ntypes + 1);
   TRY(reserve(ctx, ctx->mass_d, (size_t)ntypes + 1));
   CK(cudaMemcpyAsync(ctx->mass_d.p, mass, sizeof(double) * (ntypes + 1), cudaMemcpyHostToDevice, s));
@@ -3107,62 +3150,51 @@ static int staged_guard(b200_ctx *ctx) {
   return B200_OK;
 }
 
+// queue one per-atom integrator operation (or run it at once with `package b200 lazy no`)
+static int push_vop(b200_ctx *ctx, int kind, int groupbit, double a0, double a1 = 0.0, double a2 = 0.0) {
+  if (!ctx->setup_done) return ctx->fail(B200_EARG, "integrator stage before b200_setup");
+  if (ctx->ahead) return ctx->fail(B200_EARG, "integrator stage inside a fused run");
+  if (ctx->pending_final) TRY(flush_final(ctx));  // a deferred half-kick of b200_step comes first
+  if (ctx->vops.n == VOP_MAX) TRY(flush_vops(ctx));
+  VOps &q = ctx->vops;
+  q.kind[q.n] = kind;
+  q.groupbit[q.n] = groupbit;
+  q.a[q.n][0] = a0;
+  q.a[q.n][1] = a1;
+  q.a[q.n][2] = a2;
+  q.n++;
+  if (!ctx->lazy_ops) TRY(flush_vops(ctx));
+  return B200_OK;
+}
+
 int b200_nve_v(b200_ctx *ctx, double dtf, int groupbit) {
   if (!ctx) return B200_EARG;
-  TRY(staged_guard(ctx));
-  const int nl = ctx->nlocal, c = ctx->cur;
-  if (nl > 0) {
-    k_nve_final<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2],
-                                                        ctx->f[0], ctx->f[1], ctx->f[2], ctx->mask[c],
-                                                        ctx->mass_d.p, dtf, groupbit);
-    ctx->launches++;
-    LAUNCH_CHECK();
-  }
-  return B200_OK;
+  return push_vop(ctx, VOP_KICK, groupbit, dtf);
 }
 
 int b200_nve_x(b200_ctx *ctx, double dtv, int groupbit) {
   if (!ctx) return B200_EARG;
-  TRY(staged_guard(ctx));
-  const int nl = ctx->nlocal, c = ctx->cur;
+  if (!ctx->setup_done) return ctx->fail(B200_EARG, "integrator stage before b200_setup");
+  if (ctx->ahead) return ctx->fail(B200_EARG, "integrator stage inside a fused run");
+  if (ctx->pending_final) TRY(flush_final(ctx));
+  if (ctx->vops.n == VOP_MAX || ctx->vops_chk) TRY(flush_vops(ctx));  // room for it; one vote per queue
   // the vote decide() reads after this stage (with a changing box decide() takes it itself)
   const int chk = (check_due_next(ctx) && !ctx->box_changes) ? 1 : 0;
+  CK(cudaSetDevice(ctx->device));
   CK(cudaMemsetAsync(ctx->flags, 0, sizeof(int), ctx->stream));
-  if (nl > 0) {
-    k_nve_x<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2],
-                                                    ctx->mask[c], dtv, groupbit, chk, ctx->xh[0], ctx->xh[1],
-                                                    ctx->xh[2], ctx->triggersq, ctx->flags);
-    ctx->launches++;
-    LAUNCH_CHECK();
-  }
-  ctx->q_owned_valid = false;  // owned positions moved
-  return B200_OK;
+  ctx->vops_chk = chk;
+  ctx->q_owned_valid = false;  // owned positions move
+  return push_vop(ctx, VOP_DRIFT, groupbit, dtv);
 }
 
 int b200_scale_v(b200_ctx *ctx, double factor, int groupbit) {
   if (!ctx) return B200_EARG;
-  TRY(staged_guard(ctx));
-  const int nl = ctx->nlocal, c = ctx->cur;
-  if (nl > 0) {
-    k_scale_v<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->mask[c],
-                                                      factor, groupbit);
-    ctx->launches++;
-    LAUNCH_CHECK();
-  }
-  return B200_OK;
+  return push_vop(ctx, VOP_SCALE, groupbit, factor);
 }
 
 int b200_scale_v3(b200_ctx *ctx, const double factor[3], int groupbit) {
   if (!ctx || !factor) return B200_EARG;
-  TRY(staged_guard(ctx));
-  const int nl = ctx->nlocal, c = ctx->cur;
-  if (nl > 0) {
-    k_scale_v3<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->mask[c],
-                                                       factor[0], factor[1], factor[2], groupbit);
-    ctx->launches++;
-    LAUNCH_CHECK();
-  }
-  return B200_OK;
+  return push_vop(ctx, VOP_SCALE3, groupbit, factor[0], factor[1], factor[2]);
 }
 
 // FixLangevin::post_force (fix_langevin.cpp:383-507) on the stored forces of this step: see
@@ -3349,6 +3381,7 @@ static int graph_step(b200_ctx *ctx) {
 }
 
 static int one_step(b200_ctx *ctx, int eflag, int vflag, int *rebuilt, bool allow_fuse) {
+  TRY(flush_vops(ctx));
   const bool fcand = fuse_candidate(ctx, eflag, vflag, allow_fuse);
   if (!fcand && plain_step(ctx, eflag, vflag)) {
     if (rebuilt) *rebuilt = 0;
@@ -3504,12 +3537,16 @@ int b200_ke_sum(b200_ctx *ctx, double *mv2) {
 int b200_ke_group(b200_ctx *ctx, int groupbit, double *mv2, double tensor[6]) {
   if (!ctx) return B200_EARG;
   if (ctx->ahead) return ctx->fail(B200_EARG, "kinetic energy requested while the integrator runs ahead");
-  TRY(flush_final(ctx));
+  if (ctx->pending_final) TRY(flush_final(ctx));
   CK(cudaSetDevice(ctx->device));
   const int nl = ctx->nlocal, c = ctx->cur;
   double *acc = ctx->ke7;
   CK(cudaMemsetAsync(acc, 0, 7 * sizeof(double), ctx->stream));
-  if (nl > 0) {
+  if (ctx->vops.n > 0) {
+    // queued integrator operations (the half-kick a Nose-Hoover chain takes before it reads the
+    // temperature): one pass applies them and sums the kinetic energy of the result
+    TRY(flush_vops(ctx, groupbit, acc));
+  } else if (nl > 0) {
     k_ke_group<<<std::min(cdiv(nl, 256), 148 * 8), 256, 0, ctx->stream>>>(
         nl, ctx->xt[c], ctx->v[c][0], ctx->v[c][1], ctx->v[c][2], ctx->mask[c], ctx->mass_d.p, groupbit, acc);
     ctx->launches++;
@@ -3530,6 +3567,7 @@ int b200_ke_group(b200_ctx *ctx, int groupbit, double *mv2, double tensor[6]) {
 int b200_sync(b200_ctx *ctx) {
   if (!ctx) return B200_EARG;
   CK(cudaSetDevice(ctx->device));
+  TRY(flush_vops(ctx));
   if (ctx->stream2) CK(cudaStreamSynchronize(ctx->stream2));
   // the device error word comes back with the sync: a peer-memory halo that gave up waiting for a
   // neighbour (P2P_SPIN_LIMIT), a lost atom, a non-finite coordinate
@@ -3570,6 +3608,7 @@ int b200_set_option(b200_ctx *ctx, const char *key, const char *value) {
   else if (k == "fuse") ctx->fuse_nve = yes();
   else if (k == "eam2") { ctx->eam2 = v == "auto" ? 2 : (yes() ? 1 : 0); ctx->geom_ready = false; }
   else if (k == "build2") ctx->build2 = yes();
+  else if (k == "lazy") { TRY(flush_vops(ctx)); ctx->lazy_ops = yes(); }
   else if (k == "tpa") {
     const int t = atoi(value);
     if (t != 1 && t != 2 && t != 4 && t != 8) return ctx->fail(B200_EARG, "package b200 tpa: 1, 2, 4 or 8");
@@ -3682,6 +3721,7 @@ int b200_get_eam_rho_fp(b200_ctx *ctx, int with_ghosts, double *rho, double *fp)
 int b200_pair_peratom(b200_ctx *ctx, double *eatom, double *vatom) {
   if (!ctx) return B200_EARG;
   if (!ctx->setup_done) return ctx->fail(B200_EARG, "b200_pair_peratom before b200_setup");
+  TRY(flush_vops(ctx));
   if (ctx->ahead || ctx->pending_final)
     return ctx->fail(B200_EARG, "per-atom tallies need a step that tallied (eflag/vflag) just before");
   if (ctx->tiles_active && !ctx->full_ghost)

@@ -112,6 +112,91 @@ __global__ void __launch_bounds__(256) k_scale_v3(int nlocal, double *__restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Deferred per-atom integrator operations.  A host-driven integrator (fix nvt / npt / nph, fix nve
+// beside fix langevin) issues its per-atom loops one by one: scale, half-kick, drift, each a full
+// pass over v (and x, f).  None of them is needed before the next consumer of x or v (the rebuild
+// vote, the halo, the pair stage, a temperature sum, a download), so they are queued and executed
+// in ONE pass, operation after operation in registers, each rounded exactly as the separate
+// kernels round it (k_scale_v, k_scale_v3, k_nve_final, k_nve_x).  KE: the same pass ends with
+// ComputeTemp's sums (k_ke_group) -- the temperature a Nose-Hoover chain reads after its half-kick.
+// ---------------------------------------------------------------------------------------
+#define VOP_MAX 8
+enum { VOP_SCALE = 1, VOP_SCALE3 = 2, VOP_KICK = 3, VOP_DRIFT = 4 };
+struct VOps {
+  int n;
+  int kind[VOP_MAX], groupbit[VOP_MAX];
+  double a[VOP_MAX][3];  // SCALE: a[0]; SCALE3: per-component factor applied twice; KICK: dtf; DRIFT: dtv
+};
+
+template <bool KE>
+__global__ void __launch_bounds__(256) k_vops(
+    int nlocal, double4 *__restrict__ xt, double *__restrict__ vx, double *__restrict__ vy,
+    double *__restrict__ vz, const double *__restrict__ fx, const double *__restrict__ fy,
+    const double *__restrict__ fz, const int *__restrict__ mask, const double *__restrict__ mass, VOps ops,
+    int do_check, const double *__restrict__ xhx, const double *__restrict__ xhy,
+    const double *__restrict__ xhz, double triggersq, int *__restrict__ moved, int ke_groupbit,
+    double *__restrict__ ke_out) {
+  double s[7] = {0, 0, 0, 0, 0, 0, 0};
+  bool has_kick = false, has_drift = false;
+  for (int k = 0; k < ops.n; k++) {
+    has_kick |= ops.kind[k] == VOP_KICK;
+    has_drift |= ops.kind[k] == VOP_DRIFT;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
+    double4 p = xt[i];
+    const int m = mask[i];
+    const double mi = mass[d2type(p.w)];
+    double a = vx[i], b = vy[i], c = vz[i];
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    if (has_kick) { f0 = fx[i]; f1 = fy[i]; f2 = fz[i]; }
+    bool vdirty = false, xdirty = false;
+    for (int k = 0; k < ops.n; k++) {
+      if (!(m & ops.groupbit[k])) continue;
+      const int kind = ops.kind[k];
+      if (kind == VOP_SCALE) {
+        const double q = ops.a[k][0];
+        a = __dmul_rn(a, q); b = __dmul_rn(b, q); c = __dmul_rn(c, q);
+        vdirty = true;
+      } else if (kind == VOP_SCALE3) {
+        a = __dmul_rn(__dmul_rn(a, ops.a[k][0]), ops.a[k][0]);
+        b = __dmul_rn(__dmul_rn(b, ops.a[k][1]), ops.a[k][1]);
+        c = __dmul_rn(__dmul_rn(c, ops.a[k][2]), ops.a[k][2]);
+        vdirty = true;
+      } else if (kind == VOP_KICK) {
+        const double dtfm = ops.a[k][0] / mi;
+        a = __dadd_rn(a, __dmul_rn(dtfm, f0));
+        b = __dadd_rn(b, __dmul_rn(dtfm, f1));
+        c = __dadd_rn(c, __dmul_rn(dtfm, f2));
+        vdirty = true;
+      } else {  // VOP_DRIFT
+        const double dtv = ops.a[k][0];
+        p.x = __dadd_rn(p.x, __dmul_rn(dtv, a));
+        p.y = __dadd_rn(p.y, __dmul_rn(dtv, b));
+        p.z = __dadd_rn(p.z, __dmul_rn(dtv, c));
+        xdirty = true;
+      }
+    }
+    if (vdirty) { vx[i] = a; vy[i] = b; vz[i] = c; }
+    if (xdirty) xt[i] = p;
+    if (has_drift && do_check) {
+      const double dx = p.x - xhx[i], dy = p.y - xhy[i], dz = p.z - xhz[i];
+      if (rsq_ref(dx, dy, dz) > triggersq) *moved = 1;
+    }
+    if (KE && (m & ke_groupbit)) {
+      s[0] += (a * a + b * b + c * c) * mi;
+      s[1] += mi * a * a; s[2] += mi * b * b; s[3] += mi * c * c;
+      s[4] += mi * a * b; s[5] += mi * a * c; s[6] += mi * b * c;
+    }
+  }
+  if (KE) {
+    __shared__ double red[7 * 32];
+    block_sum<7>(s, red);
+    if (threadIdx.x == 0)
+      for (int k = 0; k < 7; k++) atomicAdd(&ke_out[k], s[k]);
+  }
+}
+
 struct RemapBox {
   double oldlo[3], oldhinv[3], newlo[3], newh[3];
 };
