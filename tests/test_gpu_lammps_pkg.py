@@ -484,8 +484,9 @@ def test_profile_fills_the_timer_breakdown(tmp_path):
 
 
 @pytest.mark.parametrize("neigh,extra", [("every 20 delay 0 check no", []), ("every 1 delay 0 check yes", []),
-                                         ("every 5 delay 0 check yes", ["-pk", "b200", "subdomains", "8"])],
-                         ids=["check-no", "check-yes", "8-subdomains"])
+                                         ("every 5 delay 0 check yes", ["-pk", "b200", "subdomains", "8"]),
+                                         ("every 1 delay 0 check yes", ["-pk", "b200", "lazy", "no"])],
+                         ids=["check-no", "check-yes", "8-subdomains", "one-kernel-per-loop"])
 def test_fix_nvt_matches_reference_executable(tmp_path, neigh, extra):
     """fix nvt under -sf b200 = fix nvt/b200: the reference's own Nose-Hoover chain (FixNH, inherited)
     on the host, its per-atom loops (nve_v, nve_x, nh_v_temp) and the temperature sum on the device.
