@@ -549,8 +549,17 @@ __global__ void __launch_bounds__(512) k_tile_build(
         const int ca = bx + F.dxlo[r] - xs, cb = bx + F.dxhi[r] + 1 - xs;
         if (TRI) {
           const int itag = tag[gi];
-          for (int s = bo[ca]; s < bo[cb]; s++)
-            if (s != li) test(s, T.gmap[s] > gi ? TILE_FWD : 0u);
+          // owned partners: a staged row is a run of consecutive global indices, so "after i in
+          // the local order" splits the candidate run at one point (and leaves out i itself)
+          {
+            const int lo = bo[ca], hi = bo[cb];
+            const int sstar = H->rowbase[srow] + (gi + 1 - H->row_o0[srow]);  // first with index > gi
+            const int sfwd = min(max(sstar, lo), hi);
+            int sback = sfwd;
+            if (sback > lo && sback - 1 == li) sback--;
+            run(lo, sback, 0u);
+            run(sfwd, hi, TILE_FWD);
+          }
           for (int s = bg[ca]; s < bg[cb]; s++) {
             const int jtag = tag[T.gmap[s]];
             bool member = true;
