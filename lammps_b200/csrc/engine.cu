@@ -3151,7 +3151,8 @@ static int staged_guard(b200_ctx *ctx) {
 }
 
 // queue one per-atom integrator operation (or run it at once with `package b200 lazy no`)
-static int push_vop(b200_ctx *ctx, int kind, int groupbit, double a0, double a1 = 0.0, double a2 = 0.0) {
+static int push_vop(b200_ctx *ctx, int kind, int groupbit, double a0, double a1 = 0.0, double a2 = 0.0,
+                    const double *more = nullptr, int nmore = 0) {
   if (!ctx->setup_done) return ctx->fail(B200_EARG, "integrator stage before b200_setup");
   if (ctx->ahead) return ctx->fail(B200_EARG, "integrator stage inside a fused run");
   if (ctx->pending_final) TRY(flush_final(ctx));  // a deferred half-kick of b200_step comes first
@@ -3162,6 +3163,7 @@ static int push_vop(b200_ctx *ctx, int kind, int groupbit, double a0, double a1 
   q.a[q.n][0] = a0;
   q.a[q.n][1] = a1;
   q.a[q.n][2] = a2;
+  for (int k = 0; k < nmore && k < 9; k++) q.a[q.n][3 + k] = more[k];
   q.n++;
   if (!ctx->lazy_ops) TRY(flush_vops(ctx));
   return B200_OK;
@@ -3260,7 +3262,7 @@ int b200_add_force(b200_ctx *ctx, const double df[3], int groupbit) {
 int b200_remap(b200_ctx *ctx, const double oldlo[3], const double oldhi[3], const double newlo[3],
                const double newhi[3], int groupbit) {
   if (!ctx || !oldlo || !oldhi || !newlo || !newhi) return B200_EARG;
-  TRY(staged_guard(ctx));
+  if (!ctx->setup_done) return ctx->fail(B200_EARG, "integrator stage before b200_setup");
   if (!ctx->geom_ready && !ctx->box_changes) return ctx->fail(B200_EARG, "b200_remap before b200_setup");
   if (ctx->tri) return ctx->fail(B200_EARG, "b200_remap: a changing triclinic box is not supported");
   RemapBox B;
@@ -3271,11 +3273,12 @@ int b200_remap(b200_ctx *ctx, const double oldlo[3], const double oldhi[3], cons
     B.newlo[d] = newlo[d];
     B.newh[d] = newhi[d] - newlo[d];
   }
-  const int nl = ctx->nlocal, c = ctx->cur;
-  if (nl > 0) {
-    k_remap<<<cdiv(nl, 256), 256, 0, ctx->stream>>>(nl, ctx->xt[c], ctx->mask[c], groupbit, B);
-    ctx->launches++;
-    LAUNCH_CHECK();
+  {
+    // the dilation of the atoms joins the queued integrator operations (it sits between the
+    // half-kick and the drift of FixNH::initial_integrate); the box itself is adopted at once
+    const double rest[9] = {B.oldhinv[0], B.oldhinv[1], B.oldhinv[2], B.newlo[0], B.newlo[1], B.newlo[2],
+                            B.newh[0],    B.newh[1],    B.newh[2]};
+    TRY(push_vop(ctx, VOP_REMAP, groupbit, B.oldlo[0], B.oldlo[1], B.oldlo[2], rest, 9));
   }
   ctx->q_owned_valid = false;
   drop_step_graph(ctx);

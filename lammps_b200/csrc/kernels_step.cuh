@@ -122,11 +122,13 @@ __global__ void __launch_bounds__(256) k_scale_v3(int nlocal, double *__restrict
 // ComputeTemp's sums (k_ke_group) -- the temperature a Nose-Hoover chain reads after its half-kick.
 // ---------------------------------------------------------------------------------------
 #define VOP_MAX 8
-enum { VOP_SCALE = 1, VOP_SCALE3 = 2, VOP_KICK = 3, VOP_DRIFT = 4 };
+enum { VOP_SCALE = 1, VOP_SCALE3 = 2, VOP_KICK = 3, VOP_DRIFT = 4, VOP_REMAP = 5 };
 struct VOps {
   int n;
   int kind[VOP_MAX], groupbit[VOP_MAX];
-  double a[VOP_MAX][3];  // SCALE: a[0]; SCALE3: per-component factor applied twice; KICK: dtf; DRIFT: dtv
+  // SCALE: a[0]; SCALE3: per-component factor applied twice; KICK: dtf; DRIFT: dtv;
+  // REMAP (FixNH::remap, k_remap): oldlo[3], 1/oldprd[3], newlo[3], newprd[3]
+  double a[VOP_MAX][12];
 };
 
 template <bool KE>
@@ -169,11 +171,20 @@ __global__ void __launch_bounds__(256) k_vops(
         b = __dadd_rn(b, __dmul_rn(dtfm, f1));
         c = __dadd_rn(c, __dmul_rn(dtfm, f2));
         vdirty = true;
-      } else {  // VOP_DRIFT
+      } else if (kind == VOP_DRIFT) {
         const double dtv = ops.a[k][0];
         p.x = __dadd_rn(p.x, __dmul_rn(dtv, a));
         p.y = __dadd_rn(p.y, __dmul_rn(dtv, b));
         p.z = __dadd_rn(p.z, __dmul_rn(dtv, c));
+        xdirty = true;
+      } else {  // VOP_REMAP: x -> lamda in the old box -> x in the new box, as k_remap
+        const double *q = ops.a[k];
+        const double l0 = __dmul_rn(q[3], __dadd_rn(p.x, -q[0]));
+        const double l1 = __dmul_rn(q[4], __dadd_rn(p.y, -q[1]));
+        const double l2 = __dmul_rn(q[5], __dadd_rn(p.z, -q[2]));
+        p.x = __dadd_rn(__dmul_rn(q[9], l0), q[6]);
+        p.y = __dadd_rn(__dmul_rn(q[10], l1), q[7]);
+        p.z = __dadd_rn(__dmul_rn(q[11], l2), q[8]);
         xdirty = true;
       }
     }
