@@ -12,6 +12,8 @@
      list tile|flat|auto neighbour list layout      tile tx ty tz   bins per tile
      overlap yes|no      interior tiles beside the halo          graph yes|no  CUDA graph
      tpa 1|2|4|8         lanes per atom of the flat kernels      mixed_fx yes|no
+     fuse yes|no         fix nve inside the lj/cut pair kernel   eam2 yes|no|auto  eam tile kernels
+     build2 yes|no       warp-per-bin list build (cross-check)
      lazy yes|no         queue the per-atom loops of host-driven integrators (nvt, npt, langevin)
                          and run them in one pass (default yes)
      langevin_rng device|host   fix langevin/b200: counter-based device stream (default) or
@@ -72,7 +74,7 @@ FixB200::FixB200(LAMMPS *lmp, int narg, char **arg) :
       options.emplace_back("tile", std::string(arg[iarg + 1]) + "," + arg[iarg + 2] + "," + arg[iarg + 3]);
       iarg += 2;
     } else if (key == "list" || key == "overlap" || key == "graph" || key == "tpa" || key == "mixed_fx" ||
-               key == "lazy") {
+               key == "lazy" || key == "fuse" || key == "eam2" || key == "build2") {
       options.emplace_back(key, arg[iarg + 1]);
     } else
       error->all(FLERR, "Unknown package b200 keyword: {}", arg[iarg]);
